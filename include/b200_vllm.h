@@ -1,0 +1,257 @@
+/*
+ * b200_vllm.h -- C ABI of the B200-native (sm_100a) forward hot path for vllm.rs.
+ *
+ * Drop-in boundary.  Every symbol below replaces one call the
+ * reference crate makes into its un-vendored native dependency `attention-rs`
+ * (or composes several of them into one fused launch).  Conventions are the
+ * reference's own (src/utils/gptq.rs:100-200, 314-333):
+ *   - raw device pointers, dims as int32, CUDA stream passed as int64 (CUstream cast);
+ *   - the caller owns every buffer; outputs may be uninitialised on entry and are
+ *     fully written; the callee never allocates, frees, synchronises or retains
+ *     pointers (=> CUDA-graph capturable); scratch comes in through an explicit
+ *     `workspace` pointer sized by the matching *_workspace_bytes() query;
+ *   - `void` return like the reference FFI; failures are latched and can be read
+ *     with b200_last_error()/b200_last_error_string() (0 = none).
+ *   - index dtypes are the reference's: slot_mapping / positions int64,
+ *     block_tables / context_lens / cu_seqlens uint32 (src/core/runner.rs:1243-1388).
+ *
+ * Native KV-cache layout (reference layout "L2", src/utils/kvcache_allocator.rs:150-173):
+ *   K and V, per layer:  [num_blocks, block_size, num_kv_heads, head_dim]  fp16.
+ *
+ * Native quantised-weight layout ("B200 tile-major", produced by the prepack
+ * entry points, same byte count as the checkpoint tensor so it can live in the
+ * buffer the reference allocates for its Marlin repack, src/utils/gptq.rs:286-298):
+ *   4-bit: u32 [N/128][K/64][2][128][4]  -- for out-channel tile nt, K chunk kc,
+ *          half h, channel c, word w: the eight K values k = kc*64 + h*32 + w*8 + j,
+ *          nibble p (p<4) holds j=2p, nibble p+4 holds j=2p+1.
+ *   8-bit: u32 [N/128][K/64][4][128][4]  -- quarter q: k = kc*64 + q*16 + w*4 + j,
+ *          byte j of the word holds K offset j (natural order).
+ *   scales stay [K/G, N] fp16 and qzeros stay in checkpoint packing (AWQ or GPTQ).
+ */
+#ifndef B200_VLLM_H
+#define B200_VLLM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ errors */
+int b200_last_error(void);                 /* 0 = ok, 1 = bad argument, 2 = CUDA error */
+const char* b200_last_error_string(void);
+void b200_clear_error(void);
+int b200_abi_version(void);
+/* kernels launched by this library since load (every launch site counts itself) */
+int64_t b200_launch_count(void);
+
+/* quantisation formats (checkpoint packing of qzeros / zero-point semantics) */
+#define B200_QFMT_AWQ 0       /* zero = nibble (order 0,2,4,6,1,3,5,7), no +1           */
+#define B200_QFMT_GPTQ 1      /* zero = field + 1 (sequential order); NULL qzeros => sym */
+
+/* epilogue flags of b200_wna16_gemm_ex */
+#define B200_EPI_NONE 0
+#define B200_EPI_SILU_MUL 1   /* out[m, n] = silu(acc[m, n]) * acc[m, n + N/2], out is [M, N/2] */
+
+/* ------------------------------------------------- quantised weight prepack
+ * Replaces attention_rs::kernels::ffi::awq_repack (gptq.rs:316-324):
+ *   in  : AWQ qweight  i32 [k, n_packed]   (n = n_packed * 32/bits)
+ *   out : B200 tile-major layout, k*n_packed u32.                              */
+void b200_awq_prepack(const void* in, void* out, int32_t k, int32_t n_packed, int32_t bits,
+                      int64_t stream);
+/* Replaces attention_rs::kernels::ffi::gptq_repack (gptq.rs:325-333):
+ *   in  : GPTQ qweight i32 [k_packed, n]   (k = k_packed * 32/bits)            */
+void b200_gptq_prepack(const void* in, void* out, int32_t k_packed, int32_t n, int32_t bits,
+                       int64_t stream);
+
+/* ------------------------------------------------- W4A16 / W8A16 GEMM
+ * C[m, n] (fp16) = A[m, k] (fp16) x dequant(B)  with fp32 accumulation.
+ * Replace marlin_awq_4bit_f16 / marlin_4bit_f16 (gptq.rs:118-146) and
+ * gemm_half_q_half_alt (gptq.rs:183-195); same argument order as those.
+ * `workspace`: b200_wna16_workspace_bytes() bytes, zero-initialised once by the
+ * caller (the reference already allocates a zeroed workspace, wna16.rs:238-241);
+ * the kernels leave it zeroed on exit.                                          */
+void b200_marlin_awq_4bit_f16(const void* a, const int32_t* b, const void* scales,
+                              const void* qzeros, const void* g_idx, void* c, int32_t m,
+                              int32_t k, int32_t n, const void* workspace, int32_t group_size,
+                              int64_t stream);
+void b200_marlin_4bit_f16(const void* a, const int32_t* b, const void* scales,
+                          const void* qzeros, const void* g_idx, void* c, int32_t m, int32_t k,
+                          int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+/* 8-bit GPTQ path (reference: gemm_half_q_half_alt, bits == 8).  Unlike the reference
+ * symbol this takes the prepacked weight, an explicit group_size and a workspace.  */
+void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const uint32_t* qzeros,
+                                const void* scales, const int32_t* g_idx, void* c, int32_t m,
+                                int32_t n, int32_t k, int32_t group_size, const void* workspace,
+                                int64_t stream);
+/* General entry: bits in {4,8}, qfmt AWQ/GPTQ, optional bias[n] (fp16, may be NULL),
+ * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05.   */
+void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
+                        const void* qzeros, const void* bias, void* c, int32_t m, int32_t k,
+                        int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,
+                        int32_t epilogue, int32_t variant, void* workspace, int64_t stream);
+int64_t b200_wna16_workspace_bytes(int32_t max_m, int32_t max_n);
+
+/* ------------------------------------------------- dense fp16 GEMM (lm_head, fp16 linears)
+ * C[m, n] = A[m, k] x W[n, k]^T ; out_f32 != 0 writes fp32 logits (llama.rs:311-320).  */
+void b200_dense_gemm_f16(const void* a, const void* w, void* c, int32_t m, int32_t n, int32_t k,
+                         int32_t out_f32, int64_t stream);
+
+/* ------------------------------------------------- RoPE + KV-cache write
+ * Replaces FusedRope::apply_inplace (rotary_emb.rs:88-104) followed by the cache
+ * write inside PagedAttention::forward (attention.rs:808-820) in ONE launch.
+ * q [T,H,D], k/v [T,Hkv,D] fp16, rotated in place (q,k); cos/sin [max_pos, rot_dim/2]
+ * (fp16 or, when cos_sin_f32 != 0, fp32); positions int64 [T]; slot_mapping int64 [T]
+ * (slot = block*block_size + offset; negative = skip the cache write).
+ * k_cache/v_cache may be NULL (RoPE only).  interleaved = GPT-J style pairs.       */
+void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                            const int64_t* positions, const int64_t* slot_mapping,
+                            void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                            int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                            int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                            int64_t stream);
+/* Cache write only (reshape_and_cache equivalent). */
+void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cache,
+                       const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
+                       int32_t head_dim, int32_t block_size, int64_t stream);
+
+/* ------------------------------------------------- paged attention, decode
+ * Replaces the decode branch of PagedAttention::forward (attention.rs:808-820).
+ * out/q [B,H,D] fp16; block_tables u32 [B, max_blocks_per_seq] (zero padded);
+ * context_lens u32 [B] (0 => row skipped, out row zeroed).  softcap <= 0 disables;
+ * window <= 0 disables sliding window.  head_dim in {64,128}, block_size == 64,
+ * H/Hkv <= 16.  Per-sequence lengths are read on the device (graph safe).          */
+void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
+                                const void* v_cache, const uint32_t* block_tables,
+                                const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                float softcap, int32_t window, void* workspace, int64_t stream);
+int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim,
+                                        int32_t max_blocks_per_seq);
+
+/* ------------------------------------------------- glue kernels (others.rs, mlp.rs, llama.rs) */
+void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
+                      int32_t hidden, float eps, int64_t stream);
+/* residual += x (fp16 rounding, as llama.rs:126-130); out = rmsnorm(residual) * weight */
+void b200_add_rmsnorm_f16(void* out, void* residual, const void* x, const void* weight,
+                          int32_t num_tokens, int32_t hidden, float eps, int64_t stream);
+void b200_silu_mul_f16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
+                       int64_t stream);
+void b200_embedding_f16(void* out, const void* table, const uint32_t* ids, int32_t num_tokens,
+                        int32_t hidden, int32_t vocab, int64_t stream);
+void b200_gather_rows_f16(void* out, const void* x, const uint32_t* rows, int32_t num_rows,
+                          int32_t hidden, int64_t stream);
+void b200_argmax_f32(uint32_t* out_ids, const float* logits, int32_t batch, int32_t vocab,
+                     int64_t stream);
+void b200_add_bias_f16(void* x, const void* bias, int32_t num_tokens, int32_t n, int64_t stream);
+
+/* ------------------------------------------------- host side: block manager / scheduler
+ * C++ mirror of src/core/{sequence,block_manager,scheduler}.rs and the input
+ * preparation of src/core/runner.rs:952-1388.  Handles are opaque.               */
+typedef struct b200_scheduler b200_scheduler;
+b200_scheduler* b200_scheduler_new(int32_t num_blocks, int32_t block_size, int32_t max_num_seqs,
+                                   int32_t max_num_batched_tokens, int32_t chunk_size,
+                                   const uint32_t* eos_ids, int32_t num_eos);
+void b200_scheduler_free(b200_scheduler*);
+/* returns seq id (scheduler.rs:186-192) */
+int64_t b200_scheduler_add(b200_scheduler*, const uint32_t* tokens, int32_t num_tokens,
+                           int32_t max_tokens);
+/* schedule(): writes indices into `running` (<= cap); returns count, *is_prefill set.
+ * Returns -1 on error (e.g. out of blocks).  (scheduler.rs:200-380)               */
+int32_t b200_scheduler_schedule(b200_scheduler*, int32_t* indices, int32_t cap,
+                                int32_t* is_prefill);
+/* filter_prefill_finished (scheduler.rs:718-785): returns number finished; writes the
+ * positions within `indices` (out_pos) and the new running indices (out_idx).      */
+int32_t b200_scheduler_filter_prefill_finished(b200_scheduler*, const int32_t* indices,
+                                               int32_t n, int32_t* out_pos, int32_t* out_idx);
+void b200_scheduler_postprocess(b200_scheduler*, const int32_t* indices, int32_t n,
+                                const uint32_t* tokens);
+void b200_scheduler_clear_finished(b200_scheduler*);
+int32_t b200_scheduler_num_running(const b200_scheduler*);
+int32_t b200_scheduler_num_waiting(const b200_scheduler*);
+int32_t b200_scheduler_num_free_blocks(const b200_scheduler*);
+/* inspect a running sequence: returns token count; copies up to cap entries */
+int32_t b200_scheduler_seq_info(const b200_scheduler*, int32_t running_idx, int64_t* seq_id,
+                                int32_t* num_cached_tokens, int32_t* status,
+                                int32_t* num_output_tokens);
+int32_t b200_scheduler_seq_block_table(const b200_scheduler*, int32_t running_idx,
+                                       uint32_t* out, int32_t cap);
+int32_t b200_scheduler_seq_tokens(const b200_scheduler*, int32_t running_idx, uint32_t* out,
+                                  int32_t cap);
+
+/* prepare_decode (runner.rs:1243-1388) + prepare_block_tables (runner.rs:952-974).
+ * Host output buffers sized [n] / [n * max_blocks_cap]; returns max_blocks (row
+ * stride used) or -1 if max_blocks_cap is too small.  *max_context_len set.        */
+int32_t b200_prepare_decode(const b200_scheduler*, const int32_t* indices, int32_t n,
+                            uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,
+                            uint32_t* context_lens, uint32_t* block_tables,
+                            int32_t max_blocks_cap, int32_t* max_context_len);
+/* prepare_prefill (runner.rs:978-1241).  Returns total tokens T (or -1 if cap too
+ * small).  cu_seqlens_* are [n+1].  *has_context != 0 when block_tables /
+ * context_lens were produced (some sequence has cached KV).                        */
+int32_t b200_prepare_prefill(const b200_scheduler*, const int32_t* indices, int32_t n,
+                             int32_t token_cap, uint32_t* input_ids, int64_t* positions,
+                             int64_t* slot_mapping, uint32_t* cu_seqlens_q,
+                             uint32_t* cu_seqlens_k, uint32_t* context_lens,
+                             uint32_t* block_tables, int32_t max_blocks_cap,
+                             int32_t* max_blocks, int32_t* max_seqlen_q, int32_t* max_seqlen_k,
+                             int32_t* max_context_len, int32_t* has_context);
+
+/* ------------------------------------------------- model runner (decode step)
+ * C++ mirror of ModelRunner::run for the decode branch (runner.rs:743-896) over
+ * LLaMaForCausalLM::forward_inner (llama.rs:269-321): every launch of one decode
+ * step, optionally captured into CUDA graphs per batch bucket (graph.rs:370-377).  */
+typedef struct b200_model_config {
+  int32_t hidden, num_layers, num_heads, num_kv_heads, head_dim, inter, vocab;
+  int32_t bits, group_size, qfmt;      /* bits = 16 => dense fp16 weights              */
+  int32_t block_size, num_blocks, max_blocks_per_seq, max_batch, max_pos;
+  int32_t qkv_bias;                    /* Qwen2: q/k/v bias                            */
+  int32_t cos_sin_f32;
+  float rms_eps, attn_scale;
+  int32_t tp_rank, tp_size;            /* shapes above are the LOCAL (per-rank) shard  */
+} b200_model_config;
+
+typedef struct b200_layer_weights {
+  const void *input_norm, *post_norm;                 /* fp16 [hidden]                  */
+  const void *qkv_w, *qkv_s, *qkv_z, *qkv_bias;       /* fused q|k|v along N            */
+  const void *o_w, *o_s, *o_z;
+  const void *gate_up_w, *gate_up_s, *gate_up_z;      /* fused gate|up along N          */
+  const void *down_w, *down_s, *down_z;
+  void *k_cache, *v_cache;
+} b200_layer_weights;
+
+typedef struct b200_runner b200_runner;
+b200_runner* b200_runner_new(const b200_model_config* cfg);
+void b200_runner_free(b200_runner*);
+void b200_runner_set_layer(b200_runner*, int32_t layer, const b200_layer_weights* w);
+void b200_runner_set_globals(b200_runner*, const void* embed, const void* final_norm,
+                             const void* lm_head, const void* cos, const void* sin);
+int64_t b200_runner_workspace_bytes(const b200_runner*);
+void b200_runner_set_workspace(b200_runner*, void* workspace, int64_t bytes);
+/* all-reduce hook for tensor parallelism: called on the stream after o_proj / down_proj
+ * with (buf, count_halfs, user, stream); NULL => single GPU (distributed.rs:438-454).  */
+typedef void (*b200_allreduce_fn)(void* buf, int64_t count, void* user, int64_t stream);
+void b200_runner_set_allreduce(b200_runner*, b200_allreduce_fn fn, void* user);
+/* One decode step from DEVICE inputs; logits (fp32 [B, vocab]) and/or greedy token
+ * ids (u32 [B]) are written to device buffers (either may be NULL).                */
+void b200_runner_decode_device(b200_runner*, const uint32_t* input_ids, const int64_t* positions,
+                               const int64_t* slot_mapping, const uint32_t* block_tables,
+                               const uint32_t* context_lens, int32_t batch, float* logits,
+                               uint32_t* out_ids, int64_t stream);
+/* ModelRunner::run equivalent for decode: HOST inputs (pinned), copies H2D, runs the
+ * step (graph replay when captured for this bucket), copies token ids D2H and
+ * synchronises the stream.  Returns 0 on success.                                   */
+int32_t b200_runner_decode_host(b200_runner*, const uint32_t* input_ids,
+                                const int64_t* positions, const int64_t* slot_mapping,
+                                const uint32_t* block_tables, int32_t max_blocks,
+                                const uint32_t* context_lens, int32_t batch,
+                                uint32_t* out_ids_host, int64_t stream);
+/* Capture CUDA graphs for the given batch buckets (graph.rs:448-690). 0 on success. */
+int32_t b200_runner_capture(b200_runner*, const int32_t* buckets, int32_t num_buckets,
+                            int64_t stream);
+int64_t b200_runner_launches_per_step(const b200_runner*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_VLLM_H */

@@ -1,0 +1,134 @@
+"""ctypes binding of the C ABI declared in include/b200_vllm.h.
+
+The product path has NO fallback: if the shared library is missing this raises, and every
+op checks the latched error state after launching.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libb200_vllm.so"
+HEADER = PKG.parent / "include" / "b200_vllm.h"
+
+_lib = None
+
+c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class ModelConfig(C.Structure):
+    """b200_model_config (include/b200_vllm.h)."""
+
+    _fields_ = [(n, c_i32) for n in (
+        "hidden", "num_layers", "num_heads", "num_kv_heads", "head_dim", "inter", "vocab",
+        "bits", "group_size", "qfmt",
+        "block_size", "num_blocks", "max_blocks_per_seq", "max_batch", "max_pos",
+        "qkv_bias", "cos_sin_f32")] + [("rms_eps", c_f32), ("attn_scale", c_f32),
+                                       ("tp_rank", c_i32), ("tp_size", c_i32)]
+
+
+class LayerWeights(C.Structure):
+    """b200_layer_weights (include/b200_vllm.h)."""
+
+    _fields_ = [(n, c_vp) for n in (
+        "input_norm", "post_norm",
+        "qkv_w", "qkv_s", "qkv_z", "qkv_bias",
+        "o_w", "o_s", "o_z",
+        "gate_up_w", "gate_up_s", "gate_up_z",
+        "down_w", "down_s", "down_z",
+        "k_cache", "v_cache")]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(None, c_vp, c_i64, c_vp, c_i64)
+
+# name -> (restype, argtypes)
+_SIGS = {
+    "b200_last_error": (C.c_int, []),
+    "b200_last_error_string": (C.c_char_p, []),
+    "b200_clear_error": (None, []),
+    "b200_abi_version": (C.c_int, []),
+    "b200_launch_count": (c_i64, []),
+    "b200_awq_prepack": (None, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64]),
+    "b200_gptq_prepack": (None, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64]),
+    "b200_marlin_awq_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
+    "b200_marlin_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
+    "b200_gemm_half_q_half_8bit": (None, [c_vp] * 6 + [c_i32] * 4 + [c_vp, c_i64]),
+    "b200_wna16_gemm_ex": (None, [c_vp] * 6 + [c_i32] * 8 + [c_vp, c_i64]),
+    "b200_wna16_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "b200_dense_gemm_f16": (None, [c_vp] * 3 + [c_i32] * 4 + [c_i64]),
+    "b200_rope_kv_write_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
+    "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
+    "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
+    "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
+    "b200_rmsnorm_f16": (None, [c_vp] * 3 + [c_i32, c_i32, c_f32, c_i64]),
+    "b200_add_rmsnorm_f16": (None, [c_vp] * 4 + [c_i32, c_i32, c_f32, c_i64]),
+    "b200_silu_mul_f16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
+    "b200_embedding_f16": (None, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64]),
+    "b200_gather_rows_f16": (None, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64]),
+    "b200_argmax_f32": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
+    "b200_add_bias_f16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
+    "b200_scheduler_new": (c_vp, [c_i32] * 5 + [c_vp, c_i32]),
+    "b200_scheduler_free": (None, [c_vp]),
+    "b200_scheduler_add": (c_i64, [c_vp, c_vp, c_i32, c_i32]),
+    "b200_scheduler_schedule": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
+    "b200_scheduler_filter_prefill_finished": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "b200_scheduler_postprocess": (None, [c_vp, c_vp, c_i32, c_vp]),
+    "b200_scheduler_clear_finished": (None, [c_vp]),
+    "b200_scheduler_num_running": (c_i32, [c_vp]),
+    "b200_scheduler_num_waiting": (c_i32, [c_vp]),
+    "b200_scheduler_num_free_blocks": (c_i32, [c_vp]),
+    "b200_scheduler_seq_info": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "b200_scheduler_seq_block_table": (c_i32, [c_vp, c_i32, c_vp, c_i32]),
+    "b200_scheduler_seq_tokens": (c_i32, [c_vp, c_i32, c_vp, c_i32]),
+    "b200_prepare_decode": (c_i32, [c_vp, c_vp, c_i32] + [c_vp] * 5 + [c_i32, c_vp]),
+    "b200_prepare_prefill": (c_i32, [c_vp, c_vp, c_i32, c_i32] + [c_vp] * 7 + [c_i32] + [c_vp] * 5),
+    "b200_runner_new": (c_vp, [C.POINTER(ModelConfig)]),
+    "b200_runner_free": (None, [c_vp]),
+    "b200_runner_set_layer": (None, [c_vp, c_i32, C.POINTER(LayerWeights)]),
+    "b200_runner_set_globals": (None, [c_vp] * 6),
+    "b200_runner_workspace_bytes": (c_i64, [c_vp]),
+    "b200_runner_set_workspace": (None, [c_vp, c_vp, c_i64]),
+    "b200_runner_set_allreduce": (None, [c_vp, ALLREDUCE_FN, c_vp]),
+    "b200_runner_decode_device": (None, [c_vp] * 6 + [c_i32, c_vp, c_vp, c_i64]),
+    "b200_runner_decode_host": (c_i32, [c_vp] * 5 + [c_i32, c_vp, c_i32, c_vp, c_i64]),
+    "b200_runner_capture": (c_i32, [c_vp, c_vp, c_i32, c_i64]),
+    "b200_runner_launches_per_step": (c_i64, [c_vp]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function name declared in include/b200_vllm.h."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)) - {"b200_allreduce_fn"})
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -m vllm_rs_b200.build` (there is no CPU fallback)")
+        _lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def check() -> None:
+    """Raise if any call since the last check latched an error."""
+    l = lib()
+    code = l.b200_last_error()
+    if code:
+        msg = l.b200_last_error_string().decode()
+        l.b200_clear_error()
+        raise B200Error(f"b200 error {code}: {msg}")

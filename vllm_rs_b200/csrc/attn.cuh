@@ -1,0 +1,23 @@
+// Internal launch interface of the paged-attention decode kernel (tensor maps prebuilt
+// once per layer by the model runner; the C ABI wrapper builds them per call).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+struct AttnMaps {
+  CUtensorMap k, v;
+};
+bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks,
+                    int Hkv, int D);
+void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
+                              const uint32_t* block_tables, const uint32_t* context_lens, int B,
+                              int H, int Hkv, int D, int max_blocks, float scale, float softcap,
+                              int window, void* workspace, cudaStream_t st);
+// RoPE + KV write with explicit row strides (in halfs) so q|k|v can live in one fused
+// GEMM output row.
+void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,
+                          int v_stride, const void* cos, const void* sin,
+                          const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
+                          void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
+                          int interleaved, int cos_sin_f32, cudaStream_t st);
+}  // namespace b200

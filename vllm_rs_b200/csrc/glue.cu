@@ -1,0 +1,386 @@
+// Memory-bound glue kernels of the decoder layer: RoPE fused with the KV-cache write,
+// RMSNorm (optionally fused with the residual add), SiLU*mul, embedding / row gather,
+// bias add and greedy argmax.  All are HBM/L2-bound elementwise or row-reduction
+// kernels: 128-bit loads, fp32 math, one rounding to fp16 on store.
+//
+// Reference call sites they replace:
+//   FusedRope::apply_inplace          /root/reference/src/models/layers/rotary_emb.rs:88-104
+//   cache write in PagedAttention     /root/reference/src/models/layers/attention.rs:808-820
+//   NormX::forward / rms_norm         /root/reference/src/models/layers/others.rs:11-66
+//   residual adds                     /root/reference/src/models/llama.rs:107-131
+//   act(gate) * up                    /root/reference/src/models/layers/mlp.rs:451-469
+//   embedding / index_select          /root/reference/src/models/llama.rs:269-310
+//   logits.argmax                     /root/reference/src/utils/logits_processor.rs:67-70
+#include "../../include/b200_vllm.h"
+#include "attn.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ RoPE + KV write
+// grid = tokens; one thread per rotation pair / per 2 copied elements.
+// Cache layout [num_blocks, block_size, Hkv, D]: slot s -> row s of [.., Hkv, D].
+template <bool kCosSinF32>
+__global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict__ k,
+                                     const __half* __restrict__ v, const void* __restrict__ cosp,
+                                     const void* __restrict__ sinp,
+                                     const int64_t* __restrict__ positions,
+                                     const int64_t* __restrict__ slot_mapping,
+                                     __half* __restrict__ k_cache, __half* __restrict__ v_cache,
+                                     int q_stride, int k_stride, int v_stride, int H, int Hkv,
+                                     int D, int rot_dim, int interleaved) {
+  const int t = blockIdx.x;
+  const int64_t pos = positions ? positions[t] : 0;
+  const int half_rot = rot_dim >> 1;
+  const int64_t slot = (slot_mapping && k_cache) ? slot_mapping[t] : -1;
+  __half* qt = q + static_cast<size_t>(t) * q_stride;
+  __half* kt = k + static_cast<size_t>(t) * k_stride;
+  const __half* vt = v ? v + static_cast<size_t>(t) * v_stride : nullptr;
+  __half* kc = slot >= 0 ? k_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
+  __half* vc = (slot >= 0 && v_cache) ? v_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
+
+  // rotation pairs of q and k
+  const int pairs_per_head = D >> 1;
+  const int total_pairs = (H + Hkv) * pairs_per_head;
+  for (int idx = threadIdx.x; idx < total_pairs; idx += blockDim.x) {
+    const int head = idx / pairs_per_head;
+    const int p = idx - head * pairs_per_head;
+    const bool is_q = head < H;
+    __half* base = is_q ? qt + head * D : kt + (head - H) * D;
+    int i0, i1;
+    bool rotate = p < half_rot;
+    if (interleaved) {
+      i0 = 2 * p;
+      i1 = 2 * p + 1;
+    } else if (rotate) {
+      i0 = p;
+      i1 = p + half_rot;
+    } else {
+      // un-rotated tail (partial rotary): elements rot_dim + 2*(p-half_rot) + {0,1}
+      i0 = rot_dim + 2 * (p - half_rot);
+      i1 = i0 + 1;
+    }
+    float x0 = __half2float(base[i0]), x1 = __half2float(base[i1]);
+    if (rotate) {
+      float cs, sn;
+      if (kCosSinF32) {
+        cs = reinterpret_cast<const float*>(cosp)[pos * half_rot + p];
+        sn = reinterpret_cast<const float*>(sinp)[pos * half_rot + p];
+      } else {
+        cs = __half2float(reinterpret_cast<const __half*>(cosp)[pos * half_rot + p]);
+        sn = __half2float(reinterpret_cast<const __half*>(sinp)[pos * half_rot + p]);
+      }
+      const float y0 = x0 * cs - x1 * sn;
+      const float y1 = x1 * cs + x0 * sn;
+      const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+      base[i0] = h0;
+      base[i1] = h1;
+      if (!is_q && kc) {
+        kc[(head - H) * D + i0] = h0;
+        kc[(head - H) * D + i1] = h1;
+      }
+    } else if (!is_q && kc) {
+      kc[(head - H) * D + i0] = base[i0];
+      kc[(head - H) * D + i1] = base[i1];
+    }
+  }
+  // V copy (8 halves per thread)
+  if (vc && vt) {
+    const int n16 = (Hkv * D) >> 3;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      reinterpret_cast<uint4*>(vc)[i] = reinterpret_cast<const uint4*>(vt)[i];
+  }
+}
+
+__global__ void kv_write_kernel(const __half* __restrict__ k, const __half* __restrict__ v,
+                                __half* __restrict__ k_cache, __half* __restrict__ v_cache,
+                                const int64_t* __restrict__ slot_mapping, int row_halfs) {
+  const int t = blockIdx.x;
+  const int64_t slot = slot_mapping[t];
+  if (slot < 0) return;
+  const int n16 = row_halfs >> 3;
+  const uint4* ks = reinterpret_cast<const uint4*>(k + static_cast<size_t>(t) * row_halfs);
+  const uint4* vs = reinterpret_cast<const uint4*>(v + static_cast<size_t>(t) * row_halfs);
+  uint4* kd = reinterpret_cast<uint4*>(k_cache + static_cast<size_t>(slot) * row_halfs);
+  uint4* vd = reinterpret_cast<uint4*>(v_cache + static_cast<size_t>(slot) * row_halfs);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+    kd[i] = ks[i];
+    vd[i] = vs[i];
+  }
+}
+
+// ------------------------------------------------------------------ RMSNorm
+// One CTA per token.  kAdd: residual = fp16(residual + x) first (llama.rs:126-130
+// performs the add in model dtype), then out = fp16(residual * rsqrt(mean sq + eps) * w).
+template <bool kAdd>
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
+               const __half* __restrict__ x, const __half* __restrict__ w, int hidden,
+               float eps) {
+  const int t = blockIdx.x;
+  const int n8 = hidden >> 3;
+  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * hidden);
+  uint4* rs = kAdd ? reinterpret_cast<uint4*>(residual + static_cast<size_t>(t) * hidden) : nullptr;
+  uint4* os = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * hidden);
+  const uint4* ws = reinterpret_cast<const uint4*>(w);
+  extern __shared__ uint4 row[];   // hidden halfs (kept on chip between the two passes)
+  __shared__ float red[8];
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    uint4 a = xs[i];
+    if (kAdd) {
+      uint4 r = rs[i];
+      __half2* ah = reinterpret_cast<__half2*>(&a);
+      const __half2* rh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ah[j] = __hadd2(ah[j], rh[j]);
+      rs[i] = a;
+    }
+    row[i] = a;
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(ah[j]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / static_cast<float>(hidden) + eps);
+  for (int i = threadIdx.x; i < n8; i += blockDim.x) {
+    uint4 a = row[i];
+    const uint4 wv = ws[i];
+    __half2* ah = reinterpret_cast<__half2*>(&a);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(ah[j]);
+      const float2 g = __half22float2(wh[j]);
+      ah[j] = __floats2half2_rn(f.x * inv * g.x, f.y * inv * g.y);
+    }
+    os[i] = a;
+  }
+}
+
+// ------------------------------------------------------------------ SiLU(gate) * up
+__global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restrict__ gate_up,
+                                int inter) {
+  const int t = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index of an 8-half vector
+  if (i * 8 >= inter) return;
+  const uint4 gv = reinterpret_cast<const uint4*>(gate_up + static_cast<size_t>(t) * 2 * inter)[i];
+  const uint4 uv =
+      reinterpret_cast<const uint4*>(gate_up + static_cast<size_t>(t) * 2 * inter + inter)[i];
+  uint4 o;
+  const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+  const __half2* uh = reinterpret_cast<const __half2*>(&uv);
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 g = __half22float2(gh[j]);
+    const float2 u = __half22float2(uh[j]);
+    oh[j] = __floats2half2_rn(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
+  }
+  reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * inter)[i] = o;
+}
+
+// ------------------------------------------------------------------ row gathers
+__global__ void gather_rows_kernel(__half* __restrict__ out, const __half* __restrict__ table,
+                                   const uint32_t* __restrict__ ids, int hidden, int nrows_src) {
+  const int t = blockIdx.x;
+  uint32_t id = ids[t];
+  if (nrows_src > 0 && id >= static_cast<uint32_t>(nrows_src)) id = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * hidden);
+  for (int i = threadIdx.x; i < (hidden >> 3); i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void add_bias_kernel(__half* __restrict__ x, const __half* __restrict__ bias, int n) {
+  const int t = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 2 >= n) return;
+  __half2* p = reinterpret_cast<__half2*>(x + static_cast<size_t>(t) * n) + i;
+  *p = __hadd2(*p, reinterpret_cast<const __half2*>(bias)[i]);
+}
+
+// ------------------------------------------------------------------ argmax (first max wins)
+__global__ void __launch_bounds__(1024)
+argmax_kernel(uint32_t* __restrict__ out_ids, const float* __restrict__ logits, int vocab) {
+  const int b = blockIdx.x;
+  const float* row = logits + static_cast<size_t>(b) * vocab;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  const int n4 = vocab >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e[j] > best) {   // ascending index within a thread: strict > keeps the first
+        best = e[j];
+        best_i = i * 4 + j;
+      }
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < vocab; i += blockDim.x)
+    if (row[i] > best || (row[i] == best && i < best_i)) {
+      best = row[i];
+      best_i = i;
+    }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) {
+      best = ov;
+      best_i = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = best_i;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    best = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
+    best_i = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) {
+        best = ov;
+        best_i = oi;
+      }
+    }
+    if (threadIdx.x == 0) out_ids[b] = best_i == 0x7fffffff ? 0u : static_cast<uint32_t>(best_i);
+  }
+}
+
+void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,
+                          int v_stride, const void* cos, const void* sin,
+                          const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
+                          void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
+                          int interleaved, int cos_sin_f32, cudaStream_t st) {
+  const int pairs = (H + Hkv) * D / 2;
+  const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
+  if (cos_sin_f32)
+    rope_kv_write_kernel<true><<<T, threads, 0, st>>>(
+        (__half*)q, (__half*)k, (const __half*)v, cos, sin, positions, slot_mapping,
+        (__half*)k_cache, (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim,
+        interleaved);
+  else
+    rope_kv_write_kernel<false><<<T, threads, 0, st>>>(
+        (__half*)q, (__half*)k, (const __half*)v, cos, sin, positions, slot_mapping,
+        (__half*)k_cache, (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim,
+        interleaved);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace b200
+
+extern "C" {
+using namespace b200;
+
+void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                            const int64_t* positions, const int64_t* slot_mapping,
+                            void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                            int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                            int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                            int64_t stream) {
+  (void)block_size;
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(head_dim % 8 == 0 && rot_dim % 2 == 0 && rot_dim <= head_dim && rot_dim > 0,
+                 "rope_kv_write: bad head_dim / rot_dim");
+  B200_CHECK_ARG(q && k && cos && sin && positions, "rope_kv_write: NULL pointer");
+  launch_rope_kv_write(q, k, v, num_heads * head_dim, num_kv_heads * head_dim,
+                       num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
+                       v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
+                       interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream));
+}
+
+void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cache,
+                       const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
+                       int32_t head_dim, int32_t block_size, int64_t stream) {
+  (void)block_size;
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG((num_kv_heads * head_dim) % 8 == 0, "kv_write: row must be a multiple of 8");
+  kv_write_kernel<<<num_tokens, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __half*)k, (const __half*)v, (__half*)k_cache, (__half*)v_cache, slot_mapping,
+      num_kv_heads * head_dim);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
+                      int32_t hidden, float eps, int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "rmsnorm: hidden % 8 != 0 or > 16384");
+  rmsnorm_kernel<false><<<num_tokens, 256, hidden * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, nullptr, (const __half*)x, (const __half*)weight, hidden, eps);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_add_rmsnorm_f16(void* out, void* residual, const void* x, const void* weight,
+                          int32_t num_tokens, int32_t hidden, float eps, int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "add_rmsnorm: hidden % 8 != 0 or > 16384");
+  rmsnorm_kernel<true><<<num_tokens, 256, hidden * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, (__half*)residual, (const __half*)x, (const __half*)weight, hidden, eps);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_silu_mul_f16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
+                       int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(inter % 8 == 0, "silu_mul: inter % 8 != 0");
+  dim3 grid((inter / 8 + 255) / 256, num_tokens);
+  silu_mul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, (const __half*)gate_up, inter);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_embedding_f16(void* out, const void* table, const uint32_t* ids, int32_t num_tokens,
+                        int32_t hidden, int32_t vocab, int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(hidden % 8 == 0, "embedding: hidden % 8 != 0");
+  gather_rows_kernel<<<num_tokens, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, (const __half*)table, ids, hidden, vocab);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_gather_rows_f16(void* out, const void* x, const uint32_t* rows, int32_t num_rows,
+                          int32_t hidden, int64_t stream) {
+  if (num_rows <= 0) return;
+  B200_CHECK_ARG(hidden % 8 == 0, "gather_rows: hidden % 8 != 0");
+  gather_rows_kernel<<<num_rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, (const __half*)x, rows, hidden, 0);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_add_bias_f16(void* x, const void* bias, int32_t num_tokens, int32_t n,
+                       int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(n % 2 == 0, "add_bias: n % 2 != 0");
+  dim3 grid((n / 2 + 255) / 256, num_tokens);
+  add_bias_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)x, (const __half*)bias, n);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_argmax_f32(uint32_t* out_ids, const float* logits, int32_t batch, int32_t vocab,
+                     int64_t stream) {
+  if (batch <= 0) return;
+  B200_CHECK_ARG(vocab > 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                     (vocab % 4 == 0 || batch == 1),
+                 "argmax: logits rows must be 16-byte aligned");
+  argmax_kernel<<<batch, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_ids, logits,
+                                                                           vocab);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+// Decode-step model runner: every launch of one LLaMA/Qwen2 decode step on one GPU (one
+// TP rank), optionally captured into CUDA graphs per batch bucket.
+//
+// C++ mirror of the decode branch of ModelRunner::run
+//   /root/reference/src/core/runner.rs:743-896   (prepare -> forward -> sample)
+// over LLaMaForCausalLM::forward_inner / LLaMaDecoderLayer::forward
+//   /root/reference/src/models/llama.rs:107-131,269-321
+// Attention::forward_ext  /root/reference/src/models/layers/attention.rs:648-839
+// MLP::forward            /root/reference/src/models/layers/mlp.rs:451-469
+// TensorParallelRowLinear /root/reference/src/models/layers/distributed.rs:438-454
+// GraphCapturer           /root/reference/src/utils/graph.rs:370-377,448-835
+//
+// Launch plan per layer (5 kernels + 2 small ones, vs 17-22 in the reference):
+//   [add+]rmsnorm -> fused qkv W4A16 GEMM (+bias) -> RoPE + KV write -> paged attention
+//   (+ split merge) -> o_proj GEMM [-> all-reduce] -> add+rmsnorm -> gate|up GEMM with
+//   SiLU*mul epilogue -> down GEMM [-> all-reduce]
+// The runner owns no device memory: weights, caches and one workspace come from the caller.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "../../../include/b200_vllm.h"
+#include "../attn.cuh"
+#include "../wna16.cuh"
+
+using namespace b200;
+namespace b200 {
+long long launch_count();
+}
+
+namespace {
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
+
+struct b200_runner {
+  b200_model_config cfg;
+  std::vector<b200_layer_weights> layers;
+  std::vector<AttnMaps> maps;
+  std::vector<bool> maps_ok;
+  const void *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr, *cos = nullptr,
+             *sin = nullptr;
+  b200_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  // workspace carve-up
+  uint8_t* ws = nullptr;
+  int64_t ws_bytes = 0;
+  __half *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *proj = nullptr,
+         *act = nullptr, *act2 = nullptr;
+  float* logits = nullptr;
+  void *attn_ws = nullptr, *wna_ws = nullptr;
+  // static (graph) input buffers
+  uint32_t *s_ids = nullptr, *s_ctx = nullptr, *s_bt = nullptr, *s_out = nullptr;
+  int64_t *s_pos = nullptr, *s_slot = nullptr;
+  // pinned host staging for padded rows
+  std::map<int, cudaGraphExec_t> graphs;
+  int64_t launches = 0;
+};
+
+static int64_t carve(b200_runner* r, uint8_t* base) {
+  const b200_model_config& c = r->cfg;
+  const size_t B = c.max_batch;
+  const size_t qkv_n = static_cast<size_t>(c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return p;
+  };
+  r->x = (__half*)take(B * c.hidden * 2);
+  r->xn = (__half*)take(B * c.hidden * 2);
+  r->qkv = (__half*)take(B * qkv_n * 2);
+  r->attn = (__half*)take(B * c.num_heads * c.head_dim * 2);
+  r->proj = (__half*)take(B * c.hidden * 2);
+  r->act = (__half*)take(B * 2 * static_cast<size_t>(c.inter) * 2);
+  r->act2 = (__half*)take(B * static_cast<size_t>(c.inter) * 2);
+  r->logits = (float*)take(B * c.vocab * 4);
+  r->attn_ws = take(b200_paged_attn_workspace_bytes(c.max_batch, c.num_heads, c.head_dim,
+                                                    c.max_blocks_per_seq));
+  const size_t max_n = std::max<size_t>(std::max<size_t>(qkv_n, 2 * c.inter), c.hidden);
+  r->wna_ws = take(b200_wna16_workspace_bytes(c.max_batch, static_cast<int32_t>(max_n)));
+  r->s_ids = (uint32_t*)take(B * 4);
+  r->s_ctx = (uint32_t*)take(B * 4);
+  r->s_out = (uint32_t*)take(B * 4);
+  r->s_pos = (int64_t*)take(B * 8);
+  r->s_slot = (int64_t*)take(B * 8);
+  r->s_bt = (uint32_t*)take(B * c.max_blocks_per_seq * 4);
+  return static_cast<int64_t>(off);
+}
+
+extern "C" {
+
+b200_runner* b200_runner_new(const b200_model_config* cfg) {
+  if (!cfg || cfg->hidden <= 0 || cfg->num_layers <= 0 || cfg->num_heads <= 0 ||
+      cfg->num_kv_heads <= 0 || cfg->max_batch <= 0 || cfg->block_size != 64 ||
+      !(cfg->bits == 4 || cfg->bits == 8 || cfg->bits == 16)) {
+    set_error(1, "runner_new: bad config");
+    return nullptr;
+  }
+  auto* r = new b200_runner();
+  r->cfg = *cfg;
+  r->layers.resize(cfg->num_layers);
+  r->maps.resize(cfg->num_layers);
+  r->maps_ok.assign(cfg->num_layers, false);
+  std::memset(r->layers.data(), 0, sizeof(b200_layer_weights) * cfg->num_layers);
+  return r;
+}
+
+void b200_runner_free(b200_runner* r) {
+  if (!r) return;
+  for (auto& g : r->graphs) cudaGraphExecDestroy(g.second);
+  delete r;
+}
+
+void b200_runner_set_layer(b200_runner* r, int32_t layer, const b200_layer_weights* w) {
+  if (layer < 0 || layer >= r->cfg.num_layers) {
+    set_error(1, "runner_set_layer: layer out of range");
+    return;
+  }
+  r->layers[layer] = *w;
+  r->maps_ok[layer] = make_attn_maps(&r->maps[layer], w->k_cache, w->v_cache, r->cfg.num_blocks,
+                                     r->cfg.num_kv_heads, r->cfg.head_dim);
+  if (!r->maps_ok[layer]) set_error(2, "runner_set_layer: cuTensorMapEncodeTiled failed");
+}
+
+void b200_runner_set_globals(b200_runner* r, const void* embed, const void* final_norm,
+                             const void* lm_head, const void* cos, const void* sin) {
+  r->embed = embed;
+  r->final_norm = final_norm;
+  r->lm_head = lm_head;
+  r->cos = cos;
+  r->sin = sin;
+}
+
+int64_t b200_runner_workspace_bytes(const b200_runner* r) {
+  b200_runner tmp;
+  tmp.cfg = r->cfg;
+  return carve(&tmp, nullptr) + 256;
+}
+
+void b200_runner_set_workspace(b200_runner* r, void* workspace, int64_t bytes) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  const int64_t need = carve(r, base);
+  if (need + (base - reinterpret_cast<uint8_t*>(workspace)) > bytes) {
+    set_error(1, "runner_set_workspace: workspace too small");
+    return;
+  }
+  r->ws = base;
+  r->ws_bytes = bytes;
+  // the GEMM split-K accumulators must start zeroed (they are left zeroed by every call)
+  cudaMemset(workspace, 0, bytes);
+}
+
+void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user) {
+  r->allreduce = fn;
+  r->allreduce_user = user;
+}
+
+static void linear(b200_runner* r, const __half* in, const void* w, const void* s, const void* z,
+                   const void* bias, __half* out, int M, int K, int N, int epilogue,
+                   int64_t stream) {
+  const b200_model_config& c = r->cfg;
+  if (c.bits == 16) {
+    b200_dense_gemm_f16(in, w, out, M, N, K, 0, stream);
+    if (bias) {
+      b200_add_bias_f16(out, bias, M, N, stream);
+    }
+    return;
+  }
+  b200_wna16_gemm_ex(in, w, s, z, bias, out, M, K, N, c.bits, c.group_size, c.qfmt, epilogue, 0,
+                     r->wna_ws, stream);
+}
+
+void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
+                               const int64_t* positions, const int64_t* slot_mapping,
+                               const uint32_t* block_tables, const uint32_t* context_lens,
+                               int32_t B, float* logits, uint32_t* out_ids, int64_t stream) {
+  const b200_model_config& c = r->cfg;
+  if (!r->ws) {
+    set_error(1, "runner_decode: workspace not set");
+    return;
+  }
+  if (B <= 0 || B > c.max_batch) {
+    set_error(1, "runner_decode: batch out of range");
+    return;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long launches0 = launch_count();
+  const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim;
+  const int qkv_n = (H + 2 * Hkv) * D;
+  b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const b200_layer_weights& w = r->layers[l];
+    if (l == 0)
+      b200_rmsnorm_f16(r->xn, r->x, w.input_norm, B, c.hidden, c.rms_eps, stream);
+    else
+      b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, B, c.hidden, c.rms_eps, stream);
+    // ---- attention block
+    linear(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
+           c.hidden, qkv_n, B200_EPI_NONE, stream);
+    __half* q = r->qkv;
+    __half* k = r->qkv + H * D;
+    __half* v = r->qkv + (H + Hkv) * D;
+    launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
+                         w.k_cache, w.v_cache, B, H, Hkv, D, D, 0, c.cos_sin_f32, st);
+    launch_paged_attn_decode(r->maps[l], r->attn, q, qkv_n, block_tables, context_lens, B, H, Hkv,
+                             D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
+    linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, B, H * D, c.hidden, B200_EPI_NONE,
+           stream);
+    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
+    // ---- MLP block
+    b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.post_norm, B, c.hidden, c.rms_eps, stream);
+    if (c.bits == 16) {
+      __half* gu = r->act;   // [B, 2*inter]
+      linear(r, r->xn, w.gate_up_w, nullptr, nullptr, nullptr, gu, B, c.hidden, 2 * c.inter,
+             B200_EPI_NONE, stream);
+      b200_silu_mul_f16(r->act2, gu, B, c.inter, stream);
+      linear(r, r->act2, w.down_w, nullptr, nullptr, nullptr, r->proj, B, c.inter, c.hidden,
+             B200_EPI_NONE, stream);
+    } else {
+      linear(r, r->xn, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, B, c.hidden,
+             2 * c.inter, B200_EPI_SILU_MUL, stream);
+      linear(r, r->act, w.down_w, w.down_s, w.down_z, nullptr, r->proj, B, c.inter, c.hidden,
+             B200_EPI_NONE, stream);
+    }
+    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
+  }
+  b200_add_rmsnorm_f16(r->xn, r->x, r->proj, r->final_norm, B, c.hidden, c.rms_eps, stream);
+  float* lg = logits ? logits : r->logits;
+  b200_dense_gemm_f16(r->xn, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
+  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+  r->launches = launch_count() - launches0;
+}
+
+static int bucket_for(const b200_runner* r, int B) {
+  for (auto& g : r->graphs)
+    if (g.first >= B) return g.first;   // std::map iterates ascending: smallest bucket >= B
+  return 0;
+}
+
+int32_t b200_runner_decode_host(b200_runner* r, const uint32_t* input_ids,
+                                const int64_t* positions, const int64_t* slot_mapping,
+                                const uint32_t* block_tables, int32_t max_blocks,
+                                const uint32_t* context_lens, int32_t B, uint32_t* out_ids_host,
+                                int64_t stream) {
+  const b200_model_config& c = r->cfg;
+  if (!r->ws || B <= 0 || B > c.max_batch || max_blocks > c.max_blocks_per_seq) {
+    set_error(1, "runner_decode_host: bad arguments");
+    return -1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bucket = bucket_for(r, B);
+  const int rows = bucket ? bucket : B;
+  if (rows > B) {
+    // graph.rs:741-767: padded rows carry context_len 0; slot -1 skips their cache write
+    cudaMemsetAsync(r->s_ids + B, 0, (rows - B) * 4, st);
+    cudaMemsetAsync(r->s_ctx + B, 0, (rows - B) * 4, st);
+    cudaMemsetAsync(r->s_pos + B, 0, (rows - B) * 8, st);
+    cudaMemsetAsync(r->s_slot + B, 0xFF, (rows - B) * 8, st);
+  }
+  cudaMemcpyAsync(r->s_ids, input_ids, B * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(r->s_pos, positions, B * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(r->s_slot, slot_mapping, B * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(r->s_ctx, context_lens, B * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpy2DAsync(r->s_bt, static_cast<size_t>(c.max_blocks_per_seq) * 4, block_tables,
+                    static_cast<size_t>(max_blocks) * 4, static_cast<size_t>(max_blocks) * 4, B,
+                    cudaMemcpyHostToDevice, st);
+  if (bucket) {
+    cudaGraphLaunch(r->graphs[bucket], st);
+  } else {
+    b200_runner_decode_device(r, r->s_ids, r->s_pos, r->s_slot, r->s_bt, r->s_ctx, B, nullptr,
+                              r->s_out, stream);
+  }
+  cudaMemcpyAsync(out_ids_host, r->s_out, B * 4, cudaMemcpyDeviceToHost, st);
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error(2, cudaGetErrorString(e));
+    return -1;
+  }
+  return b200_last_error() ? -1 : 0;
+}
+
+int32_t b200_runner_capture(b200_runner* r, const int32_t* buckets, int32_t num_buckets,
+                            int64_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!r->ws) {
+    set_error(1, "runner_capture: workspace not set");
+    return -1;
+  }
+  for (int i = num_buckets - 1; i >= 0; --i) {   // descending like graph.rs:448-690
+    const int bs = buckets[i];
+    if (bs <= 0 || bs > r->cfg.max_batch) continue;
+    // benign inputs for warm-up + capture: context_len 0 rows, no cache writes
+    cudaMemsetAsync(r->s_ids, 0, bs * 4, st);
+    cudaMemsetAsync(r->s_ctx, 0, bs * 4, st);
+    cudaMemsetAsync(r->s_pos, 0, bs * 8, st);
+    cudaMemsetAsync(r->s_slot, 0xFF, bs * 8, st);
+    cudaMemsetAsync(r->s_bt, 0, static_cast<size_t>(bs) * r->cfg.max_blocks_per_seq * 4, st);
+    b200_runner_decode_device(r, r->s_ids, r->s_pos, r->s_slot, r->s_bt, r->s_ctx, bs, nullptr,
+                              r->s_out, stream);   // warm-up (creates cuBLAS handle etc.)
+    if (cudaStreamSynchronize(st) != cudaSuccess || b200_last_error()) return -1;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      set_error(2, "runner_capture: cudaStreamBeginCapture failed");
+      return -1;
+    }
+    b200_runner_decode_device(r, r->s_ids, r->s_pos, r->s_slot, r->s_bt, r->s_ctx, bs, nullptr,
+                              r->s_out, stream);
+    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) {
+      set_error(2, "runner_capture: cudaStreamEndCapture failed");
+      return -1;
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      set_error(2, "runner_capture: cudaGraphInstantiate failed");
+      return -1;
+    }
+    cudaGraphDestroy(graph);
+    auto it = r->graphs.find(bs);
+    if (it != r->graphs.end()) cudaGraphExecDestroy(it->second);
+    r->graphs[bs] = exec;
+  }
+  return 0;
+}
+
+int64_t b200_runner_launches_per_step(const b200_runner* r) { return r->launches; }
+
+}  // extern "C"

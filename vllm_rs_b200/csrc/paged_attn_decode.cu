@@ -1,0 +1,437 @@
+// Paged-KV attention, decode step (one query token per sequence).
+//
+// Replaces the decode branch of attention_rs::PagedAttention::forward as called from
+// /root/reference/src/models/layers/attention.rs:808-820 with the metadata built by
+// ModelRunner::prepare_decode (/root/reference/src/core/runner.rs:1243-1388):
+//   block_tables u32 [B, max_blocks] (zero padded), context_lens u32 [B] -- both read
+//   on the device so the launch is CUDA-graph safe (graph.rs:741-767 pads rows with
+//   context_len 0).
+//
+// B200 design
+//   * KV cache layout [num_blocks, 64, Hkv, D] fp16 (reference layout L2).  One 4-D
+//     TMA tensor map per cache; a (page, kv-head) tile is fetched by block-table index
+//     as D/64 boxes of [64 tokens x 64 d] (128-byte rows, SWIZZLE_128B) straight into
+//     shared memory by a dedicated producer warp; 3-stage mbarrier ring, 2 CTAs/SM.
+//   * grid = (kv split, kv head, sequence): every CTA streams `pages_per_split` pages
+//     of ONE kv head and serves the whole GQA group (H/Hkv query heads share each byte
+//     fetched).  4 consumer warps each own 16 of the 64 tokens of a page:
+//     S = Q K^T and O += P V run on mma.sync m16n8k16 (rows = query heads, padded to
+//     16) with ldmatrix on the swizzled tile; online softmax in fp32 with quad
+//     shuffles.  HBM-bound: 4 flop/B of useful math, the tensor pipe is ~15% busy.
+//   * split partials (fp32 O, m, l) go to the caller's workspace and are merged by a
+//     small second kernel; sequences with a single split write fp16 output directly.
+//
+// Algorithmic bytes per launch: B * ctx * Hkv * D * 2 (K) * 2 (V) * 2 B  (+ q/out).
+#include "../../include/b200_vllm.h"
+#include "attn.cuh"
+
+namespace b200 {
+
+constexpr int kTok = 64;        // tokens per page (block_size)
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = 4;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxPagesPerSplit = 128;
+
+template <int D>
+struct AttnSmem {
+  static constexpr int kTileBytes = kTok * D * 2;       // one K (or V) page tile
+  static constexpr int kStageBytes = 2 * kTileBytes;
+  static constexpr int kDataBytes = kStages * kStageBytes;
+  static constexpr int kBarOff = kDataBytes;
+  static constexpr int kIdsOff = kBarOff + 64;
+  static constexpr int kMlOff = kIdsOff + kMaxPagesPerSplit * 4;
+  static constexpr int kTotal = kMlOff + kConsumerWarps * 16 * 2 * 4;
+  static constexpr int kAlloc = kTotal + 1024;          // manual 1024-B alignment slack
+};
+
+__device__ __forceinline__ int first_page_of(int ctx, int window) {
+  return (window > 0 && ctx > window) ? (ctx - window) / kTok : 0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 2)
+paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
+                         const __grid_constant__ CUtensorMap vmap,
+                         const __half* __restrict__ q, __half* __restrict__ out,
+                         const uint32_t* __restrict__ block_tables,
+                         const uint32_t* __restrict__ context_lens, float* __restrict__ part_o,
+                         float* __restrict__ part_ml, int q_stride, int H, int Hkv, int max_blocks,
+                         int pages_per_split, int max_splits, float scale_log2, float softcap,
+                         int window) {
+  using SM = AttnSmem<D>;
+  const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
+  const int ctx = static_cast<int>(context_lens[b]);
+  if (ctx <= 0) return;
+  const int npages = (ctx + kTok - 1) / kTok;
+  const int fpage = first_page_of(ctx, window);
+  const int page0 = fpage + split * pages_per_split;
+  const int page1 = min(page0 + pages_per_split, npages);
+  if (page0 >= page1) return;
+  const int n_cta_pages = page1 - page0;
+  const int nsplits_seq = (npages - fpage + pages_per_split - 1) / pages_per_split;
+  const int G = H / Hkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint32_t* sm_ids = reinterpret_cast<uint32_t*>(smem + SM::kIdsOff);
+  float* sm_ml = reinterpret_cast<float*>(smem + SM::kMlOff);   // [warp][16][2]
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kConsumerWarps) {
+    for (int i = lane; i < n_cta_pages; i += 32)
+      sm_ids[i] = block_tables[static_cast<size_t>(b) * max_blocks + page0 + i];
+    if (lane == 0) {
+      prefetch_tmap(&kmap);
+      prefetch_tmap(&vmap);
+    }
+  }
+  __syncthreads();
+
+  // per-thread softmax / output state (consumer warps)
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  float o_acc[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f;
+
+  const int g = lane >> 2, c = lane & 3;
+  const bool hi_rows = G > 8;
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < n_cta_pages; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
+        const int blk = static_cast<int>(sm_ids[i]);
+        uint8_t* kdst = smem + s * SM::kStageBytes;
+        uint8_t* vdst = kdst + SM::kTileBytes;
+#pragma unroll
+        for (int hb = 0; hb < D / 64; ++hb) {
+          tma_load_4d(kdst + hb * (kTok * 128), &kmap, &full_bar[s], hb * 64, hkv, 0, blk);
+          tma_load_4d(vdst + hb * (kTok * 128), &vmap, &full_bar[s], hb * 64, hkv, 0, blk);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumers
+    // Q fragments (A operand, rows = query heads of this kv group, zero padded to 16)
+    uint32_t qa[D / 16][4];
+    {
+      const __half* qb = q + static_cast<size_t>(b) * q_stride + static_cast<size_t>(hkv) * G * D;
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const int d0 = ks * 16 + 2 * c;
+        qa[ks][0] = (g < G) ? *reinterpret_cast<const uint32_t*>(qb + g * D + d0) : 0u;
+        qa[ks][1] = (g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0) : 0u;
+        qa[ks][2] = (g < G) ? *reinterpret_cast<const uint32_t*>(qb + g * D + d0 + 8) : 0u;
+        qa[ks][3] =
+            (g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0 + 8) : 0u;
+      }
+    }
+    const int t0 = warp * 16;
+    const int win_lo = (window > 0) ? ctx - window : 0;
+    const float inv_cap = softcap > 0.f ? 1.f / softcap : 0.f;
+    const float LOG2E = 1.4426950408889634f;
+    const float scale_nat = scale_log2 / LOG2E;
+
+    // ldmatrix lane address components
+    const int k_tok = t0 + (lane >> 4) * 8 + (lane & 7);    // K: matrix = lane/8
+    const int k_chunk_sel = (lane >> 3) & 1;
+    const int v_tok = t0 + ((lane >> 3) & 1) * 8 + (lane & 7);
+    const int v_chunk_sel = lane >> 4;
+
+    for (int i = 0; i < n_cta_pages; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      const int tok_base = (page0 + i) * kTok + t0;   // global index of this warp's first token
+      if (tok_base < ctx && tok_base + 16 > win_lo) {
+        const uint32_t kbase = smem_u32(smem + s * SM::kStageBytes);
+        const uint32_t vbase = kbase + SM::kTileBytes;
+        // ---- S = Q K^T for 16 tokens
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const int hb = ks >> 2;
+          const int chunk = ((ks & 3) << 1) + k_chunk_sel;
+          uint32_t r[4];
+          ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+          mma_16816(s0, qa[ks], r[0], r[1]);
+          mma_16816(s1, qa[ks], r[2], r[3]);
+        }
+        // ---- online softmax (rows g and, when G > 8, g + 8)
+        uint32_t pa[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          if (rh == 1 && !hi_rows) break;
+          float t[4] = {s0[2 * rh], s0[2 * rh + 1], s1[2 * rh], s1[2 * rh + 1]};
+          const int tk[4] = {tok_base + 2 * c, tok_base + 2 * c + 1, tok_base + 8 + 2 * c,
+                             tok_base + 9 + 2 * c};
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = softcap > 0.f ? softcap * tanhf(t[e] * scale_nat * inv_cap) * LOG2E
+                                    : t[e] * scale_log2;
+            v = (tk[e] < ctx && tk[e] >= win_lo) ? v : -INFINITY;
+            t[e] = v;
+            mx = fmaxf(mx, v);
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float m_new = fmaxf(m_run[rh], mx);
+          const float base = (m_new == -INFINITY) ? 0.f : m_new;
+          const float alpha = exp2f(m_run[rh] - base);
+          float p[4], psum = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            p[e] = exp2f(t[e] - base);
+            psum += p[e];
+          }
+          l_run[rh] = l_run[rh] * alpha + psum;
+          m_run[rh] = m_new;
+#pragma unroll
+          for (int j = 0; j < D / 8; ++j) {
+            o_acc[j][2 * rh] *= alpha;
+            o_acc[j][2 * rh + 1] *= alpha;
+          }
+          pa[rh] = pack_half2(p[0], p[1]);
+          pa[2 + rh] = pack_half2(p[2], p[3]);
+        }
+        // ---- O += P V
+        const bool partial = tok_base + 16 > ctx;
+        const uint32_t vmask_lo = (tok_base + 2 * c < ctx ? 0x0000FFFFu : 0u) |
+                                  (tok_base + 2 * c + 1 < ctx ? 0xFFFF0000u : 0u);
+        const uint32_t vmask_hi = (tok_base + 8 + 2 * c < ctx ? 0x0000FFFFu : 0u) |
+                                  (tok_base + 9 + 2 * c < ctx ? 0xFFFF0000u : 0u);
+#pragma unroll
+        for (int jj = 0; jj < D / 16; ++jj) {
+          const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
+          const int hb = chunk >> 3, c16 = chunk & 7;
+          uint32_t r[4];
+          ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
+          if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
+            r[0] &= vmask_lo; r[2] &= vmask_lo;
+            r[1] &= vmask_hi; r[3] &= vmask_hi;
+          }
+          mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
+          mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // quad-reduce the row sums, publish (m, l) per warp
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      l_run[rh] += __shfl_xor_sync(0xffffffffu, l_run[rh], 1);
+      l_run[rh] += __shfl_xor_sync(0xffffffffu, l_run[rh], 2);
+      if (c == 0) {
+        sm_ml[(warp * 16 + g + 8 * rh) * 2 + 0] = m_run[rh];
+        sm_ml[(warp * 16 + g + 8 * rh) * 2 + 1] = l_run[rh];
+      }
+    }
+  }
+  __syncthreads();   // pipeline drained: stage memory is reusable
+
+  float* sm_o = reinterpret_cast<float*>(smem);   // [warp][G][D]
+  if (warp < kConsumerWarps) {
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int row = g + 8 * rh;
+      if (row < G) {
+        float m_tot = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) m_tot = fmaxf(m_tot, sm_ml[(w * 16 + row) * 2]);
+        const float f = exp2f(m_run[rh] - m_tot);   // m_tot finite: the CTA saw >= 1 token
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          float2 v = make_float2(o_acc[j][2 * rh] * f, o_acc[j][2 * rh + 1] * f);
+          *reinterpret_cast<float2*>(&sm_o[(warp * G + row) * D + j * 8 + 2 * c]) = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * D; idx += kThreads) {
+    const int row = idx / D, d = idx - row * D;
+    float m_tot = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) m_tot = fmaxf(m_tot, sm_ml[(w * 16 + row) * 2]);
+    float l_tot = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) {
+      l_tot += sm_ml[(w * 16 + row) * 2 + 1] * exp2f(sm_ml[(w * 16 + row) * 2] - m_tot);
+      o += sm_o[(w * G + row) * D + d];
+    }
+    const int h = hkv * G + row;
+    if (nsplits_seq == 1) {
+      out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(o / l_tot);
+    } else {
+      const size_t pidx = (static_cast<size_t>(b) * H + h) * max_splits + split;
+      part_o[pidx * D + d] = o;
+      if (d == 0) {
+        part_ml[pidx * 2 + 0] = m_tot;
+        part_ml[pidx * 2 + 1] = l_tot;
+      }
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(D)
+paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ part_o,
+                         const float* __restrict__ part_ml,
+                         const uint32_t* __restrict__ context_lens, int H, int pages_per_split,
+                         int max_splits, int window) {
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const int ctx = static_cast<int>(context_lens[b]);
+  __half* o = out + (static_cast<size_t>(b) * H + h) * D;
+  if (ctx <= 0) {
+    o[d] = __float2half_rn(0.f);
+    return;
+  }
+  const int npages = (ctx + kTok - 1) / kTok;
+  const int fpage = first_page_of(ctx, window);
+  const int ns = (npages - fpage + pages_per_split - 1) / pages_per_split;
+  if (ns <= 1) return;   // written directly by the main kernel
+  const size_t base = (static_cast<size_t>(b) * H + h) * max_splits;
+  float m_tot = -INFINITY;
+  for (int s = 0; s < ns; ++s) m_tot = fmaxf(m_tot, part_ml[(base + s) * 2]);
+  float l = 0.f, acc = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    const float f = exp2f(part_ml[(base + s) * 2] - m_tot);
+    l += part_ml[(base + s) * 2 + 1] * f;
+    acc += part_o[(base + s) * D + d] * f;
+  }
+  o[d] = __float2half_rn(acc / l);
+}
+
+struct SplitPlan {
+  int pages_per_split, max_splits;
+};
+static SplitPlan plan_splits(int batch, int num_kv_heads, int max_blocks) {
+  const long slots = static_cast<long>(sm_count()) * 2;
+  const long total_pages = static_cast<long>(batch) * num_kv_heads * max_blocks;
+  long p = (total_pages + slots * 6 - 1) / (slots * 6);
+  if (p < 2) p = 2;
+  if (p > kMaxPagesPerSplit) p = kMaxPagesPerSplit;
+  if (p > max_blocks) p = max_blocks;
+  if (p < 1) p = 1;
+  SplitPlan r;
+  r.pages_per_split = static_cast<int>(p);
+  r.max_splits = (max_blocks + r.pages_per_split - 1) / r.pages_per_split;
+  return r;
+}
+
+static bool make_cache_map(CUtensorMap* map, const void* cache, int num_blocks, int Hkv, int D) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(Hkv), kTok,
+                            static_cast<uint64_t>(num_blocks)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(Hkv) * D * 2,
+                               static_cast<uint64_t>(kTok) * Hkv * D * 2};
+  const uint32_t box[4] = {64, 1, kTok, 1};
+  const uint32_t es[4] = {1, 1, 1, 1};
+  return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(cache),
+                           dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
+}
+
+bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks,
+                    int Hkv, int D) {
+  return make_cache_map(&m->k, k_cache, num_blocks, Hkv, D) &&
+         make_cache_map(&m->v, v_cache, num_blocks, Hkv, D);
+}
+
+template <int D>
+static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
+                          const uint32_t* block_tables, const uint32_t* context_lens, int B,
+                          int H, int Hkv, int max_blocks, float scale, float softcap, int window,
+                          void* workspace, cudaStream_t st) {
+  const SplitPlan sp = plan_splits(B, Hkv, max_blocks);
+  float* part_o = reinterpret_cast<float*>(workspace);
+  float* part_ml = part_o + static_cast<size_t>(B) * H * sp.max_splits * D;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(paged_attn_decode_kernel<D>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D>::kAlloc);
+    attr_set = true;
+  }
+  dim3 grid(sp.max_splits, Hkv, B);
+  paged_attn_decode_kernel<D><<<grid, kThreads, AttnSmem<D>::kAlloc, st>>>(
+      maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
+      block_tables, context_lens, part_o, part_ml, q_stride, H, Hkv, max_blocks,
+      sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
+  B200_CUDA_LAUNCH_CHECK();
+  paged_attn_reduce_kernel<D><<<dim3(H, B), D, 0, st>>>(
+      reinterpret_cast<__half*>(out), part_o, part_ml, context_lens, H, sp.pages_per_split,
+      sp.max_splits, window);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
+                              const uint32_t* block_tables, const uint32_t* context_lens, int B,
+                              int H, int Hkv, int D, int max_blocks, float scale, float softcap,
+                              int window, void* workspace, cudaStream_t st) {
+  if (D == 128)
+    launch_decode<128>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
+                       scale, softcap, window, workspace, st);
+  else
+    launch_decode<64>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
+                      scale, softcap, window, workspace, st);
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim,
+                                        int32_t max_blocks_per_seq) {
+  // worst case over kv-head counts: plan with Hkv = 1 gives the most splits per sequence
+  int max_splits = 1;
+  for (int hkv = 1; hkv <= num_heads; hkv <<= 1) {
+    b200::SplitPlan sp = b200::plan_splits(batch, hkv, max_blocks_per_seq);
+    if (sp.max_splits > max_splits) max_splits = sp.max_splits;
+  }
+  return static_cast<int64_t>(batch) * num_heads * max_splits * (head_dim + 2) * 4 + 256;
+}
+
+void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
+                                const void* v_cache, const uint32_t* block_tables,
+                                const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                float softcap, int32_t window, void* workspace,
+                                int64_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(block_size == kTok, "paged_attn_decode: block_size must be 64");
+  B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "paged_attn_decode: head_dim must be 64/128");
+  B200_CHECK_ARG(num_kv_heads > 0 && num_heads % num_kv_heads == 0 &&
+                     num_heads / num_kv_heads <= 16,
+                 "paged_attn_decode: H/Hkv must be an integer <= 16");
+  B200_CHECK_ARG(batch > 0 && max_blocks_per_seq > 0 && num_blocks > 0 && workspace != nullptr,
+                 "paged_attn_decode: bad sizes or NULL workspace");
+  AttnMaps maps;
+  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim)) {
+    set_error(2, "paged_attn_decode: cuTensorMapEncodeTiled failed");
+    return;
+  }
+  launch_paged_attn_decode(maps, out, q, num_heads * head_dim, block_tables, context_lens, batch,
+                           num_heads, num_kv_heads, head_dim, max_blocks_per_seq, scale, softcap,
+                           window, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

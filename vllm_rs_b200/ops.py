@@ -1,0 +1,176 @@
+"""Host-side operator layer over the C ABI (torch tensors are only memory + streams).
+
+Names follow the reference's layer vocabulary (src/models/layers/*.rs): WNA16 repack +
+gptq_matmul, FusedRope, PagedAttention, rms_norm ...  Every function launches hand-written
+sm_100a kernels from libb200_vllm.so; there is no CPU or eager-torch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+QFMT_AWQ, QFMT_GPTQ = 0, 1
+EPI_NONE, EPI_SILU_MUL = 0, 1
+VARIANT_AUTO, VARIANT_GEMV, VARIANT_TC = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not (t.is_cuda and t.is_contiguous()):
+            raise ValueError("b200 ops need contiguous CUDA tensors")
+
+
+# ------------------------------------------------------------------ quantised linear
+def awq_prepack(qweight: torch.Tensor, bits: int = 4) -> torch.Tensor:
+    """MarlinRepack for AWQ (gptq.rs:314-324): qweight i32 [K, N/8] -> tile-major u32."""
+    _cuda(qweight)
+    out = torch.empty_like(qweight)
+    _lib.lib().b200_awq_prepack(_p(qweight), _p(out), qweight.shape[0], qweight.shape[1], bits,
+                                _stream())
+    _lib.check()
+    return out
+
+
+def gptq_prepack(qweight: torch.Tensor, bits: int = 4) -> torch.Tensor:
+    """MarlinRepack for GPTQ (gptq.rs:325-333): qweight i32 [K/pack, N] -> tile-major u32."""
+    _cuda(qweight)
+    out = torch.empty_like(qweight)
+    _lib.lib().b200_gptq_prepack(_p(qweight), _p(out), qweight.shape[0], qweight.shape[1], bits,
+                                 _stream())
+    _lib.check()
+    return out
+
+
+def wna16_workspace(max_m: int, max_n: int, device="cuda") -> torch.Tensor:
+    n = _lib.lib().b200_wna16_workspace_bytes(max_m, max_n)
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def wna16_gemm(x, w_packed, scales, qzeros, workspace, *, k: int, n: int, bits=4, group_size=128,
+               qfmt=QFMT_AWQ, bias=None, epilogue=EPI_NONE, variant=VARIANT_AUTO, out=None):
+    """gptq_matmul (gptq.rs:243-263): y[M, N] = x[M, K] @ dequant(W)."""
+    _cuda(x, w_packed, scales, qzeros, bias, workspace)
+    m = x.shape[0]
+    n_out = n // 2 if epilogue == EPI_SILU_MUL else n
+    if out is None:
+        out = torch.empty(m, n_out, dtype=torch.float16, device=x.device)
+    _lib.lib().b200_wna16_gemm_ex(_p(x), _p(w_packed), _p(scales), _p(qzeros), _p(bias), _p(out),
+                                  m, k, n, bits, group_size, qfmt, epilogue, variant,
+                                  _p(workspace), _stream())
+    _lib.check()
+    return out
+
+
+def dense_gemm(x, w_nk, out_f32=False, out=None):
+    """Linear::forward (linear.rs:75-123): y = x @ W^T, W [N, K] fp16."""
+    _cuda(x, w_nk)
+    m, k = x.shape
+    n = w_nk.shape[0]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+    _lib.lib().b200_dense_gemm_f16(_p(x), _p(w_nk), _p(out), m, n, k, int(out_f32), _stream())
+    _lib.check()
+    return out
+
+
+# ------------------------------------------------------------------ attention side
+def rope_kv_write(q, k, v, cos, sin, positions, slot_mapping=None, k_cache=None, v_cache=None,
+                  rot_dim=None, interleaved=False):
+    """FusedRope::apply_inplace + cache write (rotary_emb.rs:88-104, attention.rs:808-820)."""
+    _cuda(q, k, v, cos, sin, positions, slot_mapping, k_cache, v_cache)
+    T, H, D = q.shape
+    Hkv = k.shape[1]
+    bs = k_cache.shape[1] if k_cache is not None else 64
+    _lib.lib().b200_rope_kv_write_f16(
+        _p(q), _p(k), _p(v), _p(cos), _p(sin), _p(positions), _p(slot_mapping), _p(k_cache),
+        _p(v_cache), T, H, Hkv, D, rot_dim or D, bs, int(interleaved),
+        int(cos.dtype == torch.float32), _stream())
+    _lib.check()
+
+
+def kv_write(k, v, k_cache, v_cache, slot_mapping):
+    _cuda(k, v, k_cache, v_cache, slot_mapping)
+    T, Hkv, D = k.shape
+    _lib.lib().b200_kv_write_f16(_p(k), _p(v), _p(k_cache), _p(v_cache), _p(slot_mapping), T, Hkv,
+                                 D, k_cache.shape[1], _stream())
+    _lib.check()
+
+
+def paged_attn_workspace(batch, num_heads, head_dim, max_blocks, device="cuda"):
+    n = _lib.lib().b200_paged_attn_workspace_bytes(batch, num_heads, head_dim, max_blocks)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scale, workspace=None,
+                           softcap=0.0, window=0, out=None):
+    """PagedAttention::forward, decode branch.  q [B,H,D]; caches [nb, 64, Hkv, D];
+    block_tables u32/i32 [B, max_blocks]; context_lens u32/i32 [B]."""
+    _cuda(q, k_cache, v_cache, block_tables, context_lens)
+    B, H, D = q.shape
+    nb, bs, Hkv, _ = k_cache.shape
+    mb = block_tables.shape[1]
+    if workspace is None:
+        workspace = paged_attn_workspace(B, H, D, mb, q.device)
+    if out is None:
+        out = torch.empty_like(q)
+    _lib.lib().b200_paged_attn_decode_f16(_p(out), _p(q), _p(k_cache), _p(v_cache),
+                                          _p(block_tables), _p(context_lens), B, H, Hkv, D, bs,
+                                          mb, nb, float(scale), float(softcap), int(window),
+                                          _p(workspace), _stream())
+    _lib.check()
+    return out
+
+
+# ------------------------------------------------------------------ glue
+def rmsnorm(x, w, eps, out=None):
+    _cuda(x, w)
+    out = torch.empty_like(x) if out is None else out
+    _lib.lib().b200_rmsnorm_f16(_p(out), _p(x), _p(w), x.shape[0], x.shape[1], eps, _stream())
+    _lib.check()
+    return out
+
+
+def add_rmsnorm(residual, x, w, eps, out=None):
+    """residual += x (in place); returns rmsnorm(residual) * w."""
+    _cuda(residual, x, w)
+    out = torch.empty_like(x) if out is None else out
+    _lib.lib().b200_add_rmsnorm_f16(_p(out), _p(residual), _p(x), _p(w), x.shape[0], x.shape[1],
+                                    eps, _stream())
+    _lib.check()
+    return out
+
+
+def silu_mul(gate_up, out=None):
+    _cuda(gate_up)
+    T, n2 = gate_up.shape
+    out = torch.empty(T, n2 // 2, dtype=gate_up.dtype, device=gate_up.device) if out is None else out
+    _lib.lib().b200_silu_mul_f16(_p(out), _p(gate_up), T, n2 // 2, _stream())
+    _lib.check()
+    return out
+
+
+def embedding(table, ids, out=None):
+    _cuda(table, ids)
+    T = ids.shape[0]
+    out = torch.empty(T, table.shape[1], dtype=table.dtype, device=table.device) if out is None else out
+    _lib.lib().b200_embedding_f16(_p(out), _p(table), _p(ids), T, table.shape[1], table.shape[0],
+                                  _stream())
+    _lib.check()
+    return out
+
+
+def argmax(logits):
+    _cuda(logits)
+    out = torch.empty(logits.shape[0], dtype=torch.int32, device=logits.device)
+    _lib.lib().b200_argmax_f32(_p(out), _p(logits), logits.shape[0], logits.shape[1], _stream())
+    _lib.check()
+    return out
