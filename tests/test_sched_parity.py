@@ -1,0 +1,198 @@
+"""Integer path, CPU only: C++ host mirror (through the C ABI) vs the Python oracle vs
+hand-derived traces from the reference source.  Everything here must be BIT-EXACT.
+
+Hand-derived expectations cite the reference rule they come from:
+  * free list starts 0..n-1 ascending, allocation pops from the FRONT (block_manager.rs:62-68,122-137)
+  * a decode step allocates one more block iff len % 64 == 1 (block_manager.rs:241-253), where
+    len already includes the token sampled in the previous step
+  * decode slot = last_block * 64 + (len - (num_blocks-1)*64) - 1 (runner.rs:1259-1262)
+  * deallocate walks the table in reverse and pushes freed ids to the BACK (block_manager.rs:227-231)
+  * prefill and decode alternate while decode work exists (scheduler.rs:264)
+"""
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import sched as osched
+
+
+@pytest.fixture(scope="module")
+def eng(lib):
+    from vllm_rs_b200 import engine
+    return engine
+
+
+def _mk(eng, num_blocks, **kw):
+    kw.setdefault("max_num_seqs", 32)
+    o = osched.Scheduler(num_blocks, 64, kw["max_num_seqs"], kw.get("max_num_batched_tokens"),
+                         kw.get("chunk_size", 8192), kw.get("eos_token_ids", ()))
+    c = eng.Scheduler(num_blocks, 64, kw["max_num_seqs"], kw.get("max_num_batched_tokens") or 0,
+                      kw.get("chunk_size", 8192), kw.get("eos_token_ids", ()))
+    return o, c
+
+
+def _same_state(o, c):
+    assert len(o.running) == c.num_running
+    assert len(o.waiting) == c.num_waiting
+    assert len(o.block_manager.free_block_ids) == c.num_free_blocks
+    for i, s in enumerate(o.running):
+        assert c.block_table(i) == s.block_table
+        assert c.tokens(i) == s.token_ids
+        info = c.seq_info(i)
+        assert (info["id"], info["num_cached_tokens"], info["status"]) == (
+            s.id, s.num_cached_tokens, s.status)
+
+
+def _step(o, c, token_fn):
+    """One engine step on both sides (engine.rs:1693-1757): schedule, prepare, postprocess."""
+    ids_o, pf_o = o.schedule()
+    ids_c, pf_c = c.schedule()
+    assert (ids_o, pf_o) == (ids_c, pf_c)
+    if not ids_o:
+        return None
+    seqs = [o.running[i] for i in ids_o]
+    if pf_o:
+        mo = osched.prepare_prefill(seqs, 64, o.chunk_size)
+        mc = c.prepare_prefill(ids_c)
+        for k in ("input_ids", "positions", "slot_mapping", "cu_seqlens_q", "cu_seqlens_k"):
+            assert list(mc[k]) == mo[k], k
+        for k in ("max_seqlen_q", "max_seqlen_k", "max_context_len"):
+            assert mc[k] == mo[k], k
+        if mo["block_tables"] is None:
+            assert mc["block_tables"] is None
+        else:
+            assert mc["block_tables"].tolist() == mo["block_tables"]
+            assert list(mc["context_lens"]) == mo["context_lens"]
+        pos_o, fin_o = o.filter_prefill_finished(ids_o)
+        pos_c, fin_c = c.filter_prefill_finished(ids_c)
+        assert (pos_o, fin_o) == (pos_c, fin_c)
+        toks = [token_fn(o.running[i]) for i in fin_o]
+        o.postprocess(fin_o, toks)
+        c.postprocess(fin_c, toks)
+    else:
+        mo = osched.prepare_decode(seqs, 64)
+        mc = c.prepare_decode(ids_c)
+        for k in ("input_ids", "positions", "slot_mapping", "context_lens"):
+            assert list(mc[k]) == mo[k], k
+        assert mc["block_tables"].tolist() == mo["block_tables"]
+        assert mc["max_context_len"] == mo["max_context_len"]
+        toks = [token_fn(s) for s in seqs]
+        o.postprocess(ids_o, toks)
+        c.postprocess(ids_c, toks)
+    o.clear_finished()
+    c.clear_finished()
+    _same_state(o, c)
+    return pf_o, mo
+
+
+def test_hand_trace_single_prompt_37(eng):
+    """BASELINE config 1 plumbing: 37-token prompt, 64 new tokens, num_blocks=128:
+    table [0] until len hits 65, then [0, 1]."""
+    o, c = _mk(eng, 128)
+    prompt = list(range(100, 137))
+    for s in (o, c):
+        s.add(osched.Sequence(prompt, 64, max_tokens=64)) if s is o else s.add(prompt, 64)
+    pf, m = _step(o, c, lambda s: 7)
+    assert pf and m["slot_mapping"] == list(range(37)) and m["positions"] == list(range(37))
+    assert m["cu_seqlens_q"] == [0, 37] and m["block_tables"] is None
+    assert o.running[0].block_table == [0] and len(o.running[0]) == 38
+    # finish rule (scheduler.rs:605): output_len >= max_tokens is tested BEFORE appending, so
+    # the sequence runs prefill + 64 decode steps and keeps 64 output tokens
+    for step in range(64):
+        pf, m = _step(o, c, lambda s: 7)
+        assert not pf
+        L = 38 + step                                   # len at schedule time
+        assert m["positions"] == [L - 1] and m["context_lens"] == [L]
+        if L <= 64:
+            assert m["block_tables"] == [[0]] and m["slot_mapping"] == [L - 1]
+        else:
+            assert m["block_tables"] == [[0, 1]] and m["slot_mapping"] == [64 + (L - 65)]
+        if not o.running:
+            break
+    # 64 outputs reached -> finished -> both blocks returned, reverse table order: 1 then 0
+    assert not o.running and c.num_running == 0
+    assert list(o.block_manager.free_block_ids)[-2:] == [1, 0]
+    assert c.num_free_blocks == 128
+
+
+@pytest.mark.parametrize("plen", [1, 63, 64, 65, 4096, 8193])
+def test_prompt_lengths(eng, plen):
+    o, c = _mk(eng, 300, max_num_batched_tokens=300 * 64)
+    toks = (np.arange(plen) % 1000).tolist()
+    o.add(osched.Sequence(toks, 64, max_tokens=3))
+    c.add(toks, 3)
+    seen_chunks = 0
+    for _ in range(12):
+        r = _step(o, c, lambda s: 5)
+        if r is None:
+            break
+        if r[0]:
+            seen_chunks += 1
+            if seen_chunks == 2:                        # second chunk attends to cached KV
+                assert r[1]["block_tables"] is not None and r[1]["context_lens"] == [plen]
+                assert r[1]["positions"][0] == 8192
+    assert seen_chunks == (2 if plen > 8192 else 1)
+    assert c.num_running == 0 and c.num_free_blocks == 300
+
+
+def test_32_concurrent_and_wraparound(eng):
+    """32 concurrent sequences, finish / realloc wrap-around of the FIFO free list."""
+    o, c = _mk(eng, 96, max_num_seqs=32)
+    rng = np.random.default_rng(0)
+    lens = rng.integers(1, 130, size=48)
+    outs = rng.integers(1, 80, size=48)
+    for L, mx in zip(lens, outs):
+        toks = rng.integers(0, 30000, size=int(L)).tolist()
+        o.add(osched.Sequence(toks, 64, max_tokens=int(mx)))
+        c.add(toks, int(mx))
+    steps = 0
+    while (o.running or o.waiting) and steps < 5000:
+        _step(o, c, lambda s: int((s.id * 7919 + len(s)) % 30000))
+        steps += 1
+    assert not o.running and not o.waiting and c.num_free_blocks == 96
+    assert sorted(o.block_manager.free_block_ids) == list(range(96))
+    assert list(o.block_manager.free_block_ids) != list(range(96))       # order was permuted
+
+
+def test_eos_and_alternation(eng):
+    o, c = _mk(eng, 64, eos_token_ids=(2,))
+    for s_, toks in ((0, [5] * 10), (1, [6] * 70)):
+        o.add(osched.Sequence(toks, 64))
+        c.add(toks)
+    assert _step(o, c, lambda s: 9)[0] is True          # both prefill together
+    o.add(osched.Sequence([7] * 5, 64))
+    c.add([7] * 5)
+    assert _step(o, c, lambda s: 9)[0] is False         # is_last_prefill -> decode first
+    assert _step(o, c, lambda s: 9)[0] is True          # then the new prompt
+    assert _step(o, c, lambda s: 2 if s.id == 0 else 9)[0] is False   # seq 0 hits EOS
+    assert [s.id for s in o.running] == [1, 2]
+    _same_state(o, c)
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 300), st.integers(1, 40)), min_size=1, max_size=12),
+       st.integers(8, 40), st.integers(1, 8))
+def test_property_random_traces(lib, reqs, num_blocks, max_seqs):
+    """Invariants on arbitrary traces: oracle == C++ every step; no block in two live tables;
+    every slot < num_blocks * 64; free + used == num_blocks."""
+    from vllm_rs_b200 import engine
+    o, c = _mk(engine, num_blocks, max_num_seqs=max_seqs)
+    for i, (L, mx) in enumerate(reqs):
+        toks = [(i * 31 + j) % 5000 for j in range(L)]
+        o.add(osched.Sequence(toks, 64, max_tokens=mx))
+        c.add(toks, mx)
+    for _ in range(400):
+        if not (o.running or o.waiting):
+            break
+        ids_before = len(o.running)
+        r = _step(o, c, lambda s: 11)
+        live = [b for s in o.running for b in s.block_table]
+        assert len(live) == len(set(live))
+        assert len(live) + len(o.block_manager.free_block_ids) == num_blocks
+        if r is not None:
+            assert all(0 <= s < num_blocks * 64 for s in r[1]["slot_mapping"])
+        elif len(o.running) == ids_before and not o.waiting:
+            break
+        elif r is None:
+            break     # head-of-line prompt can never fit: both sides agree on the stall

@@ -169,6 +169,14 @@ __global__ void wna16_finalize_kernel(float* __restrict__ acc, const __half* __r
   }
 }
 
+void wna16_finalize(float* acc, const __half* bias, __half* c, int M, int N, int epilogue,
+                    cudaStream_t st) {
+  const int cols = epilogue == B200_EPI_SILU_MUL ? N / 2 : N;
+  dim3 grid((cols + 255) / 256, M);
+  wna16_finalize_kernel<<<grid, 256, 0, st>>>(acc, bias, c, M, N, epilogue);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
 template <int BITS, int MB>
 static void launch_gemv_mb(const WnaParams& p, cudaStream_t st, int m_base) {
   const int KC = p.K / kChunkK;
@@ -208,11 +216,7 @@ static void launch_gemv_bits(const WnaParams& p, cudaStream_t st) {
       m_base += 1;
     }
   }
-  const int cols = p.epilogue == B200_EPI_SILU_MUL ? p.N / 2 : p.N;
-  dim3 grid((cols + 255) / 256, p.M);
-  wna16_finalize_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float*>(p.workspace), p.bias, p.c,
-                                              p.M, p.N, p.epilogue);
-  B200_CUDA_LAUNCH_CHECK();
+  wna16_finalize(reinterpret_cast<float*>(p.workspace), p.bias, p.c, p.M, p.N, p.epilogue, st);
 }
 
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st) {

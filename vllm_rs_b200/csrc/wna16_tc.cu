@@ -1,5 +1,303 @@
-// placeholder until the tcgen05 kernel lands (same translation unit name)
+// W4A16 / W8A16 GEMM on tcgen05 tensor cores with register dequant feeding TMEM.
+//
+// Replaces marlin_awq_4bit_f16 / marlin_4bit_f16 / gemm_half_q_half_alt
+// (/root/reference/src/utils/gptq.rs:118-195) for every M > 4 (decode batches and prefill).
+//
+// "Swap-AB" formulation: D^T[n, m] = sum_k W^T[n, k] * X[m, k].  The WEIGHT tile is the MMA
+// A operand (M_mma = 128 output channels = 128 TMEM lanes), the activations are the B operand
+// (N_mma = NT tokens, 16..256), so a decode batch of 32 runs 128x32x16 MMAs with no wasted
+// rows, and prefill simply uses NT = 256.
+//
+// Per CTA (one 128-channel weight tile x one K split x one token tile), warp roles:
+//   warps 0-7  dequant: thread = (channel c, K half h).  Packed weights arrive in shared
+//              memory through a deep ring of 4 KB cp.async.bulk copies (the tile-major prepack
+//              makes every stage one contiguous block); each thread reads its 16 bytes,
+//              dequantises to 16 half2 registers (lop3 / prmt magic numbers, exact (q - z),
+//              one rounding on the scale multiply) and writes them with tcgen05.st 32x32b.x16
+//              into its TMEM lane: the A operand never touches shared memory again.
+//   warp 8     weight producer (cp.async.bulk, 1-D)
+//   warp 9     activation producer (TMA 2-D tensor map, SWIZZLE_128B, OOB rows zero-filled)
+//   warp 10    MMA issuer: tcgen05.mma.kind::f16 with A from TMEM, B from the smem descriptor,
+//              fp32 accumulators in TMEM; tcgen05.commit releases the rings.
+//   epilogue   warps 0-3 read the accumulators with tcgen05.ld; a full-K CTA stores fp16
+//              directly, K splits meet in the fp32 workspace (red.add) + finalize kernel.
+//
+// Roofline: decode (NT <= 64) is HBM-bound on the packed weights (K*N/2 bytes per launch);
+// prefill (NT = 256) is tensor-bound: 2*M*N*K flop.
 #include "wna16.cuh"
+
 namespace b200 {
-bool launch_wna16_tc(const WnaParams&, cudaStream_t) { return false; }
+
+void wna16_finalize(float* acc, const __half* bias, __half* c, int M, int N, int epilogue,
+                    cudaStream_t st);
+
+constexpr int kDqWarps = 8;
+constexpr int kTcThreads = (kDqWarps + 3) * 32;
+constexpr int kSA = 4;              // TMEM A stages (32 columns each)
+
+template <int BITS, int NT>
+struct TcCfg {
+  static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;      // packed weights per stage
+  static constexpr int kXBytes = NT * kChunkK * 2;                 // activations per stage
+  static constexpr int kSW = BITS == 4 ? 12 : 8;                   // weight ring depth
+  static constexpr int kSX = NT <= 64 ? 6 : (NT == 128 ? 5 : 4);   // activation ring depth
+  static constexpr int kXOff = 0;
+  static constexpr int kWOff = kSX * kXBytes;                      // 1024-aligned (kXBytes % 2048 == 0)
+  static constexpr int kBarOff = kWOff + kSW * kWBytes;
+  static constexpr int kNumBars = 2 * kSW + 2 * kSX + 2 * kSA + 1;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtrOff + 16;
+  static constexpr int kAlloc = kTotal + 1024;
+  static constexpr int kDCols = NT < 32 ? 32 : NT;
+  static constexpr int kTmemCols = (kDCols + kSA * 32) <= 256 ? 256 : 512;
+};
+
+template <int BITS, int NT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __restrict__ bp,
+                const __half* __restrict__ scales, const uint32_t* __restrict__ qzeros,
+                const __half* __restrict__ bias, __half* __restrict__ c,
+                float* __restrict__ acc_out, int M, int K, int N, int group_size, int qfmt,
+                int chunks_per_split, int direct_store) {
+  using Cfg = TcCfg<BITS, NT>;
+  const int nt = blockIdx.x;
+  const int KC = K / kChunkK;
+  const int c0 = blockIdx.y * chunks_per_split;
+  const int c1 = min(c0 + chunks_per_split, KC);
+  const int nchunks = c1 - c0;
+  const int m0 = blockIdx.z * NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* wfull = bars;
+  uint64_t* wempty = wfull + Cfg::kSW;
+  uint64_t* xfull = wempty + Cfg::kSW;
+  uint64_t* xempty = xfull + Cfg::kSX;
+  uint64_t* afull = xempty + Cfg::kSX;
+  uint64_t* aempty = afull + kSA;
+  uint64_t* dfull = aempty + kSA;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kSW; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], kDqWarps);
+    }
+    for (int i = 0; i < Cfg::kSX; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    for (int i = 0; i < kSA; ++i) {
+      mbar_init(&afull[i], kDqWarps);
+      mbar_init(&aempty[i], 1);
+    }
+    mbar_init(dfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == kDqWarps + 2) {          // MMA warp owns the TMEM allocation
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == kDqWarps + 1 && lane == 0) prefetch_tmap(&xmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t d_tmem = tmem_base;                       // columns [0, kDCols)
+  const uint32_t a_tmem = tmem_base + Cfg::kDCols;         // kSA stages x 32 columns
+
+  if (warp < kDqWarps) {
+    // ------------------------------------------------------------ dequant warps
+    const int q4 = warp & 3;                 // TMEM lane quarter
+    const int h = warp >> 2;                 // K half of the chunk (32 values)
+    const int ch = q4 * 32 + lane;
+    const int n = nt * kTileN + ch;
+    int cur_g = -1;
+    DqConst dq = make_dq(__float2half(0.f), 0);
+    for (int i = 0; i < nchunks; ++i) {
+      const int sw = i % Cfg::kSW, sa = i % kSA;
+      mbar_wait(&wfull[sw], (i / Cfg::kSW) & 1);
+      const uint8_t* wst = smem + Cfg::kWOff + sw * Cfg::kWBytes;
+      uint32_t words[8];
+      if (BITS == 4) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (h * kTileN + ch) * 16);
+        words[0] = pk.x; words[1] = pk.y; words[2] = pk.z; words[3] = pk.w;
+      } else {
+        const uint4 p0 = *reinterpret_cast<const uint4*>(wst + ((2 * h) * kTileN + ch) * 16);
+        const uint4 p1 = *reinterpret_cast<const uint4*>(wst + ((2 * h + 1) * kTileN + ch) * 16);
+        words[0] = p0.x; words[1] = p0.y; words[2] = p0.z; words[3] = p0.w;
+        words[4] = p1.x; words[5] = p1.y; words[6] = p1.z; words[7] = p1.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&wempty[sw]);          // packed bytes are in registers
+      const int g = ((c0 + i) * kChunkK + h * 32) / group_size;
+      if (g != cur_g) {
+        cur_g = g;
+        dq = make_dq(scales[static_cast<size_t>(g) * N + n], load_zero<BITS>(qzeros, qfmt, g, n, N));
+      }
+      uint32_t av[16];
+      if (BITS == 4) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t o4[4];
+          dequant4_word(words[w], dq, o4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) av[w * 4 + e] = o4[e];
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          uint32_t o2[2];
+          dequant8_word(words[w], dq, o2);
+          av[w * 2] = o2[0];
+          av[w * 2 + 1] = o2[1];
+        }
+      }
+      mbar_wait(&aempty[sa], ((i / kSA) & 1) ^ 1);     // MMA of chunk i - kSA has retired
+      tc_fence_after();
+      tmem_st_x16(a_tmem + ((q4 * 32) << 16) + sa * 32 + h * 16, av);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[sa]);
+    }
+    // ------------------------------------------------------------ epilogue (warps 0-3)
+    if (warp < 4 && nchunks > 0) {
+      mbar_wait(dfull, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int j0 = 0; j0 < NT; j0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(d_tmem + ((q4 * 32) << 16) + j0, v);
+        tc_wait_ld();
+        if (direct_store) {
+          const float bv = bias ? __half2float(bias[n]) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + j0 + j;
+            if (m < M) c[static_cast<size_t>(m) * N + n] = __float2half_rn(__uint_as_float(v[j]) + bv);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + j0 + j;
+            if (m < M) atomicAdd(&acc_out[static_cast<size_t>(m) * N + n], __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == kDqWarps) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(bp) +
+                           (static_cast<size_t>(nt) * KC + c0) * Cfg::kWBytes;
+      for (int i = 0; i < nchunks; ++i) {
+        const int sw = i % Cfg::kSW;
+        mbar_wait(&wempty[sw], ((i / Cfg::kSW) & 1) ^ 1);
+        mbar_arrive_expect_tx(&wfull[sw], Cfg::kWBytes);
+        bulk_load_1d(smem + Cfg::kWOff + sw * Cfg::kWBytes, src + static_cast<size_t>(i) * Cfg::kWBytes,
+                     Cfg::kWBytes, &wfull[sw]);
+      }
+    }
+  } else if (warp == kDqWarps + 1) {
+    // ------------------------------------------------------------ activation producer
+    if (lane == 0) {
+      for (int i = 0; i < nchunks; ++i) {
+        const int sx = i % Cfg::kSX;
+        mbar_wait(&xempty[sx], ((i / Cfg::kSX) & 1) ^ 1);
+        mbar_arrive_expect_tx(&xfull[sx], Cfg::kXBytes);
+        tma_load_2d(smem + Cfg::kXOff + sx * Cfg::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, m0);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
+      for (int i = 0; i < nchunks; ++i) {
+        const int sx = i % Cfg::kSX, sa = i % kSA;
+        mbar_wait(&xfull[sx], (i / Cfg::kSX) & 1);
+        mbar_wait(&afull[sa], (i / kSA) & 1);
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + Cfg::kXOff + sx * Cfg::kXBytes));
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks)
+          tc_mma_ts(d_tmem, a_tmem + sa * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
+                    (i > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&xempty[sx]);
+        tc_commit(&aempty[sa]);
+      }
+      tc_commit(dfull);
+    }
+  }
+  __syncthreads();
+  if (warp == kDqWarps + 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+static bool make_x_map(CUtensorMap* map, const __half* a, int M, int K, int NT) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+  const uint32_t box[2] = {kChunkK, static_cast<uint32_t>(NT)};
+  const uint32_t es[2] = {1, 1};
+  return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a), dims,
+                           strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
+}
+
+template <int BITS, int NT>
+static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BITS, NT>;
+  CUtensorMap xmap;
+  if (!make_x_map(&xmap, p.a, p.M, p.K, NT)) {
+    set_error(2, "wna16_tc: cuTensorMapEncodeTiled failed");
+    return true;
+  }
+  const int KC = p.K / kChunkK;
+  const int tiles = p.N / kTileN;
+  const int m_tiles = (p.M + NT - 1) / NT;
+  const int sms = sm_count();
+  int splits = sms / (tiles * m_tiles);
+  if (splits < 1) splits = 1;
+  if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  int cps = (KC + splits - 1) / splits;
+  splits = (KC + cps - 1) / cps;
+  const int direct = (splits == 1 && p.epilogue == B200_EPI_NONE) ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wna16_tc_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         Cfg::kAlloc);
+    attr_set = true;
+  }
+  dim3 grid(tiles, splits, m_tiles);
+  wna16_tc_kernel<BITS, NT><<<grid, kTcThreads, Cfg::kAlloc, st>>>(
+      xmap, p.bp, p.scales, p.qzeros, p.bias, p.c, reinterpret_cast<float*>(p.workspace), p.M, p.K,
+      p.N, p.group_size, p.qfmt, cps, direct);
+  B200_CUDA_LAUNCH_CHECK();
+  if (!direct)
+    wna16_finalize(reinterpret_cast<float*>(p.workspace), p.bias, p.c, p.M, p.N, p.epilogue, st);
+  return true;
+}
+
+template <int BITS>
+static bool launch_tc_bits(const WnaParams& p, cudaStream_t st) {
+  if (p.M <= 16) return launch_tc_nt<BITS, 16>(p, st);
+  if (p.M <= 32) return launch_tc_nt<BITS, 32>(p, st);
+  if (p.M <= 64) return launch_tc_nt<BITS, 64>(p, st);
+  if (p.M <= 128) return launch_tc_nt<BITS, 128>(p, st);
+  return launch_tc_nt<BITS, 256>(p, st);
+}
+
+bool launch_wna16_tc(const WnaParams& p, cudaStream_t st) {
+  // the split-K accumulator in the workspace is [M, N] fp32: prefill sizes that would not fit
+  // take the direct-store route (splits == 1) by construction (tiles * m_tiles >= SM count).
+  if (p.bits == 4) return launch_tc_bits<4>(p, st);
+  return launch_tc_bits<8>(p, st);
+}
+
 }  // namespace b200

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's per-step interface over the C ABI.
+
+  Scheduler    <->  src/core/scheduler.rs  (C++ state machine in csrc/host/scheduler.cpp)
+  ModelRunner  <->  src/core/runner.rs     (decode branch; C++ launch plan in
+                                            csrc/host/model_runner.cpp, CUDA graphs per bucket)
+
+torch is used only to allocate device / pinned host memory and to name the CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import LayerWeights, ModelConfig
+
+GRAPH_BUCKETS = list(range(1, 16)) + [16, 32, 64]     # graph.rs:370-377 stops at 32; we add 64
+
+
+class Scheduler:
+    """Scheduler + BlockManager (scheduler.rs / block_manager.rs) behind the C ABI."""
+
+    def __init__(self, num_blocks, block_size=64, max_num_seqs=32, max_num_batched_tokens=0,
+                 chunk_size=8192, eos_token_ids=()):
+        self._l = _lib.lib()
+        eos = (C.c_uint32 * max(1, len(eos_token_ids)))(*eos_token_ids)
+        self._h = self._l.b200_scheduler_new(num_blocks, block_size, max_num_seqs,
+                                             max_num_batched_tokens, chunk_size, eos,
+                                             len(eos_token_ids))
+        _lib.check()
+        self.block_size = block_size
+        self.cap = 4096
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.b200_scheduler_free(self._h)
+            self._h = None
+
+    def add(self, token_ids, max_tokens=0) -> int:
+        arr = np.ascontiguousarray(token_ids, dtype=np.uint32)
+        sid = self._l.b200_scheduler_add(self._h, arr.ctypes.data, len(arr), max_tokens)
+        _lib.check()
+        return sid
+
+    def schedule(self):
+        idx = np.zeros(self.cap, dtype=np.int32)
+        pf = C.c_int32(0)
+        n = self._l.b200_scheduler_schedule(self._h, idx.ctypes.data, self.cap, C.byref(pf))
+        _lib.check()
+        if n < 0:
+            raise _lib.B200Error("schedule failed")
+        return idx[:n].tolist(), bool(pf.value)
+
+    def filter_prefill_finished(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        pos = np.zeros(max(1, len(a)), dtype=np.int32)
+        idx = np.zeros(max(1, len(a)), dtype=np.int32)
+        n = self._l.b200_scheduler_filter_prefill_finished(self._h, a.ctypes.data, len(a),
+                                                           pos.ctypes.data, idx.ctypes.data)
+        return pos[:n].tolist(), idx[:n].tolist()
+
+    def postprocess(self, ids, tokens):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        t = np.ascontiguousarray(tokens, dtype=np.uint32)
+        self._l.b200_scheduler_postprocess(self._h, a.ctypes.data, len(a), t.ctypes.data)
+
+    def clear_finished(self):
+        self._l.b200_scheduler_clear_finished(self._h)
+
+    @property
+    def num_running(self):
+        return self._l.b200_scheduler_num_running(self._h)
+
+    @property
+    def num_waiting(self):
+        return self._l.b200_scheduler_num_waiting(self._h)
+
+    @property
+    def num_free_blocks(self):
+        return self._l.b200_scheduler_num_free_blocks(self._h)
+
+    def seq_info(self, i):
+        sid, cached, st, nout = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        n = self._l.b200_scheduler_seq_info(self._h, i, C.byref(sid), C.byref(cached),
+                                            C.byref(st), C.byref(nout))
+        return dict(len=n, id=sid.value, num_cached_tokens=cached.value, status=st.value,
+                    num_output_tokens=nout.value)
+
+    def block_table(self, i):
+        n = self._l.b200_scheduler_seq_block_table(self._h, i, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._l.b200_scheduler_seq_block_table(self._h, i, out.ctypes.data, n)
+        return out[:n].tolist()
+
+    def tokens(self, i):
+        n = self._l.b200_scheduler_seq_tokens(self._h, i, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._l.b200_scheduler_seq_tokens(self._h, i, out.ctypes.data, n)
+        return out[:n].tolist()
+
+    def prepare_decode(self, ids, max_blocks_cap=1024, pinned=None):
+        """prepare_decode (runner.rs:1243-1388) into (optionally pinned) host numpy buffers."""
+        n = len(ids)
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        if pinned is None:
+            bufs = dict(input_ids=np.zeros(n, np.uint32), positions=np.zeros(n, np.int64),
+                        slot_mapping=np.zeros(n, np.int64), context_lens=np.zeros(n, np.uint32),
+                        block_tables=np.zeros(n * max_blocks_cap, np.uint32))
+        else:
+            bufs = pinned
+        mctx = C.c_int32(0)
+        mb = self._l.b200_prepare_decode(self._h, a.ctypes.data, n, bufs["input_ids"].ctypes.data,
+                                         bufs["positions"].ctypes.data,
+                                         bufs["slot_mapping"].ctypes.data,
+                                         bufs["context_lens"].ctypes.data,
+                                         bufs["block_tables"].ctypes.data, max_blocks_cap,
+                                         C.byref(mctx))
+        if mb < 0:
+            raise _lib.B200Error("prepare_decode: block table wider than cap")
+        out = {k: v[:n] for k, v in bufs.items() if k != "block_tables"}
+        out["block_tables"] = bufs["block_tables"][:n * mb].reshape(n, mb)
+        out["max_blocks"] = mb
+        out["max_context_len"] = mctx.value
+        return out
+
+    def prepare_prefill(self, ids, token_cap=1 << 17, max_blocks_cap=1024):
+        n = len(ids)
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        input_ids = np.zeros(token_cap, np.uint32)
+        positions = np.zeros(token_cap, np.int64)
+        slots = np.zeros(token_cap, np.int64)
+        cu_q = np.zeros(n + 1, np.uint32)
+        cu_k = np.zeros(n + 1, np.uint32)
+        ctx = np.zeros(n, np.uint32)
+        bt = np.zeros(n * max_blocks_cap, np.uint32)
+        mb, mq, mk, mc, hc = (C.c_int32() for _ in range(5))
+        T = self._l.b200_prepare_prefill(self._h, a.ctypes.data, n, token_cap,
+                                         input_ids.ctypes.data, positions.ctypes.data,
+                                         slots.ctypes.data, cu_q.ctypes.data, cu_k.ctypes.data,
+                                         ctx.ctypes.data, bt.ctypes.data, max_blocks_cap,
+                                         C.byref(mb), C.byref(mq), C.byref(mk), C.byref(mc),
+                                         C.byref(hc))
+        _lib.check()
+        if T < 0:
+            raise _lib.B200Error("prepare_prefill: capacity exceeded")
+        out = dict(input_ids=input_ids[:T], positions=positions[:T], slot_mapping=slots[:T],
+                   cu_seqlens_q=cu_q, cu_seqlens_k=cu_k, max_seqlen_q=mq.value,
+                   max_seqlen_k=mk.value, max_context_len=mc.value, block_tables=None,
+                   context_lens=None, max_blocks=mb.value)
+        if hc.value:
+            out["block_tables"] = bt[:n * mb.value].reshape(n, mb.value)
+            out["context_lens"] = ctx
+        return out
+
+
+@dataclass
+class QuantLinear:
+    """One prepacked W4A16/W8A16 (or dense fp16) linear, possibly several projections fused
+    along N (q|k|v, gate|up) -- wna16.rs:25-261 loads them separately."""
+    w: torch.Tensor            # tile-major packed u32, or dense fp16 [N, K]
+    s: torch.Tensor | None     # scales [K/G, N] fp16
+    z: torch.Tensor | None     # qzeros, checkpoint packing
+    k: int
+    n: int
+
+
+def fuse_awq(parts, device):
+    """parts: list of (qweight i32 [K, N_i/8], qzeros i32 [K/G, N_i/8], scales f16 [K/G, N_i])
+    numpy arrays (AWQ).  Prepack each on the GPU, concatenate along N (tile-major layout makes
+    that a plain concatenation)."""
+    ws, ss, zs, n_tot = [], [], [], 0
+    k = parts[0][0].shape[0]
+    for qw, qz, sc in parts:
+        ws.append(ops.awq_prepack(torch.from_numpy(qw).to(device)).reshape(-1))
+        zs.append(torch.from_numpy(qz).to(device))
+        ss.append(torch.from_numpy(sc).to(device))
+        n_tot += qw.shape[1] * 8
+    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, dim=1).contiguous(),
+                       torch.cat(zs, dim=1).contiguous(), k, n_tot)
+
+
+def fuse_gptq(parts, device, bits=4):
+    ws, ss, zs, n_tot = [], [], [], 0
+    k = parts[0][0].shape[0] * (32 // bits)
+    for qw, qz, sc in parts:
+        ws.append(ops.gptq_prepack(torch.from_numpy(qw).to(device), bits).reshape(-1))
+        zs.append(None if qz is None else torch.from_numpy(qz).to(device))
+        ss.append(torch.from_numpy(sc).to(device))
+        n_tot += qw.shape[1]
+    z = None if zs[0] is None else torch.cat(zs, dim=1).contiguous()
+    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, dim=1).contiguous(), z, k, n_tot)
+
+
+def fuse_dense(parts_kn, device):
+    """parts: list of fp16 torch [K, N_i] -> dense [sum N_i, K] (Linear weight layout)."""
+    w = torch.cat([p.t().contiguous() for p in parts_kn], dim=0).to(device).contiguous()
+    return QuantLinear(w, None, None, parts_kn[0].shape[0], w.shape[0])
+
+
+class ModelRunner:
+    """Decode-step runner over the C++ launch plan (b200_runner_*)."""
+
+    def __init__(self, *, hidden, num_layers, num_heads, num_kv_heads, head_dim, inter, vocab,
+                 num_blocks, max_blocks_per_seq, max_batch, bits=4, group_size=128,
+                 qfmt=ops.QFMT_AWQ, rms_eps=1e-5, qkv_bias=False, max_pos=8192, device="cuda"):
+        self._l = _lib.lib()
+        self.device = torch.device(device)
+        self.cfg = ModelConfig(
+            hidden=hidden, num_layers=num_layers, num_heads=num_heads, num_kv_heads=num_kv_heads,
+            head_dim=head_dim, inter=inter, vocab=vocab, bits=bits, group_size=group_size,
+            qfmt=qfmt, block_size=64, num_blocks=num_blocks, max_blocks_per_seq=max_blocks_per_seq,
+            max_batch=max_batch, max_pos=max_pos, qkv_bias=int(qkv_bias), cos_sin_f32=0,
+            rms_eps=rms_eps, attn_scale=1.0 / float(np.sqrt(head_dim)), tp_rank=0, tp_size=1)
+        self._h = self._l.b200_runner_new(C.byref(self.cfg))
+        _lib.check()
+        self._keep = []            # tensors whose pointers the runner holds
+        shape = (num_blocks, 64, num_kv_heads, head_dim)
+        self.k_cache = [torch.zeros(shape, dtype=torch.float16, device=self.device)
+                        for _ in range(num_layers)]
+        self.v_cache = [torch.zeros(shape, dtype=torch.float16, device=self.device)
+                        for _ in range(num_layers)]
+        nbytes = self._l.b200_runner_workspace_bytes(self._h)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._l.b200_runner_set_workspace(self._h, self.workspace.data_ptr(), nbytes)
+        _lib.check()
+        B, mb = max_batch, max_blocks_per_seq
+        self.pinned = dict(
+            input_ids=torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+            positions=torch.zeros(B, dtype=torch.int64).pin_memory().numpy(),
+            slot_mapping=torch.zeros(B, dtype=torch.int64).pin_memory().numpy(),
+            context_lens=torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+            block_tables=torch.zeros(B * mb, dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+        self.out_ids = torch.zeros(B, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        self._ar_cb = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.b200_runner_free(self._h)
+            self._h = None
+
+    def set_layer(self, l, *, input_norm, post_norm, qkv: QuantLinear, o: QuantLinear,
+                  gate_up: QuantLinear, down: QuantLinear, qkv_bias=None):
+        ts = [input_norm, post_norm, qkv.w, qkv.s, qkv.z, qkv_bias, o.w, o.s, o.z, gate_up.w,
+              gate_up.s, gate_up.z, down.w, down.s, down.z]
+        self._keep.append(ts)
+        p = [0 if t is None else t.data_ptr() for t in ts]
+        lw = LayerWeights(*p, self.k_cache[l].data_ptr(), self.v_cache[l].data_ptr())
+        self._l.b200_runner_set_layer(self._h, l, C.byref(lw))
+        _lib.check()
+
+    def set_globals(self, embed, final_norm, lm_head, cos, sin):
+        self._keep.append([embed, final_norm, lm_head, cos, sin])
+        self._l.b200_runner_set_globals(self._h, embed.data_ptr(), final_norm.data_ptr(),
+                                        lm_head.data_ptr(), cos.data_ptr(), sin.data_ptr())
+
+    def set_allreduce(self, fn):
+        """fn(ptr, count_halfs, stream) is called after each row-parallel GEMM (TP)."""
+        if fn is None:
+            self._ar_cb = None
+            self._l.b200_runner_set_allreduce(self._h, _lib.ALLREDUCE_FN(), None)
+            return
+        self._ar_cb = _lib.ALLREDUCE_FN(lambda buf, n, user, st: fn(buf, n, st))
+        self._l.b200_runner_set_allreduce(self._h, self._ar_cb, None)
+
+    def capture(self, buckets=None):
+        """warmup_capture (graph.rs:448-690)."""
+        b = [x for x in (buckets or GRAPH_BUCKETS) if x <= self.cfg.max_batch]
+        arr = (C.c_int32 * len(b))(*b)
+        # capture needs a non-default stream
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            rc = self._l.b200_runner_capture(self._h, arr, len(b), s.cuda_stream)
+        s.synchronize()
+        _lib.check()
+        if rc != 0:
+            raise _lib.B200Error("graph capture failed")
+        self._graph_stream = s
+
+    def decode_device(self, input_ids, positions, slot_mapping, block_tables, context_lens,
+                      want_logits=True):
+        """One decode step from device tensors; returns (logits f32 [B,V] | None, ids i32 [B])."""
+        B = input_ids.shape[0]
+        assert block_tables.shape[1] == self.cfg.max_blocks_per_seq
+        logits = (torch.empty(B, self.cfg.vocab, dtype=torch.float32, device=self.device)
+                  if want_logits else None)
+        ids = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._l.b200_runner_decode_device(
+            self._h, input_ids.data_ptr(), positions.data_ptr(), slot_mapping.data_ptr(),
+            block_tables.data_ptr(), context_lens.data_ptr(), B,
+            0 if logits is None else logits.data_ptr(), ids.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check()
+        return logits, ids
+
+    def run_decode(self, meta, stream=None) -> np.ndarray:
+        """ModelRunner::run for a decode batch: host metadata in, host token ids out
+        (H2D of the step inputs, graph replay or direct launch, D2H of the ids, sync)."""
+        B = len(meta["input_ids"])
+        st = stream if stream is not None else getattr(self, "_graph_stream", None)
+        sid = st.cuda_stream if st is not None else torch.cuda.current_stream().cuda_stream
+        rc = self._l.b200_runner_decode_host(
+            self._h, meta["input_ids"].ctypes.data, meta["positions"].ctypes.data,
+            meta["slot_mapping"].ctypes.data, meta["block_tables"].ctypes.data,
+            int(meta["max_blocks"]), meta["context_lens"].ctypes.data, B,
+            self.out_ids.ctypes.data, sid)
+        _lib.check()
+        if rc != 0:
+            raise _lib.B200Error("decode_host failed")
+        return self.out_ids[:B].copy()
+
+    @property
+    def launches_per_step(self):
+        return self._l.b200_runner_launches_per_step(self._h)

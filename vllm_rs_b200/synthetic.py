@@ -1,0 +1,104 @@
+"""Synthetic (random-init) checkpoints in the reference's on-disk formats, for benches and
+parity tests (there is no network for real checkpoints).  Shapes / packing follow
+src/models/layers/wna16.rs:56-83,127-152; value distributions follow SURVEY.md section 8(d)
+config 2: uniform int4 codes and zero points, scales U(0.5,1.5)*(2/15)/sqrt(K).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import ModelRunner, QuantLinear, fuse_awq
+
+SHAPES = {
+    # hidden, layers, heads, kv_heads, head_dim, inter, vocab, rope_theta
+    "llama3-8b": (4096, 32, 32, 8, 128, 14336, 128256, 500000.0),
+    "tinyllama-1.1b": (2048, 22, 32, 4, 64, 5632, 32000, 10000.0),
+    "llama3-70b": (8192, 80, 64, 8, 128, 28672, 128256, 500000.0),
+    "toy": (512, 2, 8, 2, 64, 1024, 1024, 10000.0),
+}
+
+
+def rope_tables_device(head_dim, max_pos, theta, device):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float64) / head_dim))
+    inv = inv.to(torch.float32)
+    t = torch.arange(max_pos, dtype=torch.float32).reshape(-1, 1)
+    f = t @ inv.reshape(1, -1)
+    return f.cos().to(torch.float16).to(device), f.sin().to(torch.float16).to(device)
+
+
+def _rand_awq_device(gen, K, N, group, device):
+    """AWQ tensors created directly on the GPU (random packed words are uniform nibbles)."""
+    qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), generator=gen, device=device,
+                       dtype=torch.int32)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // group, N // 8), generator=gen, device=device,
+                       dtype=torch.int32)
+    s = (torch.rand(K // group, N, generator=gen, device=device) + 0.5) * (2.0 / 15.0) / math.sqrt(K)
+    return qw, qz, s.to(torch.float16)
+
+
+def _fused_awq_device(gen, K, Ns, group, device):
+    ws, zs, ss = [], [], []
+    for N in Ns:
+        qw, qz, s = _rand_awq_device(gen, K, N, group, device)
+        ws.append(ops.awq_prepack(qw).reshape(-1))
+        zs.append(qz)
+        ss.append(s)
+    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, 1).contiguous(),
+                       torch.cat(zs, 1).contiguous(), K, sum(Ns))
+
+
+def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_batch, seed=0,
+                     group=128, num_layers=None, tp_size=1, device="cuda") -> ModelRunner:
+    """Random AWQ-int4 model of the named architecture (optionally one TP shard of it:
+    q/k/v/gate/up column-sharded, o/down row-sharded, attention.rs:445-530, mlp.rs:367-442)."""
+    hidden, L, H, Hkv, D, inter, vocab, theta = SHAPES[name]
+    L = num_layers or L
+    Hl, Hkvl, interl = H // tp_size, max(1, Hkv // tp_size), inter // tp_size
+    r = ModelRunner(hidden=hidden, num_layers=L, num_heads=Hl, num_kv_heads=Hkvl, head_dim=D,
+                    inter=interl, vocab=vocab, num_blocks=num_blocks,
+                    max_blocks_per_seq=max_blocks_per_seq, max_batch=max_batch, bits=4,
+                    group_size=group, qfmt=ops.QFMT_AWQ, device=device)
+    gen = torch.Generator(device=device).manual_seed(seed)
+
+    def norm_w():
+        return (1.0 + 0.05 * torch.randn(hidden, generator=gen, device=device)).to(torch.float16)
+
+    for l in range(L):
+        r.set_layer(
+            l, input_norm=norm_w(), post_norm=norm_w(),
+            qkv=_fused_awq_device(gen, hidden, [Hl * D, Hkvl * D, Hkvl * D], group, device),
+            o=_fused_awq_device(gen, Hl * D, [hidden], group, device),
+            gate_up=_fused_awq_device(gen, hidden, [interl, interl], group, device),
+            down=_fused_awq_device(gen, interl, [hidden], group, device))
+    embed = torch.randn(vocab, hidden, generator=gen, device=device).to(torch.float16)
+    lm_head = (0.02 * torch.randn(vocab, hidden, generator=gen, device=device)).to(torch.float16)
+    cos, sin = rope_tables_device(D, 8192, theta, device)
+    r.set_globals(embed, norm_w(), lm_head, cos, sin)
+    r.shape = dict(hidden=hidden, L=L, H=Hl, Hkv=Hkvl, D=D, inter=interl, vocab=vocab, group=group)
+    return r
+
+
+def fill_kv_random(r: ModelRunner, seed=1):
+    """KV cache ~ N(0,1) fp16 without a huge temporary."""
+    gen = torch.Generator(device=r.device).manual_seed(seed)
+    for kc, vc in zip(r.k_cache, r.v_cache):
+        kc.normal_(generator=gen)
+        vc.normal_(generator=gen)
+
+
+def decode_algorithmic_bytes(shape: dict, batch: int, ctx: int, bits=4) -> dict:
+    """Algorithmic HBM bytes of one decode step (SURVEY.md 8(d) / BASELINE.md section 4)."""
+    h, L, H, Hkv, D, inter, V, G = (shape[k] for k in
+                                    ("hidden", "L", "H", "Hkv", "D", "inter", "vocab", "group"))
+    per_layer_kn = h * (H + 2 * Hkv) * D + H * D * h + h * 2 * inter + inter * h
+    W = L * per_layer_kn * bits // 8
+    S = L * per_layer_kn // G * (2 + bits / 8)
+    LM = V * h * 2
+    KV = batch * ctx * L * 2 * Hkv * D * 2
+    KV_new = batch * L * 2 * Hkv * D * 2
+    return dict(weights=W, scales_zeros=int(S), lm_head=LM, kv_read=KV, kv_write=KV_new,
+                total=int(W + S + LM + KV + KV_new))
