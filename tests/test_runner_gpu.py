@@ -59,10 +59,12 @@ def test_decode_steps_match_oracle(lib, fmt, bias):
             torch.from_numpy(mc["input_ids"].astype(np.int32)).cuda(),
             torch.from_numpy(mc["positions"]).cuda(), torch.from_numpy(mc["slot_mapping"]).cuda(),
             bt.cuda(), torch.from_numpy(mc["context_lens"].astype(np.int32)).cuda())
-        err = (got.cpu() - ref).abs().max().item()
+        diff = (got.cpu() - ref).abs()
+        err = diff.max().item()
         max_err = max(max_err, err)
-        # logits are O(1); north star 1e-3 (fp16) -> allow 4 fp16 ulps at |x| ~ 2
-        assert err < 4e-3, f"step {step}: logits max err {err}"
+        # north star: 1e-3 in fp16 terms.  The oracle (like the reference, llama.rs:315-319)
+        # rounds logits to fp16, ours are fp32: allow 2 fp16 ulps = 2e-3 * |logit| + 2e-3
+        assert bool((diff <= 2e-3 + 2e-3 * ref.abs()).all()), f"step {step}: logits max err {err}"
         # greedy ids: identical unless the oracle's top-2 are closer than the tolerance
         ref_ids = ref.argmax(-1)
         for b in range(B):
