@@ -251,6 +251,23 @@ int32_t b200_runner_capture(b200_runner*, const int32_t* buckets, int32_t num_bu
                             int64_t stream);
 int64_t b200_runner_launches_per_step(const b200_runner*);
 
+/* ------------------------------------------------- tensor-parallel communicator
+ * One process per GPU (runner/runner.rs:73-240).  NCCL communicator from a 128-byte unique id
+ * (engine.rs:263, runner/mod.rs:33-58) + an optional one-shot NVLink all-reduce over
+ * cudaIpc-mapped peer buffers for messages <= 1 MiB.  b200_allreduce_f16 is the in-place
+ * equivalent of AllReduce::cuda_fwd (distributed.rs:335-395).                       */
+typedef struct b200_comm b200_comm;
+int32_t b200_nccl_unique_id(uint8_t* out128);
+b200_comm* b200_comm_init_rank(const uint8_t* id128, int32_t rank, int32_t world);
+int32_t b200_comm_enable_oneshot(b200_comm*, int64_t stream);
+void b200_comm_set_force_nccl(b200_comm*, int32_t force);
+void b200_comm_free(b200_comm*);
+void b200_allreduce_f16(b200_comm*, void* buf, int64_t count, int64_t stream);
+int32_t b200_comm_rank(const b200_comm*);
+int32_t b200_comm_world(const b200_comm*);
+/* the runner all-reduces o_proj / down_proj outputs through this communicator */
+void b200_runner_set_comm(b200_runner*, b200_comm*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,29 @@ import torch
 
 F16, F32 = torch.float16, torch.float32
 
+# Rounding model: h() marks every point where the reference materialises a model-dtype (fp16)
+# tensor.  `exact_mode()` turns those roundings off (fp32 everywhere, fp32 KV cache) to give the
+# "infinitely precise" result of the same weights -- used by tests to size the fp16 noise floor.
+_EXACT = False
+
+
+class exact_mode:
+    def __enter__(self):
+        global _EXACT
+        self._old, _EXACT = _EXACT, True
+
+    def __exit__(self, *a):
+        global _EXACT
+        _EXACT = self._old
+
+
+def h(x: torch.Tensor) -> torch.Tensor:
+    return x.to(F32) if _EXACT else x.to(F16)
+
+
+def store_dtype():
+    return F32 if _EXACT else F16
+
 
 @dataclass
 class ModelConfig:
@@ -81,7 +104,7 @@ def rope_tables(cfg: ModelConfig, dtype=F16):
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     xf = x.to(F32)
     inv = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
-    return (xf * inv * w.to(F32)).to(F16)
+    return h(xf * inv * w.to(F32))
 
 
 def apply_rope(q, k, cos, sin, positions, interleaved=False):
@@ -95,10 +118,10 @@ def apply_rope(q, k, cos, sin, positions, interleaved=False):
             x0, x1 = xf[..., 0::2], xf[..., 1::2]
             y = torch.stack((x0 * c - x1 * s, x1 * c + x0 * s), dim=-1).flatten(-2)
         else:
-            h = xf.shape[-1] // 2
-            x0, x1 = xf[..., :h], xf[..., h:]
+            hd = xf.shape[-1] // 2
+            x0, x1 = xf[..., :hd], xf[..., hd:]
             y = torch.cat((x0 * c - x1 * s, x1 * c + x0 * s), dim=-1)
-        return y.to(F16)
+        return h(y)
 
     return rot(q), rot(k)
 
@@ -128,7 +151,7 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
     B, H, D = q.shape
     Hkv = k_cache.shape[2]
     G = H // Hkv
-    out = torch.zeros(B, H, D, dtype=F16)
+    out = torch.zeros(B, H, D, dtype=store_dtype())
     for b in range(B):
         ctx = int(context_lens[b])
         if ctx == 0:
@@ -143,7 +166,7 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
             s = softcap * torch.tanh(s / softcap)
         p = torch.softmax(s, dim=-1)
         o = torch.einsum("hgt,thd->hgd", p, v)
-        out[b] = o.reshape(H, D).to(F16)
+        out[b] = h(o.reshape(H, D))
     return out
 
 
@@ -155,7 +178,7 @@ def attention_prefill(q, k, v, cu_q, k_cache=None, v_cache=None, block_tables=No
     T, H, D = q.shape
     Hkv = k.shape[1]
     G = H // Hkv
-    out = torch.zeros(T, H, D, dtype=F16)
+    out = torch.zeros(T, H, D, dtype=store_dtype())
     for i in range(len(cu_q) - 1):
         a, b = cu_q[i], cu_q[i + 1]
         nq = b - a
@@ -173,7 +196,7 @@ def attention_prefill(q, k, v, cu_q, k_cache=None, v_cache=None, block_tables=No
         s = s.masked_fill(mask, float("-inf"))
         p = torch.softmax(s, dim=-1)
         o = torch.einsum("hgqt,thd->qhgd", p, vv)
-        out[a:b] = o.reshape(nq, H, D).to(F16)
+        out[a:b] = h(o.reshape(nq, H, D))
     return out
 
 
@@ -182,14 +205,14 @@ def linear(x: torch.Tensor, w_kn: torch.Tensor, bias=None) -> torch.Tensor:
     y = x.to(F32) @ w_kn.to(F32)
     if bias is not None:
         y = y + bias.to(F32)
-    return y.to(F16)
+    return h(y)
 
 
 def silu_mul(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     """mlp.rs:467-468: act(gate) in fp16, then * up in fp16."""
     g = gate.to(F32)
-    act = (g * torch.sigmoid(g)).to(F16)
-    return (act.to(F32) * up.to(F32)).to(F16)
+    act = h(g * torch.sigmoid(g))
+    return h(act.to(F32) * up.to(F32))
 
 
 @dataclass
@@ -223,8 +246,8 @@ class LlamaOracle:
         self.cfg, self.w = cfg, weights
         self.cos, self.sin = rope_tables(cfg)
         shape = (num_blocks, cfg.block_size, cfg.num_kv_heads, cfg.head_dim)
-        self.k_cache = [torch.zeros(shape, dtype=F16) for _ in range(cfg.num_layers)]
-        self.v_cache = [torch.zeros(shape, dtype=F16) for _ in range(cfg.num_layers)]
+        self.k_cache = [torch.zeros(shape, dtype=store_dtype()) for _ in range(cfg.num_layers)]
+        self.v_cache = [torch.zeros(shape, dtype=store_dtype()) for _ in range(cfg.num_layers)]
         self.scale = 1.0 / math.sqrt(cfg.head_dim)
 
     def _layer(self, l, x, positions, slot_mapping, attn_fn, trace=None):
@@ -240,12 +263,12 @@ class LlamaOracle:
         kv_write(k, v, self.k_cache[l], self.v_cache[l], slot_mapping)
         a = attn_fn(l, q, k, v)
         o = linear(a.reshape(T, H * D), lw.wo)
-        x = (o.to(F32) + residual.to(F32)).to(F16)              # llama.rs:126
+        x = h(o.to(F32) + residual.to(F32))              # llama.rs:126
         residual = x
         xn = rmsnorm(x, lw.post_norm, cfg.rms_eps)
         gate, up = linear(xn, lw.wgate), linear(xn, lw.wup)
         m = linear(silu_mul(gate, up), lw.wdown)
-        x = (residual.to(F32) + m.to(F32)).to(F16)              # llama.rs:130
+        x = h(residual.to(F32) + m.to(F32))              # llama.rs:130
         if trace is not None:
             trace.append(x.clone())
         return x
@@ -260,7 +283,7 @@ class LlamaOracle:
         pos = torch.as_tensor(meta["positions"], dtype=torch.long)
         slots = torch.as_tensor(meta["slot_mapping"], dtype=torch.long)
         cu_q = meta["cu_seqlens_q"]
-        x = self.w.embed[ids]
+        x = h(self.w.embed[ids])
 
         def attn(l, q, k, v):
             return attention_prefill(q, k, v, cu_q, self.k_cache[l], self.v_cache[l],
@@ -276,7 +299,7 @@ class LlamaOracle:
         ids = torch.as_tensor(meta["input_ids"], dtype=torch.long)
         pos = torch.as_tensor(meta["positions"], dtype=torch.long)
         slots = torch.as_tensor(meta["slot_mapping"], dtype=torch.long)
-        x = self.w.embed[ids]
+        x = h(self.w.embed[ids])
 
         def attn(l, q, k, v):
             return paged_attention_decode(q, self.k_cache[l], self.v_cache[l],

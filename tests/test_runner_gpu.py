@@ -32,11 +32,18 @@ def test_decode_steps_match_oracle(lib, fmt, bias):
         osch.add(osched.Sequence(toks, 64, max_tokens=40))
         csch.add(toks, 40)
     # prefill on the oracle (the CUDA prefill path is a later row of SURVEY section 8), then hand the
-    # cache to the GPU -- from here on both sides run the reference's decode loop
+    # cache to the GPU -- from here on both sides run the reference's decode loop.  A second
+    # oracle in exact (fp32, no fp16 rounding) mode gives the true result of the same weights:
+    # the parity bar is "as close to the truth as the reference-faithful fp16 pipeline".
+    with om.exact_mode():
+        exact = om.LlamaOracle(cfg, oracle.w, NB)
     ids, pf = osch.schedule()
     ids_c, pf_c = csch.schedule()
     assert pf and (ids, pf) == (ids_c, pf_c)
-    logits = oracle.prefill(osched.prepare_prefill([osch.running[i] for i in ids], 64))
+    pmeta = osched.prepare_prefill([osch.running[i] for i in ids], 64)
+    logits = oracle.prefill(pmeta)
+    with om.exact_mode():
+        exact.prefill(pmeta)
     first = logits.argmax(-1).tolist()
     for s in (osch, csch):
         _, fin = s.filter_prefill_finished(ids)
@@ -52,6 +59,8 @@ def test_decode_steps_match_oracle(lib, fmt, bias):
         assert mc["block_tables"].tolist() == mo["block_tables"]          # bit-exact integers
         assert list(mc["slot_mapping"]) == mo["slot_mapping"]
         ref = oracle.decode(mo)
+        with om.exact_mode():
+            truth = exact.decode(mo)
         B = len(ids)
         bt = torch.zeros(B, MAXBLK, dtype=torch.int32)
         bt[:, :mc["max_blocks"]] = torch.from_numpy(mc["block_tables"].astype(np.int32))
@@ -59,17 +68,21 @@ def test_decode_steps_match_oracle(lib, fmt, bias):
             torch.from_numpy(mc["input_ids"].astype(np.int32)).cuda(),
             torch.from_numpy(mc["positions"]).cuda(), torch.from_numpy(mc["slot_mapping"]).cuda(),
             bt.cuda(), torch.from_numpy(mc["context_lens"].astype(np.int32)).cuda())
-        diff = (got.cpu() - ref).abs()
-        err = diff.max().item()
+        got = got.cpu()
+        noise = (ref - truth).abs().max().item()       # fp16 noise floor of the reference pipeline
+        err_truth = (got - truth).abs().max().item()
+        err = (got - ref).abs().max().item()
         max_err = max(max_err, err)
-        # north star: 1e-3 in fp16 terms.  The oracle (like the reference, llama.rs:315-319)
-        # rounds logits to fp16, ours are fp32: allow 2 fp16 ulps = 2e-3 * |logit| + 2e-3
-        assert bool((diff <= 2e-3 + 2e-3 * ref.abs()).all()), f"step {step}: logits max err {err}"
+        # (1) at least as accurate as the fp16 reference pipeline (x2 slack: two noise draws)
+        assert err_truth <= 2 * noise + 2e-3, f"step {step}: {err_truth} vs noise floor {noise}"
+        # (2) and within the combined noise of the fp16 oracle itself (north star: 1e-3 in fp16
+        #     terms per op; logits |x| ~ 4 after two layers of fp16 round-off)
+        assert err <= 3 * noise + 2e-3, f"step {step}: logits max err {err}, noise {noise}"
         # greedy ids: identical unless the oracle's top-2 are closer than the tolerance
         ref_ids = ref.argmax(-1)
         for b in range(B):
             if int(got_ids[b]) != int(ref_ids[b]):
-                assert ref[b].max() - ref[b, int(got_ids[b])] < 4e-3
+                assert ref[b].max() - ref[b, int(got_ids[b])] < 3 * noise + 2e-3
         # the new token's K/V landed in the same slots on both sides
         l, slot = 0, mo["slot_mapping"][0]
         exp = oracle.k_cache[l].view(-1, cfg.num_kv_heads, cfg.head_dim)[slot]

@@ -96,6 +96,15 @@ _SIGS = {
     "b200_runner_decode_host": (c_i32, [c_vp] * 5 + [c_i32, c_vp, c_i32, c_vp, c_i64]),
     "b200_runner_capture": (c_i32, [c_vp, c_vp, c_i32, c_i64]),
     "b200_runner_launches_per_step": (c_i64, [c_vp]),
+    "b200_runner_set_comm": (None, [c_vp, c_vp]),
+    "b200_nccl_unique_id": (c_i32, [c_vp]),
+    "b200_comm_init_rank": (c_vp, [c_vp, c_i32, c_i32]),
+    "b200_comm_enable_oneshot": (c_i32, [c_vp, c_i64]),
+    "b200_comm_set_force_nccl": (None, [c_vp, c_i32]),
+    "b200_comm_free": (None, [c_vp]),
+    "b200_allreduce_f16": (None, [c_vp, c_vp, c_i64, c_i64]),
+    "b200_comm_rank": (c_i32, [c_vp]),
+    "b200_comm_world": (c_i32, [c_vp]),
 }
 
 

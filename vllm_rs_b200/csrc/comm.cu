@@ -1,0 +1,275 @@
+// Tensor-parallel communicator: one process per GPU, one NCCL communicator, one collective
+// (all-reduce SUM of the row-parallel GEMM output) -- exactly the reference's data plane:
+//   Comm::from_rank(device, rank, num_shards, nccl_id)   /root/reference/src/runner/runner.rs:81-89
+//   Id shipped as 128 raw bytes                           /root/reference/src/runner/mod.rs:33-58
+//   AllReduce::cuda_fwd -> comm.all_reduce(SUM)           /root/reference/src/models/layers/distributed.rs:335-395
+// NCCL is resolved with dlopen("libnccl.so.2") so single-GPU users need no NCCL at all.
+//
+// On top of the NCCL baseline there is a one-shot all-reduce for decode-sized messages
+// (<= 1 MiB): every rank's partial sits in a peer-mapped buffer (cudaIpc over NVLink), a rank
+// signals its peers with a release store, waits for theirs with acquire loads, then sums all
+// partials in rank order straight from peer memory (775 GB/s peer loads, ~2 us latency) -- one
+// kernel, CUDA-graph capturable, bit-identical result on every rank.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <vector>
+
+#include "../../include/b200_vllm.h"
+#include "common.cuh"
+
+namespace b200 {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat16 = 6, ncclUint8 = 1, ncclSum = 0 };
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok = false;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce &&
+               api.AllGather;
+    }
+  }
+  return api;
+}
+
+constexpr int kMaxRanks = 8;
+constexpr size_t kOneShotMaxBytes = 1 << 20;          // per-rank payload limit of the one-shot path
+constexpr int kSlots = 2;                             // double-buffered payload slots
+
+struct OneShotPeers {
+  uint8_t* data[kMaxRanks];       // peer payload buffers  [kSlots][kOneShotMaxBytes]
+  uint32_t* flags[kMaxRanks];     // peer flag arrays      [kSlots][kMaxRanks]
+};
+
+// Device-resident state so that a captured launch replays correctly: `state[0]` = number of
+// completed one-shot all-reduces (sequence number), state[1] / state[2] = intra-grid arrival
+// counters (self-resetting).  Launched as a single small wave (the kernel spins on peers).
+__global__ void __launch_bounds__(512)
+oneshot_allreduce_kernel(OneShotPeers peers, __half* __restrict__ buf, size_t count, int rank,
+                         int world, uint32_t* __restrict__ state) {
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(&state[0]) + 1;   // same in every CTA
+  const int slot = seq & 1;
+  const size_t n8 = count / 8;                       // 16-byte vectors
+  uint4* mine = reinterpret_cast<uint4*>(peers.data[rank] + static_cast<size_t>(slot) * kOneShotMaxBytes);
+  const uint4* src = reinterpret_cast<const uint4*>(buf);
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  // 1. publish my partial into my own symmetric buffer
+  for (size_t i = tid; i < n8; i += nthreads) mine[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  // 2. intra-grid arrival; the last CTA signals every peer (release, system scope)
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(&state[1], 1u);
+    last = (prev == gridDim.x - 1);
+    if (last) state[1] = 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < world) {
+    uint32_t* f = peers.flags[threadIdx.x] + slot * kMaxRanks + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+  }
+  // 3. wait until every peer's partial for this sequence number has landed
+  if (threadIdx.x < world) {
+    const uint32_t* f = peers.flags[rank] + slot * kMaxRanks + threadIdx.x;
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while (static_cast<int32_t>(v - seq) < 0);
+  }
+  __syncthreads();
+  // 4. sum all partials in rank order (same order on every rank => identical results)
+  uint4* dst = reinterpret_cast<uint4*>(buf);
+  for (size_t i = tid; i < n8; i += nthreads) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < world; ++r) {
+      const uint4 v = __ldcv(reinterpret_cast<const uint4*>(
+                                 peers.data[r] + static_cast<size_t>(slot) * kOneShotMaxBytes) + i);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    dst[i] = o;
+  }
+  // 5. the last CTA to finish advances the sequence number for the next launch / replay
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(&state[2], 1u);
+    if (prev == gridDim.x - 1) {
+      state[2] = 0;
+      *reinterpret_cast<volatile uint32_t*>(&state[0]) = seq;
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_comm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, world = 1;
+  // one-shot state
+  bool oneshot = false;
+  uint8_t* my_data = nullptr;
+  uint32_t* my_flags = nullptr;
+  uint32_t* state = nullptr;
+  OneShotPeers peers;
+  std::vector<void*> opened;
+  int force_nccl = 0;
+};
+
+extern "C" {
+
+int32_t b200_nccl_unique_id(uint8_t* out128) {
+  NcclApi& a = nccl();
+  if (!a.ok) {
+    set_error(2, "comm: libnccl.so.2 not found");
+    return -1;
+  }
+  ncclUniqueId id;
+  if (a.GetUniqueId(&id) != 0) {
+    set_error(2, "comm: ncclGetUniqueId failed");
+    return -1;
+  }
+  std::memcpy(out128, id.internal, 128);
+  return 0;
+}
+
+b200_comm* b200_comm_init_rank(const uint8_t* id128, int32_t rank, int32_t world) {
+  NcclApi& a = nccl();
+  if (!a.ok || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+    set_error(1, "comm_init_rank: NCCL unavailable or bad rank/world");
+    return nullptr;
+  }
+  auto* c = new b200_comm();
+  c->rank = rank;
+  c->world = world;
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  const ncclResult_t r = a.CommInitRank(&c->nccl, world, id, rank);
+  if (r != 0) {
+    set_error(2, a.GetErrorString ? a.GetErrorString(r) : "ncclCommInitRank failed");
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+/* Enable the one-shot path: allocate the symmetric buffer, exchange cudaIpc handles with
+ * ncclAllGather, map every peer.  Returns 0 on success; on failure the communicator keeps
+ * working through NCCL only. */
+int32_t b200_comm_enable_oneshot(b200_comm* c, int64_t stream) {
+  if (!c || c->world < 2) return -1;
+  NcclApi& a = nccl();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t data_bytes = kSlots * kOneShotMaxBytes;
+  const size_t flag_bytes = kSlots * kMaxRanks * sizeof(uint32_t);
+  uint8_t* base = nullptr;
+  if (cudaMalloc(&base, data_bytes + flag_bytes + 256) != cudaSuccess) return -1;
+  cudaMemset(base, 0, data_bytes + flag_bytes + 256);
+  c->my_data = base;
+  c->my_flags = reinterpret_cast<uint32_t*>(base + data_bytes);
+  c->state = reinterpret_cast<uint32_t*>(base + data_bytes + flag_bytes);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, base) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  cudaIpcMemHandle_t* d_all = nullptr;
+  cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * c->world);
+  cudaMemcpy(d_all + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+  if (a.AllGather(d_all + c->rank, d_all, sizeof(mine), ncclUint8, c->nccl, st) != 0) return -1;
+  cudaStreamSynchronize(st);
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  cudaMemcpy(all.data(), d_all, sizeof(mine) * c->world, cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  for (int r = 0; r < c->world; ++r) {
+    uint8_t* p = base;
+    if (r != c->rank) {
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+      }
+      c->opened.push_back(q);
+      p = reinterpret_cast<uint8_t*>(q);
+    }
+    c->peers.data[r] = p;
+    c->peers.flags[r] = reinterpret_cast<uint32_t*>(p + data_bytes);
+  }
+  c->oneshot = true;
+  return 0;
+}
+
+void b200_comm_set_force_nccl(b200_comm* c, int32_t force) {
+  if (c) c->force_nccl = force;
+}
+
+void b200_comm_free(b200_comm* c) {
+  if (!c) return;
+  for (void* p : c->opened) cudaIpcCloseMemHandle(p);
+  if (c->my_data) cudaFree(c->my_data);
+  if (c->nccl) nccl().CommDestroy(c->nccl);
+  delete c;
+}
+
+/* In-place all-reduce SUM of `count` fp16 values (distributed.rs:367-369, ReduceOp::Sum). */
+void b200_allreduce_f16(b200_comm* c, void* buf, int64_t count, int64_t stream) {
+  if (!c || c->world == 1 || count <= 0) return;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t bytes = static_cast<size_t>(count) * 2;
+  if (c->oneshot && !c->force_nccl && bytes <= kOneShotMaxBytes && count % 8 == 0) {
+    const size_t n8 = count / 8;
+    int blocks = static_cast<int>((n8 + 511) / 512);
+    if (blocks > 32) blocks = 32;      // one wave by a wide margin: the kernel spins on peers
+    if (blocks < 1) blocks = 1;
+    oneshot_allreduce_kernel<<<blocks, 512, 0, st>>>(c->peers, reinterpret_cast<__half*>(buf),
+                                                    static_cast<size_t>(count), c->rank, c->world,
+                                                    c->state);
+    B200_CUDA_LAUNCH_CHECK();
+    return;
+  }
+  const ncclResult_t r = nccl().AllReduce(buf, buf, static_cast<size_t>(count), ncclFloat16, ncclSum,
+                                          c->nccl, st);
+  count_launch(1);
+  if (r != 0) set_error(2, "allreduce: ncclAllReduce failed");
+}
+
+int32_t b200_comm_rank(const b200_comm* c) { return c ? c->rank : 0; }
+int32_t b200_comm_world(const b200_comm* c) { return c ? c->world : 1; }
+
+}  // extern "C"

@@ -152,6 +152,15 @@ void b200_runner_set_workspace(b200_runner* r, void* workspace, int64_t bytes) {
   cudaMemset(workspace, 0, bytes);
 }
 
+static void comm_allreduce_thunk(void* buf, int64_t count, void* user, int64_t stream) {
+  b200_allreduce_f16(reinterpret_cast<b200_comm*>(user), buf, count, stream);
+}
+
+void b200_runner_set_comm(b200_runner* r, b200_comm* c) {
+  r->allreduce = c ? comm_allreduce_thunk : nullptr;
+  r->allreduce_user = c;
+}
+
 void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user) {
   r->allreduce = fn;
   r->allreduce_user = user;
