@@ -119,7 +119,9 @@ void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cach
  * out/q [B,H,D] fp16; block_tables u32 [B, max_blocks_per_seq] (zero padded);
  * context_lens u32 [B] (0 => row skipped, out row zeroed).  softcap <= 0 disables;
  * window <= 0 disables sliding window.  head_dim in {64,128}, block_size == 64,
- * H/Hkv <= 16.  Per-sequence lengths are read on the device (graph safe).          */
+ * H/Hkv <= 16.  Per-sequence lengths are read on the device (graph safe).  `workspace`:
+ * b200_paged_attn_workspace_bytes() bytes, zeroed once by the caller (arrival counters;
+ * the kernel leaves them zeroed).                                                    */
 void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
                                 const void* v_cache, const uint32_t* block_tables,
                                 const uint32_t* context_lens, int32_t batch, int32_t num_heads,

@@ -218,7 +218,7 @@ def test_wna16_gemm(ops, fmt, bits, K, N, M, variant):
     ref = om.linear(x, W)
     # |y| ~ 1; fp32 accumulation both sides, one fp16 rounding on output
     _close(y, ref, 2e-3, 2e-3)
-    assert int(ws.view(torch.int32).abs().sum()) == 0      # workspace left zeroed
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0      # arrival counters back at rest
     # second call reuses the workspace and must agree with the first
     y2 = ops.wna16_gemm(x.cuda(), packed, torch.from_numpy(s).cuda(),
                         None if qz is None else torch.from_numpy(qz).cuda(), ws, k=K, n=N,

@@ -18,8 +18,9 @@
 //     S = Q K^T and O += P V run on mma.sync m16n8k16 (rows = query heads, padded to
 //     16) with ldmatrix on the swizzled tile; online softmax in fp32 with quad
 //     shuffles.  HBM-bound: 4 flop/B of useful math, the tensor pipe is ~15% busy.
-//   * split partials (fp32 O, m, l) go to the caller's workspace and are merged by a
-//     small second kernel; sequences with a single split write fp16 output directly.
+//   * split partials (fp32 O, m, l) go to the caller's workspace and are merged by the LAST
+//     CTA of each (sequence, kv head) (self-resetting arrival counter, fixed split order =>
+//     deterministic, no second launch); single-split sequences write fp16 output directly.
 //
 // Algorithmic bytes per launch: B * ctx * Hkv * D * 2 (K) * 2 (V) * 2 B  (+ q/out).
 #include "../../include/b200_vllm.h"
@@ -56,13 +57,22 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
                          const __half* __restrict__ q, __half* __restrict__ out,
                          const uint32_t* __restrict__ block_tables,
                          const uint32_t* __restrict__ context_lens, float* __restrict__ part_o,
-                         float* __restrict__ part_ml, int q_stride, int H, int Hkv, int max_blocks,
+                         float* __restrict__ part_ml, unsigned* __restrict__ counters,
+                         int q_stride, int H, int Hkv, int max_blocks,
                          int pages_per_split, int max_splits, float scale_log2, float softcap,
                          int window) {
   using SM = AttnSmem<D>;
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   const int ctx = static_cast<int>(context_lens[b]);
-  if (ctx <= 0) return;
+  if (ctx <= 0) {
+    // padded graph rows (graph.rs:741-767): define the output, do no work
+    if (split == 0) {
+      const int Gz = H / Hkv;
+      for (int i = threadIdx.x; i < Gz * D; i += kThreads)
+        out[(static_cast<size_t>(b) * H + static_cast<size_t>(hkv) * Gz) * D + i] = __float2half_rn(0.f);
+    }
+    return;
+  }
   const int npages = (ctx + kTok - 1) / kTok;
   const int fpage = first_page_of(ctx, window);
   const int page0 = fpage + split * pages_per_split;
@@ -290,35 +300,35 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
       }
     }
   }
-}
-
-template <int D>
-__global__ void __launch_bounds__(D)
-paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ part_o,
-                         const float* __restrict__ part_ml,
-                         const uint32_t* __restrict__ context_lens, int H, int pages_per_split,
-                         int max_splits, int window) {
-  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  const int ctx = static_cast<int>(context_lens[b]);
-  __half* o = out + (static_cast<size_t>(b) * H + h) * D;
-  if (ctx <= 0) {
-    o[d] = __float2half_rn(0.f);
-    return;
+  if (nsplits_seq == 1) return;
+  // ---- split merge by the LAST CTA of this (sequence, kv head): self-resetting arrival
+  // counter (zero at rest => CUDA-graph replay safe), partials read back through L2.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* cnt = counters + static_cast<size_t>(b) * Hkv + hkv;
+    const unsigned old = atomicAdd(cnt, 1u);
+    s_last = (old == static_cast<unsigned>(nsplits_seq) - 1) ? 1 : 0;
+    if (s_last) *cnt = 0;
   }
-  const int npages = (ctx + kTok - 1) / kTok;
-  const int fpage = first_page_of(ctx, window);
-  const int ns = (npages - fpage + pages_per_split - 1) / pages_per_split;
-  if (ns <= 1) return;   // written directly by the main kernel
-  const size_t base = (static_cast<size_t>(b) * H + h) * max_splits;
-  float m_tot = -INFINITY;
-  for (int s = 0; s < ns; ++s) m_tot = fmaxf(m_tot, part_ml[(base + s) * 2]);
-  float l = 0.f, acc = 0.f;
-  for (int s = 0; s < ns; ++s) {
-    const float f = exp2f(part_ml[(base + s) * 2] - m_tot);
-    l += part_ml[(base + s) * 2 + 1] * f;
-    acc += part_o[(base + s) * D + d] * f;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < G * D; idx += kThreads) {
+    const int row = idx / D, d = idx - row * D;
+    const int h = hkv * G + row;
+    const size_t base = (static_cast<size_t>(b) * H + h) * max_splits;
+    float m_tot = -INFINITY;
+    for (int s = 0; s < nsplits_seq; ++s) m_tot = fmaxf(m_tot, __ldcg(&part_ml[(base + s) * 2]));
+    float l = 0.f, acc = 0.f;
+    for (int s = 0; s < nsplits_seq; ++s) {      // fixed split order => deterministic
+      const float f = exp2f(__ldcg(&part_ml[(base + s) * 2]) - m_tot);
+      l += __ldcg(&part_ml[(base + s) * 2 + 1]) * f;
+      acc += __ldcg(&part_o[(base + s) * D + d]) * f;
+    }
+    out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc / l);
   }
-  o[d] = __float2half_rn(acc / l);
 }
 
 struct SplitPlan {
@@ -362,7 +372,10 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
                           int H, int Hkv, int max_blocks, float scale, float softcap, int window,
                           void* workspace, cudaStream_t st) {
   const SplitPlan sp = plan_splits(B, Hkv, max_blocks);
-  float* part_o = reinterpret_cast<float*>(workspace);
+  // workspace: [arrival counters B*Hkv u32, zero at rest][partial O fp32][partial (m, l)]
+  unsigned* counters = reinterpret_cast<unsigned*>(workspace);
+  float* part_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
+                                           ((static_cast<size_t>(B) * Hkv * 4 + 255) / 256) * 256);
   float* part_ml = part_o + static_cast<size_t>(B) * H * sp.max_splits * D;
   static bool attr_set = false;
   if (!attr_set) {
@@ -373,12 +386,8 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
   dim3 grid(sp.max_splits, Hkv, B);
   paged_attn_decode_kernel<D><<<grid, kThreads, AttnSmem<D>::kAlloc, st>>>(
       maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
-      block_tables, context_lens, part_o, part_ml, q_stride, H, Hkv, max_blocks,
+      block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
-  B200_CUDA_LAUNCH_CHECK();
-  paged_attn_reduce_kernel<D><<<dim3(H, B), D, 0, st>>>(
-      reinterpret_cast<__half*>(out), part_o, part_ml, context_lens, H, sp.pages_per_split,
-      sp.max_splits, window);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -406,7 +415,8 @@ int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_
     b200::SplitPlan sp = b200::plan_splits(batch, hkv, max_blocks_per_seq);
     if (sp.max_splits > max_splits) max_splits = sp.max_splits;
   }
-  return static_cast<int64_t>(batch) * num_heads * max_splits * (head_dim + 2) * 4 + 256;
+  return static_cast<int64_t>(batch) * num_heads * max_splits * (head_dim + 2) * 4 +
+         static_cast<int64_t>(batch) * num_heads * 4 + 1024;
 }
 
 void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,

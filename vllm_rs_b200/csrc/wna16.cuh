@@ -92,6 +92,76 @@ __device__ __forceinline__ void dequant8_word(uint32_t x, const DqConst& d, uint
   out[1] = h2_as_u32(__hmul2(__hsub2(u32_as_h2(hi), d.zlo), d.s2));
 }
 
+// ---------------------------------------------------------------- split-K meeting point
+// Workspace layout (b200_wna16_workspace_bytes): [0, 16 KB) tile arrival counters, zero at rest
+// and self-resetting; then fp32 partials [splits][M][N] with no invariant (nothing to zero).
+constexpr int kCounterBytes = 16384;
+constexpr int kMaxSplitCols = 148 * 128 * 2;     // launchers keep splits * N below this
+
+struct SplitOut {
+  float* partials;
+  uint32_t* counters;
+  const __half* bias;
+  __half* c;
+  int M, N, splits, epilogue;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Called by the 128 epilogue threads of a CTA (thread = channel `ch` of tile `nt`) AFTER they
+// stored their fp32 partials for rows [m_lo, m_hi).  The last CTA to arrive for the tile (or,
+// with SILU_MUL, for the gate/up tile pair) sums the partials in split order -- deterministic --
+// applies bias / SiLU*mul and writes fp16.  `s_flag` is a shared int; `counter_base` separates
+// token tiles.
+__device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int ch, int m_lo,
+                                                        int m_hi, int counter_base, int* s_flag) {
+  const int N = o.N, M = o.M;
+  const int tiles = N / kTileN;
+  const bool silu = o.epilogue == B200_EPI_SILU_MUL;
+  const int half_tiles = tiles >> 1;
+  const int cidx = counter_base + (silu ? nt % half_tiles : nt);
+  const unsigned target = silu ? 2u * o.splits : static_cast<unsigned>(o.splits);
+  __threadfence();
+  named_bar_sync(2, 128);
+  if (ch == 0) {
+    const unsigned old = atomicAdd(&o.counters[cidx], 1u);
+    const int last = (old == target - 1) ? 1 : 0;
+    if (last) o.counters[cidx] = 0;                  // self-reset (graph replay safe)
+    *s_flag = last;
+  }
+  named_bar_sync(2, 128);
+  if (!*s_flag) return;
+  __threadfence();
+  if (silu) {
+    const int ng = (nt % half_tiles) * kTileN + ch, nu = ng + (N >> 1);
+    const float bg = o.bias ? __half2float(o.bias[ng]) : 0.f;
+    const float bu = o.bias ? __half2float(o.bias[nu]) : 0.f;
+    for (int m = m_lo; m < m_hi; ++m) {
+      float g = bg, u = bu;
+      for (int s = 0; s < o.splits; ++s) {
+        const float* p = o.partials + (static_cast<size_t>(s) * M + m) * N;
+        g += __ldcg(p + ng);
+        u += __ldcg(p + nu);
+      }
+      // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
+      g = __half2float(__float2half_rn(g));
+      u = __half2float(__float2half_rn(u));
+      o.c[static_cast<size_t>(m) * (N >> 1) + ng] = __float2half_rn(g / (1.f + __expf(-g)) * u);
+    }
+  } else {
+    const int n = nt * kTileN + ch;
+    const float bb = o.bias ? __half2float(o.bias[n]) : 0.f;
+    for (int m = m_lo; m < m_hi; ++m) {
+      float acc = bb;
+      for (int s = 0; s < o.splits; ++s)
+        acc += __ldcg(o.partials + (static_cast<size_t>(s) * M + m) * N + n);
+      o.c[static_cast<size_t>(m) * N + n] = __float2half_rn(acc);
+    }
+  }
+}
+
 // launchers implemented in wna16_gemv.cu / wna16_tc.cu
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported

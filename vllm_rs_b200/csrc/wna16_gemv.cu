@@ -9,9 +9,8 @@
 // A warp's 32 threads read 512 contiguous bytes of packed weights per step (16 B each =
 // 32 int4 or 16 int8 K-values of their channel), dequantise in registers (lop3 / prmt magic
 // numbers, exact (q - z), one fp16 rounding on the scale multiply) and accumulate x*w in
-// fp32 with FHFMA against activations broadcast from shared memory.  K splits meet in an
-// fp32 workspace through red.add; a finalize kernel converts, applies bias / SiLU*mul and
-// re-zeroes the workspace.  HBM-bound only for M <= 4; larger M goes to the tcgen05 path.
+// fp32 with FHFMA against activations broadcast from shared memory.  K splits store fp32
+// partials; the last CTA of a tile sums them in split order and applies bias / SiLU*mul.  HBM-bound only for M <= 4; larger M goes to the tcgen05 path.
 #include "wna16.cuh"
 
 namespace b200 {
@@ -64,7 +63,7 @@ template <int BITS, int MB>
 __global__ void __launch_bounds__(128)
 wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
                   const __half* __restrict__ scales, const uint32_t* __restrict__ qzeros,
-                  float* __restrict__ acc_out, int M, int K, int N, int group_size, int qfmt,
+                  const SplitOut so, int M, int K, int N, int group_size, int qfmt,
                   int chunks_per_cta, int m_base) {
   constexpr int SUB = BITS == 4 ? 2 : 4;
   constexpr int KSUB = kChunkK / SUB;             // K values per 16-byte load
@@ -135,46 +134,20 @@ wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
       }
     }
   }
+  __shared__ int s_flag;
+  const int m_hi = min(M, m_base + MB);
+  if (so.splits == 1 && so.epilogue == B200_EPI_NONE) {
+    const float bv = so.bias ? __half2float(so.bias[n]) : 0.f;
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+      if (m_base + m < M) so.c[static_cast<size_t>(m_base + m) * N + n] = __float2half_rn(acc[m] + bv);
+    return;
+  }
+  float* part = so.partials + static_cast<size_t>(blockIdx.y) * M * N;
 #pragma unroll
   for (int m = 0; m < MB; ++m)
-    if (m_base + m < M) atomicAdd(&acc_out[static_cast<size_t>(m_base + m) * N + n], acc[m]);
-}
-
-// fp32 workspace -> fp16 output (+bias, optional SiLU*mul), re-zero the workspace
-__global__ void wna16_finalize_kernel(float* __restrict__ acc, const __half* __restrict__ bias,
-                                      __half* __restrict__ c, int M, int N, int epilogue) {
-  const int m = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float* row = acc + static_cast<size_t>(m) * N;
-  if (epilogue == B200_EPI_SILU_MUL) {
-    const int half_n = N >> 1;
-    if (i >= half_n) return;
-    float g = row[i], u = row[i + half_n];
-    if (bias) {
-      g += __half2float(bias[i]);
-      u += __half2float(bias[i + half_n]);
-    }
-    // round the two GEMM outputs to fp16 first: same values an unfused pipeline would see
-    g = __half2float(__float2half_rn(g));
-    u = __half2float(__float2half_rn(u));
-    c[static_cast<size_t>(m) * half_n + i] = __float2half_rn(g / (1.f + __expf(-g)) * u);
-    row[i] = 0.f;
-    row[i + half_n] = 0.f;
-  } else {
-    if (i >= N) return;
-    float v = row[i];
-    if (bias) v += __half2float(bias[i]);
-    c[static_cast<size_t>(m) * N + i] = __float2half_rn(v);
-    row[i] = 0.f;
-  }
-}
-
-void wna16_finalize(float* acc, const __half* bias, __half* c, int M, int N, int epilogue,
-                    cudaStream_t st) {
-  const int cols = epilogue == B200_EPI_SILU_MUL ? N / 2 : N;
-  dim3 grid((cols + 255) / 256, M);
-  wna16_finalize_kernel<<<grid, 256, 0, st>>>(acc, bias, c, M, N, epilogue);
-  B200_CUDA_LAUNCH_CHECK();
+    if (m_base + m < M) part[static_cast<size_t>(m_base + m) * N + n] = acc[m];
+  split_arrive_and_reduce(so, nt, ch, m_base, m_hi, 0, &s_flag);
 }
 
 template <int BITS, int MB>
@@ -185,12 +158,16 @@ static void launch_gemv_mb(const WnaParams& p, cudaStream_t st, int m_base) {
   int splits = (sm_count() * 4 + tiles - 1) / tiles;
   if (splits > KC / 2) splits = KC / 2;
   if (splits < 1) splits = 1;
+  while (splits > 1 && static_cast<long>(splits) * p.N > kMaxSplitCols) --splits;
   const int cpc = (KC + splits - 1) / splits;
   splits = (KC + cpc - 1) / cpc;
+  SplitOut so;
+  so.counters = reinterpret_cast<uint32_t*>(p.workspace);
+  so.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
+  so.bias = p.bias; so.c = p.c; so.M = p.M; so.N = p.N; so.splits = splits; so.epilogue = p.epilogue;
   dim3 grid(tiles, splits);
-  wna16_gemv_kernel<BITS, MB><<<grid, 128, 0, st>>>(
-      p.a, p.bp, p.scales, p.qzeros, reinterpret_cast<float*>(p.workspace), p.M, p.K, p.N,
-      p.group_size, p.qfmt, cpc, m_base);
+  wna16_gemv_kernel<BITS, MB><<<grid, 128, 0, st>>>(p.a, p.bp, p.scales, p.qzeros, so, p.M, p.K,
+                                                    p.N, p.group_size, p.qfmt, cpc, m_base);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -216,7 +193,6 @@ static void launch_gemv_bits(const WnaParams& p, cudaStream_t st) {
       m_base += 1;
     }
   }
-  wna16_finalize(reinterpret_cast<float*>(p.workspace), p.bias, p.c, p.M, p.N, p.epilogue, st);
 }
 
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st) {
@@ -234,7 +210,8 @@ static bool check_wna(const WnaParams& p, const char** why) {
   const int g = p.group_size;
   if (g <= 0 || g % 32 != 0 || p.K % g != 0) { *why = "wna16: group_size must divide K and be a multiple of 32"; return false; }
   if (!p.a || !p.bp || !p.scales || !p.c || !p.workspace) { *why = "wna16: NULL pointer"; return false; }
-  if (p.epilogue == B200_EPI_SILU_MUL && (p.N / 2) % 8 != 0) { *why = "wna16: SILU_MUL needs N/2 % 8 == 0"; return false; }
+  if (p.epilogue == B200_EPI_SILU_MUL && (p.N / kTileN) % 2 != 0) { *why = "wna16: SILU_MUL needs an even number of 128-channel tiles"; return false; }
+  if (p.N / kTileN > kCounterBytes / 4) { *why = "wna16: N too large for the tile counters"; return false; }
   return true;
 }
 
@@ -271,10 +248,11 @@ void b200_gptq_prepack(const void* in, void* out, int32_t k_packed, int32_t n, i
 }
 
 int64_t b200_wna16_workspace_bytes(int32_t max_m, int32_t max_n) {
-  // fp32 split-K accumulator [max_m, max_n] + tile semaphores; the tcgen05 path uses
-  // the same region for its split partials.
+  // [16 KB arrival counters][fp32 split-K partials]: launchers keep splits * N <= kMaxSplitCols
+  // unless splits == 1, so max(max_n, kMaxSplitCols) columns always suffice.
   const int64_t m = max_m < 16 ? 16 : max_m;
-  return m * static_cast<int64_t>(max_n) * 4 * 2 + 65536;
+  const int64_t cols = max_n > kMaxSplitCols ? max_n : kMaxSplitCols;
+  return kCounterBytes + m * cols * 4 + 256;
 }
 
 void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,

@@ -9,18 +9,23 @@
 // rows, and prefill simply uses NT = 256.
 //
 // Per CTA (one 128-channel weight tile x one K split x one token tile), warp roles:
-//   warps 0-7  dequant: thread = (channel c, K half h).  Packed weights arrive in shared
+//   warps 0-15 dequant: thread = (channel c, K quarter kq).  Packed weights arrive in shared
 //              memory through a deep ring of 4 KB cp.async.bulk copies (the tile-major prepack
-//              makes every stage one contiguous block); each thread reads its 16 bytes,
-//              dequantises to 16 half2 registers (lop3 / prmt magic numbers, exact (q - z),
-//              one rounding on the scale multiply) and writes them with tcgen05.st 32x32b.x16
-//              into its TMEM lane: the A operand never touches shared memory again.
-//   warp 8     weight producer (cp.async.bulk, 1-D)
-//   warp 9     activation producer (TMA 2-D tensor map, SWIZZLE_128B, OOB rows zero-filled)
-//   warp 10    MMA issuer: tcgen05.mma.kind::f16 with A from TMEM, B from the smem descriptor,
+//              makes every stage one contiguous block); each thread reads its 8/16 bytes,
+//              dequantises 16 K values to 8 half2 registers (lop3 / prmt magic numbers, exact
+//              (q - z), one rounding on the scale multiply; scales and zero points of the CTA's
+//              K range are staged in shared memory once) and writes them with
+//              tcgen05.st 32x32b.x8 into its TMEM lane: the A operand never touches shared
+//              memory again.
+//   warp 16    weight producer (cp.async.bulk, 1-D)
+//   warp 17    activation producer (TMA 2-D tensor map, SWIZZLE_128B, OOB rows zero-filled)
+//   warp 18    MMA issuer: tcgen05.mma.kind::f16 with A from TMEM, B from the smem descriptor,
 //              fp32 accumulators in TMEM; tcgen05.commit releases the rings.
-//   epilogue   warps 0-3 read the accumulators with tcgen05.ld; a full-K CTA stores fp16
-//              directly, K splits meet in the fp32 workspace (red.add) + finalize kernel.
+//   epilogue   warps 0-3 read the accumulators with tcgen05.ld.  A full-K CTA stores fp16
+//              directly.  K splits store fp32 partials (plain coalesced stores, no atomics); the
+//              LAST CTA of a tile (self-resetting arrival counter) sums the partials in split
+//              order -- deterministic -- and applies bias / SiLU*mul, so there is no second
+//              kernel and nothing to zero.
 //
 // Roofline: decode (NT <= 64) is HBM-bound on the packed weights (K*N/2 bytes per launch);
 // prefill (NT = 256) is tensor-bound: 2*M*N*K flop.
@@ -28,22 +33,22 @@
 
 namespace b200 {
 
-void wna16_finalize(float* acc, const __half* bias, __half* c, int M, int N, int epilogue,
-                    cudaStream_t st);
-
-constexpr int kDqWarps = 8;
+constexpr int kDqWarps = 16;
+constexpr int kDqThreads = kDqWarps * 32;
 constexpr int kTcThreads = (kDqWarps + 3) * 32;
 constexpr int kSA = 4;              // TMEM A stages (32 columns each)
+constexpr int kSZGroups = 64;       // scale/zero groups staged in smem per CTA
 
 template <int BITS, int NT>
 struct TcCfg {
   static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;      // packed weights per stage
   static constexpr int kXBytes = NT * kChunkK * 2;                 // activations per stage
-  static constexpr int kSW = BITS == 4 ? 12 : 8;                   // weight ring depth
-  static constexpr int kSX = NT <= 64 ? 6 : (NT == 128 ? 5 : 4);   // activation ring depth
+  static constexpr int kSW = NT <= 64 ? (BITS == 4 ? 12 : 8) : (BITS == 4 ? 8 : 4);
+  static constexpr int kSX = NT <= 64 ? 6 : (NT == 128 ? 5 : 4);
   static constexpr int kXOff = 0;
   static constexpr int kWOff = kSX * kXBytes;                      // 1024-aligned (kXBytes % 2048 == 0)
-  static constexpr int kBarOff = kWOff + kSW * kWBytes;
+  static constexpr int kSZOff = kWOff + kSW * kWBytes;
+  static constexpr int kBarOff = kSZOff + kSZGroups * kTileN * 4;
   static constexpr int kNumBars = 2 * kSW + 2 * kSX + 2 * kSA + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
@@ -52,21 +57,29 @@ struct TcCfg {
   static constexpr int kTmemCols = (kDCols + kSA * 32) <= 256 ? 256 : 512;
 };
 
+struct TcArgs {
+  const uint32_t* bp;
+  const __half* scales;
+  const uint32_t* qzeros;
+  const __half* bias;
+  __half* c;
+  float* partials;        // [splits][M][N] fp32
+  uint32_t* counters;     // tile arrival counters (zero at rest)
+  int M, K, N, group_size, qfmt, chunks_per_split, splits, epilogue;
+};
+
 template <int BITS, int NT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __restrict__ bp,
-                const __half* __restrict__ scales, const uint32_t* __restrict__ qzeros,
-                const __half* __restrict__ bias, __half* __restrict__ c,
-                float* __restrict__ acc_out, int M, int K, int N, int group_size, int qfmt,
-                int chunks_per_split, int direct_store) {
+wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
   using Cfg = TcCfg<BITS, NT>;
-  const int nt = blockIdx.x;
-  const int KC = K / kChunkK;
-  const int c0 = blockIdx.y * chunks_per_split;
-  const int c1 = min(c0 + chunks_per_split, KC);
+  const int nt = blockIdx.x, split = blockIdx.y;
+  const int KC = a.K / kChunkK;
+  const int c0 = split * a.chunks_per_split;
+  const int c1 = min(c0 + a.chunks_per_split, KC);
   const int nchunks = c1 - c0;
   const int m0 = blockIdx.z * NT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, M = a.M;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -80,6 +93,8 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __rest
   uint64_t* aempty = afull + kSA;
   uint64_t* dfull = aempty + kSA;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
+  uint32_t* sz = reinterpret_cast<uint32_t*>(smem + Cfg::kSZOff);     // [group][128] (scale | z << 16)
+  __shared__ int s_is_last;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kSW; ++i) {
@@ -112,36 +127,53 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __rest
   if (warp < kDqWarps) {
     // ------------------------------------------------------------ dequant warps
     const int q4 = warp & 3;                 // TMEM lane quarter
-    const int h = warp >> 2;                 // K half of the chunk (32 values)
+    const int kq = warp >> 2;                // K quarter of the chunk (16 values)
     const int ch = q4 * 32 + lane;
     const int n = nt * kTileN + ch;
+    // stage scales / zero points of this CTA's K range
+    const int g_first = (c0 * kChunkK) / a.group_size;
+    const int g_last = (c1 * kChunkK - 1) / a.group_size;
+    const int ngroups = g_last - g_first + 1;
+    const bool sz_in_smem = ngroups <= kSZGroups;
+    if (sz_in_smem) {
+      for (int idx = threadIdx.x; idx < ngroups * kTileN; idx += kDqThreads) {
+        const int g = g_first + idx / kTileN, cc = idx % kTileN, nn = nt * kTileN + cc;
+        const uint32_t sbits = __half_as_ushort(a.scales[static_cast<size_t>(g) * N + nn]);
+        const uint32_t z = static_cast<uint32_t>(load_zero<BITS>(a.qzeros, a.qfmt, g, nn, N));
+        sz[idx] = sbits | (z << 16);
+      }
+      named_bar_sync(1, kDqThreads);
+    }
     int cur_g = -1;
     DqConst dq = make_dq(__float2half(0.f), 0);
     for (int i = 0; i < nchunks; ++i) {
       const int sw = i % Cfg::kSW, sa = i % kSA;
       mbar_wait(&wfull[sw], (i / Cfg::kSW) & 1);
       const uint8_t* wst = smem + Cfg::kWOff + sw * Cfg::kWBytes;
-      uint32_t words[8];
+      uint32_t words[4];
       if (BITS == 4) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (h * kTileN + ch) * 16);
-        words[0] = pk.x; words[1] = pk.y; words[2] = pk.z; words[3] = pk.w;
+        const uint2 pk = *reinterpret_cast<const uint2*>(wst + ((kq >> 1) * kTileN + ch) * 16 + (kq & 1) * 8);
+        words[0] = pk.x; words[1] = pk.y; words[2] = 0; words[3] = 0;
       } else {
-        const uint4 p0 = *reinterpret_cast<const uint4*>(wst + ((2 * h) * kTileN + ch) * 16);
-        const uint4 p1 = *reinterpret_cast<const uint4*>(wst + ((2 * h + 1) * kTileN + ch) * 16);
-        words[0] = p0.x; words[1] = p0.y; words[2] = p0.z; words[3] = p0.w;
-        words[4] = p1.x; words[5] = p1.y; words[6] = p1.z; words[7] = p1.w;
+        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (kq * kTileN + ch) * 16);
+        words[0] = pk.x; words[1] = pk.y; words[2] = pk.z; words[3] = pk.w;
+      }
+      const int g = ((c0 + i) * kChunkK + kq * 16) / a.group_size;
+      if (g != cur_g) {
+        cur_g = g;
+        if (sz_in_smem) {
+          const uint32_t v = sz[(g - g_first) * kTileN + ch];
+          dq = make_dq(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFF)), static_cast<int>(v >> 16));
+        } else {
+          dq = make_dq(a.scales[static_cast<size_t>(g) * N + n], load_zero<BITS>(a.qzeros, a.qfmt, g, n, N));
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&wempty[sw]);          // packed bytes are in registers
-      const int g = ((c0 + i) * kChunkK + h * 32) / group_size;
-      if (g != cur_g) {
-        cur_g = g;
-        dq = make_dq(scales[static_cast<size_t>(g) * N + n], load_zero<BITS>(qzeros, qfmt, g, n, N));
-      }
-      uint32_t av[16];
+      uint32_t av[8];
       if (BITS == 4) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < 2; ++w) {
           uint32_t o4[4];
           dequant4_word(words[w], dq, o4);
 #pragma unroll
@@ -149,7 +181,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __rest
         }
       } else {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < 4; ++w) {
           uint32_t o2[2];
           dequant8_word(words[w], dq, o2);
           av[w * 2] = o2[0];
@@ -158,42 +190,47 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const uint32_t* __rest
       }
       mbar_wait(&aempty[sa], ((i / kSA) & 1) ^ 1);     // MMA of chunk i - kSA has retired
       tc_fence_after();
-      tmem_st_x16(a_tmem + ((q4 * 32) << 16) + sa * 32 + h * 16, av);
+      tmem_st_x8(a_tmem + ((q4 * 32) << 16) + sa * 32 + kq * 8, av);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&afull[sa]);
     }
     // ------------------------------------------------------------ epilogue (warps 0-3)
-    if (warp < 4 && nchunks > 0) {
+    if (warp < 4) {
       mbar_wait(dfull, 0);
       tc_fence_after();
+      const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
+      const float bv = (direct && a.bias) ? __half2float(a.bias[n]) : 0.f;
+      float* part = a.partials + (static_cast<size_t>(split) * M) * N;
 #pragma unroll
       for (int j0 = 0; j0 < NT; j0 += 16) {
         uint32_t v[16];
         tmem_ld_x16(d_tmem + ((q4 * 32) << 16) + j0, v);
         tc_wait_ld();
-        if (direct_store) {
-          const float bv = bias ? __half2float(bias[n]) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + j0 + j;
-            if (m < M) c[static_cast<size_t>(m) * N + n] = __float2half_rn(__uint_as_float(v[j]) + bv);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + j0 + j;
-            if (m < M) atomicAdd(&acc_out[static_cast<size_t>(m) * N + n], __uint_as_float(v[j]));
+        for (int j = 0; j < 16; ++j) {
+          const int m = m0 + j0 + j;
+          if (m < M) {
+            if (direct)
+              a.c[static_cast<size_t>(m) * N + n] = __float2half_rn(__uint_as_float(v[j]) + bv);
+            else
+              part[static_cast<size_t>(m) * N + n] = __uint_as_float(v[j]);
           }
         }
       }
       tc_fence_before();
+      if (!direct) {
+        SplitOut o;
+        o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
+        o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
+        split_arrive_and_reduce(o, nt, ch, m0, min(M, m0 + NT), blockIdx.z * (N / kTileN), &s_is_last);
+      }
     }
   } else if (warp == kDqWarps) {
     // ------------------------------------------------------------ weight producer
     if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(bp) +
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.bp) +
                            (static_cast<size_t>(nt) * KC + c0) * Cfg::kWBytes;
       for (int i = 0; i < nchunks; ++i) {
         const int sw = i % Cfg::kSW;
@@ -265,9 +302,25 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
   int splits = sms / (tiles * m_tiles);
   if (splits < 1) splits = 1;
   if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  while (splits > 1 && static_cast<long>(splits) * p.N > kMaxSplitCols) --splits;
   int cps = (KC + splits - 1) / splits;
   splits = (KC + cps - 1) / cps;
-  const int direct = (splits == 1 && p.epilogue == B200_EPI_NONE) ? 1 : 0;
+  if (p.epilogue == B200_EPI_SILU_MUL && (tiles & 1)) {
+    set_error(1, "wna16_tc: SILU_MUL needs an even number of 128-channel tiles");
+    return true;
+  }
+  if (m_tiles * tiles > kCounterBytes / 4) {
+    if (!(splits == 1 && p.epilogue == B200_EPI_NONE)) {
+      set_error(1, "wna16_tc: too many tiles for the arrival counters");
+      return true;
+    }
+  }
+  TcArgs a;
+  a.bp = p.bp; a.scales = p.scales; a.qzeros = p.qzeros; a.bias = p.bias; a.c = p.c;
+  a.counters = reinterpret_cast<uint32_t*>(p.workspace);
+  a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
+  a.M = p.M; a.K = p.K; a.N = p.N; a.group_size = p.group_size; a.qfmt = p.qfmt;
+  a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(wna16_tc_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -275,12 +328,8 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(tiles, splits, m_tiles);
-  wna16_tc_kernel<BITS, NT><<<grid, kTcThreads, Cfg::kAlloc, st>>>(
-      xmap, p.bp, p.scales, p.qzeros, p.bias, p.c, reinterpret_cast<float*>(p.workspace), p.M, p.K,
-      p.N, p.group_size, p.qfmt, cps, direct);
+  wna16_tc_kernel<BITS, NT><<<grid, kTcThreads, Cfg::kAlloc, st>>>(xmap, a);
   B200_CUDA_LAUNCH_CHECK();
-  if (!direct)
-    wna16_finalize(reinterpret_cast<float*>(p.workspace), p.bias, p.c, p.M, p.N, p.epilogue, st);
   return true;
 }
 
@@ -294,8 +343,6 @@ static bool launch_tc_bits(const WnaParams& p, cudaStream_t st) {
 }
 
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st) {
-  // the split-K accumulator in the workspace is [M, N] fp32: prefill sizes that would not fit
-  // take the direct-store route (splits == 1) by construction (tiles * m_tiles >= SM count).
   if (p.bits == 4) return launch_tc_bits<4>(p, st);
   return launch_tc_bits<8>(p, st);
 }

@@ -107,7 +107,7 @@ def kv_write(k, v, k_cache, v_cache, slot_mapping):
 
 def paged_attn_workspace(batch, num_heads, head_dim, max_blocks, device="cuda"):
     n = _lib.lib().b200_paged_attn_workspace_bytes(batch, num_heads, head_dim, max_blocks)
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    return torch.zeros(n, dtype=torch.uint8, device=device)     # arrival counters start at rest
 
 
 def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scale, workspace=None,
