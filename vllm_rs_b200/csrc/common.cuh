@@ -25,6 +25,35 @@ void count_launch(int n);
   } while (0)
 
 int sm_count();
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the decode step is launched with programmaticStreamSerialization: its
+// prologue (barrier init, TMEM alloc, descriptor prefetch, and -- in the GEMM -- the weight
+// stream, which never depends on the previous kernel) overlaps the tail of its predecessor.
+// Device rule: before pdl_wait() a kernel may only READ data that no kernel of the step writes
+// (weights, scales, block tables, context lens) and must not write global memory at all.
+bool pdl_enabled();     // env B200_PDL (default on)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dep).
 CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank,
                            void* gaddr, const uint64_t* dims, const uint64_t* strides,

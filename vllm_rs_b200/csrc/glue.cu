@@ -12,6 +12,8 @@
 //   embedding / index_select          /root/reference/src/models/llama.rs:269-310
 //   logits.argmax                     /root/reference/src/utils/logits_processor.rs:67-70
 #include "../../include/b200_vllm.h"
+#include <cstdlib>
+
 #include "attn.cuh"
 
 namespace b200 {
@@ -28,6 +30,8 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
                                      __half* __restrict__ k_cache, __half* __restrict__ v_cache,
                                      int q_stride, int k_stride, int v_stride, int H, int Hkv,
                                      int D, int rot_dim, int interleaved) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x;
   const int64_t pos = positions ? positions[t] : 0;
   const int half_rot = rot_dim >> 1;
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
                const __half* __restrict__ x, const __half* __restrict__ w, int hidden,
                float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x;
   const int n8 = hidden >> 3;
   const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * hidden);
@@ -190,6 +196,8 @@ __global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restri
 // ------------------------------------------------------------------ row gathers
 __global__ void gather_rows_kernel(__half* __restrict__ out, const __half* __restrict__ table,
                                    const uint32_t* __restrict__ ids, int hidden, int nrows_src) {
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x;
   uint32_t id = ids[t];
   if (nrows_src > 0 && id >= static_cast<uint32_t>(nrows_src)) id = 0;
@@ -209,6 +217,8 @@ __global__ void add_bias_kernel(__half* __restrict__ x, const __half* __restrict
 // ------------------------------------------------------------------ argmax (first max wins)
 __global__ void __launch_bounds__(1024)
 argmax_kernel(uint32_t* __restrict__ out_ids, const float* __restrict__ logits, int vocab) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* row = logits + static_cast<size_t>(b) * vocab;
   float best = -INFINITY;
@@ -270,15 +280,13 @@ void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_s
   const int pairs = (H + Hkv) * D / 2;
   const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
   if (cos_sin_f32)
-    rope_kv_write_kernel<true><<<T, threads, 0, st>>>(
-        (__half*)q, (__half*)k, (const __half*)v, cos, sin, positions, slot_mapping,
-        (__half*)k_cache, (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim,
-        interleaved);
+    launch_pdl(rope_kv_write_kernel<true>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
+               (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
+               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved);
   else
-    rope_kv_write_kernel<false><<<T, threads, 0, st>>>(
-        (__half*)q, (__half*)k, (const __half*)v, cos, sin, positions, slot_mapping,
-        (__half*)k_cache, (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim,
-        interleaved);
+    launch_pdl(rope_kv_write_kernel<false>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
+               (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
+               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -320,8 +328,9 @@ void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_
                       int32_t hidden, float eps, int64_t stream) {
   if (num_tokens <= 0) return;
   B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "rmsnorm: hidden % 8 != 0 or > 16384");
-  rmsnorm_kernel<false><<<num_tokens, 256, hidden * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (__half*)out, nullptr, (const __half*)x, (const __half*)weight, hidden, eps);
+  launch_pdl(rmsnorm_kernel<false>, dim3(num_tokens), dim3(256), hidden * 2,
+             reinterpret_cast<cudaStream_t>(stream), (__half*)out, (__half*)nullptr, (const __half*)x,
+             (const __half*)weight, hidden, eps);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -329,8 +338,9 @@ void b200_add_rmsnorm_f16(void* out, void* residual, const void* x, const void* 
                           int32_t num_tokens, int32_t hidden, float eps, int64_t stream) {
   if (num_tokens <= 0) return;
   B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "add_rmsnorm: hidden % 8 != 0 or > 16384");
-  rmsnorm_kernel<true><<<num_tokens, 256, hidden * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (__half*)out, (__half*)residual, (const __half*)x, (const __half*)weight, hidden, eps);
+  launch_pdl(rmsnorm_kernel<true>, dim3(num_tokens), dim3(256), hidden * 2,
+             reinterpret_cast<cudaStream_t>(stream), (__half*)out, (__half*)residual, (const __half*)x,
+             (const __half*)weight, hidden, eps);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -348,8 +358,8 @@ void b200_embedding_f16(void* out, const void* table, const uint32_t* ids, int32
                         int32_t hidden, int32_t vocab, int64_t stream) {
   if (num_tokens <= 0) return;
   B200_CHECK_ARG(hidden % 8 == 0, "embedding: hidden % 8 != 0");
-  gather_rows_kernel<<<num_tokens, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (__half*)out, (const __half*)table, ids, hidden, vocab);
+  launch_pdl(gather_rows_kernel, dim3(num_tokens), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             (__half*)out, (const __half*)table, ids, hidden, vocab);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -357,8 +367,8 @@ void b200_gather_rows_f16(void* out, const void* x, const uint32_t* rows, int32_
                           int32_t hidden, int64_t stream) {
   if (num_rows <= 0) return;
   B200_CHECK_ARG(hidden % 8 == 0, "gather_rows: hidden % 8 != 0");
-  gather_rows_kernel<<<num_rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (__half*)out, (const __half*)x, rows, hidden, 0);
+  launch_pdl(gather_rows_kernel, dim3(num_rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             (__half*)out, (const __half*)x, rows, hidden, 0);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -378,8 +388,8 @@ void b200_argmax_f32(uint32_t* out_ids, const float* logits, int32_t batch, int3
   B200_CHECK_ARG(vocab > 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
                      (vocab % 4 == 0 || batch == 1),
                  "argmax: logits rows must be 16-byte aligned");
-  argmax_kernel<<<batch, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_ids, logits,
-                                                                           vocab);
+  launch_pdl(argmax_kernel, dim3(batch), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), out_ids,
+             logits, vocab);
   B200_CUDA_LAUNCH_CHECK();
 }
 

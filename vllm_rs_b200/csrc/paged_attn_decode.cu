@@ -66,6 +66,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   const int ctx = static_cast<int>(context_lens[b]);
   if (ctx <= 0) {
     // padded graph rows (graph.rs:741-767): define the output, do no work
+    pdl_trigger();
+    pdl_wait();
     if (split == 0) {
       const int Gz = H / Hkv;
       for (int i = threadIdx.x; i < Gz * D; i += kThreads)
@@ -108,6 +110,10 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     }
   }
   __syncthreads();
+  // prologue above touched only step-constant inputs (context_lens, block_tables): it overlaps
+  // the previous kernel's tail.  q and the newest KV rows come from the RoPE kernel -> wait.
+  pdl_trigger();
+  pdl_wait();
 
   // per-thread softmax / output state (consumer warps)
   float m_run[2] = {-INFINITY, -INFINITY};
@@ -315,19 +321,35 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // phase 1: one (m, l) pair per thread into shared memory, then per-(row, split) weights
+  const int ns = nsplits_seq;
+  float* sm_w = reinterpret_cast<float*>(smem);        // [G][ns] softmax weights of the splits
+  float* sm_mm = sm_w + G * ns;                        // [G][ns] split maxima
+  float* sm_ll = sm_mm + G * ns;                       // [G][ns] split sums
+  for (int t = threadIdx.x; t < G * ns; t += kThreads) {
+    const int row = t / ns, sp = t - row * ns;
+    const size_t pidx = (static_cast<size_t>(b) * H + hkv * G + row) * max_splits + sp;
+    sm_mm[t] = __ldcg(&part_ml[pidx * 2]);
+    sm_ll[t] = __ldcg(&part_ml[pidx * 2 + 1]);
+  }
+  __syncthreads();
+  for (int row = threadIdx.x; row < G; row += kThreads) {
+    float m_tot = -INFINITY, l = 0.f;
+    for (int sp = 0; sp < ns; ++sp) m_tot = fmaxf(m_tot, sm_mm[row * ns + sp]);
+    for (int sp = 0; sp < ns; ++sp) l += sm_ll[row * ns + sp] * exp2f(sm_mm[row * ns + sp] - m_tot);
+    const float inv = 1.f / l;
+    for (int sp = 0; sp < ns; ++sp) sm_w[row * ns + sp] = exp2f(sm_mm[row * ns + sp] - m_tot) * inv;
+  }
+  __syncthreads();
+  // phase 2: weighted sum of the partial outputs, fixed split order => deterministic
   for (int idx = threadIdx.x; idx < G * D; idx += kThreads) {
     const int row = idx / D, d = idx - row * D;
     const int h = hkv * G + row;
-    const size_t base = (static_cast<size_t>(b) * H + h) * max_splits;
-    float m_tot = -INFINITY;
-    for (int s = 0; s < nsplits_seq; ++s) m_tot = fmaxf(m_tot, __ldcg(&part_ml[(base + s) * 2]));
-    float l = 0.f, acc = 0.f;
-    for (int s = 0; s < nsplits_seq; ++s) {      // fixed split order => deterministic
-      const float f = exp2f(__ldcg(&part_ml[(base + s) * 2]) - m_tot);
-      l += __ldcg(&part_ml[(base + s) * 2 + 1]) * f;
-      acc += __ldcg(&part_o[(base + s) * D + d]) * f;
-    }
-    out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc / l);
+    const float* po = part_o + ((static_cast<size_t>(b) * H + h) * max_splits) * D + d;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int sp = 0; sp < ns; ++sp) acc += __ldcg(po + static_cast<size_t>(sp) * D) * sm_w[row * ns + sp];
+    out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc);
   }
 }
 
@@ -384,7 +406,7 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
     attr_set = true;
   }
   dim3 grid(sp.max_splits, Hkv, B);
-  paged_attn_decode_kernel<D><<<grid, kThreads, AttnSmem<D>::kAlloc, st>>>(
+  launch_pdl(paged_attn_decode_kernel<D>, grid, dim3(kThreads), AttnSmem<D>::kAlloc, st,
       maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
       block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);

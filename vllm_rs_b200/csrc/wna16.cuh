@@ -110,54 +110,78 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Called by the 128 epilogue threads of a CTA (thread = channel `ch` of tile `nt`) AFTER they
-// stored their fp32 partials for rows [m_lo, m_hi).  The last CTA to arrive for the tile (or,
-// with SILU_MUL, for the gate/up tile pair) sums the partials in split order -- deterministic --
-// applies bias / SiLU*mul and writes fp16.  `s_flag` is a shared int; `counter_base` separates
-// token tiles.
-__device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int ch, int m_lo,
-                                                        int m_hi, int counter_base, int* s_flag) {
+// Called by `nthreads` (128 or 512) threads of a CTA AFTER the partials of rows [m_lo, m_hi) of
+// tile `nt` were stored and fenced by their writers.  tid % 128 = channel, tid / 128 = row phase.
+// The last CTA to arrive for the tile (or, with SILU_MUL, for the gate/up tile pair) sums the
+// partials in split order -- deterministic -- applies bias / SiLU*mul and writes fp16.  Loads of
+// up to 8 rows are issued together so the L2 latency is paid `splits` times, not M * splits.
+// `s_flag` is a shared int; `counter_base` separates token tiles; `bar_id` a free named barrier.
+__device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int tid,
+                                                        int nthreads, int m_lo, int m_hi,
+                                                        int counter_base, int* s_flag, int bar_id) {
   const int N = o.N, M = o.M;
   const int tiles = N / kTileN;
   const bool silu = o.epilogue == B200_EPI_SILU_MUL;
   const int half_tiles = tiles >> 1;
   const int cidx = counter_base + (silu ? nt % half_tiles : nt);
   const unsigned target = silu ? 2u * o.splits : static_cast<unsigned>(o.splits);
-  __threadfence();
-  named_bar_sync(2, 128);
-  if (ch == 0) {
+  named_bar_sync(bar_id, nthreads);          // writers executed __threadfence() before this
+  if (tid == 0) {
     const unsigned old = atomicAdd(&o.counters[cidx], 1u);
     const int last = (old == target - 1) ? 1 : 0;
     if (last) o.counters[cidx] = 0;                  // self-reset (graph replay safe)
     *s_flag = last;
   }
-  named_bar_sync(2, 128);
+  named_bar_sync(bar_id, nthreads);
   if (!*s_flag) return;
   __threadfence();
+  const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
+  constexpr int R = 8;                               // rows in flight per thread
+  const size_t row_stride = static_cast<size_t>(nphase) * N;
   if (silu) {
     const int ng = (nt % half_tiles) * kTileN + ch, nu = ng + (N >> 1);
     const float bg = o.bias ? __half2float(o.bias[ng]) : 0.f;
     const float bu = o.bias ? __half2float(o.bias[nu]) : 0.f;
-    for (int m = m_lo; m < m_hi; ++m) {
-      float g = bg, u = bu;
+    for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
+      float g[R], u[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) { g[j] = bg; u[j] = bu; }
       for (int s = 0; s < o.splits; ++s) {
-        const float* p = o.partials + (static_cast<size_t>(s) * M + m) * N;
-        g += __ldcg(p + ng);
-        u += __ldcg(p + nu);
+        const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (mb + j * nphase < m_hi) {
+            g[j] += __ldcg(p + j * row_stride + ng);
+            u[j] += __ldcg(p + j * row_stride + nu);
+          }
       }
-      // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
-      g = __half2float(__float2half_rn(g));
-      u = __half2float(__float2half_rn(u));
-      o.c[static_cast<size_t>(m) * (N >> 1) + ng] = __float2half_rn(g / (1.f + __expf(-g)) * u);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (mb + j * nphase < m_hi) {
+          // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
+          const float gg = __half2float(__float2half_rn(g[j]));
+          const float uu = __half2float(__float2half_rn(u[j]));
+          o.c[static_cast<size_t>(mb + j * nphase) * (N >> 1) + ng] =
+              __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
+        }
     }
   } else {
     const int n = nt * kTileN + ch;
     const float bb = o.bias ? __half2float(o.bias[n]) : 0.f;
-    for (int m = m_lo; m < m_hi; ++m) {
-      float acc = bb;
-      for (int s = 0; s < o.splits; ++s)
-        acc += __ldcg(o.partials + (static_cast<size_t>(s) * M + m) * N + n);
-      o.c[static_cast<size_t>(m) * N + n] = __float2half_rn(acc);
+    for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
+      float acc[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[j] = bb;
+      for (int s = 0; s < o.splits; ++s) {
+        const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N + n;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (mb + j * nphase < m_hi) acc[j] += __ldcg(p + j * row_stride);
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (mb + j * nphase < m_hi)
+          o.c[static_cast<size_t>(mb + j * nphase) * N + n] = __float2half_rn(acc[j]);
     }
   }
 }

@@ -67,6 +67,8 @@ wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
                   int chunks_per_cta, int m_base) {
   constexpr int SUB = BITS == 4 ? 2 : 4;
   constexpr int KSUB = kChunkK / SUB;             // K values per 16-byte load
+  pdl_trigger();
+  pdl_wait();
   const int nt = blockIdx.x;
   const int ch = threadIdx.x;
   const int n = nt * kTileN + ch;
@@ -147,7 +149,8 @@ wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
 #pragma unroll
   for (int m = 0; m < MB; ++m)
     if (m_base + m < M) part[static_cast<size_t>(m_base + m) * N + n] = acc[m];
-  split_arrive_and_reduce(so, nt, ch, m_base, m_hi, 0, &s_flag);
+  __threadfence();
+  split_arrive_and_reduce(so, nt, ch, 128, m_base, m_hi, 0, &s_flag, 2);
 }
 
 template <int BITS, int MB>
@@ -166,8 +169,8 @@ static void launch_gemv_mb(const WnaParams& p, cudaStream_t st, int m_base) {
   so.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
   so.bias = p.bias; so.c = p.c; so.M = p.M; so.N = p.N; so.splits = splits; so.epilogue = p.epilogue;
   dim3 grid(tiles, splits);
-  wna16_gemv_kernel<BITS, MB><<<grid, 128, 0, st>>>(p.a, p.bp, p.scales, p.qzeros, so, p.M, p.K,
-                                                    p.N, p.group_size, p.qfmt, cpc, m_base);
+  launch_pdl(wna16_gemv_kernel<BITS, MB>, grid, dim3(128), 0, st, p.a, p.bp, p.scales, p.qzeros, so,
+             p.M, p.K, p.N, p.group_size, p.qfmt, cpc, m_base);
   B200_CUDA_LAUNCH_CHECK();
 }
 

@@ -120,6 +120,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();     // let the next kernel's prologue / weight stream start under our tail
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t d_tmem = tmem_base;                       // columns [0, kDCols)
   const uint32_t a_tmem = tmem_base + Cfg::kDCols;         // kSA stages x 32 columns
@@ -136,6 +137,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
     const int ngroups = g_last - g_first + 1;
     const bool sz_in_smem = ngroups <= kSZGroups;
     if (sz_in_smem) {
+#pragma unroll 4
       for (int idx = threadIdx.x; idx < ngroups * kTileN; idx += kDqThreads) {
         const int g = g_first + idx / kTileN, cc = idx % kTileN, nn = nt * kTileN + cc;
         const uint32_t sbits = __half_as_ushort(a.scales[static_cast<size_t>(g) * N + nn]);
@@ -196,11 +198,13 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&afull[sa]);
     }
-    // ------------------------------------------------------------ epilogue (warps 0-3)
+    // ------------------------------------------------------------ epilogue
+    // warps 0-3 drain the accumulators; all 16 dequant warps then meet for the split reduce
+    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
+    pdl_wait();        // first global writes below (c / partials / counters)
     if (warp < 4) {
       mbar_wait(dfull, 0);
       tc_fence_after();
-      const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
       const float bv = (direct && a.bias) ? __half2float(a.bias[n]) : 0.f;
       float* part = a.partials + (static_cast<size_t>(split) * M) * N;
 #pragma unroll
@@ -220,12 +224,14 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
         }
       }
       tc_fence_before();
-      if (!direct) {
-        SplitOut o;
-        o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-        o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
-        split_arrive_and_reduce(o, nt, ch, m0, min(M, m0 + NT), blockIdx.z * (N / kTileN), &s_is_last);
-      }
+      if (!direct) __threadfence();
+    }
+    if (!direct) {
+      SplitOut o;
+      o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
+      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
+      split_arrive_and_reduce(o, nt, threadIdx.x, kDqThreads, m0, min(M, m0 + NT),
+                              blockIdx.z * (N / kTileN), &s_is_last, 1);
     }
   } else if (warp == kDqWarps) {
     // ------------------------------------------------------------ weight producer
@@ -243,6 +249,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
   } else if (warp == kDqWarps + 1) {
     // ------------------------------------------------------------ activation producer
     if (lane == 0) {
+      pdl_wait();      // activations are the previous kernel's output; weights are not
       for (int i = 0; i < nchunks; ++i) {
         const int sx = i % Cfg::kSX;
         mbar_wait(&xempty[sx], ((i / Cfg::kSX) & 1) ^ 1);
@@ -328,7 +335,7 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(tiles, splits, m_tiles);
-  wna16_tc_kernel<BITS, NT><<<grid, kTcThreads, Cfg::kAlloc, st>>>(xmap, a);
+  launch_pdl(wna16_tc_kernel<BITS, NT>, grid, dim3(kTcThreads), Cfg::kAlloc, st, xmap, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
 }
