@@ -84,7 +84,8 @@ void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const ui
                                 int32_t n, int32_t k, int32_t group_size, const void* workspace,
                                 int64_t stream);
 /* General entry: bits in {4,8}, qfmt AWQ/GPTQ, optional bias[n] (fp16, may be NULL),
- * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05.   */
+ * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05,
+ * 3 = tcgen05 with a single K split (direct store, workspace untouched; prefill).      */
 void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
                         const void* qzeros, const void* bias, void* c, int32_t m, int32_t k,
                         int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,
@@ -130,6 +131,19 @@ void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
                                 float softcap, int32_t window, void* workspace, int64_t stream);
 int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim,
                                         int32_t max_blocks_per_seq);
+
+/* ------------------------------------------------- paged attention, prefill (varlen causal)
+ * Replaces the prefill branch of PagedAttention::forward (attention.rs:808-820) with the
+ * metadata of prepare_prefill (runner.rs:978-1241).  q/out [T,H,D] fp16 (T = cu_seqlens_q[B]);
+ * keys/values are read from the paged cache through block_tables for the whole context
+ * [0, context_lens[b]) -- call b200_rope_kv_write_f16 for this step's tokens first.
+ * context_lens may be NULL (no cached prefix: context = query length).  H/Hkv in {1,2,4,8}. */
+void b200_attn_prefill_f16(void* out, const void* q, const void* k_cache, const void* v_cache,
+                           const uint32_t* cu_seqlens_q, const uint32_t* context_lens,
+                           const uint32_t* block_tables, int32_t batch, int32_t num_heads,
+                           int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                           int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
+                           float scale, int64_t stream);
 
 /* ------------------------------------------------- glue kernels (others.rs, mlp.rs, llama.rs) */
 void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
@@ -211,6 +225,7 @@ typedef struct b200_model_config {
   int32_t cos_sin_f32;
   float rms_eps, attn_scale;
   int32_t tp_rank, tp_size;            /* shapes above are the LOCAL (per-rank) shard  */
+  int32_t max_prefill_tokens;          /* 0 => decode only; else tokens per prefill step */
 } b200_model_config;
 
 typedef struct b200_layer_weights {
@@ -248,6 +263,17 @@ int32_t b200_runner_decode_host(b200_runner*, const uint32_t* input_ids,
                                 const uint32_t* block_tables, int32_t max_blocks,
                                 const uint32_t* context_lens, int32_t batch,
                                 uint32_t* out_ids_host, int64_t stream);
+/* One prefill step (ModelRunner::run, prefill branch, runner.rs:743-896 with the metadata of
+ * prepare_prefill): DEVICE inputs; T = num_tokens rows.  block_tables must cover every
+ * sequence (keys are read from the paged cache after this step's KV write); context_lens may
+ * be NULL when nothing is cached.  last_rows u32 [num_seqs] = cu_seqlens_q[1:] - 1
+ * (llama.rs:306-310).  logits f32 [num_seqs, vocab] and/or greedy ids are written.        */
+void b200_runner_prefill_device(b200_runner*, const uint32_t* input_ids, const int64_t* positions,
+                                const int64_t* slot_mapping, const uint32_t* cu_seqlens_q,
+                                const uint32_t* context_lens, const uint32_t* block_tables,
+                                const uint32_t* last_rows, int32_t num_seqs, int32_t num_tokens,
+                                int32_t max_seqlen_q, int32_t max_blocks, float* logits,
+                                uint32_t* out_ids, int64_t stream);
 /* Capture CUDA graphs for the given batch buckets (graph.rs:448-690). 0 on success. */
 int32_t b200_runner_capture(b200_runner*, const int32_t* buckets, int32_t num_buckets,
                             int64_t stream);

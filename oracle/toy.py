@@ -17,7 +17,7 @@ def toy_cfg(qkv_bias=False):
                           qkv_bias=qkv_bias)
 
 
-def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks):
+def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks, max_prefill_tokens=0):
     """Random quantised checkpoint -> (oracle with dequantised weights, GPU runner)."""
     from vllm_rs_b200 import engine, ops
     rng = np.random.default_rng(seed)
@@ -42,7 +42,7 @@ def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks):
         hidden=h, num_layers=cfg.num_layers, num_heads=H, num_kv_heads=Hkv, head_dim=D, inter=I,
         vocab=cfg.vocab, num_blocks=num_blocks, max_blocks_per_seq=max_blocks, max_batch=max_batch,
         bits=bits, group_size=128, qfmt=ops.QFMT_AWQ if fmt == "awq" else ops.QFMT_GPTQ,
-        qkv_bias=cfg.qkv_bias, max_pos=cfg.max_pos)
+        qkv_bias=cfg.qkv_bias, max_pos=cfg.max_pos, max_prefill_tokens=max_prefill_tokens)
     w = om.ModelWeights(embed=torch.randn(cfg.vocab, h, generator=g).to(F16), final_norm=norm_w(),
                         lm_head=(0.05 * torch.randn(cfg.vocab, h, generator=g)).to(F16))
     for l in range(cfg.num_layers):

@@ -301,3 +301,59 @@ def test_errors_are_latched(ops):
         ops.rmsnorm(x, torch.zeros(100, dtype=F16, device="cuda"), 1e-5)   # hidden % 8 != 0
     ops.rmsnorm(torch.zeros(2, 128, dtype=F16, device="cuda"),
                 torch.ones(128, dtype=F16, device="cuda"), 1e-5)           # state cleared
+
+
+# ---------------------------------------------------------------- prefill attention
+@pytest.mark.parametrize("H,Hkv,D,cases", [
+    (32, 8, 128, [(37, 0), (64, 0), (65, 0), (130, 64), (1, 0), (200, 128)]),   # (new tokens, cached)
+    (32, 4, 64, [(300, 0), (5, 192)]),                                           # TinyLlama shapes
+    (8, 8, 128, [(100, 0), (33, 64)]),                                           # MHA
+    (4, 2, 64, [(129, 0)]),
+])
+def test_attention_prefill_paged(ops, H, Hkv, D, cases):
+    """Varlen causal prefill over the paged cache vs the oracle, fresh prompts and chunks that
+    attend to cached context (runner.rs:1068-1082).  Stale rows past the context are NaN."""
+    g = torch.Generator().manual_seed(H * D + len(cases))
+    B = len(cases)
+    ctxs = [n + c for n, c in cases]
+    nblk = [-(-c // 64) for c in ctxs]
+    nb = sum(nblk) + 3
+    perm = torch.randperm(nb, generator=g).tolist()
+    kc = torch.randn(nb, 64, Hkv, D, generator=g).to(F16)
+    vc = torch.randn(nb, 64, Hkv, D, generator=g).to(F16)
+    bt = torch.zeros(B, max(nblk), dtype=torch.int32)
+    off = 0
+    for b, n in enumerate(nblk):
+        bt[b, :n] = torch.tensor(perm[off:off + n], dtype=torch.int32)
+        off += n
+    ref = None
+    cu = [0]
+    for n, _ in cases:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    q = torch.randn(T, H, D, generator=g).to(F16)
+    scale = 1.0 / math.sqrt(D)
+    ref = om.attention_prefill(q, None, None, cu, kc, vc, bt.tolist(), ctxs, scale)
+    for b, n in enumerate(nblk):                       # poison the tail of every last page
+        last = ctxs[b] % 64
+        if last:
+            kc[bt[b, n - 1], last:] = float("nan")
+            vc[bt[b, n - 1], last:] = float("nan")
+    out = ops.attention_prefill(q.cuda(), kc.cuda(), vc.cuda(),
+                                torch.tensor(cu, dtype=torch.int32).cuda(),
+                                torch.tensor(ctxs, dtype=torch.int32).cuda(), bt.cuda(),
+                                max(n for n, _ in cases), scale)
+    assert not torch.isnan(out).any()
+    _close(out, ref, 2e-3, 2e-3)
+
+
+@pytest.mark.parametrize("M", [100, 256, 300, 700])
+def test_wna16_gemm_prefill_sizes(ops, M):
+    """tcgen05 variant at prefill token counts (NT = 128 / 256, several token tiles)."""
+    K, N = 1024, 512
+    qw, qz, s, W, x = _wna_case(K, N, M, "awq", 4, seed=M)
+    packed = ops.awq_prepack(torch.from_numpy(qw).cuda())
+    ws = ops.wna16_workspace(M, N)
+    y = ops.wna16_gemm(x.cuda(), packed, torch.from_numpy(s).cuda(), torch.from_numpy(qz).cuda(), ws,
+                       k=K, n=N, variant=2)
+    _close(y, om.linear(x, W), 2e-3, 2e-3)

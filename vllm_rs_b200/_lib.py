@@ -27,7 +27,8 @@ class ModelConfig(C.Structure):
         "bits", "group_size", "qfmt",
         "block_size", "num_blocks", "max_blocks_per_seq", "max_batch", "max_pos",
         "qkv_bias", "cos_sin_f32")] + [("rms_eps", c_f32), ("attn_scale", c_f32),
-                                       ("tp_rank", c_i32), ("tp_size", c_i32)]
+                                       ("tp_rank", c_i32), ("tp_size", c_i32),
+                                       ("max_prefill_tokens", c_i32)]
 
 
 class LayerWeights(C.Structure):
@@ -63,6 +64,7 @@ _SIGS = {
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
+    "b200_attn_prefill_f16": (None, [c_vp] * 7 + [c_i32] * 8 + [c_f32, c_i64]),
     "b200_rmsnorm_f16": (None, [c_vp] * 3 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_add_rmsnorm_f16": (None, [c_vp] * 4 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_silu_mul_f16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
@@ -95,6 +97,7 @@ _SIGS = {
     "b200_runner_decode_device": (None, [c_vp] * 6 + [c_i32, c_vp, c_vp, c_i64]),
     "b200_runner_decode_host": (c_i32, [c_vp] * 5 + [c_i32, c_vp, c_i32, c_vp, c_i64]),
     "b200_runner_capture": (c_i32, [c_vp, c_vp, c_i32, c_i64]),
+    "b200_runner_prefill_device": (None, [c_vp] * 8 + [c_i32] * 4 + [c_vp, c_vp, c_i64]),
     "b200_runner_launches_per_step": (c_i64, [c_vp]),
     "b200_runner_set_comm": (None, [c_vp, c_vp]),
     "b200_nccl_unique_id": (c_i32, [c_vp]),

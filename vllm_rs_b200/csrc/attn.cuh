@@ -13,6 +13,10 @@ void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, in
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
                               int window, void* workspace, cudaStream_t st);
+void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_stride,
+                         const uint32_t* cu_q, const uint32_t* ctx_lens,
+                         const uint32_t* block_tables, int B, int H, int Hkv, int D, int max_blocks,
+                         int max_seqlen_q, float scale, cudaStream_t st);
 // RoPE + KV write with explicit row strides (in halfs) so q|k|v can live in one fused
 // GEMM output row.
 void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,

@@ -68,13 +68,15 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
     off = align_up(off + bytes, 256);
     return p;
   };
-  r->x = (__half*)take(B * c.hidden * 2);
-  r->xn = (__half*)take(B * c.hidden * 2);
-  r->qkv = (__half*)take(B * qkv_n * 2);
-  r->attn = (__half*)take(B * c.num_heads * c.head_dim * 2);
-  r->proj = (__half*)take(B * c.hidden * 2);
-  r->act = (__half*)take(B * 2 * static_cast<size_t>(c.inter) * 2);
-  r->act2 = (__half*)take(B * static_cast<size_t>(c.inter) * 2);
+  // activation rows: a decode batch or a whole prefill step, whichever is larger
+  const size_t R = std::max<size_t>(B, c.max_prefill_tokens > 0 ? c.max_prefill_tokens : 0);
+  r->x = (__half*)take(R * c.hidden * 2);
+  r->xn = (__half*)take(R * c.hidden * 2);
+  r->qkv = (__half*)take(R * qkv_n * 2);
+  r->attn = (__half*)take(R * c.num_heads * c.head_dim * 2);
+  r->proj = (__half*)take(R * c.hidden * 2);
+  r->act = (__half*)take(R * 2 * static_cast<size_t>(c.inter) * 2);
+  r->act2 = (__half*)take(R * static_cast<size_t>(c.inter) * 2);
   r->logits = (float*)take(B * c.vocab * 4);
   r->attn_ws = take(b200_paged_attn_workspace_bytes(c.max_batch, c.num_heads, c.head_dim,
                                                     c.max_blocks_per_seq));
@@ -168,7 +170,7 @@ void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user)
 
 static void linear(b200_runner* r, const __half* in, const void* w, const void* s, const void* z,
                    const void* bias, __half* out, int M, int K, int N, int epilogue,
-                   int64_t stream) {
+                   int64_t stream, int variant = 0) {
   const b200_model_config& c = r->cfg;
   if (c.bits == 16) {
     b200_dense_gemm_f16(in, w, out, M, N, K, 0, stream);
@@ -177,8 +179,8 @@ static void linear(b200_runner* r, const __half* in, const void* w, const void* 
     }
     return;
   }
-  b200_wna16_gemm_ex(in, w, s, z, bias, out, M, K, N, c.bits, c.group_size, c.qfmt, epilogue, 0,
-                     r->wna_ws, stream);
+  b200_wna16_gemm_ex(in, w, s, z, bias, out, M, K, N, c.bits, c.group_size, c.qfmt, epilogue,
+                     variant, r->wna_ws, stream);
 }
 
 void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
@@ -238,6 +240,63 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
   b200_add_rmsnorm_f16(r->xn, r->x, r->proj, r->final_norm, B, c.hidden, c.rms_eps, stream);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(r->xn, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
+  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+  r->launches = launch_count() - launches0;
+}
+
+void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
+                                const int64_t* positions, const int64_t* slot_mapping,
+                                const uint32_t* cu_seqlens_q, const uint32_t* context_lens,
+                                const uint32_t* block_tables, const uint32_t* last_rows,
+                                int32_t B, int32_t T, int32_t max_seqlen_q, int32_t max_blocks,
+                                float* logits, uint32_t* out_ids, int64_t stream) {
+  const b200_model_config& c = r->cfg;
+  if (!r->ws || B <= 0 || B > c.max_batch || T <= 0 || T > c.max_prefill_tokens) {
+    set_error(1, "runner_prefill: workspace not set or sizes out of range");
+    return;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long launches0 = launch_count();
+  const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim;
+  const int qkv_n = (H + 2 * Hkv) * D;
+  // variant 3: tcgen05 GEMM, one K split, direct fp16 store (token tiles fill the machine)
+  const int V = c.bits == 16 ? 0 : 3;
+  b200_embedding_f16(r->x, r->embed, input_ids, T, c.hidden, c.vocab, stream);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const b200_layer_weights& w = r->layers[l];
+    if (l == 0)
+      b200_rmsnorm_f16(r->xn, r->x, w.input_norm, T, c.hidden, c.rms_eps, stream);
+    else
+      b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, T, c.hidden, c.rms_eps, stream);
+    linear(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, T,
+           c.hidden, qkv_n, B200_EPI_NONE, stream, V);
+    __half* q = r->qkv;
+    __half* k = r->qkv + H * D;
+    __half* v = r->qkv + (H + Hkv) * D;
+    launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
+                         w.k_cache, w.v_cache, T, H, Hkv, D, D, 0, c.cos_sin_f32, st);
+    launch_attn_prefill(r->maps[l], r->attn, q, qkv_n, cu_seqlens_q, context_lens, block_tables, B,
+                        H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st);
+    linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, T, H * D, c.hidden, B200_EPI_NONE,
+           stream, V);
+    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);
+    b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.post_norm, T, c.hidden, c.rms_eps, stream);
+    linear(r, r->xn, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, T, c.hidden,
+           2 * c.inter, B200_EPI_NONE, stream, V);
+    b200_silu_mul_f16(r->act2, r->act, T, c.inter, stream);
+    linear(r, r->act2, w.down_w, w.down_s, w.down_z, nullptr, r->proj, T, c.inter, c.hidden,
+           B200_EPI_NONE, stream, V);
+    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);
+  }
+  // last token of every sequence (llama.rs:306-310), then residual add + final norm + lm_head
+  __half* xs = r->xn;      // [B, hidden] gathered residual stream
+  __half* ps = r->attn;    // [B, hidden] gathered last MLP output
+  __half* ns = r->qkv;     // [B, hidden] normed
+  b200_gather_rows_f16(xs, r->x, last_rows, B, c.hidden, stream);
+  b200_gather_rows_f16(ps, r->proj, last_rows, B, c.hidden, stream);
+  b200_add_rmsnorm_f16(ns, xs, ps, r->final_norm, B, c.hidden, c.rms_eps, stream);
+  float* lg = logits ? logits : r->logits;
+  b200_dense_gemm_f16(ns, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
   if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
   r->launches = launch_count() - launches0;
 }

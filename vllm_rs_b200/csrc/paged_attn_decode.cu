@@ -18,9 +18,9 @@
 //     S = Q K^T and O += P V run on mma.sync m16n8k16 (rows = query heads, padded to
 //     16) with ldmatrix on the swizzled tile; online softmax in fp32 with quad
 //     shuffles.  HBM-bound: 4 flop/B of useful math, the tensor pipe is ~15% busy.
-//   * split partials (fp32 O, m, l) go to the caller's workspace and are merged by the LAST
-//     CTA of each (sequence, kv head) (self-resetting arrival counter, fixed split order =>
-//     deterministic, no second launch); single-split sequences write fp16 output directly.
+//   * split partials (fp32 O, m, l) go to the caller's workspace and are merged in fixed split
+//     order (deterministic) by a small second kernel launched with PDL; single-split sequences
+//     write fp16 output directly.
 //
 // Algorithmic bytes per launch: B * ctx * Hkv * D * 2 (K) * 2 (V) * 2 B  (+ q/out).
 #include "../../include/b200_vllm.h"
@@ -306,51 +306,38 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
       }
     }
   }
-  if (nsplits_seq == 1) return;
-  // ---- split merge by the LAST CTA of this (sequence, kv head): self-resetting arrival
-  // counter (zero at rest => CUDA-graph replay safe), partials read back through L2.
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned* cnt = counters + static_cast<size_t>(b) * Hkv + hkv;
-    const unsigned old = atomicAdd(cnt, 1u);
-    s_last = (old == static_cast<unsigned>(nsplits_seq) - 1) ? 1 : 0;
-    if (s_last) *cnt = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // phase 1: one (m, l) pair per thread into shared memory, then per-(row, split) weights
-  const int ns = nsplits_seq;
-  float* sm_w = reinterpret_cast<float*>(smem);        // [G][ns] softmax weights of the splits
-  float* sm_mm = sm_w + G * ns;                        // [G][ns] split maxima
-  float* sm_ll = sm_mm + G * ns;                       // [G][ns] split sums
-  for (int t = threadIdx.x; t < G * ns; t += kThreads) {
-    const int row = t / ns, sp = t - row * ns;
-    const size_t pidx = (static_cast<size_t>(b) * H + hkv * G + row) * max_splits + sp;
-    sm_mm[t] = __ldcg(&part_ml[pidx * 2]);
-    sm_ll[t] = __ldcg(&part_ml[pidx * 2 + 1]);
-  }
-  __syncthreads();
-  for (int row = threadIdx.x; row < G; row += kThreads) {
-    float m_tot = -INFINITY, l = 0.f;
-    for (int sp = 0; sp < ns; ++sp) m_tot = fmaxf(m_tot, sm_mm[row * ns + sp]);
-    for (int sp = 0; sp < ns; ++sp) l += sm_ll[row * ns + sp] * exp2f(sm_mm[row * ns + sp] - m_tot);
-    const float inv = 1.f / l;
-    for (int sp = 0; sp < ns; ++sp) sm_w[row * ns + sp] = exp2f(sm_mm[row * ns + sp] - m_tot) * inv;
-  }
-  __syncthreads();
-  // phase 2: weighted sum of the partial outputs, fixed split order => deterministic
-  for (int idx = threadIdx.x; idx < G * D; idx += kThreads) {
-    const int row = idx / D, d = idx - row * D;
-    const int h = hkv * G + row;
-    const float* po = part_o + ((static_cast<size_t>(b) * H + h) * max_splits) * D + d;
-    float acc = 0.f;
+}
+
+// Split merge: one CTA per (head, sequence).  Launched with PDL right behind the main kernel, so
+// its launch latency hides under the main kernel's tail (a fused last-CTA merge was measured
+// slower: it serialises two L2 round trips behind the last wave).
+template <int D>
+__global__ void __launch_bounds__(D)
+paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ part_o,
+                         const float* __restrict__ part_ml,
+                         const uint32_t* __restrict__ context_lens, int H, int pages_per_split,
+                         int max_splits, int window) {
+  pdl_trigger();
+  pdl_wait();
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const int ctx = static_cast<int>(context_lens[b]);
+  if (ctx <= 0) return;          // zero-filled by the main kernel
+  const int npages = (ctx + kTok - 1) / kTok;
+  const int fpage = first_page_of(ctx, window);
+  const int ns = (npages - fpage + pages_per_split - 1) / pages_per_split;
+  if (ns <= 1) return;           // written directly by the main kernel
+  const size_t base = (static_cast<size_t>(b) * H + h) * max_splits;
+  float m_tot = -INFINITY;
 #pragma unroll 8
-    for (int sp = 0; sp < ns; ++sp) acc += __ldcg(po + static_cast<size_t>(sp) * D) * sm_w[row * ns + sp];
-    out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc);
+  for (int s = 0; s < ns; ++s) m_tot = fmaxf(m_tot, part_ml[(base + s) * 2]);
+  float l = 0.f, acc = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < ns; ++s) {            // fixed split order => deterministic
+    const float f = exp2f(part_ml[(base + s) * 2] - m_tot);
+    l += part_ml[(base + s) * 2 + 1] * f;
+    acc += part_o[(base + s) * D + d] * f;
   }
+  out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc / l);
 }
 
 struct SplitPlan {
@@ -410,6 +397,10 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
       maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
       block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
+  B200_CUDA_LAUNCH_CHECK();
+  launch_pdl(paged_attn_reduce_kernel<D>, dim3(H, B), dim3(D), 0, st, reinterpret_cast<__half*>(out),
+             static_cast<const float*>(part_o), static_cast<const float*>(part_ml), context_lens, H,
+             sp.pages_per_split, sp.max_splits, window);
   B200_CUDA_LAUNCH_CHECK();
 }
 

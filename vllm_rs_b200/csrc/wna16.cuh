@@ -25,6 +25,7 @@ struct WnaParams {
   const __half* bias;     // [N] or NULL
   __half* c;              // [M, N] (or [M, N/2] with SILU_MUL)
   int M, K, N, bits, group_size, qfmt, epilogue;
+  int no_split;           // force one K split (direct fp16 store, no workspace traffic)
   void* workspace;
 };
 

@@ -273,12 +273,13 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   p.M = m; p.K = k; p.N = n; p.bits = bits;
   p.group_size = group_size <= 0 ? k : group_size;
   p.qfmt = qfmt; p.epilogue = epilogue; p.workspace = workspace;
+  p.no_split = (variant == 3) ? 1 : 0;
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (variant == 2 || (variant == 0 && m > 4)) {
+  if (variant == 2 || variant == 3 || (variant == 0 && m > 4)) {
     if (launch_wna16_tc(p, st)) return;
-    if (variant == 2) { set_error(1, "wna16: shape unsupported by the tcgen05 variant"); return; }
+    if (variant >= 2) { set_error(1, "wna16: shape unsupported by the tcgen05 variant"); return; }
   }
   launch_wna16_gemv(p, st);
 }

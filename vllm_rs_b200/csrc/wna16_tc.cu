@@ -9,13 +9,14 @@
 // rows, and prefill simply uses NT = 256.
 //
 // Per CTA (one 128-channel weight tile x one K split x one token tile), warp roles:
-//   warps 0-15 dequant: thread = (channel c, K quarter kq).  Packed weights arrive in shared
-//              memory through a deep ring of 4 KB cp.async.bulk copies (the tile-major prepack
-//              makes every stage one contiguous block); each thread reads its 8/16 bytes,
-//              dequantises 16 K values to 8 half2 registers (lop3 / prmt magic numbers, exact
+//   warps 0-15 dequant, as 4 groups of 4 warps; group j owns chunks j, j+4, ... (4 chunk
+//              latency chains in flight per SM).  Packed weights arrive in shared memory through
+//              a deep ring of 4 KB cp.async.bulk copies (the tile-major prepack makes every stage
+//              one contiguous block); thread = output channel: it reads its 32 bytes of the chunk,
+//              dequantises 64 K values to 32 half2 registers (lop3 / prmt magic numbers, exact
 //              (q - z), one rounding on the scale multiply; scales and zero points of the CTA's
-//              K range are staged in shared memory once) and writes them with
-//              tcgen05.st 32x32b.x8 into its TMEM lane: the A operand never touches shared
+//              K range are staged in shared memory once) and writes them with two
+//              tcgen05.st 32x32b.x16 into its TMEM lane: the A operand never touches shared
 //              memory again.
 //   warp 16    weight producer (cp.async.bulk, 1-D)
 //   warp 17    activation producer (TMA 2-D tensor map, SWIZZLE_128B, OOB rows zero-filled)
@@ -36,7 +37,8 @@ namespace b200 {
 constexpr int kDqWarps = 16;
 constexpr int kDqThreads = kDqWarps * 32;
 constexpr int kTcThreads = (kDqWarps + 3) * 32;
-constexpr int kSA = 4;              // TMEM A stages (32 columns each)
+constexpr int kGroups = 4;          // dequant warp groups (each owns every 4th chunk)
+constexpr int kSA = 8;              // TMEM A stages (32 columns each)
 constexpr int kSZGroups = 64;       // scale/zero groups staged in smem per CTA
 
 template <int BITS, int NT>
@@ -99,14 +101,14 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kSW; ++i) {
       mbar_init(&wfull[i], 1);
-      mbar_init(&wempty[i], kDqWarps);
+      mbar_init(&wempty[i], 4);
     }
     for (int i = 0; i < Cfg::kSX; ++i) {
       mbar_init(&xfull[i], 1);
       mbar_init(&xempty[i], 1);
     }
     for (int i = 0; i < kSA; ++i) {
-      mbar_init(&afull[i], kDqWarps);
+      mbar_init(&afull[i], 4);
       mbar_init(&aempty[i], 1);
     }
     mbar_init(dfull, 1);
@@ -128,7 +130,6 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
   if (warp < kDqWarps) {
     // ------------------------------------------------------------ dequant warps
     const int q4 = warp & 3;                 // TMEM lane quarter
-    const int kq = warp >> 2;                // K quarter of the chunk (16 values)
     const int ch = q4 * 32 + lane;
     const int n = nt * kTileN + ch;
     // stage scales / zero points of this CTA's K range
@@ -146,57 +147,81 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
       }
       named_bar_sync(1, kDqThreads);
     }
-    int cur_g = -1;
-    DqConst dq = make_dq(__float2half(0.f), 0);
-    for (int i = 0; i < nchunks; ++i) {
-      const int sw = i % Cfg::kSW, sa = i % kSA;
-      mbar_wait(&wfull[sw], (i / Cfg::kSW) & 1);
+    // Chunk-interleaved pipeline: warp group `grp` (4 warps = all 128 channels) owns chunks
+    // grp, grp + 4, ... entirely, so four chunk latency chains (smem read -> dequant ->
+    // tcgen05.st -> wait::st -> arrive) are in flight per SM instead of one; the packed words of
+    // the group's next chunk are fetched before the current one is dequantised.
+    constexpr int W = 2 * BITS;                       // packed 32-bit words per thread per chunk
+    const int grp = warp >> 2;
+    auto load_words = [&](int ci, uint32_t (&dst)[W]) {
+      const int sw = ci % Cfg::kSW;
+      mbar_wait(&wfull[sw], (ci / Cfg::kSW) & 1);
       const uint8_t* wst = smem + Cfg::kWOff + sw * Cfg::kWBytes;
-      uint32_t words[4];
-      if (BITS == 4) {
-        const uint2 pk = *reinterpret_cast<const uint2*>(wst + ((kq >> 1) * kTileN + ch) * 16 + (kq & 1) * 8);
-        words[0] = pk.x; words[1] = pk.y; words[2] = 0; words[3] = 0;
-      } else {
-        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (kq * kTileN + ch) * 16);
-        words[0] = pk.x; words[1] = pk.y; words[2] = pk.z; words[3] = pk.w;
-      }
-      const int g = ((c0 + i) * kChunkK + kq * 16) / a.group_size;
-      if (g != cur_g) {
-        cur_g = g;
-        if (sz_in_smem) {
-          const uint32_t v = sz[(g - g_first) * kTileN + ch];
-          dq = make_dq(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFF)), static_cast<int>(v >> 16));
-        } else {
-          dq = make_dq(a.scales[static_cast<size_t>(g) * N + n], load_zero<BITS>(a.qzeros, a.qfmt, g, n, N));
-        }
+#pragma unroll
+      for (int sub = 0; sub < W / 4; ++sub) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (sub * kTileN + ch) * 16);
+        dst[sub * 4 + 0] = pk.x; dst[sub * 4 + 1] = pk.y; dst[sub * 4 + 2] = pk.z; dst[sub * 4 + 3] = pk.w;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&wempty[sw]);          // packed bytes are in registers
-      uint32_t av[8];
-      if (BITS == 4) {
+      if (lane == 0) mbar_arrive(&wempty[sw]);        // packed bytes are in registers
+    };
+    int cur_g = -1;
+    DqConst dq = make_dq(__float2half(0.f), 0);
+    uint32_t cur[W];
+    if (grp < nchunks) load_words(grp, cur);
+    for (int i = grp; i < nchunks; i += kGroups) {
+      uint32_t nxt[W];
+      const bool has_next = i + kGroups < nchunks;
+      if (has_next) load_words(i + kGroups, nxt);
+      const int sa = i % kSA;
+      uint32_t av[32];
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          uint32_t o4[4];
-          dequant4_word(words[w], dq, o4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) av[w * 4 + e] = o4[e];
+      for (int hf = 0; hf < 2; ++hf) {                // two 32-K halves (group boundary safe)
+        const int g = ((c0 + i) * kChunkK + hf * 32) / a.group_size;
+        if (g != cur_g) {
+          cur_g = g;
+          if (sz_in_smem) {
+            const uint32_t v = sz[(g - g_first) * kTileN + ch];
+            dq = make_dq(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFF)), static_cast<int>(v >> 16));
+          } else {
+            dq = make_dq(a.scales[static_cast<size_t>(g) * N + n], load_zero<BITS>(a.qzeros, a.qfmt, g, n, N));
+          }
         }
-      } else {
+        if (BITS == 4) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          uint32_t o2[2];
-          dequant8_word(words[w], dq, o2);
-          av[w * 2] = o2[0];
-          av[w * 2 + 1] = o2[1];
+          for (int w = 0; w < 4; ++w) {
+            uint32_t o4[4];
+            dequant4_word(cur[hf * 4 + w], dq, o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) av[hf * 16 + w * 4 + e] = o4[e];
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            uint32_t o2[2];
+            dequant8_word(cur[(hf * 8 + w) % W], dq, o2);
+            av[hf * 16 + w * 2] = o2[0];
+            av[hf * 16 + w * 2 + 1] = o2[1];
+          }
         }
       }
       mbar_wait(&aempty[sa], ((i / kSA) & 1) ^ 1);     // MMA of chunk i - kSA has retired
       tc_fence_after();
-      tmem_st_x8(a_tmem + ((q4 * 32) << 16) + sa * 32 + kq * 8, av);
+      {
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { lo[e] = av[e]; hi[e] = av[16 + e]; }
+        tmem_st_x16(a_tmem + ((q4 * 32) << 16) + sa * 32, lo);
+        tmem_st_x16(a_tmem + ((q4 * 32) << 16) + sa * 32 + 16, hi);
+      }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&afull[sa]);
+      if (has_next) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) cur[e] = nxt[e];
+      }
     }
     // ------------------------------------------------------------ epilogue
     // warps 0-3 drain the accumulators; all 16 dequant warps then meet for the split reduce
@@ -310,6 +335,7 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
   if (splits < 1) splits = 1;
   if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
   while (splits > 1 && static_cast<long>(splits) * p.N > kMaxSplitCols) --splits;
+  if (p.no_split) splits = 1;
   int cps = (KC + splits - 1) / splits;
   splits = (KC + cps - 1) / cps;
   if (p.epilogue == B200_EPI_SILU_MUL && (tiles & 1)) {

@@ -205,7 +205,8 @@ class ModelRunner:
 
     def __init__(self, *, hidden, num_layers, num_heads, num_kv_heads, head_dim, inter, vocab,
                  num_blocks, max_blocks_per_seq, max_batch, bits=4, group_size=128,
-                 qfmt=ops.QFMT_AWQ, rms_eps=1e-5, qkv_bias=False, max_pos=8192, device="cuda"):
+                 qfmt=ops.QFMT_AWQ, rms_eps=1e-5, qkv_bias=False, max_pos=8192,
+                 max_prefill_tokens=0, device="cuda"):
         self._l = _lib.lib()
         self.device = torch.device(device)
         self.cfg = ModelConfig(
@@ -213,7 +214,8 @@ class ModelRunner:
             head_dim=head_dim, inter=inter, vocab=vocab, bits=bits, group_size=group_size,
             qfmt=qfmt, block_size=64, num_blocks=num_blocks, max_blocks_per_seq=max_blocks_per_seq,
             max_batch=max_batch, max_pos=max_pos, qkv_bias=int(qkv_bias), cos_sin_f32=0,
-            rms_eps=rms_eps, attn_scale=1.0 / float(np.sqrt(head_dim)), tp_rank=0, tp_size=1)
+            rms_eps=rms_eps, attn_scale=1.0 / float(np.sqrt(head_dim)), tp_rank=0, tp_size=1,
+            max_prefill_tokens=max_prefill_tokens)
         self._h = self._l.b200_runner_new(C.byref(self.cfg))
         _lib.check()
         self._keep = []            # tensors whose pointers the runner holds
@@ -295,6 +297,35 @@ class ModelRunner:
         _lib.check()
         return logits, ids
 
+    def prefill_device(self, meta, want_logits=True):
+        """One prefill step (prefill branch of ModelRunner::run) from prepare_prefill metadata
+        (numpy, host).  Block tables are required for every sequence: keys are read back from
+        the paged cache.  Returns (logits f32 [num_seqs, V] | None, ids i32 [num_seqs])."""
+        dev = self.device
+        B = len(meta["cu_seqlens_q"]) - 1
+        T = len(meta["input_ids"])
+
+        def d(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(dev)
+
+        ids = d(meta["input_ids"], np.int32)
+        pos = d(meta["positions"], np.int64)
+        slots = d(meta["slot_mapping"], np.int64)
+        cu = d(meta["cu_seqlens_q"], np.int32)
+        bt = d(meta["block_tables"], np.int32)
+        ctx = None if meta.get("context_lens") is None else d(meta["context_lens"], np.int32)
+        last = d(np.asarray(meta["cu_seqlens_q"][1:], dtype=np.int64) - 1, np.int32)
+        logits = (torch.empty(B, self.cfg.vocab, dtype=torch.float32, device=dev)
+                  if want_logits else None)
+        out = torch.empty(B, dtype=torch.int32, device=dev)
+        self._l.b200_runner_prefill_device(
+            self._h, ids.data_ptr(), pos.data_ptr(), slots.data_ptr(), cu.data_ptr(),
+            0 if ctx is None else ctx.data_ptr(), bt.data_ptr(), last.data_ptr(), B, T,
+            int(meta["max_seqlen_q"]), bt.shape[1], 0 if logits is None else logits.data_ptr(),
+            out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check()
+        return logits, out
+
     def run_decode(self, meta, stream=None) -> np.ndarray:
         """ModelRunner::run for a decode batch: host metadata in, host token ids out
         (H2D of the step inputs, graph replay or direct launch, D2H of the ids, sync)."""
@@ -314,3 +345,63 @@ class ModelRunner:
     @property
     def launches_per_step(self):
         return self._l.b200_runner_launches_per_step(self._h)
+
+
+class LLMEngine:
+    """The reference's 3-phase step loop (engine.rs:1693-1757) over the C++ scheduler and the
+    C++/CUDA runner: prepare_step (schedule + prepare_*) -> run_forward -> finish_step
+    (filter_prefill_finished / postprocess / clear_finished).  Greedy sampling."""
+
+    def __init__(self, runner: ModelRunner, num_blocks, max_num_seqs, eos_token_ids=(),
+                 chunk_size=8192):
+        self.runner = runner
+        self.sched = Scheduler(num_blocks, 64, max_num_seqs, 0, chunk_size, eos_token_ids)
+        self.max_blocks = runner.cfg.max_blocks_per_seq
+        self.outputs = {}
+
+    def add_request(self, token_ids, max_tokens):
+        sid = self.sched.add(token_ids, max_tokens)
+        self.outputs[sid] = []
+        return sid
+
+    def _all_block_tables(self, ids):
+        tabs = [self.sched.block_table(i) for i in ids]
+        w = max(len(t) for t in tabs)
+        bt = np.zeros((len(tabs), w), dtype=np.uint32)
+        for r, t in enumerate(tabs):
+            bt[r, :len(t)] = t
+        return bt
+
+    def step(self):
+        ids, is_prefill = self.sched.schedule()
+        if not ids:
+            return False
+        if is_prefill:
+            meta = self.sched.prepare_prefill(ids, token_cap=self.runner.cfg.max_prefill_tokens,
+                                              max_blocks_cap=self.max_blocks)
+            if meta["block_tables"] is None:            # the CUDA path always reads the paged cache
+                meta["block_tables"] = self._all_block_tables(ids)
+            _, toks = self.runner.prefill_device(meta, want_logits=False)
+            toks = toks.cpu().numpy().astype(np.uint32)
+            pos, fin = self.sched.filter_prefill_finished(ids)
+            sel = toks[pos] if len(pos) else toks[:0]
+            for i, t in zip(fin, sel):
+                self.outputs[self.sched.seq_info(i)["id"]].append(int(t))
+            self.sched.postprocess(fin, sel)
+        else:
+            meta = self.sched.prepare_decode(ids, max_blocks_cap=self.max_blocks,
+                                             pinned=self.runner.pinned)
+            toks = self.runner.run_decode(meta)
+            for i, t in zip(ids, toks):
+                self.outputs[self.sched.seq_info(i)["id"]].append(int(t))
+            self.sched.postprocess(ids, toks)
+        self.sched.clear_finished()
+        return True
+
+    def run_to_completion(self, max_steps=100000):
+        n = 0
+        while (self.sched.num_running or self.sched.num_waiting) and n < max_steps:
+            if not self.step():
+                break
+            n += 1
+        return self.outputs
