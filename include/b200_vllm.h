@@ -85,7 +85,8 @@ void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const ui
                                 int64_t stream);
 /* General entry: bits in {4,8}, qfmt AWQ/GPTQ, optional bias[n] (fp16, may be NULL),
  * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05,
- * 3 = tcgen05 with a single K split (direct store, workspace untouched; prefill).      */
+ * 3 = tcgen05 with a single K split (direct store, workspace untouched; prefill),
+ * 4 = the general tcgen05 kernel even for decode shapes (A/B testing).                 */
 void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
                         const void* qzeros, const void* bias, void* c, int32_t m, int32_t k,
                         int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,

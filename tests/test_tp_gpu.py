@@ -1,0 +1,178 @@
+"""Multi-GPU (needs >= 2 B200s: `gpurun --gpus 2`): the communicator (NCCL baseline and the
+one-shot NVLink all-reduce, eager and inside a CUDA graph) and a TP=2 sharded decode step vs the
+unsharded CPU oracle.  One process per GPU, like the reference's runner processes."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _need(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _init(rank, world, port):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    return dist
+
+
+def _allreduce_worker(rank, world, port, ret):
+    dist = _init(rank, world, port)
+    from vllm_rs_b200 import tp
+    comm = tp.init_comm_from_torch_dist(oneshot=True)
+    ok_oneshot = comm.oneshot
+    res = {}
+    for n in (8, 4096 * 32, 8192 * 64, (1 << 20) // 2 + 8):       # last one > 1 MiB -> NCCL path
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        x = torch.randn(n, generator=g, device="cuda", dtype=torch.float16)
+        parts = [torch.randn(n, generator=torch.Generator(device="cuda").manual_seed(100 + r),
+                             device="cuda", dtype=torch.float16) for r in range(world)]
+        exp = sum(p.float() for p in parts).to(torch.float16)
+        y = x.clone()
+        comm.all_reduce_(y)
+        comm.force_nccl(True)
+        z = x.clone()
+        comm.all_reduce_(z)
+        comm.force_nccl(False)
+        torch.cuda.synchronize()
+        res[n] = (float((y.float() - exp.float()).abs().max()), float((z.float() - exp.float()).abs().max()))
+    # repeated + graph-captured one-shot all-reduces must stay correct (device-side sequence numbers)
+    x = torch.full((4096,), float(rank + 1), device="cuda", dtype=torch.float16)
+    buf = x.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        comm.all_reduce_(buf)                      # warm-up on the capture stream
+        s.synchronize()
+        buf.copy_(x)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            comm.all_reduce_(buf)
+        outs = []
+        for _ in range(5):
+            buf.copy_(x)
+            graph.replay()
+            s.synchronize()
+            outs.append(float(buf[0]))
+    dist.barrier()
+    if rank == 0:
+        ret["oneshot"] = ok_oneshot
+        ret["res"] = res
+        ret["graph"] = outs
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_allreduce_oneshot_and_nccl():
+    _need(2)
+    import torch.multiprocessing as mp
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_allreduce_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["oneshot"], "cudaIpc peer mapping failed: one-shot path not enabled"
+    for n, (e1, e2) in ret["res"].items():
+        assert e1 <= 4e-3 and e2 <= 4e-3, (n, e1, e2)        # sums of two N(0,1): 1 fp16 ulp at |x|~4
+    assert ret["graph"] == [3.0] * 5
+
+
+def _tp_decode_worker(rank, world, port, ret):
+    dist = _init(rank, world, port)
+    from oracle import model as om
+    from oracle import quant as oq
+    from oracle import sched as osched
+    from oracle.toy import toy_cfg
+    from vllm_rs_b200 import engine, ops, tp
+    cfg = toy_cfg()
+    rng = np.random.default_rng(21)            # same checkpoint on every rank
+    g = torch.Generator().manual_seed(21)
+    H, Hkv, D, h, I = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden, cfg.inter
+    NB, MAXB, MAXBLK = 32, 4, 4
+
+    def qlayer(K, N):
+        qw, qz, s = oq.random_awq(rng, K, N)
+        s = (s.astype(np.float32) * 1.5).astype(np.float16)
+        return (qw, qz, s), torch.from_numpy(oq.dequant_awq(qw, qz, s, 128))
+
+    def norm_w():
+        return (1 + 0.05 * torch.randn(h, generator=g)).to(torch.float16)
+
+    runner = engine.ModelRunner(hidden=h, num_layers=cfg.num_layers, num_heads=H // world,
+                                num_kv_heads=Hkv // world, head_dim=D, inter=I // world,
+                                vocab=cfg.vocab, num_blocks=NB, max_blocks_per_seq=MAXBLK,
+                                max_batch=MAXB, device=f"cuda:{rank}")
+    w = om.ModelWeights(embed=torch.randn(cfg.vocab, h, generator=g).to(torch.float16),
+                        final_norm=norm_w(), lm_head=(0.05 * torch.randn(cfg.vocab, h, generator=g)).to(torch.float16))
+    dev = f"cuda:{rank}"
+    for l in range(cfg.num_layers):
+        parts = {n: qlayer(*kn) for n, kn in dict(q=(h, H * D), k=(h, Hkv * D), v=(h, Hkv * D),
+                                                   o=(H * D, h), g=(h, I), u=(h, I), d=(I, h)).items()}
+        lw = om.LayerWeights(norm_w(), norm_w(), *(parts[n][1] for n in "qkvogud"))
+        w.layers.append(lw)
+        col = lambda n: tp.shard_column(*parts[n][0], rank, world)                 # noqa: E731
+        row = lambda n: tp.shard_row(*parts[n][0], rank, world, 128)               # noqa: E731
+        runner.set_layer(l, input_norm=lw.input_norm.to(dev), post_norm=lw.post_norm.to(dev),
+                         qkv=engine.fuse_awq([col("q"), col("k"), col("v")], dev),
+                         o=engine.fuse_awq([row("o")], dev),
+                         gate_up=engine.fuse_awq([col("g"), col("u")], dev),
+                         down=engine.fuse_awq([row("d")], dev))
+    oracle = om.LlamaOracle(cfg, w, NB)
+    runner.set_globals(w.embed.to(dev), w.final_norm.to(dev), w.lm_head.to(dev), oracle.cos.to(dev),
+                       oracle.sin.to(dev))
+    comm = tp.attach_allreduce(runner)
+    osch = osched.Scheduler(NB, 64, MAXB)
+    for L in (20, 70, 129):
+        osch.add(osched.Sequence(np.random.default_rng(L).integers(0, cfg.vocab, size=L).tolist(), 64, max_tokens=8))
+    ids, _ = osch.schedule()
+    first = oracle.prefill(osched.prepare_prefill([osch.running[i] for i in ids], 64)).argmax(-1).tolist()
+    _, fin = osch.filter_prefill_finished(ids)
+    osch.postprocess(fin, first)
+    kvh = Hkv // world
+    for l in range(cfg.num_layers):            # this rank's kv heads of the oracle cache
+        runner.k_cache[l].copy_(oracle.k_cache[l][:, :, rank * kvh:(rank + 1) * kvh])
+        runner.v_cache[l].copy_(oracle.v_cache[l][:, :, rank * kvh:(rank + 1) * kvh])
+    ids, _ = osch.schedule()
+    mo = osched.prepare_decode([osch.running[i] for i in ids], 64)
+    ref = oracle.decode(mo)
+    B = len(ids)
+    bt = torch.zeros(B, MAXBLK, dtype=torch.int32)
+    bt[:, :mo["max_blocks"]] = torch.tensor(mo["block_tables"], dtype=torch.int32)
+    logits, _ = runner.decode_device(torch.tensor(mo["input_ids"], dtype=torch.int32).to(dev),
+                                     torch.tensor(mo["positions"], dtype=torch.int64).to(dev),
+                                     torch.tensor(mo["slot_mapping"], dtype=torch.int64).to(dev),
+                                     bt.to(dev), torch.tensor(mo["context_lens"], dtype=torch.int32).to(dev))
+    torch.cuda.synchronize()
+    ret[rank] = float((logits.cpu() - ref).abs().max())
+    allr = [torch.zeros_like(logits) for _ in range(world)]
+    dist.all_gather(allr, logits)
+    if rank == 0:
+        ret["identical"] = all(torch.equal(a, allr[0]) for a in allr)   # lm_head replicated, same logits
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_tp2_decode_matches_unsharded_oracle():
+    _need(2)
+    import torch.multiprocessing as mp
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_tp_decode_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] < 2.5e-2, ret[r]         # fp16 noise floor of the toy model (see test_runner_gpu)
+    assert ret["identical"]

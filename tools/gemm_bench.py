@@ -1,0 +1,34 @@
+"""Micro-benchmark of the W4A16 GEMM at the Llama-3-8B decode shapes (CUDA events, weights
+rotated over copies larger than L2).  python tools/gemm_bench.py [M] [variant]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vllm_rs_b200 import ops, synthetic
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+dev = "cuda"
+gen = torch.Generator(device=dev).manual_seed(0)
+shapes = {"qkv": (4096, 6144, 0), "o": (4096, 4096, 0), "gate_up": (4096, 28672, 1), "down": (14336, 4096, 0)}
+ws = ops.wna16_workspace(max(M, 16), 28672)
+out = {}
+for name, (K, N, epi) in shapes.items():
+    copies = max(2, int(300e6 // (K * N // 2)) + 1)
+    layers = [synthetic._fused_awq_device(gen, K, [N], 128, dev) for _ in range(copies)]
+    x = torch.randn(M, K, device=dev, dtype=torch.float16)
+    y = torch.empty(M, N // 2 if epi else N, device=dev, dtype=torch.float16)
+    def run(i):
+        l = layers[i % copies]
+        ops.wna16_gemm(x, l.w, l.s, l.z, ws, k=K, n=N, epilogue=epi, variant=variant, out=y)
+    for i in range(copies * 2): run(i)
+    torch.cuda.synchronize()
+    iters = copies * 6
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters): run(i)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    out[name] = (us, K * N / 2 / us / 1e3)
+print(f"M={M} variant={variant} dbg={os.environ.get('B200_TC_DBG','0')} pdl={os.environ.get('B200_PDL','1')}: " +
+      "  ".join(f"{k}: {v[0]:.1f}us {v[1]:.0f}GB/s" for k, v in out.items()) +
+      f"  | sum {sum(v[0] for v in out.values()):.1f}us")

@@ -190,5 +190,6 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
 // launchers implemented in wna16_gemv.cu / wna16_tc.cu
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported
+bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st);   // decode shapes (M <= 64)
 
 }  // namespace b200

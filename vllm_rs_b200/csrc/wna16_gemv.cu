@@ -277,7 +277,8 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (variant == 2 || variant == 3 || (variant == 0 && m > 4)) {
+  if (variant == 2 || variant == 3 || variant == 4 || (variant == 0 && m > 4)) {
+    if (variant != 4 && launch_wna16_tc_dec(p, st)) return;    // latency-optimised decode kernel
     if (launch_wna16_tc(p, st)) return;
     if (variant >= 2) { set_error(1, "wna16: shape unsupported by the tcgen05 variant"); return; }
   }

@@ -30,6 +30,8 @@
 //
 // Roofline: decode (NT <= 64) is HBM-bound on the packed weights (K*N/2 bytes per launch);
 // prefill (NT = 256) is tensor-bound: 2*M*N*K flop.
+#include <cstdlib>
+
 #include "wna16.cuh"
 
 namespace b200 {
@@ -68,6 +70,7 @@ struct TcArgs {
   float* partials;        // [splits][M][N] fp32
   uint32_t* counters;     // tile arrival counters (zero at rest)
   int M, K, N, group_size, qfmt, chunks_per_split, splits, epilogue;
+  int dbg;                // B200_TC_DBG experiment switches (0 in production)
 };
 
 template <int BITS, int NT>
@@ -175,6 +178,10 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
       if (has_next) load_words(i + kGroups, nxt);
       const int sa = i % kSA;
       uint32_t av[32];
+      if (a.dbg & 4) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) av[e] = cur[e % W];
+      } else
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {                // two 32-K halves (group boundary safe)
         const int g = ((c0 + i) * kChunkK + hf * 32) / a.group_size;
@@ -266,6 +273,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sw = i % Cfg::kSW;
         mbar_wait(&wempty[sw], ((i / Cfg::kSW) & 1) ^ 1);
+        if ((a.dbg & 2) && i >= Cfg::kSW) { mbar_arrive(&wfull[sw]); continue; }   // experiment: no weight stream
         mbar_arrive_expect_tx(&wfull[sw], Cfg::kWBytes);
         bulk_load_1d(smem + Cfg::kWOff + sw * Cfg::kWBytes, src + static_cast<size_t>(i) * Cfg::kWBytes,
                      Cfg::kWBytes, &wfull[sw]);
@@ -278,6 +286,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sx = i % Cfg::kSX;
         mbar_wait(&xempty[sx], ((i / Cfg::kSX) & 1) ^ 1);
+        if ((a.dbg & 1) && i >= Cfg::kSX) { mbar_arrive(&xfull[sx]); continue; }   // experiment: no activation stream
         mbar_arrive_expect_tx(&xfull[sx], Cfg::kXBytes);
         tma_load_2d(smem + Cfg::kXOff + sx * Cfg::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, m0);
       }
@@ -292,6 +301,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
         mbar_wait(&afull[sa], (i / kSA) & 1);
         tc_fence_after();
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + Cfg::kXOff + sx * Cfg::kXBytes));
+        if (!(a.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
           tc_mma_ts(d_tmem, a_tmem + sa * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
@@ -354,6 +364,11 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
   a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
   a.M = p.M; a.K = p.K; a.N = p.N; a.group_size = p.group_size; a.qfmt = p.qfmt;
   a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("B200_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(wna16_tc_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,0 +1,370 @@
+// W4A16 / W8A16 GEMM on tcgen05 for DECODE batches (M <= 64): latency-optimised variant.
+//
+// Same math and data layout as wna16_tc.cu (swap-AB: weight tile = MMA A operand written to TMEM
+// by the dequant threads, activations = B operand through TMA), but organised so that no chunk
+// ever waits on another role's wake-up:
+//   * 4 dequant groups (4 warps = all 128 channels each); group g owns chunks g, g+4, ... with its
+//     OWN fp32 accumulator in TMEM and its OWN two A stages.  After its 4 warps stored a chunk
+//     (named barrier of 128 threads), one thread of the group issues the four tcgen05.mma itself
+//     and commits; there is no MMA warp and no cross-role full/empty ping-pong.  Four independent
+//     latency chains per SM overlap; the four partial accumulators are summed in the epilogue.
+//   * scales / zero points of the CTA's K range arrive through cp.async.bulk issued at t = 0
+//     (no synchronous global loads on the critical path); group indices are shifts.
+//   * the weight producer never waits for the previous kernel (weights do not depend on it), so
+//     under PDL the 48 KB ring is already full when the activations become visible.
+// Measured motivation (profiles/r1_gemm_experiments.txt): v3 spent ~10 us per launch in prologue
+// + epilogue and ~900 cycles per 4 KB chunk with the tensor pipe < 10% busy.
+#include "wna16.cuh"
+
+namespace b200 {
+namespace dec {
+
+constexpr int kGroups = 4;
+constexpr int kDqWarps = 16;
+constexpr int kDqThreads = kDqWarps * 32;
+constexpr int kThreads = (kDqWarps + 2) * 32;
+constexpr int kAS = 2;               // A stages per group (32 TMEM columns each)
+constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range staged in smem
+
+template <int BITS, int NT>
+struct Cfg {
+  static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;
+  static constexpr int kXBytes = NT * kChunkK * 2;
+  static constexpr int kSW = BITS == 4 ? 12 : 8;
+  static constexpr int kSX = 8;
+  static constexpr int kXOff = 0;
+  static constexpr int kWOff = kSX * kXBytes;
+  static constexpr int kScaleOff = kWOff + kSW * kWBytes;                 // [groups][128] fp16
+  static constexpr int kZeroOff = kScaleOff + kSZGroups * kTileN * 2;     // [groups][32] u32
+  static constexpr int kBarOff = kZeroOff + kSZGroups * 32 * 4;
+  static constexpr int kNumBars = 2 * kSW + 2 * kSX + kGroups * kAS + kGroups + 1;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kAlloc = kTmemPtrOff + 16 + 1024;
+  static constexpr int kDCols = NT < 32 ? 32 : NT;                        // per-group accumulator
+  static constexpr int kACol0 = kGroups * kDCols;
+  static constexpr int kTmemCols = 512;
+  static_assert(kACol0 + kGroups * kAS * 32 <= 512, "TMEM budget");
+};
+
+struct Args {
+  const uint32_t* bp;
+  const __half* scales;
+  const uint32_t* qzeros;
+  const __half* bias;
+  __half* c;
+  float* partials;
+  uint32_t* counters;
+  int M, K, N, g_shift, qfmt, chunks_per_split, splits, epilogue;   // g_shift: log2(group_size), -1 = one group
+};
+
+template <int BITS, int NT>
+__global__ void __launch_bounds__(kThreads, 1)
+wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  using C = Cfg<BITS, NT>;
+  const int nt = blockIdx.x, split = blockIdx.y;
+  const int KC = a.K / kChunkK;
+  const int c0 = split * a.chunks_per_split;
+  const int c1 = min(c0 + a.chunks_per_split, KC);
+  const int nchunks = c1 - c0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, M = a.M;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* wfull = bars;
+  uint64_t* wempty = wfull + C::kSW;
+  uint64_t* xfull = wempty + C::kSW;
+  uint64_t* xempty = xfull + C::kSX;
+  uint64_t* afree = xempty + C::kSX;                 // [group][stage]
+  uint64_t* gdone = afree + kGroups * kAS;           // [group]
+  uint64_t* szfull = gdone + kGroups;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kTmemPtrOff);
+  const __half* sm_scale = reinterpret_cast<const __half*>(smem + C::kScaleOff);
+  const uint32_t* sm_zero = reinterpret_cast<const uint32_t*>(smem + C::kZeroOff);
+  __shared__ int s_is_last;
+
+  const int g_first = a.g_shift >= 0 ? (c0 * kChunkK) >> a.g_shift : 0;
+  const int g_last = a.g_shift >= 0 ? (c1 * kChunkK - 1) >> a.g_shift : 0;
+  const int ngroups = g_last - g_first + 1;
+  constexpr int ZW = kTileN * BITS / 32;             // zero-point words per tile row (16 / 32)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSW; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], 4);
+    }
+    for (int i = 0; i < C::kSX; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    for (int i = 0; i < kGroups * kAS; ++i) mbar_init(&afree[i], 1);
+    for (int i = 0; i < kGroups; ++i) mbar_init(&gdone[i], 1);
+    mbar_init(szfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == kDqWarps) {
+    tmem_alloc(tmem_ptr, C::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == kDqWarps + 1 && lane == 0) prefetch_tmap(&xmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kDqWarps) {
+    // ------------------------------------------------------------ weight / scale producer
+    if (lane == 0) {
+      const uint32_t zbytes = a.qzeros ? ZW * 4 : 0;
+      mbar_arrive_expect_tx(szfull, static_cast<uint32_t>(ngroups) * (kTileN * 2 + zbytes));
+      for (int g = 0; g < ngroups; ++g) {
+        bulk_load_1d(smem + C::kScaleOff + g * kTileN * 2,
+                     a.scales + static_cast<size_t>(g_first + g) * N + nt * kTileN, kTileN * 2, szfull);
+        if (a.qzeros)
+          bulk_load_1d(smem + C::kZeroOff + g * 128,
+                       a.qzeros + static_cast<size_t>(g_first + g) * (N * BITS / 32) + nt * ZW, zbytes,
+                       szfull);
+      }
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.bp) +
+                           (static_cast<size_t>(nt) * KC + c0) * C::kWBytes;
+      for (int i = 0; i < nchunks; ++i) {
+        const int sw = i % C::kSW;
+        mbar_wait(&wempty[sw], ((i / C::kSW) & 1) ^ 1);
+        mbar_arrive_expect_tx(&wfull[sw], C::kWBytes);
+        bulk_load_1d(smem + C::kWOff + sw * C::kWBytes, src + static_cast<size_t>(i) * C::kWBytes,
+                     C::kWBytes, &wfull[sw]);
+      }
+    }
+  } else if (warp == kDqWarps + 1) {
+    // ------------------------------------------------------------ activation producer
+    if (lane == 0) {
+      pdl_wait();      // activations are the previous kernel's output; weights are not
+      for (int i = 0; i < nchunks; ++i) {
+        const int sx = i % C::kSX;
+        mbar_wait(&xempty[sx], ((i / C::kSX) & 1) ^ 1);
+        mbar_arrive_expect_tx(&xfull[sx], C::kXBytes);
+        tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ dequant + MMA groups
+    const int grp = warp >> 2, q4 = warp & 3;
+    const int ch = q4 * 32 + lane;
+    const int n = nt * kTileN + ch;
+    const bool issuer = (q4 == 0 && lane == 0);
+    const uint32_t d_tmem = tmem_base + grp * C::kDCols;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    // zero-point field of this channel inside its packed word
+    const int zword = BITS == 4 ? (ch >> 3) : (ch >> 2);
+    const int zshift = BITS == 4 ? ((a.qfmt == B200_QFMT_AWQ) ? 4 * awq_nibble_of(ch & 7) : 4 * (ch & 7))
+                                 : 8 * (ch & 3);
+    const int zadd = (a.qfmt == B200_QFMT_AWQ && BITS == 4) ? 0 : 1;
+    constexpr int W = 2 * BITS;
+    auto load_words = [&](int ci, uint32_t (&dst)[W]) {
+      const int sw = ci % C::kSW;
+      mbar_wait(&wfull[sw], (ci / C::kSW) & 1);
+      const uint8_t* wst = smem + C::kWOff + sw * C::kWBytes;
+#pragma unroll
+      for (int sub = 0; sub < W / 4; ++sub) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (sub * kTileN + ch) * 16);
+        dst[sub * 4 + 0] = pk.x; dst[sub * 4 + 1] = pk.y; dst[sub * 4 + 2] = pk.z; dst[sub * 4 + 3] = pk.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&wempty[sw]);
+    };
+    uint32_t cur[W];
+    if (grp < nchunks) load_words(grp, cur);
+    mbar_wait(szfull, 0);
+    int cur_g = -1;
+    DqConst dq = make_dq(__float2half(0.f), 0);
+    const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
+    int it = 0;
+    for (int i = grp; i < nchunks; i += kGroups, ++it) {
+      uint32_t nxt[W];
+      const bool has_next = i + kGroups < nchunks;
+      if (has_next) load_words(i + kGroups, nxt);
+      uint32_t lo[16], hi[16];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK + hf * 32) >> a.g_shift) - g_first : 0;
+        if (g != cur_g) {
+          cur_g = g;
+          const int z = a.qzeros ? static_cast<int>((sm_zero[g * 32 + zword] >> zshift) & ((1u << BITS) - 1)) + zadd
+                                 : (1 << (BITS - 1));
+          dq = make_dq(sm_scale[g * kTileN + ch], z);
+        }
+        uint32_t(&dst)[16] = hf == 0 ? lo : hi;
+        if (BITS == 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            uint32_t o4[4];
+            dequant4_word(cur[hf * 4 + w], dq, o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[w * 4 + e] = o4[e];
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            uint32_t o2[2];
+            dequant8_word(cur[(hf * 8 + w) % W], dq, o2);
+            dst[w * 2] = o2[0];
+            dst[w * 2 + 1] = o2[1];
+          }
+        }
+      }
+      const int as = grp * kAS + (it % kAS);
+      const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
+      mbar_wait(&afree[as], ((it / kAS) & 1) ^ 1);        // this group's MMA of chunk it - kAS retired
+      tc_fence_after();
+      tmem_st_x16(a_tmem + lane_base, lo);
+      tmem_st_x16(a_tmem + lane_base + 16, hi);
+      tc_wait_st();
+      tc_fence_before();
+      named_bar_sync(4 + grp, 128);                       // the group's 128 lanes are all stored
+      if (issuer) {
+        const int sx = i % C::kSX;
+        mbar_wait(&xfull[sx], (i / C::kSX) & 1);
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks)
+          tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
+                    (it > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&xempty[sx]);
+        tc_commit(&afree[as]);
+        if (!has_next) tc_commit(&gdone[grp]);
+      }
+      if (has_next) {
+#pragma unroll
+        for (int e = 0; e < W; ++e) cur[e] = nxt[e];
+      }
+    }
+    // ------------------------------------------------------------ epilogue
+    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
+    pdl_wait();        // first global writes below (c / partials / counters)
+    if (warp < 4) {
+      const int active = nchunks < kGroups ? nchunks : kGroups;
+      for (int g = 0; g < active; ++g) mbar_wait(&gdone[g], 0);
+      tc_fence_after();
+      const float bv = (direct && a.bias) ? __half2float(a.bias[n]) : 0.f;
+      float* part = a.partials + (static_cast<size_t>(split) * M) * N;
+#pragma unroll
+      for (int j0 = 0; j0 < NT; j0 += 16) {
+        float acc[16];
+        {
+          uint32_t v[16];
+          tmem_ld_x16(tmem_base + lane_base + j0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+        }
+        for (int g = 1; g < active; ++g) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem_base + g * C::kDCols + lane_base + j0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = j0 + j;
+          if (m < M) {
+            if (direct)
+              a.c[static_cast<size_t>(m) * N + n] = __float2half_rn(acc[j] + bv);
+            else
+              part[static_cast<size_t>(m) * N + n] = acc[j];
+          }
+        }
+      }
+      tc_fence_before();
+      if (!direct) __threadfence();
+    }
+    if (!direct) {
+      SplitOut o;
+      o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
+      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
+      split_arrive_and_reduce(o, nt, threadIdx.x, kDqThreads, 0, M, 0, &s_is_last, 1);
+    }
+  }
+  __syncthreads();
+  if (warp == kDqWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BITS, int NT>
+static bool launch_nt(const WnaParams& p, cudaStream_t st) {
+  using C = Cfg<BITS, NT>;
+  CUtensorMap xmap;
+  const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
+  const uint32_t box[2] = {kChunkK, static_cast<uint32_t>(NT)};
+  const uint32_t es[2] = {1, 1};
+  if (encode_tensor_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.a), dims,
+                        strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS) {
+    set_error(2, "wna16_tc_dec: cuTensorMapEncodeTiled failed");
+    return true;
+  }
+  const int KC = p.K / kChunkK;
+  const int tiles = p.N / kTileN;
+  int splits = sm_count() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  while (splits > 1 && static_cast<long>(splits) * p.N > kMaxSplitCols) --splits;
+  if (p.no_split) splits = 1;
+  int cps = (KC + splits - 1) / splits;
+  splits = (KC + cps - 1) / cps;
+  Args a;
+  a.bp = p.bp; a.scales = p.scales; a.qzeros = p.qzeros; a.bias = p.bias; a.c = p.c;
+  a.counters = reinterpret_cast<uint32_t*>(p.workspace);
+  a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
+  a.M = p.M; a.K = p.K; a.N = p.N; a.qfmt = p.qfmt;
+  a.g_shift = -1;
+  if (p.group_size < p.K)
+    for (int s = 5; s < 31; ++s)
+      if ((1 << s) == p.group_size) a.g_shift = s;
+  a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         C::kAlloc);
+    attr_set = true;
+  }
+  launch_pdl(wna16_tc_dec_kernel<BITS, NT>, dim3(tiles, splits, 1), dim3(kThreads), C::kAlloc, st, xmap, a);
+  B200_CUDA_LAUNCH_CHECK();
+  return true;
+}
+
+}  // namespace dec
+
+// Decode-shape entry: false when the shape needs the general kernel (wna16_tc.cu).
+bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
+  if (p.M > 64) return false;
+  const bool pow2 = p.group_size >= p.K || (p.group_size & (p.group_size - 1)) == 0;
+  if (!pow2) return false;
+  // scale / zero staging covers 64 quantisation groups of the CTA's K range
+  const int KC = p.K / kChunkK;
+  int splits = sm_count() / (p.N / kTileN);
+  if (splits < 1) splits = 1;
+  if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  if (p.no_split) splits = 1;
+  const int cps = (KC + splits - 1) / splits;
+  const int groups_per_cta = p.group_size >= p.K ? 1 : (cps * kChunkK + p.group_size - 1) / p.group_size + 1;
+  if (groups_per_cta > dec::kSZGroups) return false;
+  if (p.epilogue == B200_EPI_SILU_MUL && ((p.N / kTileN) & 1)) return false;
+  if (p.bits == 4) {
+    if (p.M <= 16) return dec::launch_nt<4, 16>(p, st);
+    if (p.M <= 32) return dec::launch_nt<4, 32>(p, st);
+    return dec::launch_nt<4, 64>(p, st);
+  }
+  if (p.M <= 16) return dec::launch_nt<8, 16>(p, st);
+  if (p.M <= 32) return dec::launch_nt<8, 32>(p, st);
+  return dec::launch_nt<8, 64>(p, st);
+}
+
+}  // namespace b200

@@ -169,29 +169,25 @@ class QuantLinear:
 
 def fuse_awq(parts, device):
     """parts: list of (qweight i32 [K, N_i/8], qzeros i32 [K/G, N_i/8], scales f16 [K/G, N_i])
-    numpy arrays (AWQ).  Prepack each on the GPU, concatenate along N (tile-major layout makes
-    that a plain concatenation)."""
-    ws, ss, zs, n_tot = [], [], [], 0
-    k = parts[0][0].shape[0]
-    for qw, qz, sc in parts:
-        ws.append(ops.awq_prepack(torch.from_numpy(qw).to(device)).reshape(-1))
-        zs.append(torch.from_numpy(qz).to(device))
-        ss.append(torch.from_numpy(sc).to(device))
-        n_tot += qw.shape[1] * 8
-    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, dim=1).contiguous(),
-                       torch.cat(zs, dim=1).contiguous(), k, n_tot)
+    numpy arrays (AWQ checkpoint tensors of projections sharing the same input).  They are
+    concatenated along N in checkpoint format (word granularity = 8 channels) and prepacked once,
+    so only the fused N has to be a multiple of 128."""
+    qw = np.concatenate([p[0] for p in parts], axis=1)
+    qz = np.concatenate([p[1] for p in parts], axis=1)
+    sc = np.concatenate([p[2] for p in parts], axis=1)
+    w = ops.awq_prepack(torch.from_numpy(np.ascontiguousarray(qw)).to(device)).reshape(-1)
+    return QuantLinear(w, torch.from_numpy(np.ascontiguousarray(sc)).to(device),
+                       torch.from_numpy(np.ascontiguousarray(qz)).to(device), qw.shape[0], sc.shape[1])
 
 
 def fuse_gptq(parts, device, bits=4):
-    ws, ss, zs, n_tot = [], [], [], 0
-    k = parts[0][0].shape[0] * (32 // bits)
-    for qw, qz, sc in parts:
-        ws.append(ops.gptq_prepack(torch.from_numpy(qw).to(device), bits).reshape(-1))
-        zs.append(None if qz is None else torch.from_numpy(qz).to(device))
-        ss.append(torch.from_numpy(sc).to(device))
-        n_tot += qw.shape[1]
-    z = None if zs[0] is None else torch.cat(zs, dim=1).contiguous()
-    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, dim=1).contiguous(), z, k, n_tot)
+    qw = np.concatenate([p[0] for p in parts], axis=1)
+    sc = np.concatenate([p[2] for p in parts], axis=1)
+    z = None if parts[0][1] is None else torch.from_numpy(
+        np.ascontiguousarray(np.concatenate([p[1] for p in parts], axis=1))).to(device)
+    w = ops.gptq_prepack(torch.from_numpy(np.ascontiguousarray(qw)).to(device), bits).reshape(-1)
+    return QuantLinear(w, torch.from_numpy(np.ascontiguousarray(sc)).to(device), z,
+                       qw.shape[0] * (32 // bits), sc.shape[1])
 
 
 def fuse_dense(parts_kn, device):

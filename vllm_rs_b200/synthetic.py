@@ -41,14 +41,10 @@ def _rand_awq_device(gen, K, N, group, device):
 
 
 def _fused_awq_device(gen, K, Ns, group, device):
-    ws, zs, ss = [], [], []
-    for N in Ns:
-        qw, qz, s = _rand_awq_device(gen, K, N, group, device)
-        ws.append(ops.awq_prepack(qw).reshape(-1))
-        zs.append(qz)
-        ss.append(s)
-    return QuantLinear(torch.cat(ws).contiguous(), torch.cat(ss, 1).contiguous(),
-                       torch.cat(zs, 1).contiguous(), K, sum(Ns))
+    """Random AWQ projections sharing an input, fused along N then prepacked once."""
+    N = sum(Ns)
+    qw, qz, s = _rand_awq_device(gen, K, N, group, device)
+    return QuantLinear(ops.awq_prepack(qw).reshape(-1), s, qz, K, N)
 
 
 def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_batch, seed=0,
