@@ -20,14 +20,20 @@ for name, (K, N, epi) in shapes.items():
     def run(i):
         l = layers[i % copies]
         ops.wna16_gemm(x, l.w, l.s, l.z, ws, k=K, n=N, epilogue=epi, variant=variant, out=y)
-    for i in range(copies * 2): run(i)
-    torch.cuda.synchronize()
-    iters = copies * 6
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters): run(i)
-    e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / iters
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(copies * 2): run(i)
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()          # graph replay: no CPU launch overhead in the timing
+        with torch.cuda.graph(graph, stream=st):
+            for i in range(copies): run(i)
+        graph.replay(); st.synchronize()
+        reps = 6
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps): graph.replay()
+        e1.record(st); st.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * copies)
     out[name] = (us, K * N / 2 / us / 1e3)
 print(f"M={M} variant={variant} dbg={os.environ.get('B200_TC_DBG','0')} pdl={os.environ.get('B200_PDL','1')}: " +
       "  ".join(f"{k}: {v[0]:.1f}us {v[1]:.0f}GB/s" for k, v in out.items()) +
