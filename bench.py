@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--ctx", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalid as a bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefill-tokens", type=int, default=8192,
+                    help="also time one prefill chunk of this many tokens (0 = skip)")
     return ap.parse_args()
 
 
@@ -203,6 +205,7 @@ def run_b200(args):
     if args.layers:
         L = args.layers
     tp = world
+    pf_tokens = args.prefill_tokens if world == 1 else 0
     runner = synthetic.build_awq_runner(MODEL, num_blocks=num_blocks, max_blocks_per_seq=blocks_per_seq,
                                         max_batch=B, num_layers=L, tp_size=tp, device=dev)
     synthetic.fill_kv_random(runner)
@@ -321,6 +324,34 @@ def run_b200(args):
         e2e_ms = float(t.item())
     e2e_value = B * 1e3 / e2e_ms
 
+    # ---------------- prefill chunk (second half of BASELINE's metric: "prefill TFLOPS")
+    prefill = None
+    if pf_tokens > 0:
+        T = pf_tokens
+        nblk = T // 64
+        del runner, graph, sched                      # free 23 GB before building the prefill runner
+        torch.cuda.empty_cache()
+        runner = synthetic.build_awq_runner(MODEL, num_blocks=nblk + 2, max_blocks_per_seq=nblk + 1, max_batch=1,
+                                            num_layers=L, device=dev, max_prefill_tokens=T)
+        meta = dict(input_ids=rng.integers(0, vocab, size=T).astype(np.uint32),
+                    positions=np.arange(T, dtype=np.int64),
+                    slot_mapping=(np.repeat(np.arange(nblk, dtype=np.int64) * 64, 64) + np.tile(np.arange(64), nblk))[:T],
+                    cu_seqlens_q=np.array([0, T], dtype=np.uint32), context_lens=None,
+                    block_tables=np.arange(nblk, dtype=np.uint32).reshape(1, nblk), max_seqlen_q=T)
+        with torch.cuda.stream(stream):
+            runner.prefill_device(meta, want_logits=False)          # warm-up
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(2):
+                runner.prefill_device(meta, want_logits=False)
+            e1.record(stream)
+            stream.synchronize()
+        pf_ms = e0.elapsed_time(e1) / 2
+        p_lin = shape["hidden"] * (shape["H"] + 2 * shape["Hkv"]) * D + shape["H"] * D * shape["hidden"] + 3 * shape["hidden"] * shape["inter"]
+        flops = 2.0 * p_lin * L * T + L * 4.0 * shape["H"] * D * (T * (T + 1) / 2)
+        prefill = {"tokens": T, "ms": pf_ms, "tokens_per_s": T * 1e3 / pf_ms, "tflops": flops / (pf_ms * 1e-3) / 1e12,
+                   "flops": flops, "note": "one 8192-token chunk, W4A16 tcgen05 GEMM (NT=256) + mma.sync varlen causal attention over the paged cache"}
+
     out_line = {
         "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -342,6 +373,7 @@ def run_b200(args):
                      "ms_per_launch": attn_ms},
         "step_roofline": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "peak": peak,
                           "unit": "GB/s", "frac": step_gbs / peak},
+        "prefill": prefill,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -126,16 +126,22 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
   const int half_tiles = tiles >> 1;
   const int cidx = counter_base + (silu ? nt % half_tiles : nt);
   const unsigned target = silu ? 2u * o.splits : static_cast<unsigned>(o.splits);
-  named_bar_sync(bar_id, nthreads);          // writers executed __threadfence() before this
+  // Release / acquire through ONE thread (the cooperative-groups grid.sync pattern): the
+  // barrier orders every writer's stores before thread 0's fence + atomic (cumulativity), and
+  // thread 0's acquire fence before the second barrier orders the readers' loads (ld.cg, no L1).
+  named_bar_sync(bar_id, nthreads);
   if (tid == 0) {
+    __threadfence();
     const unsigned old = atomicAdd(&o.counters[cidx], 1u);
     const int last = (old == target - 1) ? 1 : 0;
-    if (last) o.counters[cidx] = 0;                  // self-reset (graph replay safe)
+    if (last) {
+      o.counters[cidx] = 0;                          // self-reset (graph replay safe)
+      __threadfence();
+    }
     *s_flag = last;
   }
   named_bar_sync(bar_id, nthreads);
   if (!*s_flag) return;
-  __threadfence();
   const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
   constexpr int R = 8;                               // rows in flight per thread
   const size_t row_stride = static_cast<size_t>(nphase) * N;

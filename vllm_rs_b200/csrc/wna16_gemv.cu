@@ -149,7 +149,6 @@ wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
 #pragma unroll
   for (int m = 0; m < MB; ++m)
     if (m_base + m < M) part[static_cast<size_t>(m_base + m) * N + n] = acc[m];
-  __threadfence();
   split_arrive_and_reduce(so, nt, ch, 128, m_base, m_hi, 0, &s_flag, 2);
 }
 

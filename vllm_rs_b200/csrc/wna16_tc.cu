@@ -256,7 +256,6 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
         }
       }
       tc_fence_before();
-      if (!direct) __threadfence();
     }
     if (!direct) {
       SplitOut o;

@@ -23,7 +23,6 @@ constexpr int kGroups = 4;
 constexpr int kDqWarps = 16;
 constexpr int kDqThreads = kDqWarps * 32;
 constexpr int kThreads = (kDqWarps + 2) * 32;
-constexpr int kAS = 2;               // A stages per group (32 TMEM columns each)
 constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range staged in smem
 
 template <int BITS, int NT>
@@ -37,10 +36,11 @@ struct Cfg {
   static constexpr int kScaleOff = kWOff + kSW * kWBytes;                 // [groups][128] fp16
   static constexpr int kZeroOff = kScaleOff + kSZGroups * kTileN * 2;     // [groups][32] u32
   static constexpr int kBarOff = kZeroOff + kSZGroups * 32 * 4;
-  static constexpr int kNumBars = 2 * kSW + 2 * kSX + kGroups * kAS + kGroups + 1;
+  static constexpr int kNumBars = 2 * kSW + 2 * kSX + kGroups * 3 + kGroups + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kAlloc = kTmemPtrOff + 16 + 1024;
   static constexpr int kDCols = NT < 32 ? 32 : NT;                        // per-group accumulator
+  static constexpr int kAS = NT <= 32 ? 3 : 2;                            // A stages per group (32 columns each)
   static constexpr int kACol0 = kGroups * kDCols;
   static constexpr int kTmemCols = 512;
   static_assert(kACol0 + kGroups * kAS * 32 <= 512, "TMEM budget");
@@ -78,6 +78,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   uint64_t* xfull = wempty + C::kSW;
   uint64_t* xempty = xfull + C::kSX;
   uint64_t* afree = xempty + C::kSX;                 // [group][stage]
+  constexpr int kAS = C::kAS;
   uint64_t* gdone = afree + kGroups * kAS;           // [group]
   uint64_t* szfull = gdone + kGroups;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kTmemPtrOff);
@@ -280,7 +281,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         }
       }
       tc_fence_before();
-      if (!direct) __threadfence();
     }
     if (!direct) {
       SplitOut o;

@@ -48,7 +48,8 @@ def _fused_awq_device(gen, K, Ns, group, device):
 
 
 def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_batch, seed=0,
-                     group=128, num_layers=None, tp_size=1, device="cuda") -> ModelRunner:
+                     group=128, num_layers=None, tp_size=1, device="cuda",
+                     max_prefill_tokens=0) -> ModelRunner:
     """Random AWQ-int4 model of the named architecture (optionally one TP shard of it:
     q/k/v/gate/up column-sharded, o/down row-sharded, attention.rs:445-530, mlp.rs:367-442)."""
     hidden, L, H, Hkv, D, inter, vocab, theta = SHAPES[name]
@@ -57,7 +58,8 @@ def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_ba
     r = ModelRunner(hidden=hidden, num_layers=L, num_heads=Hl, num_kv_heads=Hkvl, head_dim=D,
                     inter=interl, vocab=vocab, num_blocks=num_blocks,
                     max_blocks_per_seq=max_blocks_per_seq, max_batch=max_batch, bits=4,
-                    group_size=group, qfmt=ops.QFMT_AWQ, device=device)
+                    group_size=group, qfmt=ops.QFMT_AWQ, device=device,
+                    max_prefill_tokens=max_prefill_tokens)
     gen = torch.Generator(device=device).manual_seed(seed)
 
     def norm_w():
