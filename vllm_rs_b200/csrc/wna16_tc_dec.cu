@@ -4,10 +4,12 @@
 // by the dequant threads, activations = B operand through TMA), but organised so that no chunk
 // ever waits on another role's wake-up:
 //   * 4 dequant groups (4 warps = all 128 channels each); group g owns chunks g, g+4, ... with its
-//     OWN fp32 accumulator in TMEM and its OWN two A stages.  After its 4 warps stored a chunk
-//     (named barrier of 128 threads), one thread of the group issues the four tcgen05.mma itself
-//     and commits; there is no MMA warp and no cross-role full/empty ping-pong.  Four independent
-//     latency chains per SM overlap; the four partial accumulators are summed in the epilogue.
+//     OWN fp32 accumulator in TMEM and its OWN A stages, so the four groups' latency chains
+//     (smem read -> dequant -> tcgen05.st -> wait::st) never wait for each other; a warp only
+//     arrives on its stage's `stored` mbarrier and moves on (no intra-group barrier: that
+//     barrier was 20% of all stall samples when a dequant thread also issued the MMAs).  One
+//     issuer warp walks the chunks in order, issues the four tcgen05.mma into the owning group's
+//     accumulator and commits; the four partial accumulators are summed in the epilogue.
 //   * scales / zero points of the CTA's K range arrive through cp.async.bulk issued at t = 0
 //     (no synchronous global loads on the critical path); group indices are shifts.
 //   * the weight producer never waits for the previous kernel (weights do not depend on it), so
@@ -22,7 +24,7 @@ namespace dec {
 constexpr int kGroups = 4;
 constexpr int kDqWarps = 16;
 constexpr int kDqThreads = kDqWarps * 32;
-constexpr int kThreads = (kDqWarps + 2) * 32;
+constexpr int kThreads = (kDqWarps + 3) * 32;   // + weight producer, activation producer, MMA issuer
 constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range staged in smem
 
 template <int BITS, int NT>
@@ -36,7 +38,7 @@ struct Cfg {
   static constexpr int kScaleOff = kWOff + kSW * kWBytes;                 // [groups][128] fp16
   static constexpr int kZeroOff = kScaleOff + kSZGroups * kTileN * 2;     // [groups][32] u32
   static constexpr int kBarOff = kZeroOff + kSZGroups * 32 * 4;
-  static constexpr int kNumBars = 2 * kSW + 2 * kSX + kGroups * 3 + kGroups + 1;
+  static constexpr int kNumBars = 2 * kSW + 2 * kSX + 2 * kGroups * 3 + kGroups + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kAlloc = kTmemPtrOff + 16 + 1024;
   static constexpr int kDCols = NT < 32 ? 32 : NT;                        // per-group accumulator
@@ -81,6 +83,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   constexpr int kAS = C::kAS;
   uint64_t* gdone = afree + kGroups * kAS;           // [group]
   uint64_t* szfull = gdone + kGroups;
+  uint64_t* stored = szfull + 1;                     // [group][stage]: the 4 warps' lanes are in TMEM
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kTmemPtrOff);
   const __half* sm_scale = reinterpret_cast<const __half*>(smem + C::kScaleOff);
   const uint32_t* sm_zero = reinterpret_cast<const uint32_t*>(smem + C::kZeroOff);
@@ -103,6 +106,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     for (int i = 0; i < kGroups * kAS; ++i) mbar_init(&afree[i], 1);
     for (int i = 0; i < kGroups; ++i) mbar_init(&gdone[i], 1);
     mbar_init(szfull, 1);
+    for (int i = 0; i < kGroups * kAS; ++i) mbar_init(&stored[i], 4);
     fence_barrier_init();
   }
   if (warp == kDqWarps) {
@@ -150,13 +154,34 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
       }
     }
+  } else if (warp == kDqWarps + 2) {
+    // ------------------------------------------------------------ MMA issuer (all groups, chunk order)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
+      for (int i = 0; i < nchunks; ++i) {
+        const int grp = i % kGroups, it = i / kGroups;
+        const int as = grp * kAS + (it % kAS);
+        const int sx = i % C::kSX;
+        mbar_wait(&stored[as], (it / kAS) & 1);
+        mbar_wait(&xfull[sx], (i / C::kSX) & 1);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
+        const uint32_t d_tmem = tmem_base + grp * C::kDCols;
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks)
+          tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
+                    (it > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&xempty[sx]);
+        tc_commit(&afree[as]);
+        if (i + kGroups >= nchunks) tc_commit(&gdone[grp]);      // the group's last chunk
+      }
+    }
   } else {
-    // ------------------------------------------------------------ dequant + MMA groups
+    // ------------------------------------------------------------ dequant groups
     const int grp = warp >> 2, q4 = warp & 3;
     const int ch = q4 * 32 + lane;
     const int n = nt * kTileN + ch;
-    const bool issuer = (q4 == 0 && lane == 0);
-    const uint32_t d_tmem = tmem_base + grp * C::kDCols;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     // zero-point field of this channel inside its packed word
     const int zword = BITS == 4 ? (ch >> 3) : (ch >> 2);
@@ -181,7 +206,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     mbar_wait(szfull, 0);
     int cur_g = -1;
     DqConst dq = make_dq(__float2half(0.f), 0);
-    const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
     int it = 0;
     for (int i = grp; i < nchunks; i += kGroups, ++it) {
       uint32_t nxt[W];
@@ -224,20 +248,8 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       tmem_st_x16(a_tmem + lane_base + 16, hi);
       tc_wait_st();
       tc_fence_before();
-      named_bar_sync(4 + grp, 128);                       // the group's 128 lanes are all stored
-      if (issuer) {
-        const int sx = i % C::kSX;
-        mbar_wait(&xfull[sx], (i / C::kSX) & 1);
-        tc_fence_after();
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
-#pragma unroll
-        for (int ks = 0; ks < kChunkK / 16; ++ks)
-          tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
-                    (it > 0 || ks > 0) ? 1u : 0u);
-        tc_commit(&xempty[sx]);
-        tc_commit(&afree[as]);
-        if (!has_next) tc_commit(&gdone[grp]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stored[as]);            // -> the issuer warp
       if (has_next) {
 #pragma unroll
         for (int e = 0; e < W; ++e) cur[e] = nxt[e];
