@@ -177,8 +177,9 @@ def run_reference(args):
         "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"{MODEL} AWQ-int4 g128 decode batch={args.batch} ctx={args.ctx}, "
-                               "each step a bounded sample (2 of 32 layers + lm_head, layers scaled x16)"},
+        "config": {"workload": f"{MODEL} AWQ-int4 g128 decode batch={args.batch} ctx={args.ctx} layers=32 "
+                               f"block_size=64 tp=1 (BASELINE.json configs[1])",
+                   "sample": "each step = 2 of 32 layers + lm_head on the host cores, layers scaled x16"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -7,8 +7,8 @@
 //     OWN fp32 accumulator in TMEM and its OWN A stages, so the four groups' latency chains
 //     (smem read -> dequant -> tcgen05.st -> wait::st) never wait for each other; a warp only
 //     arrives on its stage's `stored` mbarrier and moves on (no intra-group barrier: that
-//     barrier was 20% of all stall samples when a dequant thread also issued the MMAs).  One
-//     issuer warp walks the chunks in order, issues the four tcgen05.mma into the owning group's
+//     barrier was 20% of all stall samples when a dequant thread also issued the MMAs).  Each
+//     group has its own issuer warp that issues the four tcgen05.mma of a chunk into the group's
 //     accumulator and commits; the four partial accumulators are summed in the epilogue.
 //   * scales / zero points of the CTA's K range arrive through cp.async.bulk issued at t = 0
 //     (no synchronous global loads on the critical path); group indices are shifts.
@@ -24,7 +24,7 @@ namespace dec {
 constexpr int kGroups = 4;
 constexpr int kDqWarps = 16;
 constexpr int kDqThreads = kDqWarps * 32;
-constexpr int kThreads = (kDqWarps + 3) * 32;   // + weight producer, activation producer, MMA issuer
+constexpr int kThreads = (kDqWarps + 2 + kGroups) * 32;   // + weight producer, activation producer, one MMA issuer warp per group
 constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range staged in smem
 
 template <int BITS, int NT>
@@ -154,19 +154,23 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
       }
     }
-  } else if (warp == kDqWarps + 2) {
-    // ------------------------------------------------------------ MMA issuer (all groups, chunk order)
+  } else if (warp >= kDqWarps + 2) {
+    // ------------------------------------------------------------ MMA issuers (one warp per group)
+    // A single in-order issuer for all groups was measured 30% slower (its wait -> issue ->
+    // commit loop takes longer per chunk than the dequant of a chunk): four independent issue
+    // loops keep the four accumulators busy.
     if (lane == 0) {
+      const int grp = warp - (kDqWarps + 2);
       const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
-      for (int i = 0; i < nchunks; ++i) {
-        const int grp = i % kGroups, it = i / kGroups;
+      const uint32_t d_tmem = tmem_base + grp * C::kDCols;
+      int it = 0;
+      for (int i = grp; i < nchunks; i += kGroups, ++it) {
         const int as = grp * kAS + (it % kAS);
         const int sx = i % C::kSX;
         mbar_wait(&stored[as], (it / kAS) & 1);
         mbar_wait(&xfull[sx], (i / C::kSX) & 1);
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-        const uint32_t d_tmem = tmem_base + grp * C::kDCols;
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
