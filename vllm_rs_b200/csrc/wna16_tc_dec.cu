@@ -31,7 +31,7 @@ template <int BITS, int NT>
 struct Cfg {
   static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;
   static constexpr int kXBytes = NT * kChunkK * 2;
-  static constexpr int kSW = BITS == 4 ? 12 : 8;
+  static constexpr int kSW = BITS == 4 ? 16 : 8;
   static constexpr int kSX = 8;
   static constexpr int kXOff = 0;
   static constexpr int kWOff = kSX * kXBytes;
@@ -193,37 +193,63 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
                                  : 8 * (ch & 3);
     const int zadd = (a.qfmt == B200_QFMT_AWQ && BITS == 4) ? 0 : 1;
     constexpr int W = 2 * BITS;
-    auto load_words = [&](int ci, uint32_t (&dst)[W]) {
-      const int sw = ci % C::kSW;
-      mbar_wait(&wfull[sw], (ci / C::kSW) & 1);
-      const uint8_t* wst = smem + C::kWOff + sw * C::kWBytes;
+    // Everything below addresses shared memory through 32-bit shared-space addresses (ld.shared):
+    // plain C++ pointers into the manually aligned buffer compile to generic LD.E.
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_wfull = smem_u32(wfull), s_wempty = smem_u32(wempty);
+    const uint32_t s_afree = smem_u32(afree), s_stored = smem_u32(stored);
+    auto bar_wait = [](uint32_t bar, uint32_t parity) {
+      uint32_t ok;
+      do {
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      } while (!ok);
+    };
+    auto bar_arrive = [](uint32_t bar) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    };
+    static_assert((C::kSW & (C::kSW - 1)) == 0 && C::kSW % kGroups == 0, "weight ring: power of two");
+    int sw = grp;                       // weight stage of the group's current chunk (i % kSW)
+    uint32_t sw_phase = 0;
+    auto load_words = [&](uint32_t (&dst)[W]) {
+      bar_wait(s_wfull + sw * 8, sw_phase);
+      const uint32_t addr = s_base + C::kWOff + sw * C::kWBytes + ch * 16;
 #pragma unroll
-      for (int sub = 0; sub < W / 4; ++sub) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (sub * kTileN + ch) * 16);
-        dst[sub * 4 + 0] = pk.x; dst[sub * 4 + 1] = pk.y; dst[sub * 4 + 2] = pk.z; dst[sub * 4 + 3] = pk.w;
-      }
+      for (int sub = 0; sub < W / 4; ++sub)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(dst[sub * 4]), "=r"(dst[sub * 4 + 1]), "=r"(dst[sub * 4 + 2]), "=r"(dst[sub * 4 + 3])
+                     : "r"(addr + sub * kTileN * 16));
       __syncwarp();
-      if (lane == 0) mbar_arrive(&wempty[sw]);
+      if (lane == 0) bar_arrive(s_wempty + sw * 8);   // packed bytes are in registers
+      sw += kGroups;
+      if (sw >= C::kSW) { sw -= C::kSW; sw_phase ^= 1; }
     };
     uint32_t cur[W];
-    if (grp < nchunks) load_words(grp, cur);
+    if (grp < nchunks) load_words(cur);
     mbar_wait(szfull, 0);
     int cur_g = -1;
     DqConst dq = make_dq(__float2half(0.f), 0);
-    int it = 0;
-    for (int i = grp; i < nchunks; i += kGroups, ++it) {
-      uint32_t nxt[W];
-      const bool has_next = i + kGroups < nchunks;
-      if (has_next) load_words(i + kGroups, nxt);
+    int as_l = 0;                       // A stage of this group, 0..kAS-1
+    uint32_t as_phase = 1;              // parity to wait for on afree (first round passes)
+    const uint32_t s_scale = s_base + C::kScaleOff + ch * 2;
+    const uint32_t s_zero = s_base + C::kZeroOff + zword * 4;
+    const uint32_t zmask = (1u << BITS) - 1;
+    for (int i = grp; i < nchunks; i += kGroups) {
       uint32_t lo[16], hi[16];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK + hf * 32) >> a.g_shift) - g_first : 0;
         if (g != cur_g) {
           cur_g = g;
-          const int z = a.qzeros ? static_cast<int>((sm_zero[g * 32 + zword] >> zshift) & ((1u << BITS) - 1)) + zadd
-                                 : (1 << (BITS - 1));
-          dq = make_dq(sm_scale[g * kTileN + ch], z);
+          unsigned short sbits;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sbits) : "r"(s_scale + g * (kTileN * 2)));
+          int z = 1 << (BITS - 1);
+          if (a.qzeros) {
+            uint32_t zw;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * 128));
+            z = static_cast<int>((zw >> zshift) & zmask) + zadd;
+          }
+          dq = make_dq(__ushort_as_half(sbits), z);
         }
         uint32_t(&dst)[16] = hf == 0 ? lo : hi;
         if (BITS == 4) {
@@ -244,20 +270,19 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
           }
         }
       }
-      const int as = grp * kAS + (it % kAS);
+      // `cur` is consumed: fetch the group's next chunk now, its latency hides under the stores
+      if (i + kGroups < nchunks) load_words(cur);
+      const int as = grp * kAS + as_l;
       const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-      mbar_wait(&afree[as], ((it / kAS) & 1) ^ 1);        // this group's MMA of chunk it - kAS retired
+      bar_wait(s_afree + as * 8, as_phase);               // this group's MMA of chunk it - kAS retired
       tc_fence_after();
       tmem_st_x16(a_tmem + lane_base, lo);
       tmem_st_x16(a_tmem + lane_base + 16, hi);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&stored[as]);            // -> the issuer warp
-      if (has_next) {
-#pragma unroll
-        for (int e = 0; e < W; ++e) cur[e] = nxt[e];
-      }
+      if (lane == 0) bar_arrive(s_stored + as * 8);       // -> the group's issuer warp
+      if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
     }
     // ------------------------------------------------------------ epilogue
     const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
