@@ -24,4 +24,6 @@ void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_s
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
                           int interleaved, int cos_sin_f32, cudaStream_t st);
+void launch_rowscale(void* out, const void* x, const float* ssq, int T, int hidden, float eps,
+                     cudaStream_t st);
 }  // namespace b200

@@ -171,6 +171,29 @@ rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
   }
 }
 
+// ------------------------------------------------------------------ folded-norm row scale
+// out[t, :] = x[t, :] * rsqrt(ssq[t] / hidden + eps): finishes an RMSNorm whose weight multiply and
+// sum of squares were fused into the producing GEMM's epilogue (model_runner.cpp, fused plan).
+__global__ void rowscale_kernel(__half* __restrict__ out, const __half* __restrict__ x,
+                                const float* __restrict__ ssq, int hidden, float inv_dim, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int t = blockIdx.x;
+  const float rs = rsqrtf(ssq[t] * inv_dim + eps);
+  const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * hidden);
+  uint4* os = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * hidden);
+  for (int i = threadIdx.x; i < (hidden >> 3); i += blockDim.x) {
+    uint4 a = xs[i];
+    __half2* ah = reinterpret_cast<__half2*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(ah[j]);
+      ah[j] = __floats2half2_rn(f.x * rs, f.y * rs);
+    }
+    os[i] = a;
+  }
+}
+
 // ------------------------------------------------------------------ SiLU(gate) * up
 __global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restrict__ gate_up,
                                 int inter) {
@@ -270,6 +293,13 @@ argmax_kernel(uint32_t* __restrict__ out_ids, const float* __restrict__ logits, 
     }
     if (threadIdx.x == 0) out_ids[b] = best_i == 0x7fffffff ? 0u : static_cast<uint32_t>(best_i);
   }
+}
+
+void launch_rowscale(void* out, const void* x, const float* ssq, int T, int hidden, float eps,
+                     cudaStream_t st) {
+  launch_pdl(rowscale_kernel, dim3(T), dim3(256), 0, st, (__half*)out, (const __half*)x, ssq, hidden,
+             1.f / static_cast<float>(hidden), eps);
+  B200_CUDA_LAUNCH_CHECK();
 }
 
 void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,

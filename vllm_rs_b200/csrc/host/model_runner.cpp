@@ -17,6 +17,7 @@
 // The runner owns no device memory: weights, caches and one workspace come from the caller.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -49,6 +50,7 @@ struct b200_runner {
   __half *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *proj = nullptr,
          *act = nullptr, *act2 = nullptr;
   float* logits = nullptr;
+  float* ssq = nullptr;          // [2 * layers + 1][max_batch] sums of squares of the folded RMSNorms
   void *attn_ws = nullptr, *wna_ws = nullptr;
   // static (graph) input buffers
   uint32_t *s_ids = nullptr, *s_ctx = nullptr, *s_bt = nullptr, *s_out = nullptr;
@@ -78,6 +80,7 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
   r->act = (__half*)take(R * 2 * static_cast<size_t>(c.inter) * 2);
   r->act2 = (__half*)take(R * static_cast<size_t>(c.inter) * 2);
   r->logits = (float*)take(B * c.vocab * 4);
+  r->ssq = (float*)take((2 * static_cast<size_t>(c.num_layers) + 1) * B * 4);
   r->attn_ws = take(b200_paged_attn_workspace_bytes(c.max_batch, c.num_heads, c.head_dim,
                                                     c.max_blocks_per_seq));
   const size_t max_n = std::max<size_t>(std::max<size_t>(qkv_n, 2 * c.inter), c.hidden);
@@ -183,6 +186,85 @@ static void linear(b200_runner* r, const __half* in, const void* w, const void* 
                      variant, r->wna_ws, stream);
 }
 
+// One quantised linear with a fused tile-finaliser epilogue (wna16.cuh, FusedEpi).
+static void linear_fused(b200_runner* r, const __half* in, const void* w, const void* s, const void* z,
+                         const void* bias, __half* out, int M, int K, int N, int epilogue,
+                         const FusedEpi& fe, cudaStream_t st) {
+  const b200_model_config& c = r->cfg;
+  WnaParams p;
+  p.a = in; p.bp = (const uint32_t*)w; p.scales = (const __half*)s; p.qzeros = (const uint32_t*)z;
+  p.bias = (const __half*)bias; p.c = out; p.M = M; p.K = K; p.N = N; p.bits = c.bits;
+  p.group_size = c.group_size <= 0 ? K : c.group_size; p.qfmt = c.qfmt; p.epilogue = epilogue;
+  p.no_split = 0; p.workspace = r->wna_ws; p.fe = &fe;
+  if (M > 4 && launch_wna16_tc_dec(p, st)) return;
+  if (M > 4 && launch_wna16_tc(p, st)) return;
+  launch_wna16_gemv(p, st);
+}
+
+static bool fused_plan_enabled(const b200_runner* r) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B200_FUSED");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  const b200_model_config& c = r->cfg;
+  return env == 1 && c.bits != 16 && r->allreduce == nullptr && !c.cos_sin_f32 &&
+         (kTileN % c.head_dim) == 0 && c.max_batch <= 64;
+}
+
+// Fused decode plan: RMSNorm weight multiply + sum of squares folded into the producing GEMM's
+// finaliser, the per-token 1/rms applied in the consuming GEMM's finaliser, RoPE + KV-cache write
+// in the qkv finaliser.  Per layer: qkv, attention (+ merge), o, gate|up, down = 6 launches.
+static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_t* positions,
+                         const int64_t* slot_mapping, const uint32_t* block_tables,
+                         const uint32_t* context_lens, int B, float* logits, uint32_t* out_ids,
+                         int64_t stream) {
+  const b200_model_config& c = r->cfg;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim, L = c.num_layers;
+  const int qkv_n = (H + 2 * Hkv) * D;
+  const float inv_h = 1.f / static_cast<float>(c.hidden);
+  const size_t MB = c.max_batch;
+  cudaMemsetAsync(r->ssq, 0, (2 * static_cast<size_t>(L) + 1) * MB * 4, st);
+  b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);
+  b200_rmsnorm_f16(r->xn, r->x, r->layers[0].input_norm, B, c.hidden, c.rms_eps, stream);
+  __half* xw = r->xn;          // GEMM input buffer: x * w_norm (the 1/rms factor rides in ssq)
+  for (int l = 0; l < L; ++l) {
+    const b200_layer_weights& w = r->layers[l];
+    FusedEpi fq;
+    std::memset(&fq, 0, sizeof(fq));
+    if (l > 0) { fq.ssq_in = r->ssq + (2 * l - 1) * MB; fq.inv_dim = inv_h; fq.eps = c.rms_eps; }
+    fq.positions = positions; fq.slots = slot_mapping;
+    fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
+    fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
+    fq.H = H; fq.Hkv = Hkv; fq.D = D;
+    linear_fused(r, xw, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
+                 c.hidden, qkv_n, kEpiRopeKv, fq, st);
+    launch_paged_attn_decode(r->maps[l], r->attn, r->qkv, qkv_n, block_tables, context_lens, B, H, Hkv,
+                             D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
+    FusedEpi fo;
+    std::memset(&fo, 0, sizeof(fo));
+    fo.resid = r->x; fo.norm_w = (const __half*)w.post_norm; fo.ssq_out = r->ssq + (2 * l) * MB;
+    linear_fused(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, xw, B, H * D, c.hidden, kEpiResidNorm, fo, st);
+    FusedEpi fg;
+    std::memset(&fg, 0, sizeof(fg));
+    fg.ssq_in = r->ssq + (2 * l) * MB; fg.inv_dim = inv_h; fg.eps = c.rms_eps;
+    linear_fused(r, xw, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, B, c.hidden,
+                 2 * c.inter, B200_EPI_SILU_MUL, fg, st);
+    FusedEpi fd;
+    std::memset(&fd, 0, sizeof(fd));
+    fd.resid = r->x;
+    fd.norm_w = (const __half*)(l + 1 < L ? r->layers[l + 1].input_norm : r->final_norm);
+    fd.ssq_out = r->ssq + (2 * l + 1) * MB;
+    linear_fused(r, r->act, w.down_w, w.down_s, w.down_z, nullptr, xw, B, c.inter, c.hidden,
+                 kEpiResidNorm, fd, st);
+  }
+  launch_rowscale(r->proj, xw, r->ssq + (2 * L - 1) * MB, B, c.hidden, c.rms_eps, st);
+  float* lg = logits ? logits : r->logits;
+  b200_dense_gemm_f16(r->proj, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
+  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+}
+
 void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
                                const int64_t* positions, const int64_t* slot_mapping,
                                const uint32_t* block_tables, const uint32_t* context_lens,
@@ -198,6 +280,12 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long launches0 = launch_count();
+  if (fused_plan_enabled(r)) {
+    decode_fused(r, input_ids, positions, slot_mapping, block_tables, context_lens, B, logits, out_ids,
+                 stream);
+    r->launches = launch_count() - launches0;
+    return;
+  }
   const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim;
   const int qkv_n = (H + 2 * Hkv) * D;
   b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);

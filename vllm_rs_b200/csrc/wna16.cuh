@@ -27,6 +27,7 @@ struct WnaParams {
   int M, K, N, bits, group_size, qfmt, epilogue;
   int no_split;           // force one K split (direct fp16 store, no workspace traffic)
   void* workspace;
+  const struct FusedEpi* fe;   // optional fused epilogue description (host pointer, copied by value)
 };
 
 // position of output channel r (0..7) inside an AWQ-packed word
@@ -99,24 +100,54 @@ __device__ __forceinline__ void dequant8_word(uint32_t x, const DqConst& d, uint
 constexpr int kCounterBytes = 16384;
 constexpr int kMaxSplitCols = 148 * 128 * 2;     // launchers keep splits * N below this
 
+// internal epilogue kinds beyond the public B200_EPI_* flags (used by the fused decode plan)
+constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m] += sum x^2
+constexpr int kEpiRopeKv = 3;      // fused q|k|v: RoPE(q, k), K/V rows written to the paged cache
+
+// Everything the tile finaliser may fuse around a GEMM of the decoder layer
+// (llama.rs:107-131, attention.rs:648-839, others.rs:11-66 restated as GEMM epilogues).
+struct FusedEpi {
+  // consumer side of a folded RMSNorm: row m of the accumulators is scaled by
+  // rsqrt(ssq_in[m] * inv_dim + eps) (the per-token factor commutes with the GEMM)
+  const float* ssq_in;
+  float inv_dim, eps;
+  // kEpiResidNorm: residual stream (in/out), weight of the NEXT norm, its sum-of-squares target
+  __half* resid;
+  const __half* norm_w;
+  float* ssq_out;
+  // kEpiRopeKv
+  const int64_t* positions;
+  const int64_t* slots;
+  const __half* cos;
+  const __half* sin;
+  __half* k_cache;
+  __half* v_cache;
+  int H, Hkv, D;
+};
+
 struct SplitOut {
   float* partials;
   uint32_t* counters;
   const __half* bias;
   __half* c;
   int M, N, splits, epilogue;
+  FusedEpi fe;
 };
+
+__device__ __forceinline__ bool epi_is_plain(const SplitOut& o) {
+  return o.epilogue == B200_EPI_NONE && o.fe.ssq_in == nullptr;
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Called by `nthreads` (128 or 512) threads of a CTA AFTER the partials of rows [m_lo, m_hi) of
-// tile `nt` were stored and fenced by their writers.  tid % 128 = channel, tid / 128 = row phase.
-// The last CTA to arrive for the tile (or, with SILU_MUL, for the gate/up tile pair) sums the
-// partials in split order -- deterministic -- applies bias / SiLU*mul and writes fp16.  Loads of
-// up to 8 rows are issued together so the L2 latency is paid `splits` times, not M * splits.
-// `s_flag` is a shared int; `counter_base` separates token tiles; `bar_id` a free named barrier.
+// tile `nt` were stored.  tid % 128 = channel, tid / 128 = row phase.  The last CTA to arrive for
+// the tile (or, with SILU_MUL, for the gate/up tile pair) sums the partials in split order --
+// deterministic -- and applies the epilogue.  Loads of 8 rows are issued together so the L2
+// latency is paid `splits` times, not M * splits.  `s_flag` is a shared int; `counter_base`
+// separates token tiles; `bar_id` a free named barrier.
 __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int tid,
                                                         int nthreads, int m_lo, int m_hi,
                                                         int counter_base, int* s_flag, int bar_id) {
@@ -145,50 +176,97 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
   const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
   constexpr int R = 8;                               // rows in flight per thread
   const size_t row_stride = static_cast<size_t>(nphase) * N;
+  const FusedEpi& fe = o.fe;
+  // column(s) this thread sums: its own, plus a partner (up-projection / RoPE pair)
+  int n0, n1 = -1;
   if (silu) {
-    const int ng = (nt % half_tiles) * kTileN + ch, nu = ng + (N >> 1);
-    const float bg = o.bias ? __half2float(o.bias[ng]) : 0.f;
-    const float bu = o.bias ? __half2float(o.bias[nu]) : 0.f;
-    for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
-      float g[R], u[R];
+    n0 = (nt % half_tiles) * kTileN + ch;
+    n1 = n0 + (N >> 1);
+  } else {
+    n0 = nt * kTileN + ch;
+    if (o.epilogue == kEpiRopeKv && n0 < (fe.H + fe.Hkv) * fe.D) {
+      const int d = n0 % fe.D, hd = fe.D >> 1;
+      n1 = d < hd ? n0 + hd : n0 - hd;
+    }
+  }
+  const float b0 = o.bias ? __half2float(o.bias[n0]) : 0.f;
+  const float b1 = (o.bias && n1 >= 0) ? __half2float(o.bias[n1]) : 0.f;
+  for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
+    float a0[R], a1[R], rs[R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) { g[j] = bg; u[j] = bu; }
-      for (int s = 0; s < o.splits; ++s) {
-        const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N;
+    for (int j = 0; j < R; ++j) {
+      a0[j] = 0.f;
+      a1[j] = 0.f;
+      rs[j] = 1.f;
+    }
+    if (fe.ssq_in) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (mb + j * nphase < m_hi) {
-            g[j] += __ldcg(p + j * row_stride + ng);
-            u[j] += __ldcg(p + j * row_stride + nu);
-          }
-      }
+      for (int j = 0; j < R; ++j)
+        if (mb + j * nphase < m_hi) rs[j] = rsqrtf(__ldcg(fe.ssq_in + mb + j * nphase) * fe.inv_dim + fe.eps);
+    }
+    for (int s = 0; s < o.splits; ++s) {
+      const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N;
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (mb + j * nphase < m_hi) {
-          // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
-          const float gg = __half2float(__float2half_rn(g[j]));
-          const float uu = __half2float(__float2half_rn(u[j]));
-          o.c[static_cast<size_t>(mb + j * nphase) * (N >> 1) + ng] =
-              __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
+          a0[j] += __ldcg(p + j * row_stride + n0);
+          if (n1 >= 0) a1[j] += __ldcg(p + j * row_stride + n1);
         }
     }
-  } else {
-    const int n = nt * kTileN + ch;
-    const float bb = o.bias ? __half2float(o.bias[n]) : 0.f;
-    for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
-      float acc[R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) acc[j] = bb;
-      for (int s = 0; s < o.splits; ++s) {
-        const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N + n;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (mb + j * nphase < m_hi) acc[j] += __ldcg(p + j * row_stride);
+    for (int j = 0; j < R; ++j) {
+      const int m = mb + j * nphase;
+      const bool valid = m < m_hi;                   // warp-uniform (a warp shares its row phase)
+      const float v0 = a0[j] * rs[j] + b0, v1 = a1[j] * rs[j] + b1;
+      if (silu) {
+        if (valid) {
+          // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
+          const float gg = __half2float(__float2half_rn(v0));
+          const float uu = __half2float(__float2half_rn(v1));
+          o.c[static_cast<size_t>(m) * (N >> 1) + n0] = __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
+        }
+      } else if (o.epilogue == kEpiResidNorm) {
+        float sq = 0.f;
+        if (valid) {
+          const size_t idx = static_cast<size_t>(m) * N + n0;
+          // llama.rs:126-130: the GEMM output is fp16, the residual add is done in fp16
+          const __half xn = __float2half_rn(__half2float(fe.resid[idx]) + __half2float(__float2half_rn(v0)));
+          fe.resid[idx] = xn;
+          const float xf = __half2float(xn);
+          o.c[idx] = __float2half_rn(xf * __half2float(fe.norm_w[n0]));
+          sq = xf * xf;
+        }
+        sq = warp_sum(sq);
+        if ((tid & 31) == 0 && valid) atomicAdd(fe.ssq_out + m, sq);
+      } else if (o.epilogue == kEpiRopeKv) {
+        if (valid) {
+          const int D = fe.D, hd = D >> 1;
+          const int hh = n0 / D, d = n0 - hh * D;
+          float outv = v0;
+          if (n1 >= 0) {
+            // the reference rotates the fp16 GEMM outputs (rotary_emb.rs:88-104)
+            const float x0 = __half2float(__float2half_rn(v0)), x1 = __half2float(__float2half_rn(v1));
+            const int64_t pos = fe.positions[m];
+            const float cs = __half2float(fe.cos[pos * hd + (d < hd ? d : d - hd)]);
+            const float sn = __half2float(fe.sin[pos * hd + (d < hd ? d : d - hd)]);
+            outv = d < hd ? x0 * cs - x1 * sn : x0 * cs + x1 * sn;
+          }
+          const __half h16 = __float2half_rn(outv);
+          if (hh < fe.H) {
+            o.c[static_cast<size_t>(m) * N + n0] = h16;                 // q stays in the fused buffer
+          } else {
+            const int64_t slot = fe.slots[m];
+            if (slot >= 0) {
+              const bool is_k = hh < fe.H + fe.Hkv;
+              __half* cache = is_k ? fe.k_cache : fe.v_cache;
+              const int kvh = hh - fe.H - (is_k ? 0 : fe.Hkv);
+              cache[(static_cast<size_t>(slot) * fe.Hkv + kvh) * D + d] = h16;
+            }
+          }
+        }
+      } else if (valid) {
+        o.c[static_cast<size_t>(m) * N + n0] = __float2half_rn(v0);
       }
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (mb + j * nphase < m_hi)
-          o.c[static_cast<size_t>(mb + j * nphase) * N + n] = __float2half_rn(acc[j]);
     }
   }
 }

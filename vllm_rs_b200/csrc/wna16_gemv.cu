@@ -11,6 +11,8 @@
 // numbers, exact (q - z), one fp16 rounding on the scale multiply) and accumulate x*w in
 // fp32 with FHFMA against activations broadcast from shared memory.  K splits store fp32
 // partials; the last CTA of a tile sums them in split order and applies bias / SiLU*mul.  HBM-bound only for M <= 4; larger M goes to the tcgen05 path.
+#include <cstring>
+
 #include "wna16.cuh"
 
 namespace b200 {
@@ -138,7 +140,7 @@ wna16_gemv_kernel(const __half* __restrict__ a, const uint32_t* __restrict__ bp,
   }
   __shared__ int s_flag;
   const int m_hi = min(M, m_base + MB);
-  if (so.splits == 1 && so.epilogue == B200_EPI_NONE) {
+  if (so.splits == 1 && epi_is_plain(so)) {
     const float bv = so.bias ? __half2float(so.bias[n]) : 0.f;
 #pragma unroll
     for (int m = 0; m < MB; ++m)
@@ -167,6 +169,7 @@ static void launch_gemv_mb(const WnaParams& p, cudaStream_t st, int m_base) {
   so.counters = reinterpret_cast<uint32_t*>(p.workspace);
   so.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
   so.bias = p.bias; so.c = p.c; so.M = p.M; so.N = p.N; so.splits = splits; so.epilogue = p.epilogue;
+  if (p.fe) so.fe = *p.fe; else memset(&so.fe, 0, sizeof(so.fe));
   dim3 grid(tiles, splits);
   launch_pdl(wna16_gemv_kernel<BITS, MB>, grid, dim3(128), 0, st, p.a, p.bp, p.scales, p.qzeros, so,
              p.M, p.K, p.N, p.group_size, p.qfmt, cpc, m_base);
@@ -273,6 +276,7 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   p.group_size = group_size <= 0 ? k : group_size;
   p.qfmt = qfmt; p.epilogue = epilogue; p.workspace = workspace;
   p.no_split = (variant == 3) ? 1 : 0;
+  p.fe = nullptr;
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

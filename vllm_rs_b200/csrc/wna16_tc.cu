@@ -31,6 +31,7 @@
 // Roofline: decode (NT <= 64) is HBM-bound on the packed weights (K*N/2 bytes per launch);
 // prefill (NT = 256) is tensor-bound: 2*M*N*K flop.
 #include <cstdlib>
+#include <cstring>
 
 #include "wna16.cuh"
 
@@ -70,6 +71,7 @@ struct TcArgs {
   float* partials;        // [splits][M][N] fp32
   uint32_t* counters;     // tile arrival counters (zero at rest)
   int M, K, N, group_size, qfmt, chunks_per_split, splits, epilogue;
+  FusedEpi fe;
   int dbg;                // B200_TC_DBG experiment switches (0 in production)
 };
 
@@ -159,12 +161,13 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
     auto load_words = [&](int ci, uint32_t (&dst)[W]) {
       const int sw = ci % Cfg::kSW;
       mbar_wait(&wfull[sw], (ci / Cfg::kSW) & 1);
-      const uint8_t* wst = smem + Cfg::kWOff + sw * Cfg::kWBytes;
+      // explicit ld.shared: a plain pointer into the manually aligned buffer compiles to generic LD.E
+      const uint32_t addr = smem_u32(smem) + Cfg::kWOff + sw * Cfg::kWBytes + ch * 16;
 #pragma unroll
-      for (int sub = 0; sub < W / 4; ++sub) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(wst + (sub * kTileN + ch) * 16);
-        dst[sub * 4 + 0] = pk.x; dst[sub * 4 + 1] = pk.y; dst[sub * 4 + 2] = pk.z; dst[sub * 4 + 3] = pk.w;
-      }
+      for (int sub = 0; sub < W / 4; ++sub)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(dst[sub * 4]), "=r"(dst[sub * 4 + 1]), "=r"(dst[sub * 4 + 2]), "=r"(dst[sub * 4 + 3])
+                     : "r"(addr + sub * kTileN * 16));
       __syncwarp();
       if (lane == 0) mbar_arrive(&wempty[sw]);        // packed bytes are in registers
     };
@@ -232,7 +235,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
     }
     // ------------------------------------------------------------ epilogue
     // warps 0-3 drain the accumulators; all 16 dequant warps then meet for the split reduce
-    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
+    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE && a.fe.ssq_in == nullptr);
     pdl_wait();        // first global writes below (c / partials / counters)
     if (warp < 4) {
       mbar_wait(dfull, 0);
@@ -260,7 +263,7 @@ wna16_tc_kernel(const __grid_constant__ CUtensorMap xmap, const TcArgs a) {
     if (!direct) {
       SplitOut o;
       o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
+      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue; o.fe = a.fe;
       split_arrive_and_reduce(o, nt, threadIdx.x, kDqThreads, m0, min(M, m0 + NT),
                               blockIdx.z * (N / kTileN), &s_is_last, 1);
     }
@@ -352,7 +355,7 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
     return true;
   }
   if (m_tiles * tiles > kCounterBytes / 4) {
-    if (!(splits == 1 && p.epilogue == B200_EPI_NONE)) {
+    if (!(splits == 1 && p.epilogue == B200_EPI_NONE && !(p.fe && p.fe->ssq_in))) {
       set_error(1, "wna16_tc: too many tiles for the arrival counters");
       return true;
     }
@@ -363,6 +366,7 @@ static bool launch_tc_nt(const WnaParams& p, cudaStream_t st) {
   a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
   a.M = p.M; a.K = p.K; a.N = p.N; a.group_size = p.group_size; a.qfmt = p.qfmt;
   a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
+  if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("B200_TC_DBG"); dbg = e ? atoi(e) : 0; }

@@ -16,6 +16,9 @@
 //     under PDL the 48 KB ring is already full when the activations become visible.
 // Measured motivation (profiles/r1_gemm_experiments.txt): v3 spent ~10 us per launch in prologue
 // + epilogue and ~900 cycles per 4 KB chunk with the tensor pipe < 10% busy.
+#include <cstdlib>
+#include <cstring>
+
 #include "wna16.cuh"
 
 namespace b200 {
@@ -57,6 +60,8 @@ struct Args {
   float* partials;
   uint32_t* counters;
   int M, K, N, g_shift, qfmt, chunks_per_split, splits, epilogue;   // g_shift: log2(group_size), -1 = one group
+  FusedEpi fe;
+  int dbg;   // B200_TC_DBG experiment switches (0 in production): 1 no MMA, 2 no tcgen05.st, 4 no dequant math, 8 no weight stream, 16 no activation stream
 };
 
 template <int BITS, int NT>
@@ -138,6 +143,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sw = i % C::kSW;
         mbar_wait(&wempty[sw], ((i / C::kSW) & 1) ^ 1);
+        if ((a.dbg & 8) && i >= C::kSW) { mbar_arrive(&wfull[sw]); continue; }
         mbar_arrive_expect_tx(&wfull[sw], C::kWBytes);
         bulk_load_1d(smem + C::kWOff + sw * C::kWBytes, src + static_cast<size_t>(i) * C::kWBytes,
                      C::kWBytes, &wfull[sw]);
@@ -150,6 +156,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sx = i % C::kSX;
         mbar_wait(&xempty[sx], ((i / C::kSX) & 1) ^ 1);
+        if ((a.dbg & 16) && i >= C::kSX) { mbar_arrive(&xfull[sx]); continue; }
         mbar_arrive_expect_tx(&xfull[sx], C::kXBytes);
         tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
       }
@@ -172,6 +179,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
+        if (!(a.dbg & 1))
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
           tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
@@ -236,6 +244,10 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     const uint32_t zmask = (1u << BITS) - 1;
     for (int i = grp; i < nchunks; i += kGroups) {
       uint32_t lo[16], hi[16];
+      if (a.dbg & 4) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { lo[e] = cur[e % W]; hi[e] = cur[(e + 3) % W]; }
+      } else
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK + hf * 32) >> a.g_shift) - g_first : 0;
@@ -276,16 +288,21 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
       bar_wait(s_afree + as * 8, as_phase);               // this group's MMA of chunk it - kAS retired
       tc_fence_after();
-      tmem_st_x16(a_tmem + lane_base, lo);
-      tmem_st_x16(a_tmem + lane_base + 16, hi);
-      tc_wait_st();
+      if (!(a.dbg & 2)) {
+        tmem_st_x16(a_tmem + lane_base, lo);
+        tmem_st_x16(a_tmem + lane_base + 16, hi);
+        tc_wait_st();
+      } else if (lo[0] == 0x12345678u && hi[3] == 0x9abcdefu) {
+        tmem_st_x16(a_tmem + lane_base, lo);      // keep the math alive for the experiment
+        tmem_st_x16(a_tmem + lane_base + 16, hi);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(s_stored + as * 8);       // -> the group's issuer warp
       if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
     }
     // ------------------------------------------------------------ epilogue
-    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE);
+    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE && a.fe.ssq_in == nullptr);
     pdl_wait();        // first global writes below (c / partials / counters)
     if (warp < 4) {
       const int active = nchunks < kGroups ? nchunks : kGroups;
@@ -326,7 +343,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     if (!direct) {
       SplitOut o;
       o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue;
+      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue; o.fe = a.fe;
       split_arrive_and_reduce(o, nt, threadIdx.x, kDqThreads, 0, M, 0, &s_is_last, 1);
     }
   }
@@ -370,6 +387,12 @@ static bool launch_nt(const WnaParams& p, cudaStream_t st) {
     for (int s = 5; s < 31; ++s)
       if ((1 << s) == p.group_size) a.g_shift = s;
   a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
+  if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("B200_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -398,6 +421,7 @@ bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
   const int groups_per_cta = p.group_size >= p.K ? 1 : (cps * kChunkK + p.group_size - 1) / p.group_size + 1;
   if (groups_per_cta > dec::kSZGroups) return false;
   if (p.epilogue == B200_EPI_SILU_MUL && ((p.N / kTileN) & 1)) return false;
+  if (p.epilogue == kEpiRopeKv && p.fe && (kTileN % p.fe->D) != 0) return false;
   if (p.bits == 4) {
     if (p.M <= 16) return dec::launch_nt<4, 16>(p, st);
     if (p.M <= 32) return dec::launch_nt<4, 32>(p, st);
