@@ -38,3 +38,31 @@ for name, (K, N, epi) in shapes.items():
 print(f"M={M} variant={variant} dbg={os.environ.get('B200_TC_DBG','0')} pdl={os.environ.get('B200_PDL','1')}: " +
       "  ".join(f"{k}: {v[0]:.1f}us {v[1]:.0f}GB/s" for k, v in out.items()) +
       f"  | sum {sum(v[0] for v in out.values()):.1f}us")
+
+# ---- chain mode: the four GEMMs of a layer back to back (what the decode step launches), over
+# several layers' worth of distinct weights -- cold instruction / L2 state between shapes.
+if os.environ.get("B200_GEMM_CHAIN", "1") != "0":
+    nl = 4
+    Ls = [{n: synthetic._fused_awq_device(gen, K, [N], 128, dev) for n, (K, N, _) in shapes.items()}
+          for _ in range(nl)]
+    x4 = torch.randn(M, 4096, device=dev, dtype=torch.float16)
+    x14 = torch.randn(M, 14336, device=dev, dtype=torch.float16)
+    ys = {n: torch.empty(M, (N // 2 if e else N), device=dev, dtype=torch.float16) for n, (K, N, e) in shapes.items()}
+    def layer(i):
+        for n, (K, N, e) in shapes.items():
+            l = Ls[i % nl][n]
+            ops.wna16_gemm(x14 if K == 14336 else x4, l.w, l.s, l.z, ws, k=K, n=N, epilogue=e,
+                           variant=variant, out=ys[n])
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(nl * 2): layer(i)
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            for i in range(nl * 4): layer(i)
+        graph.replay(); st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(6): graph.replay()
+        e1.record(st); st.synchronize()
+    print(f"chain: {e0.elapsed_time(e1) * 1e3 / (6 * nl * 4):.1f} us per layer (4 GEMMs interleaved)")

@@ -142,17 +142,184 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- tile epilogue, shared by the global-memory finaliser below and the cluster (DSMEM)
+// reducer of wna16_tc_dec.cu.  One thread = one output channel of the 128-wide tile.
+struct EpiCol {
+  int n0, n1;          // column this thread sums, partner column (up-projection / RoPE pair) or -1
+  bool pair, kv_col, silu;
+  float b0, b1, nw;
+};
+struct EpiRow {        // per-row operands that do not depend on the sums (requested early)
+  float rs, e0, e1;
+  int sl;
+};
+
+template <int EPI>
+__device__ __forceinline__ EpiCol epi_col(const SplitOut& o, int nt, int ch) {
+  const FusedEpi& fe = o.fe;
+  EpiCol c;
+  c.silu = EPI == B200_EPI_SILU_MUL;
+  c.n1 = -1;
+  if (c.silu) {
+    const int half_tiles = (o.N / kTileN) >> 1;
+    c.n0 = (nt % half_tiles) * kTileN + ch;
+    c.n1 = c.n0 + (o.N >> 1);
+  } else {
+    c.n0 = nt * kTileN + ch;
+    if (EPI == kEpiRopeKv && c.n0 < (fe.H + fe.Hkv) * fe.D) {
+      const int d = c.n0 % fe.D, hd = fe.D >> 1;
+      c.n1 = d < hd ? c.n0 + hd : c.n0 - hd;
+    }
+  }
+  c.pair = c.n1 >= 0;
+  c.kv_col = EPI == kEpiRopeKv && c.n0 >= fe.H * fe.D;
+  c.b0 = o.bias ? __half2float(o.bias[c.n0]) : 0.f;
+  c.b1 = (o.bias && c.pair) ? __half2float(o.bias[c.n1]) : 0.f;
+  c.nw = EPI == kEpiResidNorm ? __half2float(fe.norm_w[c.n0]) : 0.f;
+  return c;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_row_prefetch(const SplitOut& o, const EpiCol& c, int m, bool valid,
+                                                 EpiRow& r) {
+  const FusedEpi& fe = o.fe;
+  r.rs = 0.f;
+  r.e0 = 0.f;
+  r.e1 = 0.f;
+  r.sl = -1;
+  if (!valid) return;
+  if (fe.ssq_in) r.rs = __ldcg(fe.ssq_in + m);
+  if (EPI == kEpiResidNorm) {
+    r.e0 = __half2float(__ldcg(fe.resid + static_cast<size_t>(m) * o.N + c.n0));
+  } else if (EPI == kEpiRopeKv) {
+    if (c.pair) {
+      const int hd = fe.D >> 1;
+      const int d = c.n0 % fe.D;
+      const size_t ci = static_cast<size_t>(fe.positions[m]) * hd + (d < hd ? d : d - hd);
+      r.e0 = __half2float(fe.cos[ci]);
+      r.e1 = __half2float(fe.sin[ci]);
+    }
+    if (c.kv_col) r.sl = static_cast<int>(fe.slots[m]);
+  }
+}
+
+// a0 / a1: fp32 sums of the thread's column / partner column for row m.  Must be called by whole
+// warps with a warp-uniform m (the sum-of-squares path reduces across the warp).
+template <int EPI>
+__device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c, int m, bool valid,
+                                              float a0, float a1, const EpiRow& r, int lane) {
+  const FusedEpi& fe = o.fe;
+  const int N = o.N;
+  constexpr int epi = EPI;
+  const float scale = fe.ssq_in ? rsqrtf(r.rs * fe.inv_dim + fe.eps) : 1.f;
+  const float v0 = a0 * scale + c.b0, v1 = a1 * scale + c.b1;
+  if (c.silu) {
+    if (valid) {
+      // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
+      const float gg = __half2float(__float2half_rn(v0));
+      const float uu = __half2float(__float2half_rn(v1));
+      o.c[static_cast<size_t>(m) * (N >> 1) + c.n0] = __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
+    }
+  } else if (epi == kEpiResidNorm) {
+    float sq = 0.f;
+    if (valid) {
+      const size_t idx = static_cast<size_t>(m) * N + c.n0;
+      // llama.rs:126-130: the GEMM output is fp16, the residual add is done in fp16
+      const __half xn = __float2half_rn(r.e0 + __half2float(__float2half_rn(v0)));
+      fe.resid[idx] = xn;
+      const float xf = __half2float(xn);
+      o.c[idx] = __float2half_rn(xf * c.nw);
+      sq = xf * xf;
+    }
+    sq = warp_sum(sq);
+    if (lane == 0 && valid) atomicAdd(fe.ssq_out + m, sq);
+  } else if (epi == kEpiRopeKv) {
+    if (valid) {
+      const int D = fe.D, hd = D >> 1;
+      const int hh = c.n0 / D, d = c.n0 - hh * D;
+      float outv = v0;
+      if (c.pair) {
+        // the reference rotates the fp16 GEMM outputs (rotary_emb.rs:88-104)
+        const float x0 = __half2float(__float2half_rn(v0)), x1 = __half2float(__float2half_rn(v1));
+        outv = d < hd ? x0 * r.e0 - x1 * r.e1 : x0 * r.e0 + x1 * r.e1;
+      }
+      const __half h16 = __float2half_rn(outv);
+      if (!c.kv_col) {
+        o.c[static_cast<size_t>(m) * N + c.n0] = h16;                 // q stays in the fused buffer
+      } else if (r.sl >= 0) {
+        const bool is_k = hh < fe.H + fe.Hkv;
+        __half* cache = is_k ? fe.k_cache : fe.v_cache;
+        const int kvh = hh - fe.H - (is_k ? 0 : fe.Hkv);
+        cache[(static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d] = h16;
+      }
+    }
+  } else if (valid) {
+    o.c[static_cast<size_t>(m) * N + c.n0] = __float2half_rn(v0);
+  }
+}
+
+// Rows [m_lo, m_hi) of tile nt: sum the partials in split order (deterministic) and apply the
+// epilogue.  tid % 128 = channel, tid / 128 = row phase.
+template <int EPI>
+__device__ __forceinline__ void split_reduce_rows(const SplitOut& o, int nt, int tid, int nthreads,
+                                                  int m_lo, int m_hi) {
+  const int N = o.N, M = o.M;
+  const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
+  constexpr int R = 8;                               // rows in flight per thread
+  const size_t row_stride = static_cast<size_t>(nphase) * N;
+  const EpiCol c = epi_col<EPI>(o, nt, ch);
+  for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
+    float a0[R], a1[R];
+    EpiRow er[R];
+    // (1) every operand of the epilogue that does not depend on the sums is requested FIRST, so
+    // its L2 round trips overlap the partial loads instead of following them (the finaliser is
+    // the serial tail of every GEMM: each extra dependent round trip costs ~1 us per layer GEMM)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      a0[j] = 0.f;
+      a1[j] = 0.f;
+      epi_row_prefetch<EPI>(o, c, mb + j * nphase, mb + j * nphase < m_hi, er[j]);
+    }
+    // (2) the partials, split order (deterministic), several splits x 8 rows of loads in flight
+    const float* p0 = o.partials + static_cast<size_t>(mb) * N;
+    const size_t split_stride = static_cast<size_t>(M) * N;
+    if (c.pair) {
+#pragma unroll 2
+      for (int s = 0; s < o.splits; ++s) {
+        const float* p = p0 + s * split_stride;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (mb + j * nphase < m_hi) {
+            a0[j] += __ldcg(p + j * row_stride + c.n0);
+            a1[j] += __ldcg(p + j * row_stride + c.n1);
+          }
+      }
+    } else {
+#pragma unroll 4
+      for (int s = 0; s < o.splits; ++s) {
+        const float* p = p0 + s * split_stride + c.n0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (mb + j * nphase < m_hi) a0[j] += __ldcg(p + j * row_stride);
+      }
+    }
+    // (3) epilogue (m is warp-uniform: a warp shares its row phase)
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      epi_row_apply<EPI>(o, c, mb + j * nphase, mb + j * nphase < m_hi, a0[j], a1[j], er[j], tid & 31);
+  }
+}
+
+
 // Called by `nthreads` (128 or 512) threads of a CTA AFTER the partials of rows [m_lo, m_hi) of
 // tile `nt` were stored.  tid % 128 = channel, tid / 128 = row phase.  The last CTA to arrive for
 // the tile (or, with SILU_MUL, for the gate/up tile pair) sums the partials in split order --
 // deterministic -- and applies the epilogue.  Loads of 8 rows are issued together so the L2
 // latency is paid `splits` times, not M * splits.  `s_flag` is a shared int; `counter_base`
 // separates token tiles; `bar_id` a free named barrier.
-__device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int tid,
-                                                        int nthreads, int m_lo, int m_hi,
-                                                        int counter_base, int* s_flag, int bar_id) {
-  const int N = o.N, M = o.M;
-  const int tiles = N / kTileN;
+__device__ __forceinline__ bool split_arrive(const SplitOut& o, int nt, int tid, int nthreads,
+                                             int counter_base, int* s_flag, int bar_id) {
+  const int tiles = o.N / kTileN;
   const bool silu = o.epilogue == B200_EPI_SILU_MUL;
   const int half_tiles = tiles >> 1;
   const int cidx = counter_base + (silu ? nt % half_tiles : nt);
@@ -172,102 +339,18 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
     *s_flag = last;
   }
   named_bar_sync(bar_id, nthreads);
-  if (!*s_flag) return;
-  const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
-  constexpr int R = 8;                               // rows in flight per thread
-  const size_t row_stride = static_cast<size_t>(nphase) * N;
-  const FusedEpi& fe = o.fe;
-  // column(s) this thread sums: its own, plus a partner (up-projection / RoPE pair)
-  int n0, n1 = -1;
-  if (silu) {
-    n0 = (nt % half_tiles) * kTileN + ch;
-    n1 = n0 + (N >> 1);
-  } else {
-    n0 = nt * kTileN + ch;
-    if (o.epilogue == kEpiRopeKv && n0 < (fe.H + fe.Hkv) * fe.D) {
-      const int d = n0 % fe.D, hd = fe.D >> 1;
-      n1 = d < hd ? n0 + hd : n0 - hd;
-    }
-  }
-  const float b0 = o.bias ? __half2float(o.bias[n0]) : 0.f;
-  const float b1 = (o.bias && n1 >= 0) ? __half2float(o.bias[n1]) : 0.f;
-  for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
-    float a0[R], a1[R], rs[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      a0[j] = 0.f;
-      a1[j] = 0.f;
-      rs[j] = 1.f;
-    }
-    if (fe.ssq_in) {
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (mb + j * nphase < m_hi) rs[j] = rsqrtf(__ldcg(fe.ssq_in + mb + j * nphase) * fe.inv_dim + fe.eps);
-    }
-    for (int s = 0; s < o.splits; ++s) {
-      const float* p = o.partials + (static_cast<size_t>(s) * M + mb) * N;
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (mb + j * nphase < m_hi) {
-          a0[j] += __ldcg(p + j * row_stride + n0);
-          if (n1 >= 0) a1[j] += __ldcg(p + j * row_stride + n1);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int m = mb + j * nphase;
-      const bool valid = m < m_hi;                   // warp-uniform (a warp shares its row phase)
-      const float v0 = a0[j] * rs[j] + b0, v1 = a1[j] * rs[j] + b1;
-      if (silu) {
-        if (valid) {
-          // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
-          const float gg = __half2float(__float2half_rn(v0));
-          const float uu = __half2float(__float2half_rn(v1));
-          o.c[static_cast<size_t>(m) * (N >> 1) + n0] = __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
-        }
-      } else if (o.epilogue == kEpiResidNorm) {
-        float sq = 0.f;
-        if (valid) {
-          const size_t idx = static_cast<size_t>(m) * N + n0;
-          // llama.rs:126-130: the GEMM output is fp16, the residual add is done in fp16
-          const __half xn = __float2half_rn(__half2float(fe.resid[idx]) + __half2float(__float2half_rn(v0)));
-          fe.resid[idx] = xn;
-          const float xf = __half2float(xn);
-          o.c[idx] = __float2half_rn(xf * __half2float(fe.norm_w[n0]));
-          sq = xf * xf;
-        }
-        sq = warp_sum(sq);
-        if ((tid & 31) == 0 && valid) atomicAdd(fe.ssq_out + m, sq);
-      } else if (o.epilogue == kEpiRopeKv) {
-        if (valid) {
-          const int D = fe.D, hd = D >> 1;
-          const int hh = n0 / D, d = n0 - hh * D;
-          float outv = v0;
-          if (n1 >= 0) {
-            // the reference rotates the fp16 GEMM outputs (rotary_emb.rs:88-104)
-            const float x0 = __half2float(__float2half_rn(v0)), x1 = __half2float(__float2half_rn(v1));
-            const int64_t pos = fe.positions[m];
-            const float cs = __half2float(fe.cos[pos * hd + (d < hd ? d : d - hd)]);
-            const float sn = __half2float(fe.sin[pos * hd + (d < hd ? d : d - hd)]);
-            outv = d < hd ? x0 * cs - x1 * sn : x0 * cs + x1 * sn;
-          }
-          const __half h16 = __float2half_rn(outv);
-          if (hh < fe.H) {
-            o.c[static_cast<size_t>(m) * N + n0] = h16;                 // q stays in the fused buffer
-          } else {
-            const int64_t slot = fe.slots[m];
-            if (slot >= 0) {
-              const bool is_k = hh < fe.H + fe.Hkv;
-              __half* cache = is_k ? fe.k_cache : fe.v_cache;
-              const int kvh = hh - fe.H - (is_k ? 0 : fe.Hkv);
-              cache[(static_cast<size_t>(slot) * fe.Hkv + kvh) * D + d] = h16;
-            }
-          }
-        }
-      } else if (valid) {
-        o.c[static_cast<size_t>(m) * N + n0] = __float2half_rn(v0);
-      }
-    }
+  return *s_flag != 0;
+}
+
+__device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int nt, int tid,
+                                                        int nthreads, int m_lo, int m_hi,
+                                                        int counter_base, int* s_flag, int bar_id) {
+  if (!split_arrive(o, nt, tid, nthreads, counter_base, s_flag, bar_id)) return;
+  switch (o.epilogue) {
+    case B200_EPI_SILU_MUL: split_reduce_rows<B200_EPI_SILU_MUL>(o, nt, tid, nthreads, m_lo, m_hi); break;
+    case kEpiResidNorm: split_reduce_rows<kEpiResidNorm>(o, nt, tid, nthreads, m_lo, m_hi); break;
+    case kEpiRopeKv: split_reduce_rows<kEpiRopeKv>(o, nt, tid, nthreads, m_lo, m_hi); break;
+    default: split_reduce_rows<B200_EPI_NONE>(o, nt, tid, nthreads, m_lo, m_hi); break;
   }
 }
 

@@ -61,10 +61,9 @@ struct Args {
   uint32_t* counters;
   int M, K, N, g_shift, qfmt, chunks_per_split, splits, epilogue;   // g_shift: log2(group_size), -1 = one group
   FusedEpi fe;
-  int dbg;   // B200_TC_DBG experiment switches (0 in production): 1 no MMA, 2 no tcgen05.st, 4 no dequant math, 8 no weight stream, 16 no activation stream
 };
 
-template <int BITS, int NT>
+template <int BITS, int NT, int EPI, bool PIPE>
 __global__ void __launch_bounds__(kThreads, 1)
 wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   using C = Cfg<BITS, NT>;
@@ -143,7 +142,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sw = i % C::kSW;
         mbar_wait(&wempty[sw], ((i / C::kSW) & 1) ^ 1);
-        if ((a.dbg & 8) && i >= C::kSW) { mbar_arrive(&wfull[sw]); continue; }
         mbar_arrive_expect_tx(&wfull[sw], C::kWBytes);
         bulk_load_1d(smem + C::kWOff + sw * C::kWBytes, src + static_cast<size_t>(i) * C::kWBytes,
                      C::kWBytes, &wfull[sw]);
@@ -156,7 +154,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       for (int i = 0; i < nchunks; ++i) {
         const int sx = i % C::kSX;
         mbar_wait(&xempty[sx], ((i / C::kSX) & 1) ^ 1);
-        if ((a.dbg & 16) && i >= C::kSX) { mbar_arrive(&xfull[sx]); continue; }
         mbar_arrive_expect_tx(&xfull[sx], C::kXBytes);
         tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
       }
@@ -179,7 +176,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
         const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
-        if (!(a.dbg & 1))
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
           tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
@@ -193,7 +189,6 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     // ------------------------------------------------------------ dequant groups
     const int grp = warp >> 2, q4 = warp & 3;
     const int ch = q4 * 32 + lane;
-    const int n = nt * kTileN + ch;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     // zero-point field of this channel inside its packed word
     const int zword = BITS == 4 ? (ch >> 3) : (ch >> 2);
@@ -242,69 +237,97 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     const uint32_t s_scale = s_base + C::kScaleOff + ch * 2;
     const uint32_t s_zero = s_base + C::kZeroOff + zword * 4;
     const uint32_t zmask = (1u << BITS) - 1;
-    for (int i = grp; i < nchunks; i += kGroups) {
-      uint32_t lo[16], hi[16];
-      if (a.dbg & 4) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) { lo[e] = cur[e % W]; hi[e] = cur[(e + 3) % W]; }
-      } else
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK + hf * 32) >> a.g_shift) - g_first : 0;
-        if (g != cur_g) {
-          cur_g = g;
-          unsigned short sbits;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sbits) : "r"(s_scale + g * (kTileN * 2)));
-          int z = 1 << (BITS - 1);
-          if (a.qzeros) {
-            uint32_t zw;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * 128));
-            z = static_cast<int>((zw >> zshift) & zmask) + zadd;
-          }
-          dq = make_dq(__ushort_as_half(sbits), z);
+    auto dequant_half = [&](int i, int hf, uint32_t (&dst)[16]) {
+      const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK + hf * 32) >> a.g_shift) - g_first : 0;
+      if (g != cur_g) {
+        cur_g = g;
+        unsigned short sbits;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sbits) : "r"(s_scale + g * (kTileN * 2)));
+        int z = 1 << (BITS - 1);
+        if (a.qzeros) {
+          uint32_t zw;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * 128));
+          z = static_cast<int>((zw >> zshift) & zmask) + zadd;
         }
-        uint32_t(&dst)[16] = hf == 0 ? lo : hi;
-        if (BITS == 4) {
+        dq = make_dq(__ushort_as_half(sbits), z);
+      }
+      if (BITS == 4) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            uint32_t o4[4];
-            dequant4_word(cur[hf * 4 + w], dq, o4);
+        for (int w = 0; w < 4; ++w) {
+          uint32_t o4[4];
+          dequant4_word(cur[hf * 4 + w], dq, o4);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dst[w * 4 + e] = o4[e];
-          }
-        } else {
+          for (int e = 0; e < 4; ++e) dst[w * 4 + e] = o4[e];
+        }
+      } else {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            uint32_t o2[2];
-            dequant8_word(cur[(hf * 8 + w) % W], dq, o2);
-            dst[w * 2] = o2[0];
-            dst[w * 2 + 1] = o2[1];
-          }
+        for (int w = 0; w < 8; ++w) {
+          uint32_t o2[2];
+          dequant8_word(cur[(hf * 8 + w) % W], dq, o2);
+          dst[w * 2] = o2[0];
+          dst[w * 2 + 1] = o2[1];
         }
       }
-      // `cur` is consumed: fetch the group's next chunk now, its latency hides under the stores
-      if (i + kGroups < nchunks) load_words(cur);
-      const int as = grp * kAS + as_l;
-      const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-      bar_wait(s_afree + as * 8, as_phase);               // this group's MMA of chunk it - kAS retired
-      tc_fence_after();
-      if (!(a.dbg & 2)) {
+    };
+    if (!PIPE) {
+      for (int i = grp; i < nchunks; i += kGroups) {
+        uint32_t lo[16], hi[16];
+        dequant_half(i, 0, lo);
+        dequant_half(i, 1, hi);
+        // `cur` is consumed: fetch the group's next chunk now, its latency hides under the stores
+        if (i + kGroups < nchunks) load_words(cur);
+        const int as = grp * kAS + as_l;
+        const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
+        bar_wait(s_afree + as * 8, as_phase);             // this group's MMA of chunk it - kAS retired
+        tc_fence_after();
         tmem_st_x16(a_tmem + lane_base, lo);
         tmem_st_x16(a_tmem + lane_base + 16, hi);
         tc_wait_st();
-      } else if (lo[0] == 0x12345678u && hi[3] == 0x9abcdefu) {
-        tmem_st_x16(a_tmem + lane_base, lo);      // keep the math alive for the experiment
-        tmem_st_x16(a_tmem + lane_base + 16, hi);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(s_stored + as * 8);     // -> the group's issuer warp
+        if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) bar_arrive(s_stored + as * 8);       // -> the group's issuer warp
-      if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
+    } else {
+      // Deferred completion: the TMEM stores of chunk i are awaited (and the issuer signalled)
+      // only after the first half of chunk i+1 has been dequantised, so tcgen05.st latency
+      // overlaps ALU work instead of idling the warp.
+      int pending_as = -1;
+      for (int i = grp; i < nchunks; i += kGroups) {
+        uint32_t lo[16], hi[16];
+        dequant_half(i, 0, lo);
+        if (pending_as >= 0) {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) bar_arrive(s_stored + pending_as * 8);
+        }
+        const int as = grp * kAS + as_l;
+        const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
+        bar_wait(s_afree + as * 8, as_phase);
+        tc_fence_after();
+        tmem_st_x16(a_tmem + lane_base, lo);
+        dequant_half(i, 1, hi);
+        if (i + kGroups < nchunks) load_words(cur);
+        tmem_st_x16(a_tmem + lane_base + 16, hi);
+        pending_as = as;
+        if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
+      }
+      if (pending_as >= 0) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(s_stored + pending_as * 8);
+      }
     }
     // ------------------------------------------------------------ epilogue
-    const bool direct = (a.splits == 1 && a.epilogue == B200_EPI_NONE && a.fe.ssq_in == nullptr);
-    pdl_wait();        // first global writes below (c / partials / counters)
+    // (the kernel is templated on the epilogue kind: one lean finaliser per kernel -- code
+    // size and register allocation of this tail were measured to move the whole GEMM by 2-5 us)
+    constexpr bool kPlain = EPI == B200_EPI_NONE;    // EPI_NONE kernels never carry a row scale
+    const bool direct = kPlain && a.splits == 1;
+    pdl_wait();        // first global reads / writes below (c / partials / counters / residual)
     if (warp < 4) {
+      const int n = nt * kTileN + ch;
       const int active = nchunks < kGroups ? nchunks : kGroups;
       for (int g = 0; g < active; ++g) mbar_wait(&gdone[g], 0);
       tc_fence_after();
@@ -343,8 +366,10 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     if (!direct) {
       SplitOut o;
       o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = a.epilogue; o.fe = a.fe;
-      split_arrive_and_reduce(o, nt, threadIdx.x, kDqThreads, 0, M, 0, &s_is_last, 1);
+      o.M = M; o.N = N; o.splits = a.splits; o.epilogue = EPI; o.fe = a.fe;
+      if (kPlain) o.fe.ssq_in = nullptr;
+      if (split_arrive(o, nt, threadIdx.x, kDqThreads, 0, &s_is_last, 1))
+        split_reduce_rows<EPI>(o, nt, threadIdx.x, kDqThreads, 0, M);
     }
   }
   __syncthreads();
@@ -354,8 +379,8 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   }
 }
 
-template <int BITS, int NT>
-static bool launch_nt(const WnaParams& p, cudaStream_t st) {
+template <int BITS, int NT, int EPI, bool PIPE>
+static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   using C = Cfg<BITS, NT>;
   CUtensorMap xmap;
   const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
@@ -388,20 +413,38 @@ static bool launch_nt(const WnaParams& p, cudaStream_t st) {
       if ((1 << s) == p.group_size) a.g_shift = s;
   a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
   if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("B200_TC_DBG"); dbg = e ? atoi(e) : 0; }
-    a.dbg = dbg;
-  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT, EPI, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          C::kAlloc);
     attr_set = true;
   }
-  launch_pdl(wna16_tc_dec_kernel<BITS, NT>, dim3(tiles, splits, 1), dim3(kThreads), C::kAlloc, st, xmap, a);
+  launch_pdl(wna16_tc_dec_kernel<BITS, NT, EPI, PIPE>, dim3(tiles, splits, 1), dim3(kThreads), C::kAlloc, st,
+             xmap, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
+}
+
+template <int BITS, int NT>
+static bool launch_nt(const WnaParams& p, cudaStream_t st) {
+  // a row scale (folded RMSNorm) on a plain GEMM has no lean kernel: the general kernel takes it
+  if (p.epilogue == B200_EPI_NONE && p.fe && p.fe->ssq_in) return false;
+  static int pipe = -1;
+  if (pipe < 0) { const char* e = getenv("B200_DEC_PIPE"); pipe = e ? atoi(e) : 0; }
+  if (pipe) {
+    switch (p.epilogue) {
+      case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, true>(p, st);
+      case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm, true>(p, st);
+      case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv, true>(p, st);
+      default: return launch_epi<BITS, NT, B200_EPI_NONE, true>(p, st);
+    }
+  }
+  switch (p.epilogue) {
+    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, false>(p, st);
+    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm, false>(p, st);
+    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv, false>(p, st);
+    default: return launch_epi<BITS, NT, B200_EPI_NONE, false>(p, st);
+  }
 }
 
 }  // namespace dec
