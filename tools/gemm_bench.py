@@ -11,6 +11,8 @@ dev = "cuda"
 gen = torch.Generator(device=dev).manual_seed(0)
 shapes = {"qkv": (4096, 6144, 0), "o": (4096, 4096, 0), "gate_up": (4096, 28672, 1), "down": (14336, 4096, 0)}
 ws = ops.wna16_workspace(max(M, 16), 28672)
+if os.environ.get("B200_GEMM_ONLY"):
+    shapes = {k: v for k, v in shapes.items() if k == os.environ["B200_GEMM_ONLY"]}
 out = {}
 for name, (K, N, epi) in shapes.items():
     copies = max(2, int(300e6 // (K * N // 2)) + 1)
@@ -41,7 +43,7 @@ print(f"M={M} variant={variant} dbg={os.environ.get('B200_TC_DBG','0')} pdl={os.
 
 # ---- chain mode: the four GEMMs of a layer back to back (what the decode step launches), over
 # several layers' worth of distinct weights -- cold instruction / L2 state between shapes.
-if os.environ.get("B200_GEMM_CHAIN", "1") != "0":
+if os.environ.get("B200_GEMM_CHAIN", "1") != "0" and len(shapes) == 4:
     nl = 4
     Ls = [{n: synthetic._fused_awq_device(gen, K, [N], 128, dev) for n, (K, N, _) in shapes.items()}
           for _ in range(nl)]

@@ -179,7 +179,7 @@ __global__ void rowscale_kernel(__half* __restrict__ out, const __half* __restri
   pdl_trigger();
   pdl_wait();
   const int t = blockIdx.x;
-  const float rs = rsqrtf(ssq[t] * inv_dim + eps);
+  const float rs = rsqrtf(ssq[t * 32] * inv_dim + eps);   // kSsqStride (wna16.cuh)
   const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * hidden);
   uint4* os = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * hidden);
   for (int i = threadIdx.x; i < (hidden >> 3); i += blockDim.x) {

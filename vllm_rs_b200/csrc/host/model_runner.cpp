@@ -80,7 +80,7 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
   r->act = (__half*)take(R * 2 * static_cast<size_t>(c.inter) * 2);
   r->act2 = (__half*)take(R * static_cast<size_t>(c.inter) * 2);
   r->logits = (float*)take(B * c.vocab * 4);
-  r->ssq = (float*)take((2 * static_cast<size_t>(c.num_layers) + 1) * B * 4);
+  r->ssq = (float*)take((2 * static_cast<size_t>(c.num_layers) + 1) * B * kSsqStride * 4);
   r->attn_ws = take(b200_paged_attn_workspace_bytes(c.max_batch, c.num_heads, c.head_dim,
                                                     c.max_blocks_per_seq));
   const size_t max_n = std::max<size_t>(std::max<size_t>(qkv_n, 2 * c.inter), c.hidden);
@@ -201,15 +201,24 @@ static void linear_fused(b200_runner* r, const __half* in, const void* w, const 
   launch_wna16_gemv(p, st);
 }
 
-static bool fused_plan_enabled(const b200_runner* r) {
+// B200_FUSED: 2 (default) = classic plan with RoPE + KV write folded into the qkv finaliser,
+// 1 = fully fused plan (RMSNorms folded into the GEMM finalisers too; measured 0.3 ms / step SLOWER
+// on Llama-3-8B b=32: the residual/norm finaliser lengthens every o/down GEMM tail by more than
+// the two norm kernels cost), 0 = classic plan.
+static int fused_env() {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("B200_FUSED");
-    env = (e && e[0] == '0') ? 0 : 1;
+    env = e ? atoi(e) : 2;
   }
+  return env;
+}
+static bool rope_fusable(const b200_runner* r) {
   const b200_model_config& c = r->cfg;
-  return env == 1 && c.bits != 16 && r->allreduce == nullptr && !c.cos_sin_f32 &&
-         (kTileN % c.head_dim) == 0 && c.max_batch <= 64;
+  return c.bits != 16 && !c.cos_sin_f32 && (kTileN % c.head_dim) == 0 && c.max_batch <= 64;
+}
+static bool fused_plan_enabled(const b200_runner* r) {
+  return fused_env() == 1 && rope_fusable(r) && r->allreduce == nullptr;
 }
 
 // Fused decode plan: RMSNorm weight multiply + sum of squares folded into the producing GEMM's
@@ -225,7 +234,7 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
   const int qkv_n = (H + 2 * Hkv) * D;
   const float inv_h = 1.f / static_cast<float>(c.hidden);
   const size_t MB = c.max_batch;
-  cudaMemsetAsync(r->ssq, 0, (2 * static_cast<size_t>(L) + 1) * MB * 4, st);
+  cudaMemsetAsync(r->ssq, 0, (2 * static_cast<size_t>(L) + 1) * MB * kSsqStride * 4, st);
   b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);
   b200_rmsnorm_f16(r->xn, r->x, r->layers[0].input_norm, B, c.hidden, c.rms_eps, stream);
   __half* xw = r->xn;          // GEMM input buffer: x * w_norm (the 1/rms factor rides in ssq)
@@ -233,7 +242,7 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
     const b200_layer_weights& w = r->layers[l];
     FusedEpi fq;
     std::memset(&fq, 0, sizeof(fq));
-    if (l > 0) { fq.ssq_in = r->ssq + (2 * l - 1) * MB; fq.inv_dim = inv_h; fq.eps = c.rms_eps; }
+    if (l > 0) { fq.ssq_in = r->ssq + (2 * l - 1) * MB * kSsqStride; fq.inv_dim = inv_h; fq.eps = c.rms_eps; }
     fq.positions = positions; fq.slots = slot_mapping;
     fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
     fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
@@ -244,22 +253,22 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
                              D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
     FusedEpi fo;
     std::memset(&fo, 0, sizeof(fo));
-    fo.resid = r->x; fo.norm_w = (const __half*)w.post_norm; fo.ssq_out = r->ssq + (2 * l) * MB;
+    fo.resid = r->x; fo.norm_w = (const __half*)w.post_norm; fo.ssq_out = r->ssq + (2 * l) * MB * kSsqStride;
     linear_fused(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, xw, B, H * D, c.hidden, kEpiResidNorm, fo, st);
     FusedEpi fg;
     std::memset(&fg, 0, sizeof(fg));
-    fg.ssq_in = r->ssq + (2 * l) * MB; fg.inv_dim = inv_h; fg.eps = c.rms_eps;
+    fg.ssq_in = r->ssq + (2 * l) * MB * kSsqStride; fg.inv_dim = inv_h; fg.eps = c.rms_eps;
     linear_fused(r, xw, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, B, c.hidden,
                  2 * c.inter, B200_EPI_SILU_MUL, fg, st);
     FusedEpi fd;
     std::memset(&fd, 0, sizeof(fd));
     fd.resid = r->x;
     fd.norm_w = (const __half*)(l + 1 < L ? r->layers[l + 1].input_norm : r->final_norm);
-    fd.ssq_out = r->ssq + (2 * l + 1) * MB;
+    fd.ssq_out = r->ssq + (2 * l + 1) * MB * kSsqStride;
     linear_fused(r, r->act, w.down_w, w.down_s, w.down_z, nullptr, xw, B, c.inter, c.hidden,
                  kEpiResidNorm, fd, st);
   }
-  launch_rowscale(r->proj, xw, r->ssq + (2 * L - 1) * MB, B, c.hidden, c.rms_eps, st);
+  launch_rowscale(r->proj, xw, r->ssq + (2 * L - 1) * MB * kSsqStride, B, c.hidden, c.rms_eps, st);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(r->proj, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
   if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
@@ -296,13 +305,24 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
     else
       b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, B, c.hidden, c.rms_eps, stream);
     // ---- attention block
-    linear(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
-           c.hidden, qkv_n, B200_EPI_NONE, stream);
     __half* q = r->qkv;
-    __half* k = r->qkv + H * D;
-    __half* v = r->qkv + (H + Hkv) * D;
-    launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
-                         w.k_cache, w.v_cache, B, H, Hkv, D, D, 0, c.cos_sin_f32, st);
+    if (fused_env() == 2 && rope_fusable(r)) {
+      FusedEpi fq;
+      std::memset(&fq, 0, sizeof(fq));
+      fq.positions = positions; fq.slots = slot_mapping;
+      fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
+      fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
+      fq.H = H; fq.Hkv = Hkv; fq.D = D;
+      linear_fused(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
+                   c.hidden, qkv_n, kEpiRopeKv, fq, st);
+    } else {
+      linear(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
+             c.hidden, qkv_n, B200_EPI_NONE, stream);
+      __half* k = r->qkv + H * D;
+      __half* v = r->qkv + (H + Hkv) * D;
+      launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
+                           w.k_cache, w.v_cache, B, H, Hkv, D, D, 0, c.cos_sin_f32, st);
+    }
     launch_paged_attn_decode(r->maps[l], r->attn, q, qkv_n, block_tables, context_lens, B, H, Hkv,
                              D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
     linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, B, H * D, c.hidden, B200_EPI_NONE,

@@ -23,6 +23,7 @@
 //     write fp16 output directly.
 //
 // Algorithmic bytes per launch: B * ctx * Hkv * D * 2 (K) * 2 (V) * 2 B  (+ q/out).
+#include <cstdlib>
 #include "../../include/b200_vllm.h"
 #include "attn.cuh"
 
@@ -343,16 +344,37 @@ paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ par
 struct SplitPlan {
   int pages_per_split, max_splits;
 };
+// Pages per split from a wave model: CTAs = batch * kv heads * ceil(max_blocks / p) run in
+// waves of 2 CTAs per SM, a CTA costs p pages plus about one page of fixed work (prologue,
+// partial store).  Picks the p that minimises waves * (p + 1): e.g. 32 x 8 x 65 pages on 148 SMs
+// -> p = 9 (8 splits, 6.9 waves) rather than p = 10 (7 splits, 6.05 -> 7 waves).
 static SplitPlan plan_splits(int batch, int num_kv_heads, int max_blocks) {
   const long slots = static_cast<long>(sm_count()) * 2;
-  const long total_pages = static_cast<long>(batch) * num_kv_heads * max_blocks;
-  long p = (total_pages + slots * 6 - 1) / (slots * 6);
-  if (p < 2) p = 2;
-  if (p > kMaxPagesPerSplit) p = kMaxPagesPerSplit;
-  if (p > max_blocks) p = max_blocks;
-  if (p < 1) p = 1;
+  const long heads = static_cast<long>(batch) * num_kv_heads;
+  int hi = max_blocks < kMaxPagesPerSplit ? max_blocks : kMaxPagesPerSplit;
+  if (hi < 1) hi = 1;
+  int lo = hi < 2 ? hi : 2;
+  // keep the partial buffers bounded: at most 64 splits per sequence
+  while ((max_blocks + lo - 1) / lo > 64 && lo < hi) ++lo;
+  long best_cost = -1;
+  int best_p = lo;
+  for (int p = lo; p <= hi; ++p) {
+    const long splits = (max_blocks + p - 1) / p;
+    const long ctas = heads * splits;
+    const long waves = (ctas + slots - 1) / slots;
+    const long cost = waves * (p + 1);
+    if (best_cost < 0 || cost <= best_cost) {      // ties: fewer, larger splits
+      best_cost = cost;
+      best_p = p;
+    }
+  }
+  {
+    static int force = -1;             // B200_ATTN_PPS: experiment override of pages per split
+    if (force < 0) { const char* e = getenv("B200_ATTN_PPS"); force = e ? atoi(e) : 0; }
+    if (force > 0) best_p = force < hi ? force : hi;
+  }
   SplitPlan r;
-  r.pages_per_split = static_cast<int>(p);
+  r.pages_per_split = best_p;
   r.max_splits = (max_blocks + r.pages_per_split - 1) / r.pages_per_split;
   return r;
 }

@@ -102,6 +102,8 @@ constexpr int kMaxSplitCols = 148 * 128 * 2;     // launchers keep splits * N be
 
 // internal epilogue kinds beyond the public B200_EPI_* flags (used by the fused decode plan)
 constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m] += sum x^2
+constexpr int kSsqStride = 32;    // floats between two rows' sums of squares: one 128 B line per row, so the
+                                  // finalisers' atomics spread over L2 slices instead of serialising on one line
 constexpr int kEpiRopeKv = 3;      // fused q|k|v: RoPE(q, k), K/V rows written to the paged cache
 
 // Everything the tile finaliser may fuse around a GEMM of the decoder layer
@@ -188,7 +190,7 @@ __device__ __forceinline__ void epi_row_prefetch(const SplitOut& o, const EpiCol
   r.e1 = 0.f;
   r.sl = -1;
   if (!valid) return;
-  if (fe.ssq_in) r.rs = __ldcg(fe.ssq_in + m);
+  if (fe.ssq_in) r.rs = __ldcg(fe.ssq_in + m * kSsqStride);
   if (EPI == kEpiResidNorm) {
     r.e0 = __half2float(__ldcg(fe.resid + static_cast<size_t>(m) * o.N + c.n0));
   } else if (EPI == kEpiRopeKv) {
@@ -232,7 +234,7 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
       sq = xf * xf;
     }
     sq = warp_sum(sq);
-    if (lane == 0 && valid) atomicAdd(fe.ssq_out + m, sq);
+    if (lane == 0 && valid) atomicAdd(fe.ssq_out + m * kSsqStride, sq);
   } else if (epi == kEpiRopeKv) {
     if (valid) {
       const int D = fe.D, hd = D >> 1;
@@ -329,13 +331,13 @@ __device__ __forceinline__ bool split_arrive(const SplitOut& o, int nt, int tid,
   // thread 0's acquire fence before the second barrier orders the readers' loads (ld.cg, no L1).
   named_bar_sync(bar_id, nthreads);
   if (tid == 0) {
-    __threadfence();
-    const unsigned old = atomicAdd(&o.counters[cidx], 1u);
+    // acq_rel RMW at gpu scope: releases this CTA's partials, acquires the others' (no
+    // sequentially-consistent fence needed: one location, one reader).  The self-reset only
+    // has to be visible to the NEXT launch, which the kernel boundary orders.
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(o.counters + cidx) : "memory");
     const int last = (old == target - 1) ? 1 : 0;
-    if (last) {
-      o.counters[cidx] = 0;                          // self-reset (graph replay safe)
-      __threadfence();
-    }
+    if (last) o.counters[cidx] = 0;                  // self-reset (graph replay safe)
     *s_flag = last;
   }
   named_bar_sync(bar_id, nthreads);

@@ -430,7 +430,7 @@ static bool launch_nt(const WnaParams& p, cudaStream_t st) {
   // a row scale (folded RMSNorm) on a plain GEMM has no lean kernel: the general kernel takes it
   if (p.epilogue == B200_EPI_NONE && p.fe && p.fe->ssq_in) return false;
   static int pipe = -1;
-  if (pipe < 0) { const char* e = getenv("B200_DEC_PIPE"); pipe = e ? atoi(e) : 0; }
+  if (pipe < 0) { const char* e = getenv("B200_DEC_PIPE"); pipe = e ? atoi(e) : 1; }
   if (pipe) {
     switch (p.epilogue) {
       case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, true>(p, st);
