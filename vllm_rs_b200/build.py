@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--expt-relaxed-constexpr",
     "-I", str(ROOT / "include"),
-]
+] + os.environ.get("B200_NVCC_EXTRA", "").split()   # e.g. -DB200_DEC_TRACE (tools/dec_trace.py)
 
 
 def sources() -> list[Path]:

@@ -24,6 +24,19 @@
 namespace b200 {
 namespace dec {
 
+#ifdef B200_DEC_TRACE
+// Pipeline trace (tools/dec_trace.py): SM clock of each role's events for CTA (0,0), one slot per
+// (event, chunk).  Compiled only with -DB200_DEC_TRACE; production builds carry none of it.
+__device__ uint32_t* g_dec_trace = nullptr;
+#define DEC_TR(ev, i)                                                                        \
+  do {                                                                                       \
+    if (g_dec_trace && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256)                      \
+      g_dec_trace[(ev) * 256 + (i)] = static_cast<uint32_t>(clock64());                      \
+  } while (0)
+#else
+#define DEC_TR(ev, i) do { } while (0)
+#endif
+
 constexpr int kGroups = 4;
 constexpr int kDqWarps = 16;
 constexpr int kDqThreads = kDqWarps * 32;
@@ -32,18 +45,25 @@ constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range
 
 template <int BITS, int NT>
 struct Cfg {
-  static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;
+  static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;            // one (tile, 64-K chunk)
   static constexpr int kXBytes = NT * kChunkK * 2;
-  static constexpr int kSW = BITS == 4 ? 16 : 8;
-  static constexpr int kSX = 8;
+  // Copies move SUPER-chunks of 4 consecutive K chunks (one per dequant group): the pipeline
+  // trace (tools/dec_trace.py) showed one producer thread needs ~400 cycles per copy it issues,
+  // which with 4 KB copies WAS the chunk period of the whole kernel.
+  static constexpr int kSuper = kGroups;
+  static constexpr int kWSBytes = kSuper * kWBytes;                       // 16 KB (4-bit) / 32 KB
+  static constexpr int kXSBytes = kSuper * kXBytes;
+  static constexpr int kSWS = 96 * 1024 / kWSBytes;                       // weight super-stages (96 KB)
+  static constexpr int kSXS = 3;                                          // activation super-stages
   static constexpr int kXOff = 0;
-  static constexpr int kWOff = kSX * kXBytes;
-  static constexpr int kScaleOff = kWOff + kSW * kWBytes;                 // [groups][128] fp16
-  static constexpr int kZeroOff = kScaleOff + kSZGroups * kTileN * 2;     // [groups][32] u32
+  static constexpr int kWOff = kSXS * kXSBytes;
+  static constexpr int kScaleOff = kWOff + kSWS * kWSBytes;               // [groups][128] fp16
+  static constexpr int kZeroOff = kScaleOff + kSZGroups * kTileN * 2;     // [groups][ZW] u32
   static constexpr int kBarOff = kZeroOff + kSZGroups * 32 * 4;
-  static constexpr int kNumBars = 2 * kSW + 2 * kSX + 2 * kGroups * 3 + kGroups + 1;
+  static constexpr int kNumBars = 2 * kSWS + 2 * kSXS + 2 * kGroups * 3 + kGroups + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kAlloc = kTmemPtrOff + 16 + 1024;
+  static_assert(kAlloc <= 227 * 1024, "shared memory budget");
   static constexpr int kDCols = NT < 32 ? 32 : NT;                        // per-group accumulator
   static constexpr int kAS = NT <= 32 ? 3 : 2;                            // A stages per group (32 columns each)
   static constexpr int kACol0 = kGroups * kDCols;
@@ -59,13 +79,15 @@ struct Args {
   __half* c;
   float* partials;
   uint32_t* counters;
-  int M, K, N, g_shift, qfmt, chunks_per_split, splits, epilogue;   // g_shift: log2(group_size), -1 = one group
+  int M, K, N, g_shift, qfmt, chunks_per_split, splits, epilogue;
+  int sz_rows;   // quantisation-group rows in the scale / zero TMA boxes   // g_shift: log2(group_size), -1 = one group
   FusedEpi fe;
 };
 
-template <int BITS, int NT, int EPI, bool PIPE>
+template <int BITS, int NT, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap smap,
+                    const __grid_constant__ CUtensorMap zmap, const Args a) {
   using C = Cfg<BITS, NT>;
   const int nt = blockIdx.x, split = blockIdx.y;
   const int KC = a.K / kChunkK;
@@ -80,10 +102,10 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
                                              ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
   uint64_t* wfull = bars;
-  uint64_t* wempty = wfull + C::kSW;
-  uint64_t* xfull = wempty + C::kSW;
-  uint64_t* xempty = xfull + C::kSX;
-  uint64_t* afree = xempty + C::kSX;                 // [group][stage]
+  uint64_t* wempty = wfull + C::kSWS;
+  uint64_t* xfull = wempty + C::kSWS;
+  uint64_t* xempty = xfull + C::kSXS;
+  uint64_t* afree = xempty + C::kSXS;                 // [group][stage]
   constexpr int kAS = C::kAS;
   uint64_t* gdone = afree + kGroups * kAS;           // [group]
   uint64_t* szfull = gdone + kGroups;
@@ -94,18 +116,16 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   __shared__ int s_is_last;
 
   const int g_first = a.g_shift >= 0 ? (c0 * kChunkK) >> a.g_shift : 0;
-  const int g_last = a.g_shift >= 0 ? (c1 * kChunkK - 1) >> a.g_shift : 0;
-  const int ngroups = g_last - g_first + 1;
   constexpr int ZW = kTileN * BITS / 32;             // zero-point words per tile row (16 / 32)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::kSW; ++i) {
+    for (int i = 0; i < C::kSWS; ++i) {
       mbar_init(&wfull[i], 1);
-      mbar_init(&wempty[i], 4);
+      mbar_init(&wempty[i], kDqWarps);             // every dequant warp read its quarter
     }
-    for (int i = 0; i < C::kSX; ++i) {
+    for (int i = 0; i < C::kSXS; ++i) {
       mbar_init(&xfull[i], 1);
-      mbar_init(&xempty[i], 1);
+      mbar_init(&xempty[i], kGroups);              // one commit per chunk of the super-chunk
     }
     for (int i = 0; i < kGroups * kAS; ++i) mbar_init(&afree[i], 1);
     for (int i = 0; i < kGroups; ++i) mbar_init(&gdone[i], 1);
@@ -117,7 +137,11 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     tmem_alloc(tmem_ptr, C::kTmemCols);
     tmem_relinquish();
   }
-  if (warp == kDqWarps + 1 && lane == 0) prefetch_tmap(&xmap);
+  if (warp == kDqWarps + 1 && lane == 0) {
+    prefetch_tmap(&xmap);
+    prefetch_tmap(&smap);
+    prefetch_tmap(&zmap);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,35 +151,36 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   if (warp == kDqWarps) {
     // ------------------------------------------------------------ weight / scale producer
     if (lane == 0) {
+      // scales / zero points of the CTA's K range: one 2-D TMA box each ([groups][128 channels])
       const uint32_t zbytes = a.qzeros ? ZW * 4 : 0;
-      mbar_arrive_expect_tx(szfull, static_cast<uint32_t>(ngroups) * (kTileN * 2 + zbytes));
-      for (int g = 0; g < ngroups; ++g) {
-        bulk_load_1d(smem + C::kScaleOff + g * kTileN * 2,
-                     a.scales + static_cast<size_t>(g_first + g) * N + nt * kTileN, kTileN * 2, szfull);
-        if (a.qzeros)
-          bulk_load_1d(smem + C::kZeroOff + g * 128,
-                       a.qzeros + static_cast<size_t>(g_first + g) * (N * BITS / 32) + nt * ZW, zbytes,
-                       szfull);
-      }
+      mbar_arrive_expect_tx(szfull, static_cast<uint32_t>(a.sz_rows) * (kTileN * 2 + zbytes));
+      tma_load_2d(smem + C::kScaleOff, &smap, szfull, nt * kTileN, g_first);
+      if (a.qzeros) tma_load_2d(smem + C::kZeroOff, &zmap, szfull, nt * ZW, g_first);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a.bp) +
                            (static_cast<size_t>(nt) * KC + c0) * C::kWBytes;
-      for (int i = 0; i < nchunks; ++i) {
-        const int sw = i % C::kSW;
-        mbar_wait(&wempty[sw], ((i / C::kSW) & 1) ^ 1);
-        mbar_arrive_expect_tx(&wfull[sw], C::kWBytes);
-        bulk_load_1d(smem + C::kWOff + sw * C::kWBytes, src + static_cast<size_t>(i) * C::kWBytes,
-                     C::kWBytes, &wfull[sw]);
+      const int nsuper = (nchunks + C::kSuper - 1) / C::kSuper;
+      for (int j = 0; j < nsuper; ++j) {
+        const int ss = j % C::kSWS;
+        mbar_wait(&wempty[ss], ((j / C::kSWS) & 1) ^ 1);
+        const int left = nchunks - j * C::kSuper;
+        const uint32_t bytes = (left < C::kSuper ? left : C::kSuper) * C::kWBytes;
+        DEC_TR(0, j * C::kSuper);
+        mbar_arrive_expect_tx(&wfull[ss], bytes);
+        bulk_load_1d(smem + C::kWOff + ss * C::kWSBytes, src + static_cast<size_t>(j) * C::kWSBytes, bytes,
+                     &wfull[ss]);
       }
     }
   } else if (warp == kDqWarps + 1) {
     // ------------------------------------------------------------ activation producer
     if (lane == 0) {
       pdl_wait();      // activations are the previous kernel's output; weights are not
-      for (int i = 0; i < nchunks; ++i) {
-        const int sx = i % C::kSX;
-        mbar_wait(&xempty[sx], ((i / C::kSX) & 1) ^ 1);
-        mbar_arrive_expect_tx(&xfull[sx], C::kXBytes);
-        tma_load_2d(smem + C::kXOff + sx * C::kXBytes, &xmap, &xfull[sx], (c0 + i) * kChunkK, 0);
+      const int nsuper = (nchunks + C::kSuper - 1) / C::kSuper;
+      for (int j = 0; j < nsuper; ++j) {
+        const int xs = j % C::kSXS;
+        mbar_wait(&xempty[xs], ((j / C::kSXS) & 1) ^ 1);
+        DEC_TR(6, j * C::kSuper);
+        mbar_arrive_expect_tx(&xfull[xs], C::kXSBytes);       // TMA zero-fills rows >= M / chunks >= KC
+        tma_load_3d(smem + C::kXOff + xs * C::kXSBytes, &xmap, &xfull[xs], 0, 0, c0 + j * C::kSuper);
       }
     }
   } else if (warp >= kDqWarps + 2) {
@@ -170,17 +195,20 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       int it = 0;
       for (int i = grp; i < nchunks; i += kGroups, ++it) {
         const int as = grp * kAS + (it % kAS);
-        const int sx = i % C::kSX;
+        const int xs = it % C::kSXS;                 // chunk i = 4 * it + grp: slot grp of super-chunk it
+        DEC_TR(7, i);
         mbar_wait(&stored[as], (it / kAS) & 1);
-        mbar_wait(&xfull[sx], (i / C::kSX) & 1);
+        mbar_wait(&xfull[xs], (it / C::kSXS) & 1);
         tc_fence_after();
+        DEC_TR(5, i);
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + C::kXOff + sx * C::kXBytes));
+        const uint64_t bdesc =
+            make_smem_desc_sw128(smem_u32(smem + C::kXOff + xs * C::kXSBytes + grp * C::kXBytes));
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
           tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
                     (it > 0 || ks > 0) ? 1u : 0u);
-        tc_commit(&xempty[sx]);
+        tc_commit(&xempty[xs]);
         tc_commit(&afree[as]);
         if (i + kGroups >= nchunks) tc_commit(&gdone[grp]);      // the group's last chunk
       }
@@ -211,24 +239,24 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     auto bar_arrive = [](uint32_t bar) {
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
     };
-    static_assert((C::kSW & (C::kSW - 1)) == 0 && C::kSW % kGroups == 0, "weight ring: power of two");
-    int sw = grp;                       // weight stage of the group's current chunk (i % kSW)
-    uint32_t sw_phase = 0;
-    auto load_words = [&](uint32_t (&dst)[W]) {
-      bar_wait(s_wfull + sw * 8, sw_phase);
-      const uint32_t addr = s_base + C::kWOff + sw * C::kWBytes + ch * 16;
+    int ss = 0;                         // weight super-stage of the group's current chunk
+    uint32_t ss_phase = 0;
+    auto load_words = [&](uint32_t (&dst)[W], int ci) {
+      if (q4 == 0 && lane == 0) DEC_TR(1, ci);
+      bar_wait(s_wfull + ss * 8, ss_phase);
+      if (q4 == 0 && lane == 0) DEC_TR(2, ci);
+      const uint32_t addr = s_base + C::kWOff + ss * C::kWSBytes + grp * C::kWBytes + ch * 16;
 #pragma unroll
       for (int sub = 0; sub < W / 4; ++sub)
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(dst[sub * 4]), "=r"(dst[sub * 4 + 1]), "=r"(dst[sub * 4 + 2]), "=r"(dst[sub * 4 + 3])
                      : "r"(addr + sub * kTileN * 16));
       __syncwarp();
-      if (lane == 0) bar_arrive(s_wempty + sw * 8);   // packed bytes are in registers
-      sw += kGroups;
-      if (sw >= C::kSW) { sw -= C::kSW; sw_phase ^= 1; }
+      if (lane == 0) bar_arrive(s_wempty + ss * 8);   // packed bytes are in registers
+      if (++ss == C::kSWS) { ss = 0; ss_phase ^= 1; }
     };
     uint32_t cur[W];
-    if (grp < nchunks) load_words(cur);
+    if (grp < nchunks) load_words(cur, grp);
     mbar_wait(szfull, 0);
     int cur_g = -1;
     DqConst dq = make_dq(__float2half(0.f), 0);
@@ -246,7 +274,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         int z = 1 << (BITS - 1);
         if (a.qzeros) {
           uint32_t zw;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * 128));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * (ZW * 4)));
           z = static_cast<int>((zw >> zshift) & zmask) + zadd;
         }
         dq = make_dq(__ushort_as_half(sbits), z);
@@ -269,26 +297,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         }
       }
     };
-    if (!PIPE) {
-      for (int i = grp; i < nchunks; i += kGroups) {
-        uint32_t lo[16], hi[16];
-        dequant_half(i, 0, lo);
-        dequant_half(i, 1, hi);
-        // `cur` is consumed: fetch the group's next chunk now, its latency hides under the stores
-        if (i + kGroups < nchunks) load_words(cur);
-        const int as = grp * kAS + as_l;
-        const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-        bar_wait(s_afree + as * 8, as_phase);             // this group's MMA of chunk it - kAS retired
-        tc_fence_after();
-        tmem_st_x16(a_tmem + lane_base, lo);
-        tmem_st_x16(a_tmem + lane_base + 16, hi);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) bar_arrive(s_stored + as * 8);     // -> the group's issuer warp
-        if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
-      }
-    } else {
+    {
       // Deferred completion: the TMEM stores of chunk i are awaited (and the issuer signalled)
       // only after the first half of chunk i+1 has been dequantised, so tcgen05.st latency
       // overlaps ALU work instead of idling the warp.
@@ -301,14 +310,16 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(s_stored + pending_as * 8);
+          if (q4 == 0 && lane == 0) DEC_TR(4, i - kGroups);
         }
         const int as = grp * kAS + as_l;
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
         bar_wait(s_afree + as * 8, as_phase);
         tc_fence_after();
+        if (q4 == 0 && lane == 0) DEC_TR(3, i);
         tmem_st_x16(a_tmem + lane_base, lo);
         dequant_half(i, 1, hi);
-        if (i + kGroups < nchunks) load_words(cur);
+        if (i + kGroups < nchunks) load_words(cur, i + kGroups);
         tmem_st_x16(a_tmem + lane_base + 16, hi);
         pending_as = as;
         if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
@@ -379,20 +390,9 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   }
 }
 
-template <int BITS, int NT, int EPI, bool PIPE>
+template <int BITS, int NT, int EPI>
 static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   using C = Cfg<BITS, NT>;
-  CUtensorMap xmap;
-  const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
-  const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
-  const uint32_t box[2] = {kChunkK, static_cast<uint32_t>(NT)};
-  const uint32_t es[2] = {1, 1};
-  if (encode_tensor_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.a), dims,
-                        strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS) {
-    set_error(2, "wna16_tc_dec: cuTensorMapEncodeTiled failed");
-    return true;
-  }
   const int KC = p.K / kChunkK;
   const int tiles = p.N / kTileN;
   int splits = sm_count() / tiles;
@@ -402,25 +402,72 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   if (p.no_split) splits = 1;
   int cps = (KC + splits - 1) / splits;
   splits = (KC + cps - 1) / cps;
+  const bool grouped = p.group_size < p.K;
+  const int total_groups = grouped ? p.K / p.group_size : 1;
+  int sz_rows = grouped ? (cps * kChunkK + p.group_size - 1) / p.group_size + 1 : 1;
+  if (sz_rows > kSZGroups) sz_rows = kSZGroups;
+  // activations as a 3-D tensor {64 K elements, M rows, K/64 chunks}: one TMA box brings 4 chunks,
+  // each landing as its own [NT rows][128 B] swizzled tile (the MMA B operand of one chunk)
+  CUtensorMap xmap, smap, zmap;
+  {
+    const uint64_t dims[3] = {kChunkK, static_cast<uint64_t>(p.M), static_cast<uint64_t>(KC)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(p.K) * 2, kChunkK * 2};
+    const uint32_t box[3] = {kChunkK, static_cast<uint32_t>(NT), static_cast<uint32_t>(C::kSuper)};
+    const uint32_t es[3] = {1, 1, 1};
+    if (encode_tensor_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(p.a), dims,
+                          strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS) {
+      set_error(2, "wna16_tc_dec: cuTensorMapEncodeTiled (activations) failed");
+      return true;
+    }
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(total_groups)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(p.N) * 2};
+    const uint32_t box[2] = {kTileN, static_cast<uint32_t>(sz_rows)};
+    const uint32_t es[2] = {1, 1};
+    if (encode_tensor_map(&smap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.scales), dims,
+                          strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B) != CUDA_SUCCESS) {
+      set_error(2, "wna16_tc_dec: cuTensorMapEncodeTiled (scales) failed");
+      return true;
+    }
+  }
+  zmap = smap;
+  if (p.qzeros) {
+    constexpr int ZW = kTileN * BITS / 32;
+    const uint64_t zcols = static_cast<uint64_t>(p.N) * BITS / 32;
+    const uint64_t dims[2] = {zcols, static_cast<uint64_t>(total_groups)};
+    const uint64_t strides[1] = {zcols * 4};
+    const uint32_t box[2] = {ZW, static_cast<uint32_t>(sz_rows)};
+    const uint32_t es[2] = {1, 1};
+    if (encode_tensor_map(&zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(p.qzeros), dims,
+                          strides, box, es, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B) != CUDA_SUCCESS) {
+      set_error(2, "wna16_tc_dec: cuTensorMapEncodeTiled (zero points) failed");
+      return true;
+    }
+  }
   Args a;
   a.bp = p.bp; a.scales = p.scales; a.qzeros = p.qzeros; a.bias = p.bias; a.c = p.c;
   a.counters = reinterpret_cast<uint32_t*>(p.workspace);
   a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
   a.M = p.M; a.K = p.K; a.N = p.N; a.qfmt = p.qfmt;
   a.g_shift = -1;
-  if (p.group_size < p.K)
+  if (grouped)
     for (int s = 5; s < 31; ++s)
       if ((1 << s) == p.group_size) a.g_shift = s;
   a.chunks_per_split = cps; a.splits = splits; a.epilogue = p.epilogue;
+  a.sz_rows = sz_rows;
   if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT, EPI, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(wna16_tc_dec_kernel<BITS, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          C::kAlloc);
     attr_set = true;
   }
-  launch_pdl(wna16_tc_dec_kernel<BITS, NT, EPI, PIPE>, dim3(tiles, splits, 1), dim3(kThreads), C::kAlloc, st,
-             xmap, a);
+  launch_pdl(wna16_tc_dec_kernel<BITS, NT, EPI>, dim3(tiles, splits, 1), dim3(kThreads), C::kAlloc, st,
+             xmap, smap, zmap, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
 }
@@ -429,25 +476,22 @@ template <int BITS, int NT>
 static bool launch_nt(const WnaParams& p, cudaStream_t st) {
   // a row scale (folded RMSNorm) on a plain GEMM has no lean kernel: the general kernel takes it
   if (p.epilogue == B200_EPI_NONE && p.fe && p.fe->ssq_in) return false;
-  static int pipe = -1;
-  if (pipe < 0) { const char* e = getenv("B200_DEC_PIPE"); pipe = e ? atoi(e) : 1; }
-  if (pipe) {
-    switch (p.epilogue) {
-      case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, true>(p, st);
-      case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm, true>(p, st);
-      case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv, true>(p, st);
-      default: return launch_epi<BITS, NT, B200_EPI_NONE, true>(p, st);
-    }
-  }
   switch (p.epilogue) {
-    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, false>(p, st);
-    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm, false>(p, st);
-    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv, false>(p, st);
-    default: return launch_epi<BITS, NT, B200_EPI_NONE, false>(p, st);
+    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL>(p, st);
+    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm>(p, st);
+    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv>(p, st);
+    default: return launch_epi<BITS, NT, B200_EPI_NONE>(p, st);
   }
 }
 
 }  // namespace dec
+
+#ifdef B200_DEC_TRACE
+extern "C" void b200_debug_set_dec_trace(void* buf) {
+  uint32_t* p = static_cast<uint32_t*>(buf);
+  cudaMemcpyToSymbol(dec::g_dec_trace, &p, sizeof(p));
+}
+#endif
 
 // Decode-shape entry: false when the shape needs the general kernel (wna16_tc.cu).
 bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
