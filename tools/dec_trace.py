@@ -19,7 +19,7 @@ layers = [synthetic._fused_awq_device(gen, K, [N], 128, dev) for _ in range(copi
 x = torch.randn(M, K, device=dev, dtype=torch.float16)
 y = torch.empty(M, N // 2 if epi else N, device=dev, dtype=torch.float16)
 ws = ops.wna16_workspace(max(M, 16), 28672)
-tr = torch.zeros(8 * 256, device=dev, dtype=torch.int32)
+tr = torch.zeros(16 * 256, device=dev, dtype=torch.int32)
 def run(i):
     l = layers[i % copies]
     ops.wna16_gemm(x, l.w, l.s, l.z, ws, k=K, n=N, epilogue=epi, out=y)
@@ -28,12 +28,16 @@ torch.cuda.synchronize()
 lib.b200_debug_set_dec_trace(ctypes.c_void_p(tr.data_ptr()))
 for i in range(copies): run(i)          # back to back: the traced launch follows a warm pipeline
 torch.cuda.synchronize()
-t = tr.cpu().view(8, 256).numpy().astype("int64") & 0xFFFFFFFF
-nz = t[t > 0]
+t = tr.cpu().view(16, 256).numpy().astype("int64") & 0xFFFFFFFF
+nz = t[:8][t[:8] > 0]
 t0 = nz.min()
 names = ["w_issue", "dq_wait", "dq_got", "dq_store", "dq_arrive", "mma_issue", "x_issue", "mma_wait"]
-nch = int((t[0] > 0).sum())
+nch = int((t[2] > 0).sum())
 print(f"{name} M={M}: {nch} chunks in CTA (0,0); times in cycles since first event")
 print("chunk " + " ".join(f"{n:>10s}" for n in names))
 for i in range(nch):
     print(f"{i:5d} " + " ".join(f"{(t[e][i] - t0) if t[e][i] else -1:10d}" for e in range(8)))
+print("epilogue of tile 0 per split: start, accumulators complete, partials stored, arrived, reduced (last only), exit")
+for sp in range(8):
+    if t[8 + sp][0]:
+        print(f"split {sp}: " + " ".join(f"{(t[8 + sp][k] - t0) if t[8 + sp][k] else -1:9d}" for k in range(6)))

@@ -201,15 +201,15 @@ static void linear_fused(b200_runner* r, const __half* in, const void* w, const 
   launch_wna16_gemv(p, st);
 }
 
-// B200_FUSED: 2 (default) = classic plan with RoPE + KV write folded into the qkv finaliser,
-// 1 = fully fused plan (RMSNorms folded into the GEMM finalisers too; measured 0.3 ms / step SLOWER
-// on Llama-3-8B b=32: the residual/norm finaliser lengthens every o/down GEMM tail by more than
-// the two norm kernels cost), 0 = classic plan.
+// B200_FUSED: 1 (default) = fully fused plan (RMSNorms folded into the GEMM finalisers, RoPE + KV
+// write in the qkv finaliser: 6 launches per layer), 2 = classic plan with only the RoPE + KV write
+// folded into the qkv finaliser, 0 = classic plan (9 launches per layer).  Llama-3-8B b=32 ctx=4096:
+// 5.19 / 5.29 / 5.33 ms per step.
 static int fused_env() {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("B200_FUSED");
-    env = e ? atoi(e) : 2;
+    env = e ? atoi(e) : 1;
   }
   return env;
 }

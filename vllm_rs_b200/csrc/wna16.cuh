@@ -144,17 +144,33 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---- tile epilogue, shared by the global-memory finaliser below and the cluster (DSMEM)
-// reducer of wna16_tc_dec.cu.  One thread = one output channel of the 128-wide tile.
+// ---- tile finaliser.  A thread owns FOUR consecutive output channels of the 128-wide tile
+// (one 16-byte load per split and row) and a warp owns whole rows: the partials of a row come in
+// as 32 x float4, the sum of squares of a row is one warp reduction and one atomic.
 struct EpiCol {
-  int n0, n1;          // column this thread sums, partner column (up-projection / RoPE pair) or -1
+  int n0, n1;          // first of the 4 columns this thread sums, partner columns (up-projection /
+                       // RoPE pair) or -1
   bool pair, kv_col, silu;
-  float b0, b1, nw;
+  float b0[4], b1[4], nw[4];
 };
 struct EpiRow {        // per-row operands that do not depend on the sums (requested early)
-  float rs, e0, e1;
+  float rs;
+  float e0[4], e1[4];
   int sl;
+  int64_t pos;
 };
+
+__device__ __forceinline__ void half4_to_float(const void* p, float (&f)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 lo = __half22float2(u32_as_h2(u.x)), hi = __half22float2(u32_as_h2(u.y));
+  f[0] = lo.x; f[1] = lo.y; f[2] = hi.x; f[3] = hi.y;
+}
+__device__ __forceinline__ void store_half4(void* p, const float (&f)[4]) {
+  uint2 u;
+  u.x = h2_as_u32(__floats2half2_rn(f[0], f[1]));
+  u.y = h2_as_u32(__floats2half2_rn(f[2], f[3]));
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
 template <int EPI>
 __device__ __forceinline__ EpiCol epi_col(const SplitOut& o, int nt, int ch) {
@@ -175,9 +191,17 @@ __device__ __forceinline__ EpiCol epi_col(const SplitOut& o, int nt, int ch) {
   }
   c.pair = c.n1 >= 0;
   c.kv_col = EPI == kEpiRopeKv && c.n0 >= fe.H * fe.D;
-  c.b0 = o.bias ? __half2float(o.bias[c.n0]) : 0.f;
-  c.b1 = (o.bias && c.pair) ? __half2float(o.bias[c.n1]) : 0.f;
-  c.nw = EPI == kEpiResidNorm ? __half2float(fe.norm_w[c.n0]) : 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    c.b0[e] = 0.f;
+    c.b1[e] = 0.f;
+    c.nw[e] = 0.f;
+  }
+  if (o.bias) {
+    half4_to_float(o.bias + c.n0, c.b0);
+    if (c.pair) half4_to_float(o.bias + c.n1, c.b1);
+  }
+  if (EPI == kEpiResidNorm) half4_to_float(fe.norm_w + c.n0, c.nw);
   return c;
 }
 
@@ -186,52 +210,78 @@ __device__ __forceinline__ void epi_row_prefetch(const SplitOut& o, const EpiCol
                                                  EpiRow& r) {
   const FusedEpi& fe = o.fe;
   r.rs = 0.f;
-  r.e0 = 0.f;
-  r.e1 = 0.f;
   r.sl = -1;
+  r.pos = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    r.e0[e] = 0.f;
+    r.e1[e] = 0.f;
+  }
   if (!valid) return;
-  if (fe.ssq_in) r.rs = __ldcg(fe.ssq_in + m * kSsqStride);
+  if (fe.ssq_in) r.rs = fe.ssq_in[m * kSsqStride];
   if (EPI == kEpiResidNorm) {
-    r.e0 = __half2float(__ldcg(fe.resid + static_cast<size_t>(m) * o.N + c.n0));
+    half4_to_float(fe.resid + static_cast<size_t>(m) * o.N + c.n0, r.e0);
   } else if (EPI == kEpiRopeKv) {
-    if (c.pair) {
-      const int hd = fe.D >> 1;
-      const int d = c.n0 % fe.D;
-      const size_t ci = static_cast<size_t>(fe.positions[m]) * hd + (d < hd ? d : d - hd);
-      r.e0 = __half2float(fe.cos[ci]);
-      r.e1 = __half2float(fe.sin[ci]);
-    }
+    if (c.pair) r.pos = fe.positions[m];
     if (c.kv_col) r.sl = static_cast<int>(fe.slots[m]);
   }
 }
+// second wave of operand loads: those whose address depends on a first-wave value (cos / sin rows
+// of the token's position).  Issued after the partial loads so the two latencies overlap.
+template <int EPI>
+__device__ __forceinline__ void epi_row_prefetch2(const SplitOut& o, const EpiCol& c, bool valid, EpiRow& r) {
+  if (EPI != kEpiRopeKv) return;
+  const FusedEpi& fe = o.fe;
+  if (valid && c.pair) {
+    const int hd = fe.D >> 1;
+    const int d = c.n0 % fe.D;
+    const size_t ci = static_cast<size_t>(r.pos) * hd + (d < hd ? d : d - hd);
+    half4_to_float(fe.cos + ci, r.e0);
+    half4_to_float(fe.sin + ci, r.e1);
+  }
+}
 
-// a0 / a1: fp32 sums of the thread's column / partner column for row m.  Must be called by whole
-// warps with a warp-uniform m (the sum-of-squares path reduces across the warp).
+// a0 / a1: fp32 sums of the thread's 4 columns / partner columns for row m.  Called by whole
+// warps with a warp-uniform m (the sum-of-squares path reduces across the warp = the tile row).
 template <int EPI>
 __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c, int m, bool valid,
-                                              float a0, float a1, const EpiRow& r, int lane) {
+                                              const float (&a0)[4], const float (&a1)[4],
+                                              const EpiRow& r, int lane) {
   const FusedEpi& fe = o.fe;
   const int N = o.N;
   constexpr int epi = EPI;
   const float scale = fe.ssq_in ? rsqrtf(r.rs * fe.inv_dim + fe.eps) : 1.f;
-  const float v0 = a0 * scale + c.b0, v1 = a1 * scale + c.b1;
+  float v0[4], v1[4], out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v0[e] = a0[e] * scale + c.b0[e];
+    v1[e] = a1[e] * scale + c.b1[e];
+  }
   if (c.silu) {
     if (valid) {
-      // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
-      const float gg = __half2float(__float2half_rn(v0));
-      const float uu = __half2float(__float2half_rn(v1));
-      o.c[static_cast<size_t>(m) * (N >> 1) + c.n0] = __float2half_rn(gg / (1.f + __expf(-gg)) * uu);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // round the two GEMM outputs to fp16 first: the values an unfused pipeline would see
+        const float gg = __half2float(__float2half_rn(v0[e]));
+        const float uu = __half2float(__float2half_rn(v1[e]));
+        out[e] = gg / (1.f + __expf(-gg)) * uu;
+      }
+      store_half4(o.c + static_cast<size_t>(m) * (N >> 1) + c.n0, out);
     }
   } else if (epi == kEpiResidNorm) {
     float sq = 0.f;
     if (valid) {
       const size_t idx = static_cast<size_t>(m) * N + c.n0;
-      // llama.rs:126-130: the GEMM output is fp16, the residual add is done in fp16
-      const __half xn = __float2half_rn(r.e0 + __half2float(__float2half_rn(v0)));
-      fe.resid[idx] = xn;
-      const float xf = __half2float(xn);
-      o.c[idx] = __float2half_rn(xf * c.nw);
-      sq = xf * xf;
+      float xn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // llama.rs:126-130: the GEMM output is fp16, the residual add is done in fp16
+        xn[e] = __half2float(__float2half_rn(r.e0[e] + __half2float(__float2half_rn(v0[e]))));
+        out[e] = xn[e] * c.nw[e];
+        sq += xn[e] * xn[e];
+      }
+      store_half4(fe.resid + idx, xn);
+      store_half4(o.c + idx, out);
     }
     sq = warp_sum(sq);
     if (lane == 0 && valid) atomicAdd(fe.ssq_out + m * kSsqStride, sq);
@@ -239,82 +289,94 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
     if (valid) {
       const int D = fe.D, hd = D >> 1;
       const int hh = c.n0 / D, d = c.n0 - hh * D;
-      float outv = v0;
-      if (c.pair) {
-        // the reference rotates the fp16 GEMM outputs (rotary_emb.rs:88-104)
-        const float x0 = __half2float(__float2half_rn(v0)), x1 = __half2float(__float2half_rn(v1));
-        outv = d < hd ? x0 * r.e0 - x1 * r.e1 : x0 * r.e0 + x1 * r.e1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        out[e] = v0[e];
+        if (c.pair) {
+          // the reference rotates the fp16 GEMM outputs (rotary_emb.rs:88-104)
+          const float x0 = __half2float(__float2half_rn(v0[e])), x1 = __half2float(__float2half_rn(v1[e]));
+          out[e] = d < hd ? x0 * r.e0[e] - x1 * r.e1[e] : x0 * r.e0[e] + x1 * r.e1[e];
+        }
       }
-      const __half h16 = __float2half_rn(outv);
       if (!c.kv_col) {
-        o.c[static_cast<size_t>(m) * N + c.n0] = h16;                 // q stays in the fused buffer
+        store_half4(o.c + static_cast<size_t>(m) * N + c.n0, out);       // q stays in the fused buffer
       } else if (r.sl >= 0) {
         const bool is_k = hh < fe.H + fe.Hkv;
         __half* cache = is_k ? fe.k_cache : fe.v_cache;
         const int kvh = hh - fe.H - (is_k ? 0 : fe.Hkv);
-        cache[(static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d] = h16;
+        store_half4(cache + (static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d, out);
       }
     }
   } else if (valid) {
-    o.c[static_cast<size_t>(m) * N + c.n0] = __float2half_rn(v0);
+    store_half4(o.c + static_cast<size_t>(m) * N + c.n0, v0);
   }
 }
 
 // Rows [m_lo, m_hi) of tile nt: sum the partials in split order (deterministic) and apply the
-// epilogue.  tid % 128 = channel, tid / 128 = row phase.
+// epilogue.  lane = 4 channels, warp = row phase.  ALL loads of a batch (2 rows x up to 4 splits
+// x float4) are issued before the first add: an in-order warp that meets a dependent add between
+// two loads pays an L2 round trip per add -- the previous scalar version took 3 us for 32 loads,
+// the longest piece of every GEMM's serial tail (tools/dec_trace.py).
 template <int EPI>
 __device__ __forceinline__ void split_reduce_rows(const SplitOut& o, int nt, int tid, int nthreads,
                                                   int m_lo, int m_hi) {
   const int N = o.N, M = o.M;
-  const int ch = tid & 127, phase = tid >> 7, nphase = nthreads >> 7;
-  constexpr int R = 8;                               // rows in flight per thread
-  const size_t row_stride = static_cast<size_t>(nphase) * N;
-  const EpiCol c = epi_col<EPI>(o, nt, ch);
+  const int lane = tid & 31, phase = tid >> 5, nphase = nthreads >> 5;
+  constexpr int R = 2;                                 // rows in flight per thread
+  constexpr bool kMayPair = EPI == B200_EPI_SILU_MUL || EPI == kEpiRopeKv;
+  constexpr int U = kMayPair ? 2 : 4;                  // splits per load batch
+  const EpiCol c = epi_col<EPI>(o, nt, lane * 4);
+  const size_t split_stride = static_cast<size_t>(M) * N;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int mb = m_lo + phase; mb < m_hi; mb += R * nphase) {
-    float a0[R], a1[R];
+    float a0[R][4], a1[R][4];
     EpiRow er[R];
-    // (1) every operand of the epilogue that does not depend on the sums is requested FIRST, so
-    // its L2 round trips overlap the partial loads instead of following them (the finaliser is
-    // the serial tail of every GEMM: each extra dependent round trip costs ~1 us per layer GEMM)
+    // (1) operands of the epilogue that do not depend on the sums are requested first
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-      a0[j] = 0.f;
-      a1[j] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a0[j][e] = 0.f;
+        a1[j][e] = 0.f;
+      }
       epi_row_prefetch<EPI>(o, c, mb + j * nphase, mb + j * nphase < m_hi, er[j]);
     }
-    // (2) the partials, split order (deterministic), several splits x 8 rows of loads in flight
-    const float* p0 = o.partials + static_cast<size_t>(mb) * N;
-    const size_t split_stride = static_cast<size_t>(M) * N;
-    if (c.pair) {
-#pragma unroll 2
-      for (int s = 0; s < o.splits; ++s) {
-        const float* p = p0 + s * split_stride;
+    // (2) the partials: load a whole batch, then add in split order
+    for (int s0 = 0; s0 < o.splits; s0 += U) {
+      float4 v0[U][R], v1[U][R];
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (mb + j * nphase < m_hi) {
-            a0[j] += __ldcg(p + j * row_stride + c.n0);
-            a1[j] += __ldcg(p + j * row_stride + c.n1);
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int m = mb + j * nphase;
+          const bool ok = (s0 + u < o.splits) && (m < m_hi);
+          const float* row = o.partials + (s0 + u) * split_stride + static_cast<size_t>(m) * N;
+          v0[u][j] = ok ? *reinterpret_cast<const float4*>(row + c.n0) : zero4;
+          if (kMayPair) v1[u][j] = (ok && c.pair) ? *reinterpret_cast<const float4*>(row + c.n1) : zero4;
+        }
+      if (s0 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) epi_row_prefetch2<EPI>(o, c, mb + j * nphase < m_hi, er[j]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          a0[j][0] += v0[u][j].x; a0[j][1] += v0[u][j].y; a0[j][2] += v0[u][j].z; a0[j][3] += v0[u][j].w;
+          if (kMayPair) {
+            a1[j][0] += v1[u][j].x; a1[j][1] += v1[u][j].y; a1[j][2] += v1[u][j].z; a1[j][3] += v1[u][j].w;
           }
-      }
-    } else {
-#pragma unroll 4
-      for (int s = 0; s < o.splits; ++s) {
-        const float* p = p0 + s * split_stride + c.n0;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (mb + j * nphase < m_hi) a0[j] += __ldcg(p + j * row_stride);
-      }
+        }
     }
     // (3) epilogue (m is warp-uniform: a warp shares its row phase)
 #pragma unroll
     for (int j = 0; j < R; ++j)
-      epi_row_apply<EPI>(o, c, mb + j * nphase, mb + j * nphase < m_hi, a0[j], a1[j], er[j], tid & 31);
+      epi_row_apply<EPI>(o, c, mb + j * nphase, mb + j * nphase < m_hi, a0[j], a1[j], er[j], lane);
   }
 }
 
-
 // Called by `nthreads` (128 or 512) threads of a CTA AFTER the partials of rows [m_lo, m_hi) of
-// tile `nt` were stored.  tid % 128 = channel, tid / 128 = row phase.  The last CTA to arrive for
+// tile `nt` were stored.  The last CTA to arrive for
 // the tile (or, with SILU_MUL, for the gate/up tile pair) sums the partials in split order --
 // deterministic -- and applies the epilogue.  Loads of 8 rows are issued together so the L2
 // latency is paid `splits` times, not M * splits.  `s_flag` is a shared int; `counter_base`

@@ -33,8 +33,15 @@ __device__ uint32_t* g_dec_trace = nullptr;
     if (g_dec_trace && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256)                      \
       g_dec_trace[(ev) * 256 + (i)] = static_cast<uint32_t>(clock64());                      \
   } while (0)
+// epilogue events of tile 0, one row per split: row 8 + blockIdx.y, column = event id
+#define DEC_TRE(k)                                                                           \
+  do {                                                                                       \
+    if (g_dec_trace && blockIdx.x == 0 && blockIdx.y < 8 && threadIdx.x == 0)               \
+      g_dec_trace[(8 + blockIdx.y) * 256 + (k)] = static_cast<uint32_t>(clock64());          \
+  } while (0)
 #else
 #define DEC_TR(ev, i) do { } while (0)
+#define DEC_TRE(k) do { } while (0)
 #endif
 
 constexpr int kGroups = 4;
@@ -336,12 +343,14 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // size and register allocation of this tail were measured to move the whole GEMM by 2-5 us)
     constexpr bool kPlain = EPI == B200_EPI_NONE;    // EPI_NONE kernels never carry a row scale
     const bool direct = kPlain && a.splits == 1;
+    DEC_TRE(0);
     pdl_wait();        // first global reads / writes below (c / partials / counters / residual)
     if (warp < 4) {
       const int n = nt * kTileN + ch;
       const int active = nchunks < kGroups ? nchunks : kGroups;
       for (int g = 0; g < active; ++g) mbar_wait(&gdone[g], 0);
       tc_fence_after();
+      DEC_TRE(1);
       const float bv = (direct && a.bias) ? __half2float(a.bias[n]) : 0.f;
       float* part = a.partials + (static_cast<size_t>(split) * M) * N;
 #pragma unroll
@@ -373,17 +382,23 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         }
       }
       tc_fence_before();
+      DEC_TRE(2);
     }
     if (!direct) {
       SplitOut o;
       o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
       o.M = M; o.N = N; o.splits = a.splits; o.epilogue = EPI; o.fe = a.fe;
       if (kPlain) o.fe.ssq_in = nullptr;
-      if (split_arrive(o, nt, threadIdx.x, kDqThreads, 0, &s_is_last, 1))
+      const bool last = split_arrive(o, nt, threadIdx.x, kDqThreads, 0, &s_is_last, 1);
+      DEC_TRE(3);
+      if (last) {
         split_reduce_rows<EPI>(o, nt, threadIdx.x, kDqThreads, 0, M);
+        DEC_TRE(4);
+      }
     }
   }
   __syncthreads();
+  DEC_TRE(5);
   if (warp == kDqWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
