@@ -306,7 +306,7 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
       b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, B, c.hidden, c.rms_eps, stream);
     // ---- attention block
     __half* q = r->qkv;
-    if (fused_env() == 2 && rope_fusable(r)) {
+    if (fused_env() != 0 && rope_fusable(r)) {     // also the TP path (no collective touches q|k|v)
       FusedEpi fq;
       std::memset(&fq, 0, sizeof(fq));
       fq.positions = positions; fq.slots = slot_mapping;

@@ -112,9 +112,11 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   }
   __syncthreads();
   // prologue above touched only step-constant inputs (context_lens, block_tables): it overlaps
-  // the previous kernel's tail.  q and the newest KV rows come from the RoPE kernel -> wait.
+  // the previous kernel's tail.  q and the newest KV rows come from the previous kernel: the
+  // consumers wait here, the producer streams every page EXCEPT the sequence's last one (the only
+  // page this step writes) before it waits -- the ring is full when q becomes visible.
   pdl_trigger();
-  pdl_wait();
+  if (warp != kConsumerWarps) pdl_wait();
 
   // per-thread softmax / output state (consumer warps)
   float m_run[2] = {-INFINITY, -INFINITY};
@@ -133,6 +135,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (page0 + i == npages - 1) pdl_wait();       // the page holding this step's new token
         mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
         const int blk = static_cast<int>(sm_ids[i]);
         uint8_t* kdst = smem + s * SM::kStageBytes;
