@@ -214,6 +214,23 @@ int32_t b200_prepare_prefill(const b200_scheduler*, const int32_t* indices, int3
                              int32_t* max_blocks, int32_t* max_seqlen_q, int32_t* max_seqlen_k,
                              int32_t* max_context_len, int32_t* has_context);
 
+/* ------------------------------------------------- KV-cache planning (host, integer)
+ * Mirror of KVCacheAllocator::{per_block_bytes, plan_allocation, auto_decide_params}
+ * (src/utils/kvcache_allocator.rs:447-468, 553-612, 616-707) for dense (non-MLA, non-hybrid)
+ * models.  `available_bytes` is what get_rank_available_memory returns: free * kv_fraction,
+ * minimum over ranks.  user_max_num_seqs / user_max_model_len <= 0 mean "auto-decide".
+ * Returns 0, or -1 for InvalidConfiguration, -2 for InsufficientGpuMemory.             */
+typedef struct b200_kvcache_plan {
+  int64_t per_block_bytes, num_gpu_blocks, num_cpu_blocks, max_num_seqs, max_model_len;
+  int64_t kvcache_memory_bytes, max_num_batched_tokens;
+} b200_kvcache_plan;
+int32_t b200_kvcache_plan_allocation(int64_t available_bytes, int32_t num_layers,
+                                     int32_t num_kv_heads, int32_t head_dim, int32_t num_shards,
+                                     int32_t block_size, int32_t dtype_size,
+                                     int64_t config_model_len, int64_t user_max_num_seqs,
+                                     int64_t user_max_model_len, float cpu_mem_fold,
+                                     b200_kvcache_plan* out);
+
 /* ------------------------------------------------- model runner (decode step)
  * C++ mirror of ModelRunner::run for the decode branch (runner.rs:743-896) over
  * LLaMaForCausalLM::forward_inner (llama.rs:269-321): every launch of one decode

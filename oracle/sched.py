@@ -273,3 +273,43 @@ def prepare_prefill(seqs, block_size, chunk_size=CHUNK_SIZE_CUDA):   # runner.rs
         out["block_tables"], out["max_blocks"] = prepare_block_tables(seqs)
         out["context_lens"] = [s.num_cached_tokens + n for s, n in zip(seqs, prefill_tokens)]
     return out
+
+
+def kvcache_plan(available, num_layers, num_kv_heads, head_dim, num_shards=1, block_size=64, dtype_size=2,
+                 config_model_len=8192, user_max_num_seqs=None, user_max_model_len=None, cpu_mem_fold=0.5):
+    """KVCacheAllocator::plan_allocation for dense models (kvcache_allocator.rs:126-141, 447-468,
+    553-612, 616-707).  Raises ValueError('invalid') / MemoryError like the two KVCacheError arms."""
+    shards = max(num_shards, 1)
+    heads = num_kv_heads // shards if num_kv_heads >= shards else 1       # :126-137
+    per_block = block_size * heads * head_dim * dtype_size * 2 * num_layers   # :460-466
+    if per_block == 0:
+        raise ValueError("invalid")
+    total_blocks = available // per_block
+    if user_max_num_seqs and user_max_model_len:                       # :636-648
+        blocks_per_seq = -(-user_max_model_len // block_size)
+        if user_max_num_seqs * blocks_per_seq * per_block > available:
+            raise MemoryError
+        max_seqs, max_len = user_max_num_seqs, user_max_model_len
+    else:                                                              # auto_decide_params :553-612
+        if total_blocks == 0:
+            raise MemoryError
+        total_tokens = total_blocks * block_size
+        if total_tokens <= config_model_len:
+            max_seqs, max_len = 1, total_tokens
+        else:
+            max_seqs, max_len = 1, total_tokens
+            for cand in (config_model_len, config_model_len // 2, config_model_len // 4, config_model_len // 8,
+                         16 * 1024, 8 * 1024, 4 * 1024, 1024):
+                if cand == 0:
+                    continue
+                bps = -(-cand // block_size)
+                if total_blocks >= bps:
+                    max_seqs, max_len = min(total_blocks // bps, 8), cand
+                    break
+    if total_blocks == 0 or max_seqs == 0:
+        raise MemoryError
+    import numpy as _np
+    return dict(per_block_bytes=per_block, num_gpu_blocks=total_blocks,
+                num_cpu_blocks=int(_np.float32(total_blocks) * _np.float32(cpu_mem_fold)),   # `as f32 * fold` :681
+                max_num_seqs=max_seqs, max_model_len=max_len, kvcache_memory_bytes=total_blocks * per_block,
+                max_num_batched_tokens=total_blocks * block_size)

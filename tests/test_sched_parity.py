@@ -196,3 +196,56 @@ def test_property_random_traces(lib, reqs, num_blocks, max_seqs):
             break
         elif r is None:
             break     # head-of-line prompt can never fit: both sides agree on the stall
+
+
+# ---------------------------------------------------------------- KV-cache planning (a20)
+def test_kvcache_plan_known_answers():
+    """Hand-derived from kvcache_allocator.rs:447-468,616-707:
+    Llama-3-8B fp16, 32 layers x 8 kv heads x 128: 128 KiB/token -> 8 MiB per 64-token block."""
+    from oracle import sched as osched
+    from vllm_rs_b200 import engine
+    kw = dict(num_layers=32, num_kv_heads=8, head_dim=128, block_size=64, dtype_size=2)
+    for fn in (osched.kvcache_plan, engine.plan_kvcache):
+        p = fn(17 * 2**30 + 12345, **kw, config_model_len=8192)
+        assert p["per_block_bytes"] == 8 * 2**20
+        assert p["num_gpu_blocks"] == 2176 and p["max_num_batched_tokens"] == 2176 * 64
+        assert (p["max_num_seqs"], p["max_model_len"]) == (8, 8192)        # 2176 // 128 = 17 -> capped at 8
+        assert p["num_cpu_blocks"] == 1088 and p["kvcache_memory_bytes"] == 2176 * 8 * 2**20
+        # fewer tokens than one full context: a single sequence gets everything
+        p = fn(100 * 8 * 2**20, **kw, config_model_len=8192)
+        assert (p["max_num_seqs"], p["max_model_len"], p["num_gpu_blocks"]) == (1, 6400, 100)
+        # TP=8 (Llama-3-70B: 80 layers, 8 kv heads -> 1 per rank) and kv heads < shards (replicated groups)
+        p = fn(2**30, num_layers=80, num_kv_heads=8, head_dim=128, num_shards=8)
+        assert p["per_block_bytes"] == 64 * 1 * 128 * 2 * 2 * 80
+        assert fn(2**30, num_layers=80, num_kv_heads=4, head_dim=128, num_shards=8)["per_block_bytes"] == p["per_block_bytes"]
+        # fp8 cache halves the block
+        assert fn(2**30, **{**kw, "dtype_size": 1})["per_block_bytes"] == 4 * 2**20
+        # user limits that do not fit / no room for one block
+        with pytest.raises(MemoryError):
+            fn(2**30, **kw, **({"user_max_num_seqs": 32, "user_max_model_len": 4096} if fn is osched.kvcache_plan
+                               else {"max_num_seqs": 32, "max_model_len": 4096}))
+        with pytest.raises(MemoryError):
+            fn(2**20, **kw)
+        with pytest.raises(ValueError):
+            fn(2**30, **{**kw, "head_dim": 0})
+
+
+def test_kvcache_plan_matches_oracle_randomised():
+    from oracle import sched as osched
+    from vllm_rs_b200 import engine
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        kw = dict(num_layers=int(rng.integers(1, 90)), num_kv_heads=int(rng.choice([1, 2, 4, 8, 16, 32])),
+                  head_dim=int(rng.choice([64, 128, 256])), num_shards=int(rng.choice([1, 2, 4, 8])),
+                  block_size=int(rng.choice([16, 32, 64])), dtype_size=int(rng.choice([1, 2])),
+                  config_model_len=int(rng.choice([2048, 8192, 32768, 131072])),
+                  cpu_mem_fold=float(rng.choice([0.0, 0.2, 0.5, 1.0])))
+        avail = int(rng.integers(0, 160 * 2**30))
+        user = (int(rng.integers(1, 64)), int(rng.integers(64, 20000))) if rng.random() < 0.4 else (None, None)
+        try:
+            want = osched.kvcache_plan(avail, **kw, user_max_num_seqs=user[0], user_max_model_len=user[1])
+        except MemoryError:
+            with pytest.raises(MemoryError):
+                engine.plan_kvcache(avail, **kw, max_num_seqs=user[0], max_model_len=user[1])
+            continue
+        assert engine.plan_kvcache(avail, **kw, max_num_seqs=user[0], max_model_len=user[1]) == want

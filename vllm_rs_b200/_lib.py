@@ -43,6 +43,13 @@ class LayerWeights(C.Structure):
         "k_cache", "v_cache")]
 
 
+class KvCachePlan(C.Structure):
+    """b200_kvcache_plan (include/b200_vllm.h)."""
+
+    _fields_ = [(n, c_i64) for n in ("per_block_bytes", "num_gpu_blocks", "num_cpu_blocks", "max_num_seqs",
+                                     "max_model_len", "kvcache_memory_bytes", "max_num_batched_tokens")]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, c_vp, c_i64, c_vp, c_i64)
 
 # name -> (restype, argtypes)
@@ -87,6 +94,7 @@ _SIGS = {
     "b200_scheduler_seq_tokens": (c_i32, [c_vp, c_i32, c_vp, c_i32]),
     "b200_prepare_decode": (c_i32, [c_vp, c_vp, c_i32] + [c_vp] * 5 + [c_i32, c_vp]),
     "b200_prepare_prefill": (c_i32, [c_vp, c_vp, c_i32, c_i32] + [c_vp] * 7 + [c_i32] + [c_vp] * 5),
+    "b200_kvcache_plan_allocation": (c_i32, [c_i64] + [c_i32] * 6 + [c_i64] * 3 + [c_f32, C.POINTER(KvCachePlan)]),
     "b200_runner_new": (c_vp, [C.POINTER(ModelConfig)]),
     "b200_runner_free": (None, [c_vp]),
     "b200_runner_set_layer": (None, [c_vp, c_i32, C.POINTER(LayerWeights)]),

@@ -427,4 +427,59 @@ int32_t b200_prepare_prefill(const b200_scheduler* s, const int32_t* indices, in
   return static_cast<int32_t>(T);
 }
 
+// KVCacheAllocator::plan_allocation for dense models
+//   /root/reference/src/utils/kvcache_allocator.rs:126-141 (kv heads per shard), 447-468
+//   (per_block_bytes), 553-612 (auto_decide_params), 616-707 (plan_allocation)
+int32_t b200_kvcache_plan_allocation(int64_t available, int32_t num_layers, int32_t num_kv_heads,
+                                     int32_t head_dim, int32_t num_shards, int32_t block_size,
+                                     int32_t dtype_size, int64_t config_model_len,
+                                     int64_t user_max_num_seqs, int64_t user_max_model_len,
+                                     float cpu_mem_fold, b200_kvcache_plan* out) {
+  if (!out) return -1;
+  std::memset(out, 0, sizeof(*out));
+  const int64_t shards = num_shards <= 0 ? 1 : num_shards;
+  const int64_t heads = num_kv_heads >= shards ? num_kv_heads / shards : 1;
+  const int64_t bs = block_size;
+  const int64_t per_block = bs * heads * head_dim * dtype_size * 2 * num_layers;
+  out->per_block_bytes = per_block;
+  if (per_block <= 0 || available < 0) return -1;
+  const int64_t total_blocks = available / per_block;
+  int64_t max_seqs = 0, max_len = 0;
+  if (user_max_num_seqs > 0 && user_max_model_len > 0) {
+    const int64_t blocks_per_seq = (user_max_model_len + bs - 1) / bs;
+    if (user_max_num_seqs * blocks_per_seq * per_block > available) return -2;
+    max_seqs = user_max_num_seqs;
+    max_len = user_max_model_len;
+  } else {
+    if (total_blocks == 0) return -2;
+    const int64_t total_tokens = total_blocks * bs;
+    if (total_tokens <= config_model_len) {
+      max_seqs = 1;
+      max_len = total_tokens;
+    } else {
+      const int64_t cand[8] = {config_model_len, config_model_len / 2, config_model_len / 4,
+                               config_model_len / 8, 16 * 1024, 8 * 1024, 4 * 1024, 1024};
+      max_seqs = 1;
+      max_len = total_tokens;
+      for (int64_t len : cand) {
+        if (len == 0) continue;
+        const int64_t blocks_per_seq = (len + bs - 1) / bs;
+        if (total_blocks >= blocks_per_seq) {
+          max_seqs = std::min<int64_t>(total_blocks / blocks_per_seq, 8);
+          max_len = len;
+          break;
+        }
+      }
+    }
+  }
+  if (total_blocks == 0 || max_seqs == 0) return -2;
+  out->num_gpu_blocks = total_blocks;
+  out->num_cpu_blocks = static_cast<int64_t>(static_cast<float>(total_blocks) * cpu_mem_fold);
+  out->max_num_seqs = max_seqs;
+  out->max_model_len = max_len;
+  out->kvcache_memory_bytes = total_blocks * per_block;
+  out->max_num_batched_tokens = total_blocks * bs;
+  return 0;
+}
+
 }  // extern "C"

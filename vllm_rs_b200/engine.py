@@ -156,6 +156,23 @@ class Scheduler:
         return out
 
 
+def plan_kvcache(available_bytes, *, num_layers, num_kv_heads, head_dim, num_shards=1, block_size=64,
+                 dtype_size=2, config_model_len=8192, max_num_seqs=None, max_model_len=None,
+                 cpu_mem_fold=0.5) -> dict:
+    """KVCacheAllocator::plan_allocation (kvcache_allocator.rs:616-707) through the C ABI.
+    Raises ValueError (InvalidConfiguration) / MemoryError (InsufficientGpuMemory)."""
+    out = _lib.KvCachePlan()
+    rc = _lib.lib().b200_kvcache_plan_allocation(int(available_bytes), num_layers, num_kv_heads, head_dim, num_shards,
+                                          block_size, dtype_size, int(config_model_len),
+                                          int(max_num_seqs or 0), int(max_model_len or 0),
+                                          float(cpu_mem_fold), C.byref(out))
+    if rc == -1:
+        raise ValueError("invalid KV-cache configuration")
+    if rc == -2:
+        raise MemoryError("insufficient GPU memory for the KV cache")
+    return {n: int(getattr(out, n)) for n, _ in out._fields_}
+
+
 @dataclass
 class QuantLinear:
     """One prepacked W4A16/W8A16 (or dense fp16) linear, possibly several projections fused
