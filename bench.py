@@ -185,6 +185,16 @@ def run_reference(args):
     }))
 
 
+def _prof(which, start):
+    """B200_PROFILE=decode|prefill brackets that region with cudaProfilerStart/Stop so that
+    `ncu --profile-from-start off` lists exactly its launches (a run under ncu is never a bench value)."""
+    if os.environ.get("B200_PROFILE") == which:
+        import torch
+        rt = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        (rt.cudaProfilerStart if start else rt.cudaProfilerStop)()
+
+
 # ---------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import numpy as np
@@ -250,11 +260,13 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
+            _prof("decode", True)
             e0.record(stream)
             for _ in range(K):
                 graph.replay()
             e1.record(stream)
             stream.synchronize()
+            _prof("decode", False)
             barrier()
             ms = e0.elapsed_time(e1)
             # keep sampling under load a little longer so short runs still get >= a few samples
@@ -342,16 +354,21 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             runner.prefill_device(meta, want_logits=False)          # warm-up
             stream.synchronize()
+            _prof("prefill", True)
             e0.record(stream)
             for _ in range(2):
                 runner.prefill_device(meta, want_logits=False)
             e1.record(stream)
             stream.synchronize()
+            _prof("prefill", False)
         pf_ms = e0.elapsed_time(e1) / 2
         p_lin = shape["hidden"] * (shape["H"] + 2 * shape["Hkv"]) * D + shape["H"] * D * shape["hidden"] + 3 * shape["hidden"] * shape["inter"]
         flops = 2.0 * p_lin * L * T + L * 4.0 * shape["H"] * D * (T * (T + 1) / 2)
         prefill = {"tokens": T, "ms": pf_ms, "tokens_per_s": T * 1e3 / pf_ms, "tflops": flops / (pf_ms * 1e-3) / 1e12,
-                   "flops": flops, "note": "one 8192-token chunk, W4A16 tcgen05 GEMM (NT=256) + mma.sync varlen causal attention over the paged cache"}
+                   "flops": flops, "launches": int(runner.launches_per_step),
+                   "note": "one 8192-token chunk: per projection a W4->fp16 dequant pass + dense tcgen05 GEMM (CTA pairs, "
+                           "256x256 tiles) when T >= B200_PREFILL_DENSE_MIN_T (default 1024), else the in-kernel-dequant "
+                           "W4A16 tcgen05 GEMM (NT=256); mma.sync varlen causal attention over the paged cache"}
 
     out_line = {
         "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",

@@ -92,11 +92,25 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
                         int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,
                         int32_t epilogue, int32_t variant, void* workspace, int64_t stream);
 int64_t b200_wna16_workspace_bytes(int32_t max_m, int32_t max_n);
+/* Dequantise a prepacked weight to fp16 out[n, k] (row = output channel, K-major): the weight
+ * operand of b200_dense_gemm_f16.  Large prefill steps dequantise a layer once and run the dense
+ * tcgen05 GEMM instead of re-dequantising per token tile (no reference counterpart: Marlin
+ * re-dequantises, gptq.rs:118-146).                                                      */
+void b200_wna16_dequant_f16(const void* b_packed, const void* scales, const void* qzeros, void* out,
+                            int32_t k, int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,
+                            int64_t stream);
 
 /* ------------------------------------------------- dense fp16 GEMM (lm_head, fp16 linears)
- * C[m, n] = A[m, k] x W[n, k]^T ; out_f32 != 0 writes fp32 logits (llama.rs:311-320).  */
+ * C[m, n] = A[m, k] x W[n, k]^T ; out_f32 != 0 writes fp32 logits (llama.rs:311-320).
+ * Replaces Linear::forward -> cuBLAS (linear.rs:75-123) with a tcgen05 kernel (TMA-fed SS-mode
+ * MMA, CTA pairs for m > 128, weight-streaming swapped form for m <= 128).               */
 void b200_dense_gemm_f16(const void* a, const void* w, void* c, int32_t m, int32_t n, int32_t k,
                          int32_t out_f32, int64_t stream);
+/* Same with an optional fused bias[n] (fp16, may be NULL) and an explicit implementation:
+ * mode -1 = default (env B200_DENSE), 0 = cuBLAS (the reference's own call, A/B baseline),
+ * 1 = tcgen05 single-CTA tiles, 2 = tcgen05 CTA pairs.                                   */
+void b200_dense_gemm_ex(const void* a, const void* w, const void* bias, void* c, int32_t m,
+                        int32_t n, int32_t k, int32_t out_f32, int32_t mode, int64_t stream);
 
 /* ------------------------------------------------- RoPE + KV-cache write
  * Replaces FusedRope::apply_inplace (rotary_emb.rs:88-104) followed by the cache

@@ -18,12 +18,41 @@ F16 = torch.float16
 from oracle.toy import build_pair as _build, sync_cache_to_gpu as _sync_cache_to_gpu, toy_cfg as _toy_cfg
 
 
-@pytest.mark.parametrize("fmt,bias", [("awq", False), ("gptq", True), ("gptq8", False)])
-def test_decode_steps_match_oracle(lib, fmt, bias):
+# Per-rank shapes of the tensor-parallel configs in BASELINE.json, run here as whole (1-layer) models
+# on one GPU so that every kernel is checked at the tile counts a TP rank really launches:
+#   Llama-3-8B TP=8: 4 q heads, 1 kv head, inter 1792 (qkv N = 768, o K = 512, down K = 1792)
+#   Llama-3-8B TP=4: 8 q heads, 2 kv heads, inter 3584
+#   Llama-3-70B TP=8 (configs[4]): hidden 8192, 8 q heads, 1 kv head, inter 3584
+RANK_SHAPES = {
+    "toy": None,
+    "l3-8b-tp8": dict(hidden=4096, num_heads=4, num_kv_heads=1, head_dim=128, inter=1792),
+    "l3-8b-tp4": dict(hidden=4096, num_heads=8, num_kv_heads=2, head_dim=128, inter=3584),
+    "l3-70b-tp8": dict(hidden=8192, num_heads=8, num_kv_heads=1, head_dim=128, inter=3584),
+}
+
+
+def _shape_cfg(shape, bias):
+    if RANK_SHAPES[shape] is None:
+        return _toy_cfg(bias)
+    return om.ModelConfig(num_layers=1, vocab=1024, rope_theta=500000.0, rms_eps=1e-5, max_pos=2048,
+                          qkv_bias=bias, **RANK_SHAPES[shape])
+
+
+@pytest.mark.parametrize("fmt,bias,shape,plan", [
+    ("awq", False, "toy", "fused"), ("gptq", True, "toy", "fused"), ("gptq8", False, "toy", "fused"),
+    ("awq", False, "toy", "classic"),
+    ("awq", False, "l3-8b-tp8", "classic"), ("awq", False, "l3-8b-tp4", "classic"),
+    ("gptq", False, "l3-70b-tp8", "classic"), ("awq", False, "l3-8b-tp8", "fused"),
+])
+def test_decode_steps_match_oracle(lib, fmt, bias, shape, plan):
     from vllm_rs_b200 import engine
-    cfg = _toy_cfg(bias)
+    cfg = _shape_cfg(shape, bias)
     NB, MAXB, MAXBLK = 64, 8, 8
     oracle, runner = _build(cfg, fmt, seed=3, num_blocks=NB, max_batch=MAXB, max_blocks=MAXBLK)
+    if plan == "classic":
+        # a tensor-parallel rank runs the classic launch plan (an all-reduce follows o_proj / down_proj);
+        # a no-op all-reduce is the world-size-1 collective and selects that plan on one GPU
+        runner.set_allreduce(lambda buf, n, st: None)
     osch = osched.Scheduler(NB, 64, MAXB)
     csch = engine.Scheduler(NB, 64, MAXB)
     rng = np.random.default_rng(1)

@@ -66,7 +66,9 @@ _SIGS = {
     "b200_gemm_half_q_half_8bit": (None, [c_vp] * 6 + [c_i32] * 4 + [c_vp, c_i64]),
     "b200_wna16_gemm_ex": (None, [c_vp] * 6 + [c_i32] * 8 + [c_vp, c_i64]),
     "b200_wna16_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "b200_wna16_dequant_f16": (None, [c_vp] * 4 + [c_i32] * 5 + [c_i64]),
     "b200_dense_gemm_f16": (None, [c_vp] * 3 + [c_i32] * 4 + [c_i64]),
+    "b200_dense_gemm_ex": (None, [c_vp] * 4 + [c_i32] * 5 + [c_i64]),
     "b200_rope_kv_write_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),

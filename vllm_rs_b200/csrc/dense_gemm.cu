@@ -2,9 +2,13 @@
 //   C[m, n] = A[m, k] x W[n, k]^T, fp32 accumulate, fp16 or fp32 output.
 // Reference: Linear::forward -> candle -> cuBLAS (/root/reference/src/models/layers/linear.rs:75-123)
 // and the f32 logits cast in /root/reference/src/models/llama.rs:311-320.
-// This is a plain library GEMM (cuBLAS), exactly what the reference uses for it.
+// Default: the hand-written tcgen05 kernel of dense_gemm_tc.cu.  B200_DENSE=cublas selects the
+// library GEMM the reference itself calls (kept as the A/B baseline and for shapes the kernel does
+// not take: K % 64 != 0, N % 8 != 0); B200_DENSE=tc1 forces single-CTA tiles for M > 128.
 #include <cublas_v2.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "../../include/b200_vllm.h"
@@ -27,13 +31,30 @@ static cublasHandle_t cublas_for_device() {
   }
   return g_cublas[dev];
 }
+bool launch_dense_gemm_tc(const void* x, const void* w, void* c, const void* bias, int M, int N, int K,
+                          int out_f32, int mode, cudaStream_t st);
+// 0 = cuBLAS, 1 = tcgen05 single-CTA tiles, 2 = tcgen05 CTA pairs
+static int dense_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("B200_DENSE");
+    mode = 2;
+    if (e && !strcmp(e, "cublas")) mode = 0;
+    if (e && !strcmp(e, "tc1")) mode = 1;
+  }
+  return mode;
+}
 }  // namespace b200
 
-extern "C" void b200_dense_gemm_f16(const void* a, const void* w, void* c, int32_t m, int32_t n,
-                                    int32_t k, int32_t out_f32, int64_t stream) {
+extern "C" void b200_dense_gemm_ex(const void* a, const void* w, const void* bias, void* c, int32_t m,
+                                   int32_t n, int32_t k, int32_t out_f32, int32_t mode, int64_t stream) {
   using namespace b200;
   if (m <= 0) return;
   B200_CHECK_ARG(a && w && c && n > 0 && k > 0, "dense_gemm: bad arguments");
+  if (mode < 0) mode = dense_mode();
+  if (mode != 0 &&
+      launch_dense_gemm_tc(a, w, c, bias, m, n, k, out_f32, mode, reinterpret_cast<cudaStream_t>(stream)))
+    return;
   cublasHandle_t h = cublas_for_device();
   if (!h) {
     set_error(2, "dense_gemm: cublasCreate failed");
@@ -46,4 +67,15 @@ extern "C" void b200_dense_gemm_f16(const void* a, const void* w, void* c, int32
                                   CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
   count_launch(1);
   if (s != CUBLAS_STATUS_SUCCESS) set_error(2, "dense_gemm: cublasGemmEx failed");
+  if (bias) {
+    if (out_f32)
+      set_error(1, "dense_gemm: bias with fp32 output is only fused in the tcgen05 kernel");
+    else
+      b200_add_bias_f16(c, bias, m, n, stream);
+  }
+}
+
+extern "C" void b200_dense_gemm_f16(const void* a, const void* w, void* c, int32_t m, int32_t n,
+                                    int32_t k, int32_t out_f32, int64_t stream) {
+  b200_dense_gemm_ex(a, w, nullptr, c, m, n, k, out_f32, -1, stream);
 }

@@ -29,6 +29,8 @@
 using namespace b200;
 namespace b200 {
 long long launch_count();
+void launch_wna16_dequant(const uint32_t* bp, const __half* scales, const uint32_t* qzeros, __half* out,
+                          int K, int N, int bits, int group_size, int qfmt, cudaStream_t st);
 }
 
 namespace {
@@ -52,6 +54,7 @@ struct b200_runner {
   float* logits = nullptr;
   float* ssq = nullptr;          // [2 * layers + 1][max_batch] sums of squares of the folded RMSNorms
   void *attn_ws = nullptr, *wna_ws = nullptr;
+  __half* wdeq = nullptr;        // fp16 [N, K] scratch of ONE projection (large quantised prefill steps)
   // static (graph) input buffers
   uint32_t *s_ids = nullptr, *s_ctx = nullptr, *s_bt = nullptr, *s_out = nullptr;
   int64_t *s_pos = nullptr, *s_slot = nullptr;
@@ -59,6 +62,19 @@ struct b200_runner {
   std::map<int, cudaGraphExec_t> graphs;
   int64_t launches = 0;
 };
+
+// Prefill steps of at least this many tokens run quantised linears as "dequantise the layer's weight
+// once to fp16, then the dense tcgen05 GEMM" (dense_gemm_tc.cu); smaller steps keep the in-kernel
+// dequant GEMM (wna16_tc.cu), which re-dequantises per 256-token tile.  B200_PREFILL_DENSE_MIN_T.
+static int prefill_dense_min_tokens() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_PREFILL_DENSE_MIN_T");
+    v = e ? atoi(e) : 1024;
+    if (v <= 0) v = 1 << 30;
+  }
+  return v;
+}
 
 static int64_t carve(b200_runner* r, uint8_t* base) {
   const b200_model_config& c = r->cfg;
@@ -85,6 +101,11 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
                                                     c.max_blocks_per_seq));
   const size_t max_n = std::max<size_t>(std::max<size_t>(qkv_n, 2 * c.inter), c.hidden);
   r->wna_ws = take(b200_wna16_workspace_bytes(c.max_batch, static_cast<int32_t>(max_n)));
+  if (c.bits != 16 && c.max_prefill_tokens >= prefill_dense_min_tokens()) {
+    const size_t kn = std::max<size_t>(static_cast<size_t>(c.hidden) * std::max<size_t>(qkv_n, 2 * c.inter),
+                                       static_cast<size_t>(c.inter) * c.hidden);
+    r->wdeq = (__half*)take(kn * 2);
+  }
   r->s_ids = (uint32_t*)take(B * 4);
   r->s_ctx = (uint32_t*)take(B * 4);
   r->s_out = (uint32_t*)take(B * 4);
@@ -180,6 +201,15 @@ static void linear(b200_runner* r, const __half* in, const void* w, const void* 
     if (bias) {
       b200_add_bias_f16(out, bias, M, N, stream);
     }
+    return;
+  }
+  if (r->wdeq && epilogue == B200_EPI_NONE && M >= prefill_dense_min_tokens() && N % kTileN == 0 &&
+      K % kChunkK == 0) {
+    const int g = c.group_size <= 0 ? K : c.group_size;
+    launch_wna16_dequant((const uint32_t*)w, (const __half*)s, (const uint32_t*)z, r->wdeq, K, N, c.bits, g,
+                         c.qfmt, reinterpret_cast<cudaStream_t>(stream));
+    b200_dense_gemm_f16(in, r->wdeq, out, M, N, K, 0, stream);
+    if (bias) b200_add_bias_f16(out, bias, M, N, stream);
     return;
   }
   b200_wna16_gemm_ex(in, w, s, z, bias, out, M, K, N, c.bits, c.group_size, c.qfmt, epilogue,

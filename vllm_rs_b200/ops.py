@@ -70,14 +70,28 @@ def wna16_gemm(x, w_packed, scales, qzeros, workspace, *, k: int, n: int, bits=4
     return out
 
 
-def dense_gemm(x, w_nk, out_f32=False, out=None):
-    """Linear::forward (linear.rs:75-123): y = x @ W^T, W [N, K] fp16."""
-    _cuda(x, w_nk)
+DENSE_AUTO, DENSE_CUBLAS, DENSE_TC1, DENSE_TC2 = -1, 0, 1, 2
+
+
+def dense_gemm(x, w_nk, out_f32=False, out=None, bias=None, mode=DENSE_AUTO):
+    """Linear::forward (linear.rs:75-123): y = x @ W^T (+ bias), W [N, K] fp16."""
+    _cuda(x, w_nk, bias)
     m, k = x.shape
     n = w_nk.shape[0]
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
-    _lib.lib().b200_dense_gemm_f16(_p(x), _p(w_nk), _p(out), m, n, k, int(out_f32), _stream())
+    _lib.lib().b200_dense_gemm_ex(_p(x), _p(w_nk), _p(bias), _p(out), m, n, k, int(out_f32), mode, _stream())
+    _lib.check()
+    return out
+
+
+def wna16_dequant(w_packed, scales, qzeros, *, k: int, n: int, bits=4, group_size=128, qfmt=QFMT_AWQ, out=None):
+    """Prepacked W4 / W8 weight -> fp16 [N, K] (the weight operand of dense_gemm)."""
+    _cuda(w_packed, scales, qzeros)
+    if out is None:
+        out = torch.empty(n, k, dtype=torch.float16, device=w_packed.device)
+    _lib.lib().b200_wna16_dequant_f16(_p(w_packed), _p(scales), _p(qzeros), _p(out), k, n, bits, group_size,
+                                      qfmt, _stream())
     _lib.check()
     return out
 
