@@ -176,6 +176,35 @@ void b200_argmax_f32(uint32_t* out_ids, const float* logits, int32_t batch, int3
                      int64_t stream);
 void b200_add_bias_f16(void* x, const void* bias, int32_t num_tokens, int32_t n, int64_t stream);
 
+/* ------------------------------------------------- sampling (logits_processor.rs, runner.rs:1390-1570)
+ * Device replacement of attention_rs::sampler::Sampler::sample_cuda (logits_processor.rs:226-229):
+ * full-vocabulary softmax(logits / temperature) -> top_k (1..256) -> top-p cut on the
+ * un-renormalised top-k probabilities -> multinomial; out_ids u32 [batch].  `seed_dev` points to
+ * ONE u64 in device memory (the step seed, LogitsProcessor's rng.next_u64()), so a captured graph
+ * changes it with a copy.  Row b draws u = f(seed, b) (this library's definition; the reference
+ * kernel's is not source-visible).  Greedy (Sampling::ArgMax) is b200_argmax_f32.          */
+void b200_sample_topk_topp_f32(uint32_t* out_ids, const float* logits, int32_t batch, int32_t vocab,
+                               int32_t top_k, float top_p, float temperature,
+                               const uint64_t* seed_dev, int64_t stream);
+/* apply_batch_repeat_penalty (logits_processor.rs:308-343): context u32 [batch, context_cap] holds
+ * each row's penalty window (the caller applies the "last 128 tokens once more than 128 exist"
+ * rule of runner.rs:1522-1533), context_lens i32 [batch].  In place on fp32 logits.        */
+void b200_apply_penalties_f32(float* logits, int32_t batch, int32_t vocab, const uint32_t* context,
+                              const int32_t* context_lens, int32_t context_cap,
+                              float frequency_penalty, float presence_penalty, int64_t stream);
+/* LogitsProcessor::get_strategy + the (k, p, t) of sample_with_strategy (logits_processor.rs:48-70,
+ * 208-216).  has_* = 0 is None.  Returns 0 ArgMax, 1 All, 2 TopK, 3 TopP, 4 TopKThenTopP.       */
+int32_t b200_sampling_strategy(int32_t has_temperature, float temperature, int32_t has_top_k,
+                               int64_t top_k, int32_t has_top_p, float top_p, int32_t* k, float* p,
+                               float* t);
+/* rand::rngs::StdRng::seed_from_u64 (logits_processor.rs:29-30): ChaCha12 keyed by the PCG32
+ * expansion of the seed; next_u64 is the per-step kernel seed (logits_processor.rs:222-225).  */
+typedef struct b200_rng b200_rng;
+b200_rng* b200_rng_new(uint64_t seed);
+void b200_rng_free(b200_rng*);
+uint32_t b200_rng_next_u32(b200_rng*);
+uint64_t b200_rng_next_u64(b200_rng*);
+
 /* ------------------------------------------------- host side: block manager / scheduler
  * C++ mirror of src/core/{sequence,block_manager,scheduler}.rs and the input
  * preparation of src/core/runner.rs:952-1388.  Handles are opaque.               */
@@ -310,6 +339,12 @@ void b200_runner_prefill_device(b200_runner*, const uint32_t* input_ids, const i
 int32_t b200_runner_capture(b200_runner*, const int32_t* buckets, int32_t num_buckets,
                             int64_t stream);
 int64_t b200_runner_launches_per_step(const b200_runner*);
+/* Sampling of the decode / prefill steps: top_k == 0 => greedy argmax (default); otherwise the
+ * device sampler above with these (k, p, t) (the strategy cached at prefill, runner.rs:1402-1510).
+ * b200_runner_set_step_seed copies the step seed into the runner's device slot on `stream`
+ * (call once per step before b200_runner_decode_host / _device; graph-replay safe).          */
+void b200_runner_set_sampling(b200_runner*, int32_t top_k, float top_p, float temperature);
+void b200_runner_set_step_seed(b200_runner*, uint64_t seed, int64_t stream);
 
 /* ------------------------------------------------- tensor-parallel communicator
  * One process per GPU (runner/runner.rs:73-240).  NCCL communicator from a 128-byte unique id

@@ -36,7 +36,16 @@ namespace dg {
 constexpr int kThreads = 192;
 constexpr int kBM = 128;       // P rows per CTA = TMEM lanes
 constexpr int kBK = 64;        // K elements per stage (one 128-byte swizzle row)
-constexpr int kGroupP = 8;     // P tiles per rasterisation group (L2 reuse of the Q panels)
+// P tiles per rasterisation group: a group's P panel (group_p * 128 * CG rows x K) stays in L2 while
+// the Q panels stream past it once per group.  B200_DENSE_GROUP_P overrides (A/B testing).
+static int group_p_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_DENSE_GROUP_P");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 template <int BN, int CG>
 struct Cfg {
@@ -60,15 +69,15 @@ struct Args {
   int M, N;            // logical output [M, N], row stride N
   int p_rows, q_rows;  // rows of the P / Q operand (swap: N / M, else M / N)
   int KB;              // K / 64
-  int tiles_p, tiles_q;
+  int tiles_p, tiles_q, group_p;
 };
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_p, int tiles_q, int& p, int& q) {
-  const int per_group = kGroupP * tiles_q;
+__device__ __forceinline__ void tile_coords(int t, const Args& a, int& p, int& q) {
+  const int per_group = a.group_p * a.tiles_q;
   const int g = t / per_group, r = t - g * per_group;
-  const int rows = min(kGroupP, tiles_p - g * kGroupP);
+  const int rows = min(a.group_p, a.tiles_p - g * a.group_p);
   q = r / rows;
-  p = g * kGroupP + (r - q * rows);
+  p = g * a.group_p + (r - q * rows);
 }
 
 template <int BN, int CG, bool SWAP, bool OUT_F32>
@@ -131,7 +140,7 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap pmap, const __grid_cons
       uint32_t kit = 0;
       for (int t = unit; t < ntiles; t += nunits) {
         int p, q;
-        tile_coords(t, a.tiles_p, a.tiles_q, p, q);
+        tile_coords(t, a, p, q);
         const int prow = (p * CG + static_cast<int>(rank)) * kBM;
         const int qrow = q * BN + static_cast<int>(rank) * C::kQRows;
         for (int kb = 0; kb < a.KB; ++kb, ++kit) {
@@ -193,7 +202,7 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap pmap, const __grid_cons
     int it = 0;
     for (int t = unit; t < ntiles; t += nunits, ++it) {
       int p, q;
-      tile_coords(t, a.tiles_p, a.tiles_q, p, q);
+      tile_coords(t, a, p, q);
       const int buf = it & 1;
       mbar_wait_bounded(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -298,6 +307,15 @@ static bool launch_cfg(const void* x, const void* w, void* c, const __half* bias
   a.KB = K / kBK;
   a.tiles_p = (a.p_rows + kBM * CG - 1) / (kBM * CG);
   a.tiles_q = (a.q_rows + BN - 1) / BN;
+  // keep the group's P panel within ~32 MB of L2: rows * K * 2 bytes
+  {
+    const long panel_rows = (32L << 20) / (static_cast<long>(K) * 2);
+    int gp = static_cast<int>(panel_rows / (kBM * CG));
+    if (gp < 4) gp = 4;
+    if (gp > 32) gp = 32;
+    if (group_p_env() > 0) gp = group_p_env();
+    a.group_p = gp;
+  }
   CUtensorMap pmap, qmap;
   if (!make_map(&pmap, pbase, a.p_rows, K, kBM) || !make_map(&qmap, qbase, a.q_rows, K, C::kQRows)) {
     set_error(2, "dense_gemm_tc: cuTensorMapEncodeTiled failed");

@@ -29,6 +29,8 @@
 using namespace b200;
 namespace b200 {
 long long launch_count();
+void launch_sample_topk_topp(uint32_t* out_ids, const float* logits, int B, int V, int k, float p, float t,
+                             const uint64_t* seed_dev, cudaStream_t st);
 void launch_wna16_dequant(const uint32_t* bp, const __half* scales, const uint32_t* qzeros, __half* out,
                           int K, int N, int bits, int group_size, int qfmt, cudaStream_t st);
 }
@@ -59,6 +61,9 @@ struct b200_runner {
   uint32_t *s_ids = nullptr, *s_ctx = nullptr, *s_bt = nullptr, *s_out = nullptr;
   int64_t *s_pos = nullptr, *s_slot = nullptr;
   // pinned host staging for padded rows
+  uint64_t* s_seed = nullptr;    // step seed of the device sampler
+  int samp_k = 0;                // 0 = greedy
+  float samp_p = 1.f, samp_t = 1.f;
   std::map<int, cudaGraphExec_t> graphs;
   int64_t launches = 0;
 };
@@ -112,6 +117,7 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
   r->s_pos = (int64_t*)take(B * 8);
   r->s_slot = (int64_t*)take(B * 8);
   r->s_bt = (uint32_t*)take(B * c.max_blocks_per_seq * 4);
+  r->s_seed = (uint64_t*)take(8);
   return static_cast<int64_t>(off);
 }
 
@@ -190,6 +196,15 @@ void b200_runner_set_comm(b200_runner* r, b200_comm* c) {
 void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user) {
   r->allreduce = fn;
   r->allreduce_user = user;
+}
+
+// ModelRunner::sample (runner.rs:1390-1570) for the cached strategy: greedy argmax or the device sampler
+static void pick_tokens(b200_runner* r, uint32_t* out_ids, const float* logits, int B, int64_t stream) {
+  if (r->samp_k > 0)
+    launch_sample_topk_topp(out_ids, logits, B, r->cfg.vocab, std::min(r->samp_k, r->cfg.vocab), r->samp_p,
+                            r->samp_t, r->s_seed, reinterpret_cast<cudaStream_t>(stream));
+  else
+    b200_argmax_f32(out_ids, logits, B, r->cfg.vocab, stream);
 }
 
 static void linear(b200_runner* r, const __half* in, const void* w, const void* s, const void* z,
@@ -301,7 +316,7 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
   launch_rowscale(r->proj, xw, r->ssq + (2 * L - 1) * MB * kSsqStride, B, c.hidden, c.rms_eps, st);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(r->proj, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
-  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+  if (out_ids) pick_tokens(r, out_ids, lg, B, stream);
 }
 
 void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
@@ -378,7 +393,7 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
   b200_add_rmsnorm_f16(r->xn, r->x, r->proj, r->final_norm, B, c.hidden, c.rms_eps, stream);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(r->xn, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
-  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+  if (out_ids) pick_tokens(r, out_ids, lg, B, stream);
   r->launches = launch_count() - launches0;
 }
 
@@ -435,7 +450,7 @@ void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
   b200_add_rmsnorm_f16(ns, xs, ps, r->final_norm, B, c.hidden, c.rms_eps, stream);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(ns, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
-  if (out_ids) b200_argmax_f32(out_ids, lg, B, c.vocab, stream);
+  if (out_ids) pick_tokens(r, out_ids, lg, B, stream);
   r->launches = launch_count() - launches0;
 }
 
@@ -532,5 +547,27 @@ int32_t b200_runner_capture(b200_runner* r, const int32_t* buckets, int32_t num_
 }
 
 int64_t b200_runner_launches_per_step(const b200_runner* r) { return r->launches; }
+
+void b200_runner_set_sampling(b200_runner* r, int32_t top_k, float top_p, float temperature) {
+  if (top_k < 0 || top_k > 256 || (top_k > 0 && !(temperature > 0.f))) {
+    set_error(1, "runner_set_sampling: top_k must be 0 (greedy) or 1..256 with a positive temperature");
+    return;
+  }
+  if (top_k != r->samp_k) {           // graphs captured for the other strategy no longer apply
+    for (auto& g : r->graphs) cudaGraphExecDestroy(g.second);
+    r->graphs.clear();
+  }
+  r->samp_k = top_k;
+  r->samp_p = top_p;
+  r->samp_t = temperature;
+}
+
+void b200_runner_set_step_seed(b200_runner* r, uint64_t seed, int64_t stream) {
+  if (!r->ws) {
+    set_error(1, "runner_set_step_seed: workspace not set");
+    return;
+  }
+  cudaMemcpyAsync(r->s_seed, &seed, 8, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

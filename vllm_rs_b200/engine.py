@@ -280,6 +280,17 @@ class ModelRunner:
         self._ar_cb = _lib.ALLREDUCE_FN(lambda buf, n, user, st: fn(buf, n, st))
         self._l.b200_runner_set_allreduce(self._h, self._ar_cb, None)
 
+    def set_sampling(self, top_k=0, top_p=1.0, temperature=1.0):
+        """Strategy cached at prefill (runner.rs:1402-1510): top_k = 0 is greedy, else the device sampler."""
+        self._l.b200_runner_set_sampling(self._h, int(top_k), float(top_p), float(temperature))
+        _lib.check()
+
+    def set_step_seed(self, seed, stream=None):
+        """The step's kernel seed = LogitsProcessor's rng.next_u64() (logits_processor.rs:222-225)."""
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self._l.b200_runner_set_step_seed(self._h, int(seed) & ((1 << 64) - 1), st)
+        _lib.check()
+
     def capture(self, buckets=None):
         """warmup_capture (graph.rs:448-690)."""
         b = [x for x in (buckets or GRAPH_BUCKETS) if x <= self.cfg.max_batch]

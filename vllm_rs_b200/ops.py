@@ -205,3 +205,29 @@ def argmax(logits):
     _lib.lib().b200_argmax_f32(_p(out), _p(logits), logits.shape[0], logits.shape[1], _stream())
     _lib.check()
     return out
+
+
+# ------------------------------------------------------------------ sampling
+def sample_topk_topp(logits, top_k, top_p, temperature, seed, out=None):
+    """Device sampler (logits_processor.rs:199-231): logits f32 [B, V] -> ids i32 [B].  `seed` is a
+    python int (copied to a device u64) or a 1-element int64 CUDA tensor."""
+    _cuda(logits)
+    B, V = logits.shape
+    if not torch.is_tensor(seed):
+        seed = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed], dtype=torch.int64).to(logits.device)
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=logits.device)
+    _lib.lib().b200_sample_topk_topp_f32(_p(out), _p(logits), B, V, top_k, float(top_p), float(temperature),
+                                         _p(seed), _stream())
+    _lib.check()
+    return out
+
+
+def apply_penalties(logits, context, context_lens, frequency_penalty, presence_penalty):
+    """apply_batch_repeat_penalty (logits_processor.rs:308-343), in place.  context i32 [B, cap]."""
+    _cuda(logits, context, context_lens)
+    B, V = logits.shape
+    _lib.lib().b200_apply_penalties_f32(_p(logits), B, V, _p(context), _p(context_lens), context.shape[1],
+                                        float(frequency_penalty), float(presence_penalty), _stream())
+    _lib.check()
+    return logits
