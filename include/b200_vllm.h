@@ -160,6 +160,16 @@ void b200_attn_prefill_f16(void* out, const void* q, const void* k_cache, const 
                            int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
                            float scale, int64_t stream);
 
+/* Same, with the row count of q / out (num_tokens = cu_seqlens_q[batch], which the tcgen05 kernel's q
+ * tensor map needs as a HOST value) and an explicit implementation: mode -1 = default (tcgen05 for
+ * head_dim 128, env B200_PREFILL_ATTN), 0 = mma.sync kernel, 1 = tcgen05, 2 = tcgen05 bring-up switch. */
+void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k_cache, const void* v_cache,
+                              const uint32_t* cu_seqlens_q, const uint32_t* context_lens,
+                              const uint32_t* block_tables, int32_t batch, int32_t num_heads,
+                              int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                              int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
+                              int32_t num_tokens, int32_t mode, float scale, int64_t stream);
+
 /* ------------------------------------------------- glue kernels (others.rs, mlp.rs, llama.rs) */
 void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
                       int32_t hidden, float eps, int64_t stream);

@@ -74,6 +74,7 @@ _SIGS = {
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
     "b200_attn_prefill_f16": (None, [c_vp] * 7 + [c_i32] * 8 + [c_f32, c_i64]),
+    "b200_attn_prefill_ex_f16": (None, [c_vp] * 7 + [c_i32] * 10 + [c_f32, c_i64]),
     "b200_rmsnorm_f16": (None, [c_vp] * 3 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_add_rmsnorm_f16": (None, [c_vp] * 4 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_silu_mul_f16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),

@@ -16,7 +16,13 @@ void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, in
 void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_stride,
                          const uint32_t* cu_q, const uint32_t* ctx_lens,
                          const uint32_t* block_tables, int B, int H, int Hkv, int D, int max_blocks,
-                         int max_seqlen_q, float scale, cudaStream_t st);
+                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows = 0, int mode = -1);
+// tcgen05 version (head_dim 128); false when the shape / mode is not taken.  total_rows = rows of the q
+// buffer (bounds of its tensor map); mode -1 = env B200_PREFILL_ATTN (default tcgen05), 0 = mma.sync.
+bool launch_attn_prefill_tc(const AttnMaps& maps, void* out, const void* q, int q_stride, const uint32_t* cu_q,
+                            const uint32_t* ctx_lens, const uint32_t* block_tables, int B, int H, int Hkv, int D,
+                            int max_blocks, int max_seqlen_q, int total_rows, float scale, int mode,
+                            cudaStream_t st);
 // RoPE + KV write with explicit row strides (in halfs) so q|k|v can live in one fused
 // GEMM output row.
 void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,

@@ -276,7 +276,11 @@ static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stri
 void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_stride,
                          const uint32_t* cu_q, const uint32_t* ctx_lens,
                          const uint32_t* block_tables, int B, int H, int Hkv, int D, int max_blocks,
-                         int max_seqlen_q, float scale, cudaStream_t st) {
+                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows, int mode) {
+  // total_rows > 0: the caller knows the extent of the q buffer, which the tcgen05 kernel's q tensor map needs
+  if (total_rows > 0 && launch_attn_prefill_tc(maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, D,
+                                               max_blocks, max_seqlen_q, total_rows, scale, mode, st))
+    return;
   if (D == 128)
     launch_pf<128>(maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, max_blocks,
                    max_seqlen_q, scale, st);
@@ -286,6 +290,33 @@ void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_s
 }
 
 }  // namespace b200
+
+extern "C" void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k_cache,
+                                         const void* v_cache, const uint32_t* cu_seqlens_q,
+                                         const uint32_t* context_lens, const uint32_t* block_tables,
+                                         int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                                         int32_t head_dim, int32_t block_size,
+                                         int32_t max_blocks_per_seq, int32_t num_blocks,
+                                         int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
+                                         int64_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(block_size == 64, "attn_prefill: block_size must be 64");
+  B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "attn_prefill: head_dim must be 64/128");
+  const int G = num_kv_heads > 0 ? num_heads / num_kv_heads : 0;
+  B200_CHECK_ARG(num_kv_heads > 0 && num_heads % num_kv_heads == 0 &&
+                     (G == 1 || G == 2 || G == 4 || G == 8),
+                 "attn_prefill: H/Hkv must be 1, 2, 4 or 8");
+  B200_CHECK_ARG(batch > 0 && max_seqlen_q > 0 && num_tokens > 0 && block_tables && cu_seqlens_q,
+                 "attn_prefill: bad sizes or NULL metadata");
+  AttnMaps maps;
+  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim)) {
+    set_error(2, "attn_prefill: cuTensorMapEncodeTiled failed");
+    return;
+  }
+  launch_attn_prefill(maps, out, q, num_heads * head_dim, cu_seqlens_q, context_lens, block_tables,
+                      batch, num_heads, num_kv_heads, head_dim, max_blocks_per_seq, max_seqlen_q,
+                      scale, reinterpret_cast<cudaStream_t>(stream), num_tokens, mode);
+}
 
 extern "C" void b200_attn_prefill_f16(void* out, const void* q, const void* k_cache,
                                       const void* v_cache, const uint32_t* cu_seqlens_q,

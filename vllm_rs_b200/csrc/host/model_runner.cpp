@@ -429,7 +429,7 @@ void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
     launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
                          w.k_cache, w.v_cache, T, H, Hkv, D, D, 0, c.cos_sin_f32, st);
     launch_attn_prefill(r->maps[l], r->attn, q, qkv_n, cu_seqlens_q, context_lens, block_tables, B,
-                        H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st);
+                        H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st, T);
     linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, T, H * D, c.hidden, B200_EPI_NONE,
            stream, V);
     if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);

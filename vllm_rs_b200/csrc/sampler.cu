@@ -227,7 +227,11 @@ penalties_kernel(float* __restrict__ logits, int V, const uint32_t* __restrict__
       if (j < i) first = false;
     }
   }
-  if (first) logits[static_cast<size_t>(row) * V + t] -= static_cast<float>(count) * frequency + presence;
+  if (first) {
+    // the reference's expression, left to right, without FMA contraction (logits_processor.rs:302-304)
+    float* lp = logits + static_cast<size_t>(row) * V + t;
+    *lp = __fsub_rn(__fsub_rn(*lp, __fmul_rn(static_cast<float>(count), frequency)), presence);
+  }
 }
 
 }  // namespace

@@ -144,19 +144,22 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
     return out
 
 
+ATTN_AUTO, ATTN_MMA, ATTN_TC, ATTN_TC_SWAPDESC = -1, 0, 1, 2
+
+
 def attention_prefill(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables, max_seqlen_q,
-                      scale, out=None):
-    """PagedAttention::forward, prefill branch over the paged cache (see b200_attn_prefill_f16)."""
+                      scale, out=None, mode=ATTN_AUTO):
+    """PagedAttention::forward, prefill branch over the paged cache (see b200_attn_prefill_ex_f16)."""
     _cuda(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables)
     T, H, D = q.shape
     nb, bs, Hkv, _ = k_cache.shape
     B = cu_seqlens_q.shape[0] - 1
     if out is None:
         out = torch.empty_like(q)
-    _lib.lib().b200_attn_prefill_f16(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q),
-                                     _p(context_lens), _p(block_tables), B, H, Hkv, D, bs,
-                                     block_tables.shape[1], nb, int(max_seqlen_q), float(scale),
-                                     _stream())
+    _lib.lib().b200_attn_prefill_ex_f16(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q),
+                                        _p(context_lens), _p(block_tables), B, H, Hkv, D, bs,
+                                        block_tables.shape[1], nb, int(max_seqlen_q), T, mode, float(scale),
+                                        _stream())
     _lib.check()
     return out
 
