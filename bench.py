@@ -368,7 +368,8 @@ def run_b200(args):
                    "flops": flops, "launches": int(runner.launches_per_step),
                    "note": "one 8192-token chunk: per projection a W4->fp16 dequant pass + dense tcgen05 GEMM (CTA pairs, "
                            "256x256 tiles) when T >= B200_PREFILL_DENSE_MIN_T (default 1024), else the in-kernel-dequant "
-                           "W4A16 tcgen05 GEMM (NT=256); mma.sync varlen causal attention over the paged cache"}
+                           "W4A16 tcgen05 GEMM (NT=256); tcgen05 varlen causal attention over the paged cache "
+                           "(attn_prefill_tc.cu; B200_PREFILL_ATTN=mma selects the mma.sync kernel)"}
 
     out_line = {
         "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",
