@@ -370,8 +370,15 @@ void b200_comm_free(b200_comm*);
 void b200_allreduce_f16(b200_comm*, void* buf, int64_t count, int64_t stream);
 int32_t b200_comm_rank(const b200_comm*);
 int32_t b200_comm_world(const b200_comm*);
-/* the runner all-reduces o_proj / down_proj outputs through this communicator */
+/* the runner all-reduces o_proj / down_proj outputs through this communicator.  With the one-shot
+ * path enabled, decode steps (batch <= 64) run the FUSED form: the row-parallel GEMM's tile
+ * finalisers store their partial straight into every rank's receive buffer over NVLink and one
+ * kernel waits for all ranks' tiles, sums them in rank order, adds the residual and applies the
+ * next RMSNorm (3 launches and an NVLink round trip fewer per all-reduce; bit-identical to the
+ * unfused GEMM -> all-reduce -> add+norm).  b200_runner_set_tp_fused: -1 env B200_TP_FUSED
+ * (default on), 0 off, 1 on.                                                            */
 void b200_runner_set_comm(b200_runner*, b200_comm*);
+void b200_runner_set_tp_fused(b200_runner*, int32_t on);
 
 #ifdef __cplusplus
 }

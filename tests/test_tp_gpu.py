@@ -102,7 +102,7 @@ def _tp_decode_worker(rank, world, port, ret):
     rng = np.random.default_rng(21)            # same checkpoint on every rank
     g = torch.Generator().manual_seed(21)
     H, Hkv, D, h, I = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden, cfg.inter
-    NB, MAXB, MAXBLK = 32, 4, 4
+    NB, MAXB, MAXBLK = 32, 8, 4
 
     def qlayer(K, N):
         qw, qz, s = oq.random_awq(rng, K, N)
@@ -136,7 +136,7 @@ def _tp_decode_worker(rank, world, port, ret):
                        oracle.sin.to(dev))
     comm = tp.attach_allreduce(runner)
     osch = osched.Scheduler(NB, 64, MAXB)
-    for L in (20, 70, 129):
+    for L in (20, 70, 129, 5, 64, 33):          # 6 rows: the tcgen05 decode GEMM (M > 4), not the flat GEMV
         osch.add(osched.Sequence(np.random.default_rng(L).integers(0, cfg.vocab, size=L).tolist(), 64, max_tokens=8))
     ids, _ = osch.schedule()
     first = oracle.prefill(osched.prepare_prefill([osch.running[i] for i in ids], 64)).argmax(-1).tolist()
@@ -152,16 +152,41 @@ def _tp_decode_worker(rank, world, port, ret):
     B = len(ids)
     bt = torch.zeros(B, MAXBLK, dtype=torch.int32)
     bt[:, :mo["max_blocks"]] = torch.tensor(mo["block_tables"], dtype=torch.int32)
-    logits, _ = runner.decode_device(torch.tensor(mo["input_ids"], dtype=torch.int32).to(dev),
-                                     torch.tensor(mo["positions"], dtype=torch.int64).to(dev),
-                                     torch.tensor(mo["slot_mapping"], dtype=torch.int64).to(dev),
-                                     bt.to(dev), torch.tensor(mo["context_lens"], dtype=torch.int32).to(dev))
+    args = (torch.tensor(mo["input_ids"], dtype=torch.int32).to(dev),
+            torch.tensor(mo["positions"], dtype=torch.int64).to(dev),
+            torch.tensor(mo["slot_mapping"], dtype=torch.int64).to(dev),
+            bt.to(dev), torch.tensor(mo["context_lens"], dtype=torch.int32).to(dev))
+    # default plan: fused GEMM -> push over NVLink -> reduce + add + norm (one kernel per all-reduce)
+    logits, _ = runner.decode_device(*args)
     torch.cuda.synchronize()
+    fused_launches = runner.launches_per_step
     ret[rank] = float((logits.cpu() - ref).abs().max())
+    # classic plan: GEMM, one-shot all-reduce, add+norm as separate launches -- same arithmetic, same bits
+    runner._l.b200_runner_set_tp_fused(runner._h, 0)
+    classic, _ = runner.decode_device(*args)
+    torch.cuda.synchronize()
+    classic_launches = runner.launches_per_step
+    runner._l.b200_runner_set_tp_fused(runner._h, 1)
+    # repeated + graph-captured fused steps (device-side call numbers, alternating receive buffers)
+    s_ = torch.cuda.Stream()
+    with torch.cuda.stream(s_):
+        again, _ = runner.decode_device(*args)
+        s_.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s_):
+            glog, _ = runner.decode_device(*args)
+        reps = []
+        for _ in range(4):
+            graph.replay()
+            s_.synchronize()
+            reps.append(glog.clone())
     allr = [torch.zeros_like(logits) for _ in range(world)]
     dist.all_gather(allr, logits)
     if rank == 0:
         ret["identical"] = all(torch.equal(a, allr[0]) for a in allr)   # lm_head replicated, same logits
+        ret["fused_equals_classic"] = bool(torch.equal(logits, classic))
+        ret["replays_identical"] = bool(torch.equal(again, logits)) and all(torch.equal(x, logits) for x in reps)
+        ret["launches"] = (int(fused_launches), int(classic_launches))
     dist.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -176,3 +201,8 @@ def test_tp2_decode_matches_unsharded_oracle():
     for r in range(world):
         assert ret[r] < 2.5e-2, ret[r]         # fp16 noise floor of the toy model (see test_runner_gpu)
     assert ret["identical"]
+    assert ret["fused_equals_classic"], "fused GEMM -> NVLink push -> reduce+norm differs from the unfused plan"
+    assert ret["replays_identical"]
+    fused, classic = ret["launches"]
+    print(f"launches per step: fused {fused}, classic {classic}")
+    assert fused < classic

@@ -17,6 +17,7 @@
 
 #include "../../include/b200_vllm.h"
 #include "common.cuh"
+#include "wna16.cuh"
 
 namespace b200 {
 
@@ -135,6 +136,111 @@ oneshot_allreduce_kernel(OneShotPeers peers, __half* __restrict__ buf, size_t co
   }
 }
 
+// ---------------------------------------------------------------- fused GEMM -> all-reduce -> add + RMSNorm
+// Receive side of the kEpiPushPeers GEMM epilogue (wna16.cuh): every rank's row-parallel GEMM stores
+// its fp16 partial tiles straight into recv[buf][src] on ALL ranks while it is still computing other
+// tiles, and bumps cnt[buf][src] once per finished tile.  This kernel -- the only one between the
+// GEMM and the next layer's GEMM -- waits until every source has delivered `tiles` tiles of call
+// number `seq`, sums the partials in rank order (fp32, rounded once to fp16: the all-reduce result of
+// distributed.rs:367-369), adds the residual in fp16 (llama.rs:126-130) and applies the next RMSNorm.
+// Replaces three launches (copy + one-shot all-reduce, add_rmsnorm) and one NVLink round trip.
+// Two buffers alternate between the o_proj and down_proj call sites: a rank can only push into
+// buffer A again after it passed the wait on buffer B, which every peer feeds only after it finished
+// reading A -- so no slot is overwritten while it is being read.
+constexpr size_t kPushSlotBytes = 1 << 20;            // [M <= 64][hidden <= 8192] fp16
+constexpr int kPushBufs = 2;
+
+struct PushState {
+  uint32_t seq[kPushBufs];        // completed calls per buffer
+  uint32_t done[kPushBufs];       // intra-grid arrival counters (self-resetting)
+};
+
+__global__ void __launch_bounds__(1024)
+tp_reduce_add_rmsnorm_kernel(const __half* __restrict__ recv, const uint32_t* __restrict__ cnt,
+                             PushState* __restrict__ state, int buf, int world, uint32_t tiles,
+                             __half* __restrict__ resid, const __half* __restrict__ weight,
+                             __half* __restrict__ out, int hidden, float eps) {
+  const int m = blockIdx.x, tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(&state->seq[buf]) + 1;
+  if (tid < world) {
+    const uint32_t want = seq * tiles;
+    const uint32_t* c = cnt + buf * kMaxRanks + tid;
+    uint32_t v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+      if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer died
+    } while (static_cast<int32_t>(v - want) < 0);
+  }
+  __syncthreads();
+  __shared__ float red[32];
+  const int n8 = hidden / 8;
+  float x[8];
+  float sq = 0.f;
+  const bool active = tid < n8;
+  if (active) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < world; ++r) {
+      const uint4 v = __ldcv(reinterpret_cast<const uint4*>(
+                                 recv + (static_cast<size_t>(buf) * kMaxRanks + r) * (kPushSlotBytes / 2) +
+                                 static_cast<size_t>(m) * hidden) + tid);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    uint4 rv = *(reinterpret_cast<const uint4*>(resid + static_cast<size_t>(m) * hidden) + tid);
+    __half2* rh = reinterpret_cast<__half2*>(&rv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(rh[j]);
+      // all-reduce result rounded to fp16, then the fp16 residual add
+      const float a0 = __half2float(__float2half_rn(acc[2 * j])), a1 = __half2float(__float2half_rn(acc[2 * j + 1]));
+      x[2 * j] = __half2float(__float2half_rn(f.x + a0));
+      x[2 * j + 1] = __half2float(__float2half_rn(f.y + a1));
+      rh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      sq += x[2 * j] * x[2 * j] + x[2 * j + 1] * x[2 * j + 1];
+    }
+    *(reinterpret_cast<uint4*>(resid + static_cast<size_t>(m) * hidden) + tid) = rv;
+  }
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  if (tid < 32) {
+    float t = tid < (blockDim.x >> 5) ? red[tid] : 0.f;
+    t = warp_sum(t);
+    if (tid == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float rs = rsqrtf(red[0] / static_cast<float>(hidden) + eps);
+  if (active) {
+    const uint4 wv = *(reinterpret_cast<const uint4*>(weight) + tid);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 w = __half22float2(wh[j]);
+      oh[j] = __floats2half2_rn(x[2 * j] * rs * w.x, x[2 * j + 1] * rs * w.y);
+    }
+    *(reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * hidden) + tid) = ov;
+  }
+  // the last row to finish advances the call number for the next launch / graph replay
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t prev = atomicAdd(&state->done[buf], 1u);
+    if (prev == gridDim.x - 1) {
+      state->done[buf] = 0;
+      *reinterpret_cast<volatile uint32_t*>(&state->seq[buf]) = seq;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -150,6 +256,8 @@ struct b200_comm {
   OneShotPeers peers;
   std::vector<void*> opened;
   int force_nccl = 0;
+  // fused push path (kEpiPushPeers): this rank's receive area and every peer's view of it
+  size_t push_off = 0, cnt_off = 0, pstate_off = 0;
 };
 
 extern "C" {
@@ -199,8 +307,16 @@ int32_t b200_comm_enable_oneshot(b200_comm* c, int64_t stream) {
   const size_t data_bytes = kSlots * kOneShotMaxBytes;
   const size_t flag_bytes = kSlots * kMaxRanks * sizeof(uint32_t);
   uint8_t* base = nullptr;
-  if (cudaMalloc(&base, data_bytes + flag_bytes + 256) != cudaSuccess) return -1;
-  cudaMemset(base, 0, data_bytes + flag_bytes + 256);
+  const size_t push_off = data_bytes + flag_bytes + 256;
+  const size_t push_bytes = static_cast<size_t>(kPushBufs) * kMaxRanks * kPushSlotBytes;
+  const size_t cnt_off = push_off + push_bytes;
+  const size_t pstate_off = cnt_off + 256;
+  const size_t total = pstate_off + 256;
+  if (cudaMalloc(&base, total) != cudaSuccess) return -1;
+  cudaMemset(base, 0, total);
+  c->push_off = push_off;
+  c->cnt_off = cnt_off;
+  c->pstate_off = pstate_off;
   c->my_data = base;
   c->my_flags = reinterpret_cast<uint32_t*>(base + data_bytes);
   c->state = reinterpret_cast<uint32_t*>(base + data_bytes + flag_bytes);
@@ -273,3 +389,36 @@ int32_t b200_comm_rank(const b200_comm* c) { return c ? c->rank : 0; }
 int32_t b200_comm_world(const b200_comm* c) { return c ? c->world : 1; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- internal (model_runner.cpp)
+namespace b200 {
+
+// Fill the kEpiPushPeers fields of a GEMM epilogue for call-site buffer `buf` (0 = o_proj, 1 = down_proj).
+bool comm_push_targets(b200_comm* c, int buf, int M, int N, FusedEpi* fe) {
+  if (!c || !c->oneshot || c->force_nccl || buf < 0 || buf >= kPushBufs) return false;
+  if (static_cast<size_t>(M) * N * 2 > kPushSlotBytes || N % 8 != 0) return false;
+  for (int r = 0; r < c->world; ++r) {
+    uint8_t* base = c->peers.data[r];
+    fe->push[r] = reinterpret_cast<__half*>(base + c->push_off +
+                                            (static_cast<size_t>(buf) * kMaxRanks + c->rank) * kPushSlotBytes);
+    fe->push_cnt[r] = reinterpret_cast<uint32_t*>(base + c->cnt_off) + buf * kMaxRanks + c->rank;
+  }
+  fe->push_world = c->world;
+  return true;
+}
+
+// x += all-reduce(pushed partials); out = rmsnorm(x) * weight.  `tiles` = 128-channel tiles every rank pushes.
+void comm_reduce_add_rmsnorm(b200_comm* c, int buf, int tiles, void* resid, const void* weight, void* out,
+                             int M, int hidden, float eps, cudaStream_t st) {
+  int threads = ((hidden / 8 + 31) / 32) * 32;
+  if (threads < 32) threads = 32;
+  launch_pdl(tp_reduce_add_rmsnorm_kernel, dim3(M), dim3(threads), 0, st,
+             reinterpret_cast<const __half*>(c->my_data + c->push_off),
+             reinterpret_cast<const uint32_t*>(c->my_data + c->cnt_off),
+             reinterpret_cast<PushState*>(c->my_data + c->pstate_off), buf, c->world,
+             static_cast<uint32_t>(tiles), reinterpret_cast<__half*>(resid),
+             reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(out), hidden, eps);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace b200

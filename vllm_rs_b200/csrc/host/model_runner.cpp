@@ -29,6 +29,9 @@
 using namespace b200;
 namespace b200 {
 long long launch_count();
+bool comm_push_targets(b200_comm* c, int buf, int M, int N, FusedEpi* fe);
+void comm_reduce_add_rmsnorm(b200_comm* c, int buf, int tiles, void* resid, const void* weight, void* out,
+                             int M, int hidden, float eps, cudaStream_t st);
 void launch_sample_topk_topp(uint32_t* out_ids, const float* logits, int B, int V, int k, float p, float t,
                              const uint64_t* seed_dev, cudaStream_t st);
 void launch_wna16_dequant(const uint32_t* bp, const __half* scales, const uint32_t* qzeros, __half* out,
@@ -48,6 +51,8 @@ struct b200_runner {
              *sin = nullptr;
   b200_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  b200_comm* comm = nullptr;     // set by b200_runner_set_comm: enables the fused GEMM -> all-reduce -> norm plan
+  int tp_fused = -1;             // -1 = env B200_TP_FUSED (default on), 0 / 1 forced
   // workspace carve-up
   uint8_t* ws = nullptr;
   int64_t ws_bytes = 0;
@@ -191,11 +196,21 @@ static void comm_allreduce_thunk(void* buf, int64_t count, void* user, int64_t s
 void b200_runner_set_comm(b200_runner* r, b200_comm* c) {
   r->allreduce = c ? comm_allreduce_thunk : nullptr;
   r->allreduce_user = c;
+  r->comm = c;
+}
+
+void b200_runner_set_tp_fused(b200_runner* r, int32_t on) {
+  if (r->tp_fused != on) {
+    for (auto& g : r->graphs) cudaGraphExecDestroy(g.second);
+    r->graphs.clear();
+  }
+  r->tp_fused = on;
 }
 
 void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user) {
   r->allreduce = fn;
   r->allreduce_user = user;
+  r->comm = nullptr;
 }
 
 // ModelRunner::sample (runner.rs:1390-1570) for the cached strategy: greedy argmax or the device sampler
@@ -264,6 +279,33 @@ static bool rope_fusable(const b200_runner* r) {
 }
 static bool fused_plan_enabled(const b200_runner* r) {
   return fused_env() == 1 && rope_fusable(r) && r->allreduce == nullptr;
+}
+
+static bool tp_fused_enabled(const b200_runner* r) {
+  if (!r->comm || r->cfg.bits == 16) return false;
+  if (r->tp_fused >= 0) return r->tp_fused != 0;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B200_TP_FUSED");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env == 1;
+}
+
+// Row-parallel linear of a TP rank followed by all-reduce, residual add and the next RMSNorm
+// (distributed.rs:438-454 + llama.rs:126-130 + others.rs:11-66).  Fused form: the GEMM's tile
+// finalisers push the partial into every rank's receive buffer (kEpiPushPeers) and ONE kernel waits,
+// sums, adds and normalises.  Returns false when the shape needs the classic three launches.
+static bool row_linear_reduce_norm(b200_runner* r, int buf, const __half* in, const void* w, const void* s,
+                                   const void* z, int M, int K, const void* norm_w, cudaStream_t st) {
+  const b200_model_config& c = r->cfg;
+  if (!tp_fused_enabled(r) || M > 64) return false;
+  FusedEpi fe;
+  std::memset(&fe, 0, sizeof(fe));
+  if (!comm_push_targets(r->comm, buf, M, c.hidden, &fe)) return false;
+  linear_fused(r, in, w, s, z, nullptr, r->proj, M, K, c.hidden, kEpiPushPeers, fe, st);
+  comm_reduce_add_rmsnorm(r->comm, buf, c.hidden / kTileN, r->x, norm_w, r->xn, M, c.hidden, c.rms_eps, st);
+  return true;
 }
 
 // Fused decode plan: RMSNorm weight multiply + sum of squares folded into the producing GEMM's
@@ -343,12 +385,16 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
   const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim;
   const int qkv_n = (H + 2 * Hkv) * D;
   b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);
+  bool normed = false;     // r->xn already holds rmsnorm(x) for the coming block (fused TP reduce wrote it)
   for (int l = 0; l < c.num_layers; ++l) {
     const b200_layer_weights& w = r->layers[l];
-    if (l == 0)
-      b200_rmsnorm_f16(r->xn, r->x, w.input_norm, B, c.hidden, c.rms_eps, stream);
-    else
-      b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, B, c.hidden, c.rms_eps, stream);
+    if (!normed) {
+      if (l == 0)
+        b200_rmsnorm_f16(r->xn, r->x, w.input_norm, B, c.hidden, c.rms_eps, stream);
+      else
+        b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.input_norm, B, c.hidden, c.rms_eps, stream);
+    }
+    normed = false;
     // ---- attention block
     __half* q = r->qkv;
     if (fused_env() != 0 && rope_fusable(r)) {     // also the TP path (no collective touches q|k|v)
@@ -370,11 +416,15 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
     }
     launch_paged_attn_decode(r->maps[l], r->attn, q, qkv_n, block_tables, context_lens, B, H, Hkv,
                              D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
-    linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, B, H * D, c.hidden, B200_EPI_NONE,
-           stream);
-    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
+    // o_proj (row-parallel) -> all-reduce -> residual add -> post-attention norm
+    if (!row_linear_reduce_norm(r, 0, r->attn, w.o_w, w.o_s, w.o_z, B, H * D, w.post_norm, st)) {
+      linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, B, H * D, c.hidden, B200_EPI_NONE,
+             stream);
+      if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
+      b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.post_norm, B, c.hidden, c.rms_eps, stream);
+    }
     // ---- MLP block
-    b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.post_norm, B, c.hidden, c.rms_eps, stream);
+    const void* next_norm = l + 1 < c.num_layers ? r->layers[l + 1].input_norm : r->final_norm;
     if (c.bits == 16) {
       __half* gu = r->act;   // [B, 2*inter]
       linear(r, r->xn, w.gate_up_w, nullptr, nullptr, nullptr, gu, B, c.hidden, 2 * c.inter,
@@ -382,15 +432,21 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
       b200_silu_mul_f16(r->act2, gu, B, c.inter, stream);
       linear(r, r->act2, w.down_w, nullptr, nullptr, nullptr, r->proj, B, c.inter, c.hidden,
              B200_EPI_NONE, stream);
+      if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
     } else {
       linear(r, r->xn, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, B, c.hidden,
              2 * c.inter, B200_EPI_SILU_MUL, stream);
-      linear(r, r->act, w.down_w, w.down_s, w.down_z, nullptr, r->proj, B, c.inter, c.hidden,
-             B200_EPI_NONE, stream);
+      // down_proj (row-parallel) -> all-reduce -> residual add -> the NEXT block's norm
+      if (row_linear_reduce_norm(r, 1, r->act, w.down_w, w.down_s, w.down_z, B, c.inter, next_norm, st)) {
+        normed = true;
+      } else {
+        linear(r, r->act, w.down_w, w.down_s, w.down_z, nullptr, r->proj, B, c.inter, c.hidden,
+               B200_EPI_NONE, stream);
+        if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
+      }
     }
-    if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(B) * c.hidden, r->allreduce_user, stream);
   }
-  b200_add_rmsnorm_f16(r->xn, r->x, r->proj, r->final_norm, B, c.hidden, c.rms_eps, stream);
+  if (!normed) b200_add_rmsnorm_f16(r->xn, r->x, r->proj, r->final_norm, B, c.hidden, c.rms_eps, stream);
   float* lg = logits ? logits : r->logits;
   b200_dense_gemm_f16(r->xn, r->lm_head, lg, B, c.vocab, c.hidden, 1, stream);
   if (out_ids) pick_tokens(r, out_ids, lg, B, stream);

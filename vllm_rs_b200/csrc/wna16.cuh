@@ -105,6 +105,10 @@ constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m
 constexpr int kSsqStride = 32;    // floats between two rows' sums of squares: one 128 B line per row, so the
                                   // finalisers' atomics spread over L2 slices instead of serialising on one line
 constexpr int kEpiRopeKv = 3;      // fused q|k|v: RoPE(q, k), K/V rows written to the paged cache
+constexpr int kEpiPushPeers = 4;   // row-parallel GEMM of a TP rank: the fp16 partial tile is stored into
+                                   // EVERY rank's receive buffer over NVLink and a per-source tile counter is
+                                   // bumped there -- the all-reduce's transfer, tile by tile, under the GEMM
+constexpr int kMaxTpRanks = 8;
 
 // Everything the tile finaliser may fuse around a GEMM of the decoder layer
 // (llama.rs:107-131, attention.rs:648-839, others.rs:11-66 restated as GEMM epilogues).
@@ -125,6 +129,10 @@ struct FusedEpi {
   __half* k_cache;
   __half* v_cache;
   int H, Hkv, D;
+  // kEpiPushPeers: rank r's receive slot for THIS rank's partial [M, N] and its tile counter
+  __half* push[kMaxTpRanks];
+  uint32_t* push_cnt[kMaxTpRanks];
+  int push_world;
 };
 
 struct SplitOut {
@@ -307,9 +315,23 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
         store_half4(cache + (static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d, out);
       }
     }
+  } else if (epi == kEpiPushPeers) {
+    if (valid) {
+      const size_t idx = static_cast<size_t>(m) * N + c.n0;
+      for (int p = 0; p < fe.push_world; ++p) store_half4(fe.push[p] + idx, v0);   // peer-mapped (NVLink) stores
+    }
   } else if (valid) {
     store_half4(o.c + static_cast<size_t>(m) * N + c.n0, v0);
   }
+}
+
+// After the finaliser of a kEpiPushPeers tile: make the tile's remote stores visible system-wide,
+// then bump this rank's tile counter on every peer (release, system scope).
+__device__ __forceinline__ void push_signal(const FusedEpi& fe, int tid, int nthreads, int bar_id) {
+  __threadfence_system();
+  named_bar_sync(bar_id, nthreads);
+  if (tid < fe.push_world)
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(fe.push_cnt[tid]) : "memory");
 }
 
 // Rows [m_lo, m_hi) of tile nt: sum the partials in split order (deterministic) and apply the
@@ -414,6 +436,10 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
     case B200_EPI_SILU_MUL: split_reduce_rows<B200_EPI_SILU_MUL>(o, nt, tid, nthreads, m_lo, m_hi); break;
     case kEpiResidNorm: split_reduce_rows<kEpiResidNorm>(o, nt, tid, nthreads, m_lo, m_hi); break;
     case kEpiRopeKv: split_reduce_rows<kEpiRopeKv>(o, nt, tid, nthreads, m_lo, m_hi); break;
+    case kEpiPushPeers:
+      split_reduce_rows<kEpiPushPeers>(o, nt, tid, nthreads, m_lo, m_hi);
+      push_signal(o.fe, tid, nthreads, bar_id);
+      break;
     default: split_reduce_rows<B200_EPI_NONE>(o, nt, tid, nthreads, m_lo, m_hi); break;
   }
 }

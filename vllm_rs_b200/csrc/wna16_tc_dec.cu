@@ -393,6 +393,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       DEC_TRE(3);
       if (last) {
         split_reduce_rows<EPI>(o, nt, threadIdx.x, kDqThreads, 0, M);
+        if (EPI == kEpiPushPeers) push_signal(o.fe, threadIdx.x, kDqThreads, 1);
         DEC_TRE(4);
       }
     }
@@ -495,6 +496,7 @@ static bool launch_nt(const WnaParams& p, cudaStream_t st) {
     case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL>(p, st);
     case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm>(p, st);
     case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv>(p, st);
+    case kEpiPushPeers: return launch_epi<BITS, NT, kEpiPushPeers>(p, st);
     default: return launch_epi<BITS, NT, B200_EPI_NONE>(p, st);
   }
 }
