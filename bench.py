@@ -185,6 +185,15 @@ def run_reference(args):
     }))
 
 
+def _trace(msg):
+    """B200_BENCH_TRACE=1: progress lines on stderr (which phase a multi-GPU run is in)."""
+    if os.environ.get("B200_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
+
+
 def _prof(which, start):
     """B200_PROFILE=decode|prefill brackets that region with cudaProfilerStart/Stop so that
     `ncu --profile-from-start off` lists exactly its launches (a run under ncu is never a bench value)."""
@@ -220,11 +229,13 @@ def run_b200(args):
     runner = synthetic.build_awq_runner(MODEL, num_blocks=num_blocks, max_blocks_per_seq=blocks_per_seq,
                                         max_batch=B, num_layers=L, tp_size=tp, device=dev)
     synthetic.fill_kv_random(runner)
+    _trace("runner built")
     if tp > 1:
         from vllm_rs_b200 import tp as tpmod
         tpmod.attach_allreduce(runner)
     shape = runner.shape
     torch.cuda.synchronize()
+    _trace("comm attached")
 
     # ---------------- device-resident value: graph replays of one step at ctx
     g = torch.Generator(device=dev).manual_seed(1)
@@ -244,13 +255,16 @@ def run_b200(args):
         for _ in range(2):
             step_direct()
         stream.synchronize()
+        _trace("2 eager steps done")
         launches_per_step = runner.launches_per_step
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
             step_direct()
+        _trace("graph captured")
         for _ in range(W):
             graph.replay()
         stream.synchronize()
+        _trace("warm-up replays done")
 
         def barrier():
             if world > 1:
@@ -281,6 +295,7 @@ def run_b200(args):
         ms = float(t.item())
     ms_per_step = ms / K
     value = B * 1e3 / ms_per_step
+    _trace(f"timed region done: {ms_per_step:.3f} ms/step")
 
     # ---------------- roofline of the dominant kernel (paged attention decode), timed alone
     peak, peak_src = measured_peaks()
@@ -310,7 +325,9 @@ def run_b200(args):
     assert is_prefill and len(idx) == B, (is_prefill, len(idx))
     _, fin = sched.filter_prefill_finished(idx)     # KV of the prompts is the random fill above
     sched.postprocess(fin, rng.integers(0, vocab, size=B))
+    _trace("attention roofline done; capturing the runner's own graph")
     runner.capture([B])
+    _trace("runner graph captured")
 
     def engine_step():
         ii, pf = sched.schedule()
@@ -336,6 +353,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = B * 1e3 / e2e_ms
+    _trace("e2e done")
 
     # ---------------- prefill chunk (second half of BASELINE's metric: "prefill TFLOPS")
     prefill = None
@@ -388,7 +406,10 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "paged_attn_decode_kernel<128> (+ split merge)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the
+                     # committed `ncu --set full` capture profiles/r1_attn_decode_ncu_full.txt (537.18 + 8.35 MB)
+                     "traffic": 545532160 if (B, ctx, tp, L) == (32, 4096, 1, 32) else None,
+                     "peak_source": peak_src, "bytes_per_launch": attn_bytes,
                      "ms_per_launch": attn_ms},
         "step_roofline": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "peak": peak,
                           "unit": "GB/s", "frac": step_gbs / peak},

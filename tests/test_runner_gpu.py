@@ -248,3 +248,45 @@ def test_prefill_step_and_engine_loop(lib):
             checked += 1
         assert len(g_out[sid]) == len(o_out[sid]) == 7    # prefill token + 6 decode tokens
     assert checked >= 15
+
+
+@pytest.mark.parametrize("fmt", ["awq", "gptq8"])
+def test_large_prefill_step_dense_route(lib, fmt):
+    """A prefill step of >= 1024 tokens takes the other launch plan: per projection a W4/W8 -> fp16
+    dequant pass + the dense tcgen05 GEMM (CTA pairs), SiLU * mul inside the gate|up GEMM epilogue,
+    tcgen05 attention (head_dim 128).  Checked against the oracle at the logits (noise-floor bar as in
+    the other runner tests) and against the oracle's KV cache."""
+    cfg = om.ModelConfig(hidden=512, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=128, inter=1024,
+                         vocab=1024, rope_theta=10000.0, rms_eps=1e-5, max_pos=4096)
+    NB, MAXB, MAXBLK = 48, 4, 16
+    oracle, runner = _build(cfg, fmt, seed=5, num_blocks=NB, max_batch=MAXB, max_blocks=MAXBLK,
+                            max_prefill_tokens=2048)
+    with om.exact_mode():
+        exact = om.LlamaOracle(cfg, oracle.w, NB)
+    rng = np.random.default_rng(9)
+    osch = osched.Scheduler(NB, 64, MAXB, chunk_size=8192)
+    for L in (700, 500):
+        osch.add(osched.Sequence(rng.integers(0, cfg.vocab, size=L).tolist(), 64, max_tokens=4))
+    ids, pf = osch.schedule()
+    assert pf and len(ids) == 2
+    seqs = [osch.running[i] for i in ids]
+    meta = osched.prepare_prefill(seqs, 64, 8192)
+    assert len(meta["input_ids"]) == 1200
+    ref = oracle.prefill(meta)
+    with om.exact_mode():
+        truth = exact.prefill(meta)
+    m2 = dict(meta)
+    m2["block_tables"] = osched.prepare_block_tables(seqs)[0]
+    m2 = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m2.items()}
+    got, ids_gpu = runner.prefill_device(m2)
+    launches_big = runner.launches_per_step
+    noise = (ref - truth).abs().max().item()
+    err = (got.cpu() - truth).abs().max().item()
+    print(f"[{fmt}] large prefill: noise {noise:.2e} err_truth {err:.2e} launches {launches_big}")
+    assert err <= 3 * noise + 2e-3, f"prefill logits {err} vs noise floor {noise}"
+    for l in range(cfg.num_layers):
+        d = (runner.k_cache[l].cpu().float() - oracle.k_cache[l].float()).abs().max()
+        assert d < 2e-2, d
+    for b in range(2):
+        if ref[b].sort(descending=True).values[:2].diff().abs() > 3 * noise + 2e-3:
+            assert int(ids_gpu[b]) == int(ref[b].argmax())

@@ -80,7 +80,11 @@ __device__ __forceinline__ void tile_coords(int t, const Args& a, int& p, int& q
   p = g * a.group_p + (r - q * rows);
 }
 
-template <int BN, int CG, bool SWAP, bool OUT_F32>
+// SILU (prefill gate|up projection, BN = 256, fp16 out): the weight rows arrive interleaved in blocks of
+// 128 (gate channels [128t, 128t+128) then up channels of the same range, see wna16_dequant_kernel), so
+// accumulator columns c and c + 128 of a tile are gate / up of ONE output channel and the epilogue
+// writes silu(gate) * up straight into [M, N/2] (mlp.rs:451-469) -- no [M, N] round trip through HBM.
+template <int BN, int CG, bool SWAP, bool OUT_F32, bool SILU = false>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap pmap, const __grid_constant__ CUtensorMap qmap,
                      const Args a) {
@@ -207,6 +211,32 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap pmap, const __grid_cons
       mbar_wait_bounded(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       const int prow = (p * CG + static_cast<int>(rank)) * kBM + q4 * 32 + lane;    // this thread's P row
+      if (SILU) {
+        const int half_n = a.N >> 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t g[32], u[32];
+          tmem_ld_x32(tmem_base + lane_base + buf * BN + c0, g);
+          tmem_ld_x32(tmem_base + lane_base + buf * BN + BN / 2 + c0, u);
+          tc_wait_ld();
+          const int col = q * (BN / 2) + c0;          // output channel of g[0]
+          if (prow < a.M && col < half_n) {
+            __half* dst = reinterpret_cast<__half*>(a.c) + static_cast<size_t>(prow) * half_n + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // the two GEMM outputs are rounded to fp16 first: the values the unfused pipeline sees
+                const float2 gg = __half22float2(u32_as_h2(pack_half2(__uint_as_float(g[j + 2 * e]), __uint_as_float(g[j + 2 * e + 1]))));
+                const float2 uu = __half22float2(u32_as_h2(pack_half2(__uint_as_float(u[j + 2 * e]), __uint_as_float(u[j + 2 * e + 1]))));
+                w[e] = pack_half2(gg.x / (1.f + __expf(-gg.x)) * uu.x, gg.y / (1.f + __expf(-gg.y)) * uu.y);
+              }
+              if (col + j + 8 <= half_n) *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -294,7 +324,7 @@ static bool make_map(CUtensorMap* map, const void* base, int rows, int K, int bo
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
 }
 
-template <int BN, int CG, bool SWAP, bool OUT_F32>
+template <int BN, int CG, bool SWAP, bool OUT_F32, bool SILU = false>
 static bool launch_cfg(const void* x, const void* w, void* c, const __half* bias, int M, int N, int K,
                        cudaStream_t st) {
   using C = Cfg<BN, CG>;
@@ -319,7 +349,7 @@ static bool launch_cfg(const void* x, const void* w, void* c, const __half* bias
     set_error(2, "dense_gemm_tc: cuTensorMapEncodeTiled failed");
     return true;
   }
-  auto kern = dense_gemm_tc_kernel<BN, CG, SWAP, OUT_F32>;
+  auto kern = dense_gemm_tc_kernel<BN, CG, SWAP, OUT_F32, SILU>;
   static bool attr_set = false;
   static int max_units = 0;
   if (!attr_set) {
@@ -366,6 +396,17 @@ bool launch_dense_gemm_tc(const void* x, const void* w, void* c, const void* bia
                  : dg::launch_out<false>(x, w, c, b, M, N, K, mode, st);
 }
 
+// gate|up projection with the SiLU * mul epilogue: w rows interleaved in 128-blocks (gate, up, gate, ...),
+// out [M, N/2] fp16.  false: shape not supported (the caller runs GEMM + silu_mul instead).
+bool launch_dense_gemm_tc_silu(const void* x, const void* w, void* out, int M, int N, int K, int mode,
+                               cudaStream_t st) {
+  if (K % dg::kBK != 0 || N % 256 != 0 || M <= 128) return false;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return false;
+  if (mode == 1) return dg::launch_cfg<256, 1, false, false, true>(x, w, out, nullptr, M, N, K, st);
+  return dg::launch_cfg<256, 2, false, false, true>(x, w, out, nullptr, M, N, K, st);
+}
+
 // ---------------------------------------------------------------- W4 / W8 -> fp16 [N, K]
 // One pass over a prepacked (tile-major) quantised weight: thread = output channel, it reads the
 // 32 / 64 packed bytes of a 64-K chunk and writes the chunk's 128 bytes of fp16((q - z) * s) into
@@ -375,8 +416,13 @@ template <int BITS>
 __global__ void __launch_bounds__(kTileN)
 wna16_dequant_kernel(const uint32_t* __restrict__ bp, const __half* __restrict__ scales,
                      const uint32_t* __restrict__ qzeros, __half* __restrict__ out, int K, int N,
-                     int group_size, int qfmt, int chunks_per_cta) {
+                     int group_size, int qfmt, int chunks_per_cta, int interleave) {
   const int nt = blockIdx.x, ch = threadIdx.x, n = nt * kTileN + ch;
+  // interleave: the fused gate|up weight ([gate tiles | up tiles] along N) is written as
+  // gate tile 0, up tile 0, gate tile 1, ... so a 256-row GEMM tile holds both halves of 128 channels
+  const int half_tiles = gridDim.x >> 1;
+  const int dst_tile = interleave ? (nt < half_tiles ? 2 * nt : 2 * (nt - half_tiles) + 1) : nt;
+  const int n_dst = dst_tile * kTileN + ch;
   const int KC = K / kChunkK;
   const int c0 = blockIdx.y * chunks_per_cta, c1 = min(c0 + chunks_per_cta, KC);
   constexpr int W = 2 * BITS;                                  // packed words per thread per chunk
@@ -418,21 +464,21 @@ wna16_dequant_kernel(const uint32_t* __restrict__ bp, const __half* __restrict__
         }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(n) * K + kc * kChunkK);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(n_dst) * K + kc * kChunkK);
 #pragma unroll
     for (int e = 0; e < 8; ++e) dst[e] = make_uint4(o[e * 4], o[e * 4 + 1], o[e * 4 + 2], o[e * 4 + 3]);
   }
 }
 
 void launch_wna16_dequant(const uint32_t* bp, const __half* scales, const uint32_t* qzeros, __half* out,
-                          int K, int N, int bits, int group_size, int qfmt, cudaStream_t st) {
+                          int K, int N, int bits, int group_size, int qfmt, cudaStream_t st, int interleave) {
   const int KC = K / kChunkK;
   const int cpc = 8;
   dim3 grid(N / kTileN, (KC + cpc - 1) / cpc);
   if (bits == 4)
-    wna16_dequant_kernel<4><<<grid, kTileN, 0, st>>>(bp, scales, qzeros, out, K, N, group_size, qfmt, cpc);
+    wna16_dequant_kernel<4><<<grid, kTileN, 0, st>>>(bp, scales, qzeros, out, K, N, group_size, qfmt, cpc, interleave);
   else
-    wna16_dequant_kernel<8><<<grid, kTileN, 0, st>>>(bp, scales, qzeros, out, K, N, group_size, qfmt, cpc);
+    wna16_dequant_kernel<8><<<grid, kTileN, 0, st>>>(bp, scales, qzeros, out, K, N, group_size, qfmt, cpc, interleave);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -449,5 +495,5 @@ extern "C" void b200_wna16_dequant_f16(const void* b_packed, const void* scales,
   B200_CHECK_ARG(g % 32 == 0 && k % g == 0, "wna16_dequant: bad group size");
   launch_wna16_dequant(static_cast<const uint32_t*>(b_packed), static_cast<const __half*>(scales),
                        static_cast<const uint32_t*>(qzeros), static_cast<__half*>(out), k, n, bits, g, qfmt,
-                       reinterpret_cast<cudaStream_t>(stream));
+                       reinterpret_cast<cudaStream_t>(stream), 0);
 }

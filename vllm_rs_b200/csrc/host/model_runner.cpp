@@ -35,7 +35,9 @@ void comm_reduce_add_rmsnorm(b200_comm* c, int buf, int tiles, void* resid, cons
 void launch_sample_topk_topp(uint32_t* out_ids, const float* logits, int B, int V, int k, float p, float t,
                              const uint64_t* seed_dev, cudaStream_t st);
 void launch_wna16_dequant(const uint32_t* bp, const __half* scales, const uint32_t* qzeros, __half* out,
-                          int K, int N, int bits, int group_size, int qfmt, cudaStream_t st);
+                          int K, int N, int bits, int group_size, int qfmt, cudaStream_t st, int interleave);
+bool launch_dense_gemm_tc_silu(const void* x, const void* w, void* out, int M, int N, int K, int mode,
+                               cudaStream_t st);
 }
 
 namespace {
@@ -84,6 +86,15 @@ static int prefill_dense_min_tokens() {
     if (v <= 0) v = 1 << 30;
   }
   return v;
+}
+
+static bool prefill_silu_fused() {       // B200_PREFILL_SILU_FUSED=0: unfused GEMM + silu_mul (A/B arm)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_PREFILL_SILU_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static int64_t carve(b200_runner* r, uint8_t* base) {
@@ -237,7 +248,7 @@ static void linear(b200_runner* r, const __half* in, const void* w, const void* 
       K % kChunkK == 0) {
     const int g = c.group_size <= 0 ? K : c.group_size;
     launch_wna16_dequant((const uint32_t*)w, (const __half*)s, (const uint32_t*)z, r->wdeq, K, N, c.bits, g,
-                         c.qfmt, reinterpret_cast<cudaStream_t>(stream));
+                         c.qfmt, reinterpret_cast<cudaStream_t>(stream), 0);
     b200_dense_gemm_f16(in, r->wdeq, out, M, N, K, 0, stream);
     if (bias) b200_add_bias_f16(out, bias, M, N, stream);
     return;
@@ -490,9 +501,21 @@ void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
            stream, V);
     if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);
     b200_add_rmsnorm_f16(r->xn, r->x, r->proj, w.post_norm, T, c.hidden, c.rms_eps, stream);
-    linear(r, r->xn, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, T, c.hidden,
-           2 * c.inter, B200_EPI_NONE, stream, V);
-    b200_silu_mul_f16(r->act2, r->act, T, c.inter, stream);
+    // gate|up with SiLU * mul in the GEMM epilogue when the step is large enough for the dequant + dense
+    // route (the dequant pass interleaves gate / up rows so both land in one accumulator tile)
+    bool mlp_fused = false;
+    if (r->wdeq && T >= prefill_dense_min_tokens() && c.inter % kTileN == 0 && c.hidden % kChunkK == 0 &&
+        prefill_silu_fused()) {
+      const int g = c.group_size <= 0 ? c.hidden : c.group_size;
+      launch_wna16_dequant((const uint32_t*)w.gate_up_w, (const __half*)w.gate_up_s, (const uint32_t*)w.gate_up_z,
+                           r->wdeq, c.hidden, 2 * c.inter, c.bits, g, c.qfmt, st, 1);
+      mlp_fused = launch_dense_gemm_tc_silu(r->xn, r->wdeq, r->act2, T, 2 * c.inter, c.hidden, 2, st);
+    }
+    if (!mlp_fused) {
+      linear(r, r->xn, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, T, c.hidden,
+             2 * c.inter, B200_EPI_NONE, stream, V);
+      b200_silu_mul_f16(r->act2, r->act, T, c.inter, stream);
+    }
     linear(r, r->act2, w.down_w, w.down_s, w.down_z, nullptr, r->proj, T, c.inter, c.hidden,
            B200_EPI_NONE, stream, V);
     if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);

@@ -109,7 +109,10 @@ def init_comm_from_torch_dist(oneshot=True) -> Comm:
 
 
 def attach_allreduce(runner, oneshot=True) -> Comm:
+    import os
     comm = init_comm_from_torch_dist(oneshot)
+    if os.environ.get("B200_FORCE_NCCL") == "1":       # A/B arm: every all-reduce through ncclAllReduce
+        comm.force_nccl(True)
     runner._l.b200_runner_set_comm(runner._h, comm._h)
     runner._comm = comm
     return comm
