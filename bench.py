@@ -283,16 +283,19 @@ def run_b200(args):
             _prof("decode", False)
             barrier()
             ms = e0.elapsed_time(e1)
-            # keep sampling under load a little longer so short runs still get >= a few samples
-            t_end = time.time() + 1.0
-            while time.time() < t_end:
+            # keep the GPU under load ~1 s more so short runs still get a few clock samples.  The number
+            # of extra replays must be IDENTICAL on every rank (each replay contains the TP exchange: a
+            # rank that replays once more than its peers waits for them forever), so it is derived from
+            # the rank-agreed step time, never from a local wall clock.
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            extra = max(1, min(2000, int(1000.0 / max(ms / K, 1e-3))))
+            for _ in range(extra):
                 graph.replay()
             stream.synchronize()
         clocks = clk.summary()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / K
     value = B * 1e3 / ms_per_step
     _trace(f"timed region done: {ms_per_step:.3f} ms/step")

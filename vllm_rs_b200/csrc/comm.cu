@@ -99,8 +99,10 @@ oneshot_allreduce_kernel(OneShotPeers peers, __half* __restrict__ buf, size_t co
   if (threadIdx.x < world) {
     const uint32_t* f = peers.flags[rank] + slot * kMaxRanks + threadIdx.x;
     uint32_t v;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer died or ran a different step count
     } while (static_cast<int32_t>(v - seq) < 0);
   }
   __syncthreads();
