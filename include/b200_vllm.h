@@ -240,6 +240,21 @@ void b200_scheduler_clear_finished(b200_scheduler*);
 int32_t b200_scheduler_num_running(const b200_scheduler*);
 int32_t b200_scheduler_num_waiting(const b200_scheduler*);
 int32_t b200_scheduler_num_free_blocks(const b200_scheduler*);
+/* Prefix cache (src/core/prefix_cache.rs; block_manager.rs:179-221,275-299,346-442,552-604,
+ * 657-672; scheduler.rs:60-104,288-337,617-620,1167-1175).  enable: max_tokens >= 0 is
+ * `prefix_cache_max_tokens`, < 0 the default 65 % of the blocks; returns the capacity in blocks
+ * (0 = disabled, as build_prefix_cache_config does).  Once enabled, allocate() shares the cached
+ * full blocks of a matching prompt prefix (never the whole prompt), postprocess() inserts a
+ * finished sequence's full blocks before dropping its references, and schedule() evicts 10 % of
+ * the cache when a sequence cannot append or usage is over 95 %.  hash_block is the chain hash
+ * (Rust DefaultHasher = SipHash-1-3, zero key, over parent u64 | len usize | tokens u32 LE).      */
+int32_t b200_scheduler_enable_prefix_cache(b200_scheduler*, int64_t max_tokens);
+int32_t b200_scheduler_prefix_cache_blocks(const b200_scheduler*);
+int32_t b200_scheduler_evict_prefix_cache_blocks(b200_scheduler*, int32_t num_blocks);
+int32_t b200_scheduler_block_ref_count(const b200_scheduler*, int32_t block_id);
+/* free_block_ids in pop order; returns the count, copies up to cap */
+int32_t b200_scheduler_free_block_ids(const b200_scheduler*, uint32_t* out, int32_t cap);
+uint64_t b200_prefix_hash_block(uint64_t parent_hash, const uint32_t* tokens, int32_t n);
 /* inspect a running sequence: returns token count; copies up to cap entries */
 int32_t b200_scheduler_seq_info(const b200_scheduler*, int32_t running_idx, int64_t* seq_id,
                                 int32_t* num_cached_tokens, int32_t* status,

@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Line-for-line Python restatement of
 
   /root/reference/src/core/sequence.rs:150-238          Sequence
-  /root/reference/src/core/block_manager.rs:51-299      BlockManager (no prefix cache / swap)
+  /root/reference/src/core/block_manager.rs:51-299,346-442,552-604,645-697   BlockManager (prefix cache, no swap)
+  /root/reference/src/core/prefix_cache.rs              PrefixCache (hash chain of full blocks, leaf LRU)
   /root/reference/src/core/scheduler.rs:186-380         add, schedule
   /root/reference/src/core/scheduler.rs:500-654         postprocess, clear_finished
   /root/reference/src/core/scheduler.rs:718-785         filter_prefill_finished
@@ -19,6 +20,16 @@ from dataclasses import dataclass, field
 
 WAITING, RUNNING, FINISHED = 0, 1, 2
 MIN_NUM_SCHEDULED_REQS = 5        # scheduler.rs:44
+KVCACHE_SWAP_THRESHOLD = 0.95     # scheduler.rs:48
+PREFIX_CACHE_RATIO_NORMAL = 0.65  # scheduler.rs:55
+PREFIX_CACHE_PRESSURE_EVICT_PERCENT = 0.1   # scheduler.rs:58
+
+
+def prefix_cache_max_blocks(num_blocks, block_size, max_tokens=None):
+    """build_prefix_cache_config (scheduler.rs:60-104) for a plain (non-PD) engine with the cache enabled."""
+    import numpy as _np
+    n = max_tokens // block_size if max_tokens is not None else int(_np.float32(num_blocks) * _np.float32(PREFIX_CACHE_RATIO_NORMAL))
+    return min(n, num_blocks)
 CHUNK_SIZE_CUDA = 8192            # scheduler.rs:203 / runner.rs:989
 
 
@@ -67,25 +78,260 @@ class Sequence:
         return c
 
 
-class BlockManager:
-    """block_manager.rs:51-299 without prefix cache, CPU swap or mamba state."""
 
-    def __init__(self, num_blocks, block_size):
+M64 = (1 << 64) - 1
+
+
+def siphash(data: bytes, k0: int = 0, k1: int = 0, c_rounds: int = 1, d_rounds: int = 3) -> int:
+    """SipHash-c-d (Aumasson & Bernstein).  Rust's `DefaultHasher::new()` -- what prefix_cache.rs:337-349
+    hashes with -- is SipHash-1-3 with the all-zero key (std is not part of /root/reference; this is the
+    published algorithm, pinned in tests/ against the paper's SipHash-2-4 vector)."""
+    v0 = k0 ^ 0x736F6D6570736575
+    v1 = k1 ^ 0x646F72616E646F6D
+    v2 = k0 ^ 0x6C7967656E657261
+    v3 = k1 ^ 0x7465646279746573
+
+    def rotl(x, b):
+        return ((x << b) | (x >> (64 - b))) & M64
+
+    def rnd(v0, v1, v2, v3):
+        v0 = (v0 + v1) & M64; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32)
+        v2 = (v2 + v3) & M64; v3 = rotl(v3, 16); v3 ^= v2
+        v0 = (v0 + v3) & M64; v3 = rotl(v3, 21); v3 ^= v0
+        v2 = (v2 + v1) & M64; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32)
+        return v0, v1, v2, v3
+
+    n = len(data)
+    for off in range(0, n - n % 8, 8):
+        m = int.from_bytes(data[off:off + 8], "little")
+        v3 ^= m
+        for _ in range(c_rounds):
+            v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+        v0 ^= m
+    b = ((n & 0xFF) << 56) | int.from_bytes(data[n - n % 8:], "little")
+    v3 ^= b
+    for _ in range(c_rounds):
+        v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+    v0 ^= b
+    v2 ^= 0xFF
+    for _ in range(d_rounds):
+        v0, v1, v2, v3 = rnd(v0, v1, v2, v3)
+    return v0 ^ v1 ^ v2 ^ v3
+
+
+def hash_block(parent_hash: int, tokens) -> int:
+    """prefix_cache.rs:337-342: `parent_hash.hash(h); tokens.hash(h)` -- u64 LE, then the slice as its
+    length (usize LE) followed by the raw little-endian u32s."""
+    data = parent_hash.to_bytes(8, "little") + len(tokens).to_bytes(8, "little")
+    data += b"".join(int(t).to_bytes(4, "little") for t in tokens)
+    return siphash(data)
+
+
+class PrefixCache:
+    """prefix_cache.rs:38-350 (no image seeds): entries hash -> [parent, block_id, children, access_id],
+    the set of leaves and a lazily-invalidated LRU queue of (leaf hash, access id)."""
+
+    def __init__(self, block_size, max_cached_blocks):
+        self.block_size = block_size
+        self.max_cached_blocks = max_cached_blocks
+        self.entries = {}
+        self.leaf_set = set()
+        self.leaf_lru = deque()
+        self.access_counter = 0
+
+    def enabled(self):                                          # :59-61
+        return self.max_cached_blocks > 0
+
+    def cached_blocks(self):
+        return len(self.entries)
+
+    def _next_access_id(self):                                  # :332-335
+        self.access_counter = (self.access_counter + 1) & M64
+        return self.access_counter
+
+    def _compact_lru_if_needed(self):                           # :316-330
+        threshold = max(len(self.entries), 64) * 4
+        if len(self.leaf_lru) <= threshold:
+            return
+        self.leaf_lru = deque((h, a) for h, a in self.leaf_lru
+                              if h in self.leaf_set and h in self.entries and self.entries[h][3] == a)
+
+    def _touch_leaf(self, h):                                   # :307-314
+        if h in self.leaf_set and h in self.entries:
+            self.leaf_lru.append((h, self.entries[h][3]))
+        self._compact_lru_if_needed()
+
+    def _touch(self, h):                                        # :297-305
+        if h in self.entries:
+            self.entries[h][3] = self._next_access_id()
+            self._touch_leaf(h)
+
+    def match_prefix(self, tokens):                             # :67-116 -> (matched_blocks, last_hash)
+        if not self.enabled():
+            return 0, None
+        full_blocks = len(tokens) // self.block_size
+        matched, parent, last = 0, 0, None
+        for i in range(full_blocks):
+            h = hash_block(parent, tokens[i * self.block_size:(i + 1) * self.block_size])
+            if h in self.entries:
+                matched += 1
+                parent = h
+                last = h
+                self._touch(h)
+            else:
+                break
+        return matched, last
+
+    def blocks_for_match(self, last_hash):                      # :118-132
+        blocks, cur = [], last_hash
+        while cur is not None and cur in self.entries:
+            blocks.append(self.entries[cur][1])
+            cur = self.entries[cur][0]
+        return blocks[::-1]
+
+    def insert_prefix(self, tokens, blocks):                    # :174-262 -> (inserted, evicted)
+        if not self.enabled():
+            return [], []
+        max_blocks = min(len(tokens) // self.block_size, len(blocks))
+        if max_blocks == 0:
+            return [], []
+        inserted, parent = [], None
+        for i in range(max_blocks):
+            base = parent if parent is not None else 0
+            h = hash_block(base, tokens[i * self.block_size:(i + 1) * self.block_size])
+            if h in self.entries:
+                self.entries[h][3] = self._next_access_id()
+                self._touch_leaf(h)
+            else:
+                if parent is not None and parent in self.entries:
+                    pe = self.entries[parent]
+                    if pe[2] == 0:
+                        self.leaf_set.discard(parent)
+                    pe[2] += 1
+                a = self._next_access_id()
+                self.entries[h] = [parent, blocks[i], 0, a]
+                self.leaf_set.add(h)
+                self.leaf_lru.append((h, a))
+                inserted.append(blocks[i])
+            parent = h
+        excess = max(len(self.entries) - self.max_cached_blocks, 0)
+        evicted = self.evict_blocks(excess) if excess > 0 else []
+        return inserted, evicted
+
+    def evict_blocks(self, num_blocks):                         # :264-295
+        evicted = []
+        while num_blocks > 0:
+            if not self.leaf_lru:
+                break
+            h, a = self.leaf_lru.popleft()
+            if h not in self.leaf_set or h not in self.entries:
+                continue
+            e = self.entries[h]
+            if e[3] != a or e[2] > 0:
+                continue
+            del self.entries[h]
+            self.leaf_set.discard(h)
+            evicted.append(e[1])
+            num_blocks -= 1
+            if e[0] is not None and e[0] in self.entries:
+                pe = self.entries[e[0]]
+                if pe[2] > 0:
+                    pe[2] -= 1
+                if pe[2] == 0:
+                    self.leaf_set.add(e[0])
+                    self.leaf_lru.append((e[0], pe[3]))
+        return evicted
+
+
+class BlockManager:
+    """block_manager.rs:51-299,346-442,552-697 without CPU swap or mamba state."""
+
+    def __init__(self, num_blocks, block_size, prefix_cache_blocks=0):
         self.ref_count = [0] * num_blocks                      # block_manager.rs:62-68
         self.free_block_ids = deque(range(num_blocks))
         self.used_block_ids = set()
         self.block_size = block_size
+        self.num_blocks = num_blocks
+        # :80-84: the cache exists only when enabled with a positive capacity
+        self.prefix_cache = PrefixCache(block_size, prefix_cache_blocks) if prefix_cache_blocks > 0 else None
 
     def _allocate_block(self, block_id):                       # block_manager.rs:113-120
         assert self.ref_count[block_id] == 0
         self.ref_count[block_id] = 1
         self.used_block_ids.add(block_id)
 
-    def can_allocate(self, seq):                               # block_manager.rs:202-208
-        return len(self.free_block_ids) >= seq.num_blocks()
+    def _adjusted_matched_blocks(self, tokens_len, matched):    # :291-299: never reuse the WHOLE prompt
+        full_blocks = tokens_len // self.block_size
+        if matched == full_blocks and tokens_len % self.block_size == 0 and matched > 0:
+            return matched - 1
+        return matched
 
-    def allocate(self, seq):                                   # allocate_fresh, :122-137
+    def required_blocks(self, seq):                            # :179-200 (the match touches the LRU)
+        if self.prefix_cache is not None:
+            matched, _ = self.prefix_cache.match_prefix(seq.token_ids)
+            return max(seq.num_blocks() - self._adjusted_matched_blocks(len(seq), matched), 0)
+        return seq.num_blocks()
+
+    def can_allocate(self, seq):                               # block_manager.rs:202-204
+        return len(self.free_block_ids) >= self.required_blocks(seq)
+
+    def _increment_block_ref(self, b):                         # :275-282
+        if self.ref_count[b] == 0:
+            if b in self.free_block_ids:
+                self.free_block_ids.remove(b)
+            self.used_block_ids.add(b)
+        self.ref_count[b] += 1
+
+    def _decrement_block_ref(self, b):                         # :283-289, 139-144
+        self.ref_count[b] = max(self.ref_count[b] - 1, 0)
+        if self.ref_count[b] == 0 and b in self.used_block_ids:
+            self.used_block_ids.remove(b)
+            self.free_block_ids.append(b)
+
+    def _allocate_with_prefix(self, seq):                      # :346-442
+        pc = self.prefix_cache
+        matched, last_hash = pc.match_prefix(seq.token_ids)
+        matched = self._adjusted_matched_blocks(len(seq), matched)
+        if matched > 0 and last_hash is not None:
+            for b in pc.blocks_for_match(last_hash)[:matched]:
+                self._increment_block_ref(b)
+                seq.block_table.append(b)
+        seq.num_cached_tokens = matched * self.block_size
+        for _ in range(len(seq.block_table), seq.num_blocks()):
+            if not self.free_block_ids:
+                raise RuntimeError("No free blocks available, retry later!")
+            b = self.free_block_ids.popleft()
+            self._allocate_block(b)
+            seq.block_table.append(b)
+
+    def cache_sequence(self, seq):                             # :552-604
+        pc = self.prefix_cache
+        if pc is None or not pc.enabled():
+            return
+        full_blocks = len(seq) // self.block_size
+        if full_blocks == 0 or len(seq.block_table) < full_blocks:
+            return
+        inserted, evicted = pc.insert_prefix(seq.token_ids, seq.block_table[:full_blocks])
+        for b in inserted:
+            self._increment_block_ref(b)
+        for b in evicted:
+            self._decrement_block_ref(b)
+
+    def evict_prefix_cache_blocks(self, num_blocks):           # :657-672
+        if self.prefix_cache is None or num_blocks == 0:
+            return 0
+        evicted = self.prefix_cache.evict_blocks(num_blocks)
+        for b in evicted:
+            self._decrement_block_ref(b)
+        return len(evicted)
+
+    def prefix_cache_blocks(self):                             # :612-616
+        return self.prefix_cache.cached_blocks() if self.prefix_cache is not None else 0
+
+    def allocate(self, seq):                                   # :210-221; allocate_fresh :122-137
         assert not seq.block_table
+        if self.prefix_cache is not None:
+            return self._allocate_with_prefix(seq)
         seq.num_cached_tokens = 0
         for _ in range(seq.num_blocks()):
             if not self.free_block_ids:
@@ -94,12 +340,9 @@ class BlockManager:
             self._allocate_block(b)
             seq.block_table.append(b)
 
-    def deallocate(self, seq):                                 # :227-231, 283-289, 139-144
+    def deallocate(self, seq):                                 # :227-231
         for b in reversed(seq.block_table):
-            self.ref_count[b] = max(self.ref_count[b] - 1, 0)
-            if self.ref_count[b] == 0 and b in self.used_block_ids:
-                self.used_block_ids.remove(b)
-                self.free_block_ids.append(b)
+            self._decrement_block_ref(b)
 
     def can_append(self, seq):                                 # :233-239
         need = 1
@@ -120,10 +363,10 @@ class Scheduler:
     """scheduler.rs (CUDA build, no PD / swap / tool-call handling)."""
 
     def __init__(self, num_blocks, block_size=64, max_num_seqs=32, max_num_batched_tokens=None,
-                 chunk_size=CHUNK_SIZE_CUDA, eos_token_ids=()):
+                 chunk_size=CHUNK_SIZE_CUDA, eos_token_ids=(), prefix_cache_blocks=0):
         self.waiting = deque()
         self.running = []
-        self.block_manager = BlockManager(num_blocks, block_size)
+        self.block_manager = BlockManager(num_blocks, block_size, prefix_cache_blocks)
         self.next_seq_id = 0
         self.eos_token_id = list(eos_token_ids)
         self.block_size = block_size
@@ -164,6 +407,20 @@ class Scheduler:
         if scheduled_ids:
             self.is_last_prefill = True
             return scheduled_ids, True
+        # :288-337 without CPU swap: sequences that cannot append are "preempt" candidates; when there are
+        # any, or the cache is over 95 % full, 10 % of the prefix cache (at least one block) is evicted
+        import numpy as _np
+        f32 = _np.float32
+        preempt = [i for i, q in enumerate(self.running) if not self.block_manager.can_append(q)]
+        bm = self.block_manager
+        usage = f32(1.0) - (f32(len(bm.free_block_ids)) * f32(1.0) / f32(bm.num_blocks))        # :1255-1259
+        swap_in = (not preempt) and (usage < f32(KVCACHE_SWAP_THRESHOLD) * f32(0.9)
+                                     or (not self.running and usage <= f32(0.3)))
+        if not swap_in and (preempt or usage > f32(KVCACHE_SWAP_THRESHOLD)):
+            cached = bm.prefix_cache_blocks()                                                   # :1167-1175
+            if cached > 0:
+                blocks = max(int(_np.ceil(f32(cached) * f32(PREFIX_CACHE_PRESSURE_EVICT_PERCENT))), 1)
+                bm.evict_prefix_cache_blocks(blocks)
         decode_ids = []
         decode_max_seqs = max(self.max_num_seqs, MIN_NUM_SCHEDULED_REQS)
         for idx, seq in enumerate(self.running):
@@ -210,6 +467,7 @@ class Scheduler:
                     or len(seq.output_ids) >= seq.max_tokens
                     or len(seq) > self.max_num_batched_tokens):
                 seq.status = FINISHED
+                self.block_manager.cache_sequence(seq)                  # :617-620: cache, then drop the refs
                 self.block_manager.deallocate(seq)
             else:
                 seq.append_token(token)

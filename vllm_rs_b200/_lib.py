@@ -101,6 +101,12 @@ _SIGS = {
     "b200_scheduler_num_running": (c_i32, [c_vp]),
     "b200_scheduler_num_waiting": (c_i32, [c_vp]),
     "b200_scheduler_num_free_blocks": (c_i32, [c_vp]),
+    "b200_scheduler_enable_prefix_cache": (c_i32, [c_vp, c_i64]),
+    "b200_scheduler_prefix_cache_blocks": (c_i32, [c_vp]),
+    "b200_scheduler_evict_prefix_cache_blocks": (c_i32, [c_vp, c_i32]),
+    "b200_scheduler_block_ref_count": (c_i32, [c_vp, c_i32]),
+    "b200_scheduler_free_block_ids": (c_i32, [c_vp, c_vp, c_i32]),
+    "b200_prefix_hash_block": (C.c_uint64, [C.c_uint64, c_vp, c_i32]),
     "b200_scheduler_seq_info": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200_scheduler_seq_block_table": (c_i32, [c_vp, c_i32, c_vp, c_i32]),
     "b200_scheduler_seq_tokens": (c_i32, [c_vp, c_i32, c_vp, c_i32]),

@@ -8,13 +8,19 @@
 //   /root/reference/src/core/runner.rs:952-1388 (prepare_block_tables / prefill / decode)
 // Block ids, block tables, slot mappings, context lens and cu_seqlens must be BIT-EXACT
 // with the reference; tests/ compare this file against oracle/ on scripted traces.
-// Out of scope here: prefix cache, CPU swap, PD transfer, mamba state,
+//   /root/reference/src/core/prefix_cache.rs (hash chain of full blocks + leaf LRU) and
+//   block_manager.rs:179-221,275-299,346-442,552-604,657-672 (allocate_with_prefix, cache_sequence,
+//        reference-counted sharing, eviction); scheduler.rs:288-337,1167-1175 (eviction under pressure)
+// Out of scope here: CPU swap, PD transfer, mamba state, image seeds,
 // tool-call / stop-sequence detection (EOS and max_tokens are handled).
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <string>
+#include <cmath>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -50,19 +56,246 @@ struct Sequence {
   }
 };
 
+// SipHash-1-3 with the all-zero key = Rust's DefaultHasher::new() (prefix_cache.rs:337-349)
+struct SipHasher13 {
+  uint64_t v0 = 0x736F6D6570736575ull, v1 = 0x646F72616E646F6Dull, v2 = 0x6C7967656E657261ull,
+           v3 = 0x7465646279746573ull;
+  uint64_t tail = 0;
+  size_t ntail = 0, length = 0;
+  static uint64_t rotl(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+  void round() {
+    v0 += v1; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32);
+    v2 += v3; v3 = rotl(v3, 16); v3 ^= v2;
+    v0 += v3; v3 = rotl(v3, 21); v3 ^= v0;
+    v2 += v1; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32);
+  }
+  void write(const uint8_t* p, size_t n) {
+    length += n;
+    for (size_t i = 0; i < n; ++i) {
+      tail |= static_cast<uint64_t>(p[i]) << (8 * ntail);
+      if (++ntail == 8) {
+        v3 ^= tail; round(); v0 ^= tail;
+        tail = 0; ntail = 0;
+      }
+    }
+  }
+  void write_u64(uint64_t x) {
+    uint8_t b[8];
+    for (int i = 0; i < 8; ++i) b[i] = static_cast<uint8_t>(x >> (8 * i));
+    write(b, 8);
+  }
+  uint64_t finish() {
+    const uint64_t b = (static_cast<uint64_t>(length & 0xFF) << 56) | tail;
+    v3 ^= b; round(); v0 ^= b;
+    v2 ^= 0xFF;
+    round(); round(); round();
+    return v0 ^ v1 ^ v2 ^ v3;
+  }
+};
+
+// prefix_cache.rs:337-342: parent_hash.hash(h); tokens.hash(h) (slice = usize length + raw LE u32s)
+uint64_t hash_block(uint64_t parent_hash, const uint32_t* tokens, size_t n) {
+  SipHasher13 h;
+  h.write_u64(parent_hash);
+  h.write_u64(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint8_t b[4] = {static_cast<uint8_t>(tokens[i]), static_cast<uint8_t>(tokens[i] >> 8),
+                    static_cast<uint8_t>(tokens[i] >> 16), static_cast<uint8_t>(tokens[i] >> 24)};
+    h.write(b, 4);
+  }
+  return h.finish();
+}
+
+// prefix_cache.rs:38-350 (no image seeds)
+class PrefixCache {
+ public:
+  PrefixCache(size_t block_size, size_t max_cached) : block_size_(block_size), max_cached_(max_cached) {}
+  bool enabled() const { return max_cached_ > 0; }
+  size_t cached_blocks() const { return entries_.size(); }
+
+  // match_prefix (:67-116): number of leading full blocks present; touches every hit
+  size_t match_prefix(const std::vector<uint32_t>& tokens, bool* has_last, uint64_t* last_hash) {
+    *has_last = false;
+    if (!enabled()) return 0;
+    const size_t full = tokens.size() / block_size_;
+    size_t matched = 0;
+    uint64_t parent = 0;
+    for (size_t i = 0; i < full; ++i) {
+      const uint64_t h = hash_block(parent, tokens.data() + i * block_size_, block_size_);
+      if (!entries_.count(h)) break;
+      ++matched;
+      parent = h;
+      *has_last = true;
+      *last_hash = h;
+      touch(h);
+    }
+    return matched;
+  }
+  std::vector<size_t> blocks_for_match(uint64_t last_hash) const {       // :118-132
+    std::vector<size_t> blocks;
+    bool has = true;
+    uint64_t cur = last_hash;
+    while (has) {
+      auto it = entries_.find(cur);
+      if (it == entries_.end()) break;
+      blocks.push_back(it->second.block_id);
+      has = it->second.has_parent;
+      cur = it->second.parent;
+    }
+    std::reverse(blocks.begin(), blocks.end());
+    return blocks;
+  }
+  // insert_prefix (:174-262)
+  void insert_prefix(const std::vector<uint32_t>& tokens, const std::vector<size_t>& blocks,
+                     std::vector<size_t>* inserted, std::vector<size_t>* evicted) {
+    if (!enabled()) return;
+    const size_t max_blocks = std::min(tokens.size() / block_size_, blocks.size());
+    if (max_blocks == 0) return;
+    bool has_parent = false;
+    uint64_t parent = 0;
+    for (size_t i = 0; i < max_blocks; ++i) {
+      const uint64_t h = hash_block(has_parent ? parent : 0, tokens.data() + i * block_size_, block_size_);
+      auto it = entries_.find(h);
+      if (it != entries_.end()) {
+        it->second.access_id = next_access_id();
+        touch_leaf(h);
+      } else {
+        if (has_parent) {
+          auto pit = entries_.find(parent);
+          if (pit != entries_.end()) {
+            if (pit->second.children == 0) leaf_set_.erase(parent);
+            pit->second.children += 1;
+          }
+        }
+        const uint64_t a = next_access_id();
+        entries_[h] = Entry{has_parent, parent, blocks[i], 0, a};
+        leaf_set_.insert(h);
+        leaf_lru_.push_back({h, a});
+        inserted->push_back(blocks[i]);
+      }
+      has_parent = true;
+      parent = h;
+    }
+    if (entries_.size() > max_cached_) evict_blocks(entries_.size() - max_cached_, evicted);
+  }
+  // evict_blocks (:264-295): least-recently-used leaves first, parents become leaves
+  void evict_blocks(size_t num, std::vector<size_t>* evicted) {
+    while (num > 0) {
+      if (leaf_lru_.empty()) break;
+      const auto [h, a] = leaf_lru_.front();
+      leaf_lru_.pop_front();
+      if (!leaf_set_.count(h)) continue;
+      auto it = entries_.find(h);
+      if (it == entries_.end()) continue;
+      if (it->second.access_id != a || it->second.children > 0) continue;
+      const Entry e = it->second;
+      entries_.erase(it);
+      leaf_set_.erase(h);
+      evicted->push_back(e.block_id);
+      --num;
+      if (e.has_parent) {
+        auto pit = entries_.find(e.parent);
+        if (pit != entries_.end()) {
+          if (pit->second.children > 0) pit->second.children -= 1;
+          if (pit->second.children == 0) {
+            leaf_set_.insert(e.parent);
+            leaf_lru_.push_back({e.parent, pit->second.access_id});
+          }
+        }
+      }
+    }
+  }
+
+ private:
+  struct Entry {
+    bool has_parent;
+    uint64_t parent;
+    size_t block_id, children;
+    uint64_t access_id;
+  };
+  uint64_t next_access_id() { return ++access_counter_; }
+  void touch(uint64_t h) {                                               // :297-305
+    auto it = entries_.find(h);
+    if (it == entries_.end()) return;
+    it->second.access_id = next_access_id();
+    touch_leaf(h);
+  }
+  void touch_leaf(uint64_t h) {                                          // :307-314
+    if (leaf_set_.count(h)) {
+      auto it = entries_.find(h);
+      if (it != entries_.end()) leaf_lru_.push_back({h, it->second.access_id});
+    }
+    compact_lru_if_needed();
+  }
+  void compact_lru_if_needed() {                                         // :316-330
+    const size_t threshold = std::max<size_t>(entries_.size(), 64) * 4;
+    if (leaf_lru_.size() <= threshold) return;
+    std::deque<std::pair<uint64_t, uint64_t>> kept;
+    for (const auto& [h, a] : leaf_lru_) {
+      if (!leaf_set_.count(h)) continue;
+      auto it = entries_.find(h);
+      if (it != entries_.end() && it->second.access_id == a) kept.push_back({h, a});
+    }
+    leaf_lru_.swap(kept);
+  }
+  size_t block_size_, max_cached_;
+  std::unordered_map<uint64_t, Entry> entries_;
+  std::unordered_set<uint64_t> leaf_set_;
+  std::deque<std::pair<uint64_t, uint64_t>> leaf_lru_;
+  uint64_t access_counter_ = 0;
+};
+
 class BlockManager {
  public:
-  BlockManager(size_t num_blocks, size_t block_size) : block_size_(block_size) {
+  BlockManager(size_t num_blocks, size_t block_size) : block_size_(block_size), num_blocks_(num_blocks) {
     ref_.assign(num_blocks, 0);
     for (size_t i = 0; i < num_blocks; ++i) free_.push_back(i);
   }
+  void enable_prefix_cache(size_t max_cached) {                          // block_manager.rs:80-84
+    prefix_.reset(max_cached > 0 ? new PrefixCache(block_size_, max_cached) : nullptr);
+  }
   size_t num_free() const { return free_.size(); }
-  bool can_allocate(const Sequence& s) const { return free_.size() >= s.num_blocks(); }
-  // allocate_fresh, block_manager.rs:122-137
+  size_t num_total() const { return num_blocks_; }
+  size_t ref_count(size_t id) const { return id < ref_.size() ? ref_[id] : 0; }
+  size_t prefix_cache_blocks() const { return prefix_ ? prefix_->cached_blocks() : 0; }
+  int32_t copy_free(uint32_t* out, int32_t cap) const {
+    int32_t i = 0;
+    for (size_t id : free_) {
+      if (out && i < cap) out[i] = static_cast<uint32_t>(id);
+      ++i;
+    }
+    return i;
+  }
+  // required_blocks / can_allocate (block_manager.rs:179-204): the prefix match touches the LRU
+  bool can_allocate(const Sequence& s) {
+    size_t need = s.num_blocks();
+    if (prefix_) {
+      bool has_last;
+      uint64_t last;
+      const size_t matched = adjusted(s.len(), prefix_->match_prefix(s.token_ids, &has_last, &last));
+      need = need > matched ? need - matched : 0;
+    }
+    return free_.size() >= need;
+  }
+  // allocate (block_manager.rs:210-221): allocate_with_prefix (:346-442) or allocate_fresh (:122-137)
   bool allocate(Sequence& s) {
-    s.num_cached_tokens = 0;
+    size_t matched = 0;
+    if (prefix_) {
+      bool has_last;
+      uint64_t last = 0;
+      matched = adjusted(s.len(), prefix_->match_prefix(s.token_ids, &has_last, &last));
+      if (matched > 0 && has_last) {
+        std::vector<size_t> cached = prefix_->blocks_for_match(last);
+        if (cached.size() > matched) cached.resize(matched);
+        for (size_t id : cached) {
+          increment_ref(id);
+          s.block_table.push_back(static_cast<uint32_t>(id));
+        }
+      }
+    }
+    s.num_cached_tokens = matched * block_size_;
     const size_t need = s.num_blocks();
-    for (size_t i = 0; i < need; ++i) {
+    for (size_t i = s.block_table.size(); i < need; ++i) {
       if (free_.empty()) return false;
       const size_t id = free_.front();
       free_.pop_front();
@@ -73,11 +306,25 @@ class BlockManager {
   }
   // block_manager.rs:227-231: reverse table order, freed ids go to the BACK of the list
   void deallocate(const Sequence& s) {
-    for (auto it = s.block_table.rbegin(); it != s.block_table.rend(); ++it) {
-      const size_t id = *it;
-      if (ref_[id] > 0) --ref_[id];
-      if (ref_[id] == 0 && used_.erase(id)) free_.push_back(id);
-    }
+    for (auto it = s.block_table.rbegin(); it != s.block_table.rend(); ++it) decrement_ref(*it);
+  }
+  // cache_sequence (block_manager.rs:552-604): the cache takes its own reference on new entries
+  void cache_sequence(const Sequence& s) {
+    if (!prefix_ || !prefix_->enabled()) return;
+    const size_t full = s.len() / block_size_;
+    if (full == 0 || s.block_table.size() < full) return;
+    std::vector<size_t> blocks(s.block_table.begin(), s.block_table.begin() + full);
+    std::vector<size_t> inserted, evicted;
+    prefix_->insert_prefix(s.token_ids, blocks, &inserted, &evicted);
+    for (size_t id : inserted) increment_ref(id);
+    for (size_t id : evicted) decrement_ref(id);
+  }
+  size_t evict_prefix_cache_blocks(size_t n) {                           // :657-672
+    if (!prefix_ || n == 0) return 0;
+    std::vector<size_t> evicted;
+    prefix_->evict_blocks(n, &evicted);
+    for (size_t id : evicted) decrement_ref(id);
+    return evicted.size();
   }
   // block_manager.rs:233-239
   bool can_append(const Sequence& s) const {
@@ -98,14 +345,31 @@ class BlockManager {
   }
 
  private:
-  void take(size_t id) {
+  size_t adjusted(size_t tokens_len, size_t matched) const {             // :291-299
+    const size_t full = tokens_len / block_size_;
+    if (matched == full && tokens_len % block_size_ == 0 && matched > 0) return matched - 1;
+    return matched;
+  }
+  void take(size_t id) {                                                 // allocate_block :113-120
     ref_[id] = 1;
     used_.insert(id);
   }
-  size_t block_size_;
+  void increment_ref(size_t id) {                                        // :275-282
+    if (ref_[id] == 0) {
+      free_.erase(std::remove(free_.begin(), free_.end(), id), free_.end());
+      used_.insert(id);
+    }
+    ref_[id] += 1;
+  }
+  void decrement_ref(size_t id) {                                        // :283-289, 139-144
+    if (ref_[id] > 0) --ref_[id];
+    if (ref_[id] == 0 && used_.erase(id)) free_.push_back(id);
+  }
+  size_t block_size_, num_blocks_;
   std::vector<uint32_t> ref_;
   std::deque<size_t> free_;
   std::unordered_set<size_t> used_;
+  std::unique_ptr<PrefixCache> prefix_;
 };
 
 constexpr size_t kMinNumScheduledReqs = 5;   // scheduler.rs:44
@@ -202,6 +466,22 @@ int32_t b200_scheduler_schedule(b200_scheduler* s, int32_t* indices, int32_t cap
   }
   // ---- decode phase (scheduler.rs:285-378); swap / preemption is out of scope: a
   // sequence that cannot append is skipped this step exactly as the reference's filter does
+  {
+    // scheduler.rs:288-337 without CPU swap: when some sequence cannot append, or the cache is over
+    // 95 % full, 10 % of the prefix cache (at least one block) is evicted (scheduler.rs:1167-1175)
+    bool any_preempt = false;
+    for (const Sequence& q : s->running) any_preempt = any_preempt || !s->bm.can_append(q);
+    const float usage = 1.0f - (static_cast<float>(s->bm.num_free()) * 1.0f / static_cast<float>(s->bm.num_total()));
+    const bool swap_in = !any_preempt && (usage < 0.95f * 0.9f || (s->running.empty() && usage <= 0.3f));
+    if (!swap_in && (any_preempt || usage > 0.95f)) {
+      const size_t cached = s->bm.prefix_cache_blocks();
+      if (cached > 0) {
+        size_t blocks = static_cast<size_t>(std::ceil(static_cast<float>(cached) * 0.1f));
+        if (blocks < 1) blocks = 1;
+        s->bm.evict_prefix_cache_blocks(blocks);
+      }
+    }
+  }
   std::vector<size_t> decode;
   for (size_t idx = 0; idx < s->running.size(); ++idx) {
     if (decode.size() >= max_seqs_limit) break;
@@ -271,6 +551,7 @@ void b200_scheduler_postprocess(b200_scheduler* s, const int32_t* indices, int32
     if (is_eos || seq.output_ids.size() >= seq.max_tokens ||
         seq.len() > s->max_num_batched_tokens) {
       seq.status = Status::Finished;
+      s->bm.cache_sequence(seq);     // scheduler.rs:617-620: the cache takes its references first
       s->bm.deallocate(seq);
     } else {
       seq.append_token(tok);
@@ -295,6 +576,34 @@ int32_t b200_scheduler_num_waiting(const b200_scheduler* s) {
 }
 int32_t b200_scheduler_num_free_blocks(const b200_scheduler* s) {
   return static_cast<int32_t>(s->bm.num_free());
+}
+
+// build_prefix_cache_config (scheduler.rs:60-104) for a plain (non-PD) engine + BlockManager::new
+// (block_manager.rs:80-84).  max_tokens < 0: the default 65 % of the blocks (f32 arithmetic as there).
+// Returns the resulting capacity in blocks (0 = disabled).  Call before the first add().
+int32_t b200_scheduler_enable_prefix_cache(b200_scheduler* s, int64_t max_tokens) {
+  size_t max_cached = max_tokens >= 0
+                          ? static_cast<size_t>(max_tokens) / s->block_size
+                          : static_cast<size_t>(static_cast<float>(s->bm.num_total()) * 0.65f);
+  max_cached = std::min(max_cached, s->bm.num_total());
+  s->bm.enable_prefix_cache(max_cached);
+  return static_cast<int32_t>(max_cached);
+}
+int32_t b200_scheduler_prefix_cache_blocks(const b200_scheduler* s) {
+  return static_cast<int32_t>(s->bm.prefix_cache_blocks());
+}
+int32_t b200_scheduler_evict_prefix_cache_blocks(b200_scheduler* s, int32_t n) {
+  return n > 0 ? static_cast<int32_t>(s->bm.evict_prefix_cache_blocks(n)) : 0;
+}
+int32_t b200_scheduler_block_ref_count(const b200_scheduler* s, int32_t block_id) {
+  return block_id < 0 ? -1 : static_cast<int32_t>(s->bm.ref_count(block_id));
+}
+// free_block_ids in pop order (the next allocation takes out[0])
+int32_t b200_scheduler_free_block_ids(const b200_scheduler* s, uint32_t* out, int32_t cap) {
+  return s->bm.copy_free(out, cap);
+}
+uint64_t b200_prefix_hash_block(uint64_t parent_hash, const uint32_t* tokens, int32_t n) {
+  return hash_block(parent_hash, tokens, n > 0 ? n : 0);
 }
 
 int32_t b200_scheduler_seq_info(const b200_scheduler* s, int32_t i, int64_t* seq_id,

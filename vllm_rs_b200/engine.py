@@ -82,6 +82,26 @@ class Scheduler:
     def num_free_blocks(self):
         return self._l.b200_scheduler_num_free_blocks(self._h)
 
+    def enable_prefix_cache(self, max_tokens=None) -> int:
+        """build_prefix_cache_config (scheduler.rs:60-104); returns the capacity in blocks."""
+        return self._l.b200_scheduler_enable_prefix_cache(self._h, -1 if max_tokens is None else int(max_tokens))
+
+    @property
+    def prefix_cache_blocks(self):
+        return self._l.b200_scheduler_prefix_cache_blocks(self._h)
+
+    def evict_prefix_cache_blocks(self, n):
+        return self._l.b200_scheduler_evict_prefix_cache_blocks(self._h, int(n))
+
+    def block_ref_count(self, block_id):
+        return self._l.b200_scheduler_block_ref_count(self._h, int(block_id))
+
+    def free_block_ids(self):
+        n = self._l.b200_scheduler_free_block_ids(self._h, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._l.b200_scheduler_free_block_ids(self._h, out.ctypes.data, n)
+        return out[:n].tolist()
+
     def seq_info(self, i):
         sid, cached, st, nout = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
         n = self._l.b200_scheduler_seq_info(self._h, i, C.byref(sid), C.byref(cached),
