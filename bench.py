@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--ctx", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalid as a bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp8-kv", action="store_true", help="skip the extra FP8-KV-cache decode leg")
     ap.add_argument("--prefill-tokens", type=int, default=8192,
                     help="also time one prefill chunk of this many tokens (0 = skip)")
     return ap.parse_args()
@@ -392,6 +393,55 @@ def run_b200(args):
                            "W4A16 tcgen05 GEMM (NT=256); tcgen05 varlen causal attention over the paged cache "
                            "(attn_prefill_tc.cu; B200_PREFILL_ATTN=mma selects the mma.sync kernel)"}
 
+    # ---------------- the same decode step with the FP8 KV cache (`--fp8-kvcache`): NOT the
+    # headline configuration (BASELINE.json's metric is the default fp16 cache) -- reported beside it.  Last,
+    # and guarded, so nothing here can disturb the numbers above.
+    fp8_kv = None
+    if world == 1 and not args.no_fp8_kv and D == 128:
+        try:
+            runner = graph = None
+            torch.cuda.empty_cache()
+            r8 = synthetic.build_awq_runner(MODEL, num_blocks=num_blocks, max_blocks_per_seq=blocks_per_seq,
+                                            max_batch=B, num_layers=L, device=dev, kv_fp8=True)
+            synthetic.fill_kv_random(r8)
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    r8.decode_device(ids, pos, slots, bt, cl, want_logits=False)
+                stream.synchronize()
+                g8 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g8, stream=stream):
+                    r8.decode_device(ids, pos, slots, bt, cl, want_logits=False)
+                for _ in range(W):
+                    g8.replay()
+                stream.synchronize()
+                e0.record(stream)
+                for _ in range(K):
+                    g8.replay()
+                e1.record(stream)
+                stream.synchronize()
+                ms8 = e0.elapsed_time(e1) / K
+                for rep in range(2):
+                    e0.record(stream)
+                    for li in range(L):
+                        ops.paged_attention_decode(q, r8.k_cache[li], r8.v_cache[li], bt, cl, scale, ws, out=out)
+                    e1.record(stream)
+                    stream.synchronize()
+                a8_ms = e0.elapsed_time(e1) / L
+            a8_bytes = B * ctx * shape["Hkv"] * D * 2 * 1 + 2 * B * shape["H"] * D * 2
+            alg8 = synthetic.decode_algorithmic_bytes(shape, B, ctx, kv_bytes=1)
+            fp8_kv = {"value": B * 1e3 / ms8, "unit": "tokens/s", "ms_per_step": ms8,
+                      "kv_format": "e4m3, scale 1 (library-defined; parity unpinned)",
+                      "attention": {"kernel": "paged_attn_decode_kernel<128, fp8>", "ms_per_launch": a8_ms,
+                                    "bytes_per_launch": a8_bytes, "achieved": a8_bytes / (a8_ms * 1e-3) / 1e9,
+                                    "peak": peak, "unit": "GB/s", "frac": a8_bytes / (a8_ms * 1e-3) / 1e9 / peak},
+                      "step_roofline": {"algorithmic_bytes": alg8["total"],
+                                        "achieved": alg8["total"] / (ms8 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": alg8["total"] / (ms8 * 1e-3) / 1e9 / peak}}
+            del r8, g8
+        except Exception as e:      # noqa: BLE001 -- the headline numbers stand on their own
+            fp8_kv = {"error": repr(e)}
+        _trace("fp8 KV leg done")
+
     out_line = {
         "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -417,6 +467,7 @@ def run_b200(args):
         "step_roofline": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "peak": peak,
                           "unit": "GB/s", "frac": step_gbs / peak},
         "prefill": prefill,
+        "fp8_kv": fp8_kv,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -125,6 +125,17 @@ void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, co
                             int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
                             int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
                             int64_t stream);
+/* Same with an FP8 KV cache (`--fp8-kvcache`; kvcache_allocator.rs:188-193,776 allocates the caches as
+ * U8 in the same [num_blocks, block_size, Hkv, D] shape): the rotated fp16 K row and the V row are
+ * stored as e4m3 bytes (round to nearest even, saturating at +-448, scale 1 -- attention-rs's own
+ * format is not source-visible, so this is the library's definition).  q / k are still rotated in
+ * place as fp16.                                                                                   */
+void b200_rope_kv_write_fp8kv_f16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                                  const int64_t* positions, const int64_t* slot_mapping,
+                                  void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                                  int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                                  int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                                  int64_t stream);
 /* Cache write only (reshape_and_cache equivalent). */
 void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cache,
                        const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
@@ -146,6 +157,14 @@ void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
                                 float softcap, int32_t window, void* workspace, int64_t stream);
 int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim,
                                         int32_t max_blocks_per_seq);
+/* Decode attention over an FP8 (e4m3, scale 1) KV cache: same arguments, k_cache / v_cache are
+ * u8 [num_blocks, 64, Hkv, 128]; half the HBM bytes per step.  head_dim must be 128.             */
+void b200_paged_attn_decode_fp8kv_f16(void* out, const void* q, const void* k_cache,
+                                      const void* v_cache, const uint32_t* block_tables,
+                                      const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                      int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                      int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                      float softcap, int32_t window, void* workspace, int64_t stream);
 
 /* ------------------------------------------------- paged attention, prefill (varlen causal)
  * Replaces the prefill branch of PagedAttention::forward (attention.rs:808-820) with the
@@ -312,6 +331,7 @@ typedef struct b200_model_config {
   float rms_eps, attn_scale;
   int32_t tp_rank, tp_size;            /* shapes above are the LOCAL (per-rank) shard  */
   int32_t max_prefill_tokens;          /* 0 => decode only; else tokens per prefill step */
+  int32_t kv_fp8;                      /* EngineConfig.fp8_kvcache: caches are e4m3 bytes (head_dim 128) */
 } b200_model_config;
 
 typedef struct b200_layer_weights {

@@ -126,21 +126,38 @@ def apply_rope(q, k, cos, sin, positions, interleaved=False):
     return rot(q), rot(k)
 
 
+E4M3_MAX = 448.0
+
+
+def to_e4m3(x: torch.Tensor) -> torch.Tensor:
+    """fp16 -> e4m3 bytes of the FP8 KV cache (`--fp8-kvcache`: kvcache_allocator.rs:188-193,776 makes the
+    cache U8; attention.rs:615 passes only the flag on to attention-rs, whose storage format is not
+    source-visible -- PARITY UNPINNED).  Defined here as: scale 1, round to nearest even, saturate."""
+    return x.to(F32).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def from_e4m3(b: torch.Tensor) -> torch.Tensor:
+    return b.view(torch.float8_e4m3fn).to(F32)
+
+
 def kv_write(k, v, k_cache, v_cache, slot_mapping):
-    """cache [nb, bs, Hkv, D]; slot = block*bs + offset (runner.rs:1259-1262)."""
+    """cache [nb, bs, Hkv, D] (fp16, or uint8 = e4m3); slot = block*bs + offset (runner.rs:1259-1262)."""
     nb, bs = k_cache.shape[0], k_cache.shape[1]
     kc = k_cache.view(nb * bs, *k_cache.shape[2:])
     vc = v_cache.view(nb * bs, *v_cache.shape[2:])
+    fp8 = k_cache.dtype == torch.uint8
     for t, slot in enumerate(slot_mapping.tolist()):
         if slot >= 0:
-            kc[slot] = k[t]
-            vc[slot] = v[t]
+            kc[slot] = to_e4m3(k[t]) if fp8 else k[t]
+            vc[slot] = to_e4m3(v[t]) if fp8 else v[t]
 
 
 def gather_kv(cache, block_table, ctx_len):
     bs = cache.shape[1]
     nblk = -(-ctx_len // bs)
     blocks = cache[torch.as_tensor(block_table[:nblk], dtype=torch.long)]
+    if cache.dtype == torch.uint8:
+        blocks = from_e4m3(blocks)
     return blocks.reshape(nblk * bs, *cache.shape[2:])[:ctx_len]     # [ctx, Hkv, D]
 
 
@@ -242,12 +259,14 @@ class ModelWeights:
 class LlamaOracle:
     """LLaMaForCausalLM::forward_inner over a paged cache (one (K,V) pair per layer)."""
 
-    def __init__(self, cfg: ModelConfig, weights: ModelWeights, num_blocks: int):
+    def __init__(self, cfg: ModelConfig, weights: ModelWeights, num_blocks: int, kv_fp8: bool = False):
         self.cfg, self.w = cfg, weights
         self.cos, self.sin = rope_tables(cfg)
         shape = (num_blocks, cfg.block_size, cfg.num_kv_heads, cfg.head_dim)
-        self.k_cache = [torch.zeros(shape, dtype=store_dtype()) for _ in range(cfg.num_layers)]
-        self.v_cache = [torch.zeros(shape, dtype=store_dtype()) for _ in range(cfg.num_layers)]
+        self.kv_fp8 = kv_fp8
+        dt = torch.uint8 if kv_fp8 else store_dtype()
+        self.k_cache = [torch.zeros(shape, dtype=dt) for _ in range(cfg.num_layers)]
+        self.v_cache = [torch.zeros(shape, dtype=dt) for _ in range(cfg.num_layers)]
         self.scale = 1.0 / math.sqrt(cfg.head_dim)
 
     def _layer(self, l, x, positions, slot_mapping, attn_fn, trace=None):
@@ -284,10 +303,15 @@ class LlamaOracle:
         slots = torch.as_tensor(meta["slot_mapping"], dtype=torch.long)
         cu_q = meta["cu_seqlens_q"]
         x = h(self.w.embed[ids])
+        bts, ctxs = meta["block_tables"], meta["context_lens"]
+        if self.kv_fp8 and ctxs is None:
+            # FP8 cache: keys / values are ALWAYS read back from the cache (written first), so the result
+            # does not depend on chunking or prefix hits; needs the tables of every sequence
+            bts = meta["all_block_tables"]
+            ctxs = [cu_q[i + 1] - cu_q[i] for i in range(len(cu_q) - 1)]
 
         def attn(l, q, k, v):
-            return attention_prefill(q, k, v, cu_q, self.k_cache[l], self.v_cache[l],
-                                     meta["block_tables"], meta["context_lens"], self.scale)
+            return attention_prefill(q, k, v, cu_q, self.k_cache[l], self.v_cache[l], bts, ctxs, self.scale)
 
         for l in range(self.cfg.num_layers):
             x = self._layer(l, x, pos, slots, attn, trace)

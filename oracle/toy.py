@@ -11,13 +11,20 @@ from . import quant as oq
 F16 = torch.float16
 
 
+def toy_cfg_d128(qkv_bias=False):
+    """head_dim 128 variant (the FP8 KV cache tiles are one 128-byte row per token)."""
+    return om.ModelConfig(hidden=512, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=128,
+                          inter=1024, vocab=1024, rope_theta=10000.0, rms_eps=1e-5, max_pos=2048,
+                          qkv_bias=qkv_bias)
+
+
 def toy_cfg(qkv_bias=False):
     return om.ModelConfig(hidden=512, num_layers=2, num_heads=8, num_kv_heads=2, head_dim=64,
                           inter=1024, vocab=1024, rope_theta=10000.0, rms_eps=1e-5, max_pos=2048,
                           qkv_bias=qkv_bias)
 
 
-def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks, max_prefill_tokens=0):
+def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks, max_prefill_tokens=0, kv_fp8=False):
     """Random quantised checkpoint -> (oracle with dequantised weights, GPU runner)."""
     from vllm_rs_b200 import engine, ops
     rng = np.random.default_rng(seed)
@@ -42,7 +49,7 @@ def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks, max_prefill_to
         hidden=h, num_layers=cfg.num_layers, num_heads=H, num_kv_heads=Hkv, head_dim=D, inter=I,
         vocab=cfg.vocab, num_blocks=num_blocks, max_blocks_per_seq=max_blocks, max_batch=max_batch,
         bits=bits, group_size=128, qfmt=ops.QFMT_AWQ if fmt == "awq" else ops.QFMT_GPTQ,
-        qkv_bias=cfg.qkv_bias, max_pos=cfg.max_pos, max_prefill_tokens=max_prefill_tokens)
+        qkv_bias=cfg.qkv_bias, max_pos=cfg.max_pos, max_prefill_tokens=max_prefill_tokens, kv_fp8=kv_fp8)
     w = om.ModelWeights(embed=torch.randn(cfg.vocab, h, generator=g).to(F16), final_norm=norm_w(),
                         lm_head=(0.05 * torch.randn(cfg.vocab, h, generator=g)).to(F16))
     for l in range(cfg.num_layers):
@@ -59,7 +66,7 @@ def build_pair(cfg, fmt, seed, num_blocks, max_batch, max_blocks, max_prefill_to
         runner.set_layer(l, input_norm=lw.input_norm.cuda(), post_norm=lw.post_norm.cuda(),
                          qkv=fuse([pq, pk, pv], "cuda"), o=fuse([po], "cuda"),
                          gate_up=fuse([pg, pu], "cuda"), down=fuse([pd], "cuda"), qkv_bias=bias)
-    oracle = om.LlamaOracle(cfg, w, num_blocks)
+    oracle = om.LlamaOracle(cfg, w, num_blocks, kv_fp8=kv_fp8)
     runner.set_globals(w.embed.cuda(), w.final_norm.cuda(), w.lm_head.cuda(), oracle.cos.cuda(),
                        oracle.sin.cuda())
     return oracle, runner

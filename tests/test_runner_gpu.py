@@ -290,3 +290,79 @@ def test_large_prefill_step_dense_route(lib, fmt):
     for b in range(2):
         if ref[b].sort(descending=True).values[:2].diff().abs() > 3 * noise + 2e-3:
             assert int(ids_gpu[b]) == int(ref[b].argmax())
+
+
+def _oracle_loop(osch, oracle, chunk, out, margin):
+    """The reference's step loop on the oracle; appends greedy tokens and top-2 margins per seq id."""
+    for _ in range(400):
+        if not (osch.running or osch.waiting):
+            break
+        ids, pf = osch.schedule()
+        if not ids:
+            break
+        seqs = [osch.running[i] for i in ids]
+        if pf:
+            logits = oracle.prefill(osched.prepare_prefill(seqs, 64, chunk))
+            pos, fin = osch.filter_prefill_finished(ids)
+            srt = logits.sort(-1, descending=True).values
+            for j, i in zip(pos, fin):
+                out.setdefault(osch.running[i].id, []).append(int(logits[j].argmax()))
+                margin.setdefault(osch.running[i].id, []).append(float(srt[j, 0] - srt[j, 1]))
+            osch.postprocess(fin, logits.argmax(-1)[pos].tolist() if pos else [])
+        else:
+            logits = oracle.decode(osched.prepare_decode(seqs, 64))
+            srt = logits.sort(-1, descending=True).values
+            toks = logits.argmax(-1).tolist()
+            for j, s in enumerate(seqs):
+                out.setdefault(s.id, []).append(toks[j])
+                margin.setdefault(s.id, []).append(float(srt[j, 0] - srt[j, 1]))
+            osch.postprocess(ids, toks)
+        osch.clear_finished()
+
+
+def test_engine_loop_with_prefix_cache(lib):
+    """Prefix-cache hits end to end: a finished request leaves its full blocks in the
+    cache; later requests with the same prefix share those pages by reference count, prefill only the
+    uncached tail (attention over the cached pages + the new tokens) and must produce the oracle's
+    tokens.  Block sharing / cached-token counts are compared bit-exact on the way."""
+    from vllm_rs_b200 import engine
+    cfg = _toy_cfg()
+    NB, MAXB, MAXBLK = 64, 8, 16
+    oracle, runner = _build(cfg, "awq", seed=23, num_blocks=NB, max_batch=MAXB, max_blocks=MAXBLK,
+                            max_prefill_tokens=1024)
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, cfg.vocab, size=200).tolist()
+    waves = [[base[:150]],                                                   # cold: 2 full blocks get cached
+             [base[:150] + rng.integers(0, cfg.vocab, size=40).tolist(),     # hit: 2 blocks (+ the first's outputs differ)
+              base[:128],                                                    # entirely cached blocks: keeps 1 block out
+              base[:70] + rng.integers(0, cfg.vocab, size=100).tolist()],    # hit: 1 block
+             [base[:200]]]                                                   # hit after the second wave extended the chain
+    cap = osched.prefix_cache_max_blocks(NB, 64, None)
+    osch = osched.Scheduler(NB, 64, MAXB, chunk_size=8192, prefix_cache_blocks=cap)
+    eng = engine.LLMEngine(runner, NB, MAXB, prefix_cache=True)
+    o_out, o_margin, hits = {}, {}, []
+    for l in range(cfg.num_layers):
+        runner.k_cache[l].zero_()
+        runner.v_cache[l].zero_()
+    for wave in waves:
+        for p in wave:
+            osch.add(osched.Sequence(p, 64, max_tokens=5))
+            eng.add_request(p, 5)
+        # peek at the allocation the first schedule() of this wave makes, on both sides
+        _oracle_loop(osch, oracle, 8192, o_out, o_margin)
+        eng.step()
+        hits.append([eng.sched.seq_info(i)["num_cached_tokens"] for i in range(eng.sched.num_running)])
+        eng.run_to_completion()
+        assert eng.sched.free_block_ids() == list(osch.block_manager.free_block_ids)
+        assert eng.sched.prefix_cache_blocks == osch.block_manager.prefix_cache_blocks()
+    assert hits[0] == [0] and hits[1] == [128, 64, 64] and hits[2][0] >= 128, hits
+    g_out = eng.outputs
+    checked = 0
+    for sid in sorted(o_out):
+        assert len(g_out[sid]) == len(o_out[sid]) == 6
+        for t, (a, b) in enumerate(zip(o_out[sid], g_out[sid])):
+            if o_margin[sid][t] < 3e-2:
+                break
+            assert a == b, f"seq {sid} step {t}: oracle {a} vs gpu {b} (margin {o_margin[sid][t]})"
+            checked += 1
+    assert checked >= 12

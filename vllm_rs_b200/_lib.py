@@ -28,7 +28,7 @@ class ModelConfig(C.Structure):
         "block_size", "num_blocks", "max_blocks_per_seq", "max_batch", "max_pos",
         "qkv_bias", "cos_sin_f32")] + [("rms_eps", c_f32), ("attn_scale", c_f32),
                                        ("tp_rank", c_i32), ("tp_size", c_i32),
-                                       ("max_prefill_tokens", c_i32)]
+                                       ("max_prefill_tokens", c_i32), ("kv_fp8", c_i32)]
 
 
 class LayerWeights(C.Structure):
@@ -70,8 +70,10 @@ _SIGS = {
     "b200_dense_gemm_f16": (None, [c_vp] * 3 + [c_i32] * 4 + [c_i64]),
     "b200_dense_gemm_ex": (None, [c_vp] * 4 + [c_i32] * 5 + [c_i64]),
     "b200_rope_kv_write_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
+    "b200_rope_kv_write_fp8kv_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
+    "b200_paged_attn_decode_fp8kv_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
     "b200_attn_prefill_f16": (None, [c_vp] * 7 + [c_i32] * 8 + [c_f32, c_i64]),
     "b200_attn_prefill_ex_f16": (None, [c_vp] * 7 + [c_i32] * 10 + [c_f32, c_i64]),

@@ -12,11 +12,24 @@
 //   embedding / index_select          /root/reference/src/models/llama.rs:269-310
 //   logits.argmax                     /root/reference/src/utils/logits_processor.rs:67-70
 #include "../../include/b200_vllm.h"
+#include <cuda_fp8.h>
 #include <cstdlib>
 
 #include "attn.cuh"
 
 namespace b200 {
+
+// fp16 -> e4m3 byte of the FP8 KV cache: round to nearest even, saturate to +-448 (scale 1)
+__device__ __forceinline__ uint8_t half_to_e4m3(__half x) {
+  return static_cast<uint8_t>(__nv_cvt_halfraw_to_fp8(static_cast<__half_raw>(x), __NV_SATFINITE, __NV_E4M3));
+}
+__device__ __forceinline__ uint32_t half2x2_to_e4m3x4(uint32_t lo, uint32_t hi) {
+  __half2_raw a, b;
+  a.x = static_cast<unsigned short>(lo & 0xFFFFu); a.y = static_cast<unsigned short>(lo >> 16);
+  b.x = static_cast<unsigned short>(hi & 0xFFFFu); b.y = static_cast<unsigned short>(hi >> 16);
+  return static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(a, __NV_SATFINITE, __NV_E4M3)) |
+         (static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(b, __NV_SATFINITE, __NV_E4M3)) << 16);
+}
 
 // ------------------------------------------------------------------ RoPE + KV write
 // grid = tokens; one thread per rotation pair / per 2 copied elements.
@@ -29,7 +42,7 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
                                      const int64_t* __restrict__ slot_mapping,
                                      __half* __restrict__ k_cache, __half* __restrict__ v_cache,
                                      int q_stride, int k_stride, int v_stride, int H, int Hkv,
-                                     int D, int rot_dim, int interleaved) {
+                                     int D, int rot_dim, int interleaved, int kv_fp8) {
   pdl_trigger();
   pdl_wait();
   const int t = blockIdx.x;
@@ -41,6 +54,10 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
   const __half* vt = v ? v + static_cast<size_t>(t) * v_stride : nullptr;
   __half* kc = slot >= 0 ? k_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
   __half* vc = (slot >= 0 && v_cache) ? v_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
+  // FP8 cache: same [slot][Hkv][D] indexing over one-byte elements
+  uint8_t* kc8 = slot >= 0 ? reinterpret_cast<uint8_t*>(k_cache) + static_cast<size_t>(slot) * Hkv * D : nullptr;
+  uint8_t* vc8 = (slot >= 0 && v_cache) ? reinterpret_cast<uint8_t*>(v_cache) + static_cast<size_t>(slot) * Hkv * D
+                                        : nullptr;
 
   // rotation pairs of q and k
   const int pairs_per_head = D >> 1;
@@ -79,19 +96,84 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
       base[i0] = h0;
       base[i1] = h1;
       if (!is_q && kc) {
-        kc[(head - H) * D + i0] = h0;
-        kc[(head - H) * D + i1] = h1;
+        if (kv_fp8) {
+          kc8[(head - H) * D + i0] = half_to_e4m3(h0);
+          kc8[(head - H) * D + i1] = half_to_e4m3(h1);
+        } else {
+          kc[(head - H) * D + i0] = h0;
+          kc[(head - H) * D + i1] = h1;
+        }
       }
     } else if (!is_q && kc) {
-      kc[(head - H) * D + i0] = base[i0];
-      kc[(head - H) * D + i1] = base[i1];
+      if (kv_fp8) {
+        kc8[(head - H) * D + i0] = half_to_e4m3(base[i0]);
+        kc8[(head - H) * D + i1] = half_to_e4m3(base[i1]);
+      } else {
+        kc[(head - H) * D + i0] = base[i0];
+        kc[(head - H) * D + i1] = base[i1];
+      }
     }
   }
   // V copy (8 halves per thread)
   if (vc && vt) {
     const int n16 = (Hkv * D) >> 3;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x)
-      reinterpret_cast<uint4*>(vc)[i] = reinterpret_cast<const uint4*>(vt)[i];
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+      const uint4 x = reinterpret_cast<const uint4*>(vt)[i];
+      if (kv_fp8)
+        reinterpret_cast<uint2*>(vc8)[i] = make_uint2(half2x2_to_e4m3x4(x.x, x.y), half2x2_to_e4m3x4(x.z, x.w));
+      else
+        reinterpret_cast<uint4*>(vc)[i] = x;
+    }
+  }
+}
+
+// FP8 KV cache -> fp16 scratch pages for the prefill attention kernels (which read fp16 tiles): page i
+// of sequence b (block table entry) lands in scratch block b * max_blocks + i, for K and V.
+// grid = (max_blocks, B); ctx = context_lens[b], or the query length when context_lens is NULL.
+__global__ void kv_fp8_gather_kernel(const uint8_t* __restrict__ k8, const uint8_t* __restrict__ v8,
+                                     __half* __restrict__ ks, __half* __restrict__ vs,
+                                     const uint32_t* __restrict__ block_tables,
+                                     const uint32_t* __restrict__ context_lens,
+                                     const uint32_t* __restrict__ cu_q, int max_blocks, int page_elems) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int ctx = context_lens ? static_cast<int>(context_lens[b]) : static_cast<int>(cu_q[b + 1] - cu_q[b]);
+  if (i * 64 >= ctx) return;
+  const size_t src = static_cast<size_t>(block_tables[static_cast<size_t>(b) * max_blocks + i]) * page_elems;
+  const size_t dst = (static_cast<size_t>(b) * max_blocks + i) * page_elems;
+  for (int e = threadIdx.x * 8; e < page_elems; e += blockDim.x * 8) {
+#pragma unroll
+    for (int kv = 0; kv < 2; ++kv) {
+      const uint2 x = *reinterpret_cast<const uint2*>((kv ? v8 : k8) + src + e);
+      uint32_t o[4];
+      const uint32_t w[2] = {x.x, x.y};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __half2_raw a = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w[j] & 0xFFFFu), __NV_E4M3);
+        const __half2_raw c = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w[j] >> 16), __NV_E4M3);
+        o[2 * j] = static_cast<uint32_t>(a.x) | (static_cast<uint32_t>(a.y) << 16);
+        o[2 * j + 1] = static_cast<uint32_t>(c.x) | (static_cast<uint32_t>(c.y) << 16);
+      }
+      *reinterpret_cast<uint4*>((kv ? vs : ks) + dst + e) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+__global__ void scratch_block_table_kernel(uint32_t* __restrict__ bt, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bt[i] = static_cast<uint32_t>(i);
+}
+
+void launch_kv_fp8_gather(const void* k8, const void* v8, void* ks, void* vs, uint32_t* scratch_bt,
+                          const uint32_t* block_tables, const uint32_t* context_lens, const uint32_t* cu_q,
+                          int B, int max_blocks, int Hkv, int D, cudaStream_t st) {
+  launch_pdl(kv_fp8_gather_kernel, dim3(max_blocks, B), dim3(256), 0, st, (const uint8_t*)k8, (const uint8_t*)v8,
+             (__half*)ks, (__half*)vs, block_tables, context_lens, cu_q, max_blocks, 64 * Hkv * D);
+  B200_CUDA_LAUNCH_CHECK();
+  if (scratch_bt) {
+    const int n = B * max_blocks;
+    scratch_block_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(scratch_bt, n);
+    B200_CUDA_LAUNCH_CHECK();
   }
 }
 
@@ -306,17 +388,17 @@ void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_s
                           int v_stride, const void* cos, const void* sin,
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
-                          int interleaved, int cos_sin_f32, cudaStream_t st) {
+                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8) {
   const int pairs = (H + Hkv) * D / 2;
   const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
   if (cos_sin_f32)
     launch_pdl(rope_kv_write_kernel<true>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
                (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
-               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved);
+               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
   else
     launch_pdl(rope_kv_write_kernel<false>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
                (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
-               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved);
+               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -340,6 +422,23 @@ void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, co
                        num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
                        v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
                        interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream));
+}
+
+void b200_rope_kv_write_fp8kv_f16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                                  const int64_t* positions, const int64_t* slot_mapping,
+                                  void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                                  int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                                  int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                                  int64_t stream) {
+  (void)block_size;
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(head_dim % 8 == 0 && rot_dim % 2 == 0 && rot_dim <= head_dim && rot_dim > 0,
+                 "rope_kv_write: bad head_dim / rot_dim");
+  B200_CHECK_ARG(q && k && cos && sin && positions, "rope_kv_write: NULL pointer");
+  launch_rope_kv_write(q, k, v, num_heads * head_dim, num_kv_heads * head_dim,
+                       num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
+                       v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
+                       interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream), 1);
 }
 
 void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cache,

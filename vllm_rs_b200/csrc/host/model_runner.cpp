@@ -64,6 +64,11 @@ struct b200_runner {
   float* ssq = nullptr;          // [2 * layers + 1][max_batch] sums of squares of the folded RMSNorms
   void *attn_ws = nullptr, *wna_ws = nullptr;
   __half* wdeq = nullptr;        // fp16 [N, K] scratch of ONE projection (large quantised prefill steps)
+  // --fp8-kvcache: fp16 scratch pages (+ identity block table, tensor maps) the prefill attention reads
+  __half *kv_sk = nullptr, *kv_sv = nullptr;
+  uint32_t* kv_sbt = nullptr;
+  AttnMaps kv_smaps;
+  bool kv_smaps_ok = false;
   // static (graph) input buffers
   uint32_t *s_ids = nullptr, *s_ctx = nullptr, *s_bt = nullptr, *s_out = nullptr;
   int64_t *s_pos = nullptr, *s_slot = nullptr;
@@ -127,6 +132,13 @@ static int64_t carve(b200_runner* r, uint8_t* base) {
                                        static_cast<size_t>(c.inter) * c.hidden);
     r->wdeq = (__half*)take(kn * 2);
   }
+  if (c.kv_fp8 && c.max_prefill_tokens > 0) {
+    const size_t pages = B * static_cast<size_t>(c.max_blocks_per_seq);
+    const size_t page_bytes = 64 * static_cast<size_t>(c.num_kv_heads) * c.head_dim * 2;
+    r->kv_sk = (__half*)take(pages * page_bytes);
+    r->kv_sv = (__half*)take(pages * page_bytes);
+    r->kv_sbt = (uint32_t*)take(pages * 4);
+  }
   r->s_ids = (uint32_t*)take(B * 4);
   r->s_ctx = (uint32_t*)take(B * 4);
   r->s_out = (uint32_t*)take(B * 4);
@@ -144,6 +156,10 @@ b200_runner* b200_runner_new(const b200_model_config* cfg) {
       cfg->num_kv_heads <= 0 || cfg->max_batch <= 0 || cfg->block_size != 64 ||
       !(cfg->bits == 4 || cfg->bits == 8 || cfg->bits == 16)) {
     set_error(1, "runner_new: bad config");
+    return nullptr;
+  }
+  if (cfg->kv_fp8 && cfg->head_dim != 128) {
+    set_error(1, "runner_new: the fp8 KV cache needs head_dim 128");
     return nullptr;
   }
   auto* r = new b200_runner();
@@ -168,7 +184,7 @@ void b200_runner_set_layer(b200_runner* r, int32_t layer, const b200_layer_weigh
   }
   r->layers[layer] = *w;
   r->maps_ok[layer] = make_attn_maps(&r->maps[layer], w->k_cache, w->v_cache, r->cfg.num_blocks,
-                                     r->cfg.num_kv_heads, r->cfg.head_dim);
+                                     r->cfg.num_kv_heads, r->cfg.head_dim, r->cfg.kv_fp8 != 0);
   if (!r->maps_ok[layer]) set_error(2, "runner_set_layer: cuTensorMapEncodeTiled failed");
 }
 
@@ -196,6 +212,11 @@ void b200_runner_set_workspace(b200_runner* r, void* workspace, int64_t bytes) {
   }
   r->ws = base;
   r->ws_bytes = bytes;
+  if (r->kv_sk) {
+    r->kv_smaps_ok = make_attn_maps(&r->kv_smaps, r->kv_sk, r->kv_sv, r->cfg.max_batch * r->cfg.max_blocks_per_seq,
+                                    r->cfg.num_kv_heads, r->cfg.head_dim, false);
+    if (!r->kv_smaps_ok) set_error(2, "runner_set_workspace: cuTensorMapEncodeTiled (fp8 scratch) failed");
+  }
   // the GEMM split-K accumulators must start zeroed (they are left zeroed by every call)
   cudaMemset(workspace, 0, bytes);
 }
@@ -344,7 +365,7 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
     fq.positions = positions; fq.slots = slot_mapping;
     fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
     fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
-    fq.H = H; fq.Hkv = Hkv; fq.D = D;
+    fq.H = H; fq.Hkv = Hkv; fq.D = D; fq.kv_fp8 = c.kv_fp8;
     linear_fused(r, xw, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
                  c.hidden, qkv_n, kEpiRopeKv, fq, st);
     launch_paged_attn_decode(r->maps[l], r->attn, r->qkv, qkv_n, block_tables, context_lens, B, H, Hkv,
@@ -414,7 +435,7 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
       fq.positions = positions; fq.slots = slot_mapping;
       fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
       fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
-      fq.H = H; fq.Hkv = Hkv; fq.D = D;
+      fq.H = H; fq.Hkv = Hkv; fq.D = D; fq.kv_fp8 = c.kv_fp8;
       linear_fused(r, r->xn, w.qkv_w, w.qkv_s, w.qkv_z, c.qkv_bias ? w.qkv_bias : nullptr, r->qkv, B,
                    c.hidden, qkv_n, kEpiRopeKv, fq, st);
     } else {
@@ -423,7 +444,7 @@ void b200_runner_decode_device(b200_runner* r, const uint32_t* input_ids,
       __half* k = r->qkv + H * D;
       __half* v = r->qkv + (H + Hkv) * D;
       launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
-                           w.k_cache, w.v_cache, B, H, Hkv, D, D, 0, c.cos_sin_f32, st);
+                           w.k_cache, w.v_cache, B, H, Hkv, D, D, 0, c.cos_sin_f32, st, c.kv_fp8);
     }
     launch_paged_attn_decode(r->maps[l], r->attn, q, qkv_n, block_tables, context_lens, B, H, Hkv,
                              D, c.max_blocks_per_seq, c.attn_scale, 0.f, 0, r->attn_ws, st);
@@ -475,6 +496,10 @@ void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
     set_error(1, "runner_prefill: workspace not set or sizes out of range");
     return;
   }
+  if (c.kv_fp8 && (!r->kv_smaps_ok || max_blocks > c.max_blocks_per_seq)) {
+    set_error(1, "runner_prefill: fp8 KV scratch not available for this step");
+    return;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long launches0 = launch_count();
   const int H = c.num_heads, Hkv = c.num_kv_heads, D = c.head_dim;
@@ -494,9 +519,19 @@ void b200_runner_prefill_device(b200_runner* r, const uint32_t* input_ids,
     __half* k = r->qkv + H * D;
     __half* v = r->qkv + (H + Hkv) * D;
     launch_rope_kv_write(q, k, v, qkv_n, qkv_n, qkv_n, r->cos, r->sin, positions, slot_mapping,
-                         w.k_cache, w.v_cache, T, H, Hkv, D, D, 0, c.cos_sin_f32, st);
-    launch_attn_prefill(r->maps[l], r->attn, q, qkv_n, cu_seqlens_q, context_lens, block_tables, B,
-                        H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st, T);
+                         w.k_cache, w.v_cache, T, H, Hkv, D, D, 0, c.cos_sin_f32, st, c.kv_fp8);
+    if (c.kv_fp8) {
+      // every key / value of the step is read back from the e4m3 cache (the result does not depend on
+      // how the prompt was chunked or which prefix came from the prefix cache): expand the context
+      // pages to fp16 scratch blocks, then the fp16 prefill kernels run on those
+      launch_kv_fp8_gather(w.k_cache, w.v_cache, r->kv_sk, r->kv_sv, l == 0 ? r->kv_sbt : nullptr, block_tables,
+                           context_lens, cu_seqlens_q, B, max_blocks, Hkv, D, st);
+      launch_attn_prefill(r->kv_smaps, r->attn, q, qkv_n, cu_seqlens_q, context_lens, r->kv_sbt, B,
+                          H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st, T);
+    } else {
+      launch_attn_prefill(r->maps[l], r->attn, q, qkv_n, cu_seqlens_q, context_lens, block_tables, B,
+                          H, Hkv, D, max_blocks, max_seqlen_q, c.attn_scale, st, T);
+    }
     linear(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, r->proj, T, H * D, c.hidden, B200_EPI_NONE,
            stream, V);
     if (r->allreduce) r->allreduce(r->proj, static_cast<int64_t>(T) * c.hidden, r->allreduce_user, stream);

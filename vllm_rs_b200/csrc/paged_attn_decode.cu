@@ -23,6 +23,19 @@
 //     write fp16 output directly.
 //
 // Algorithmic bytes per launch: B * ctx * Hkv * D * 2 (K) * 2 (V) * 2 B  (+ q/out).
+//
+// FP8 KV cache (`--fp8-kvcache`, kvcache_allocator.rs:188-193,776: cache dtype U8, same
+// [num_blocks, 64, Hkv, D] shape; attention.rs:615 hands only the flag to attention-rs, so the
+// storage format is this library's: e4m3, scale 1, saturating round-to-nearest from the fp16 K/V).
+// The F8 instantiation streams half the bytes: a (page, head) tile is ONE box of 64 rows x 128 B,
+// 6 stages keep the same bytes in flight, and the consumers expand e4m3 -> fp16 in registers:
+//   * K: the same ldmatrix addresses now return 4 BYTES of one token row per lane; the contraction
+//     index is permuted (lane c's k-slots {2c,2c+1,2c+8,2c+9} <-> d = 16 ks + 4c + {0,1,2,3}) and the
+//     Q fragments are loaded with the same permutation, so no shuffles are needed;
+//   * V: ldmatrix.trans on the byte tile yields (d even, d odd) byte pairs of two tokens; one prmt
+//     regroups them into the {token 2c, 2c+1, 2c+8, 2c+9} bytes of an even-d and an odd-d n-tile, whose
+//     output columns are un-permuted when O is written out.
+#include <cuda_fp8.h>
 #include <cstdlib>
 #include "../../include/b200_vllm.h"
 #include "attn.cuh"
@@ -35,34 +48,51 @@ constexpr int kConsumerWarps = 4;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxPagesPerSplit = 128;
 
-template <int D>
+template <int D, bool F8 = false>
 struct AttnSmem {
-  static constexpr int kTileBytes = kTok * D * 2;       // one K (or V) page tile
+  // F8: 4 stages x 16 KB and 3 CTAs per SM keep the same 192 KB in flight per SM as 3 x 32 KB x 2 CTAs, with
+  // 12 instead of 8 consumer warps to hide the (now twice as frequent) ldmatrix -> cvt -> mma -> softmax chain
+  static constexpr int kNumStages = F8 ? 4 : kStages;
+  static constexpr int kCtasPerSm = F8 ? 3 : 2;
+  static constexpr int kTileBytes = kTok * D * (F8 ? 1 : 2);      // one K (or V) page tile
   static constexpr int kStageBytes = 2 * kTileBytes;
-  static constexpr int kDataBytes = kStages * kStageBytes;
+  static constexpr int kDataBytes = kNumStages * kStageBytes;
   static constexpr int kBarOff = kDataBytes;
-  static constexpr int kIdsOff = kBarOff + 64;
+  static constexpr int kIdsOff = kBarOff + 128;
   static constexpr int kMlOff = kIdsOff + kMaxPagesPerSplit * 4;
   static constexpr int kTotal = kMlOff + kConsumerWarps * 16 * 2 * 4;
   static constexpr int kAlloc = kTotal + 1024;          // manual 1024-B alignment slack
 };
 
+// four e4m3 bytes -> half2 of bytes (0,1) and half2 of bytes (2,3).  Same instruction cuda_fp8.hpp's
+// __nv_cvt_fp8x2_to_halfraw2 emits (low byte -> low half), written inline so the two f16x2 results stay
+// whole 32-bit registers (the struct round trip cost two PRMTs per conversion).
+__device__ __forceinline__ void e4m3x4_to_half2x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f16x2.e4m3x2 %0, l;\n\t"
+      "cvt.rn.f16x2.e4m3x2 %1, h;\n\t}\n"
+      : "=r"(lo), "=r"(hi)
+      : "r"(w));
+}
+
 __device__ __forceinline__ int first_page_of(int ctx, int window) {
   return (window > 0 && ctx > window) ? (ctx - window) / kTok : 0;
 }
 
-template <int D>
-__global__ void __launch_bounds__(kThreads, 2)
-paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
-                         const __grid_constant__ CUtensorMap vmap,
-                         const __half* __restrict__ q, __half* __restrict__ out,
-                         const uint32_t* __restrict__ block_tables,
-                         const uint32_t* __restrict__ context_lens, float* __restrict__ part_o,
-                         float* __restrict__ part_ml, unsigned* __restrict__ counters,
-                         int q_stride, int H, int Hkv, int max_blocks,
-                         int pages_per_split, int max_splits, float scale_log2, float softcap,
-                         int window) {
-  using SM = AttnSmem<D>;
+// HI = false promises H / Hkv <= 8: rows 8..15 of every A fragment are the constant 0, which frees the 16
+// registers the fp8 instantiation needs to fit 3 CTAs per SM without spilling.
+template <int D, bool F8, bool HI>
+__device__ __forceinline__ void
+paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
+                       const __half* __restrict__ q, __half* __restrict__ out,
+                       const uint32_t* __restrict__ block_tables,
+                       const uint32_t* __restrict__ context_lens, float* __restrict__ part_o,
+                       float* __restrict__ part_ml, unsigned* __restrict__ counters,
+                       int q_stride, int H, int Hkv, int max_blocks,
+                       int pages_per_split, int max_splits, float scale_log2, float softcap,
+                       int window) {
+  using SM = AttnSmem<D, F8>;
+  constexpr int kNS = SM::kNumStages;
+  static_assert(!F8 || D == 128, "fp8 tiles are one 128-byte row per token");
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   const int ctx = static_cast<int>(context_lens[b]);
   if (ctx <= 0) {
@@ -90,13 +120,13 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
-  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* empty_bar = full_bar + kNS;
   uint32_t* sm_ids = reinterpret_cast<uint32_t*>(smem + SM::kIdsOff);
   float* sm_ml = reinterpret_cast<float*>(smem + SM::kMlOff);   // [warp][16][2]
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
     }
@@ -126,24 +156,29 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
   for (int j = 0; j < D / 8; ++j) o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f;
 
   const int g = lane >> 2, c = lane & 3;
-  const bool hi_rows = G > 8;
+  const bool hi_rows = HI && G > 8;
 
   if (warp == kConsumerWarps) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int i = 0; i < n_cta_pages; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
+        const int s = i % kNS;
+        const uint32_t ph = (i / kNS) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (page0 + i == npages - 1) pdl_wait();       // the page holding this step's new token
         mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
         const int blk = static_cast<int>(sm_ids[i]);
         uint8_t* kdst = smem + s * SM::kStageBytes;
         uint8_t* vdst = kdst + SM::kTileBytes;
+        if (F8) {
+          tma_load_4d(kdst, &kmap, &full_bar[s], 0, hkv, 0, blk);       // 64 rows x 128 e4m3 bytes
+          tma_load_4d(vdst, &vmap, &full_bar[s], 0, hkv, 0, blk);
+        } else {
 #pragma unroll
-        for (int hb = 0; hb < D / 64; ++hb) {
-          tma_load_4d(kdst + hb * (kTok * 128), &kmap, &full_bar[s], hb * 64, hkv, 0, blk);
-          tma_load_4d(vdst + hb * (kTok * 128), &vmap, &full_bar[s], hb * 64, hkv, 0, blk);
+          for (int hb = 0; hb < D / 64; ++hb) {
+            tma_load_4d(kdst + hb * (kTok * 128), &kmap, &full_bar[s], hb * 64, hkv, 0, blk);
+            tma_load_4d(vdst + hb * (kTok * 128), &vmap, &full_bar[s], hb * 64, hkv, 0, blk);
+          }
         }
       }
     }
@@ -155,12 +190,14 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
       const __half* qb = q + static_cast<size_t>(b) * q_stride + static_cast<size_t>(hkv) * G * D;
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks) {
-        const int d0 = ks * 16 + 2 * c;
+        // F8: k-slots {2c, 2c+1 | 2c+8, 2c+9} of step ks stand for d = 16 ks + 4c + {0, 1 | 2, 3}
+        const int d0 = ks * 16 + (F8 ? 4 : 2) * c;
+        constexpr int kHi = F8 ? 2 : 8;
         qa[ks][0] = (g < G) ? *reinterpret_cast<const uint32_t*>(qb + g * D + d0) : 0u;
-        qa[ks][1] = (g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0) : 0u;
-        qa[ks][2] = (g < G) ? *reinterpret_cast<const uint32_t*>(qb + g * D + d0 + 8) : 0u;
+        qa[ks][1] = (HI && g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0) : 0u;
+        qa[ks][2] = (g < G) ? *reinterpret_cast<const uint32_t*>(qb + g * D + d0 + kHi) : 0u;
         qa[ks][3] =
-            (g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0 + 8) : 0u;
+            (HI && g + 8 < G) ? *reinterpret_cast<const uint32_t*>(qb + (g + 8) * D + d0 + kHi) : 0u;
       }
     }
     const int t0 = warp * 16;
@@ -176,8 +213,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
     const int v_chunk_sel = lane >> 4;
 
     for (int i = 0; i < n_cta_pages; ++i) {
-      const int s = i % kStages;
-      const uint32_t ph = (i / kStages) & 1;
+      const int s = i % kNS;
+      const uint32_t ph = (i / kNS) & 1;
       mbar_wait(&full_bar[s], ph);
       const int tok_base = (page0 + i) * kTok + t0;   // global index of this warp's first token
       if (tok_base < ctx && tok_base + 16 > win_lo) {
@@ -185,14 +222,39 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
         const uint32_t vbase = kbase + SM::kTileBytes;
         // ---- S = Q K^T for 16 tokens
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        if (F8) {
+          // one 16-byte chunk of a token row = one whole k-step; matrices = (token half) x (chunk pair)
+          // even / odd k-steps accumulate separately: 4 dependent MMAs per chain instead of 8
+          float s0b[4] = {0.f, 0.f, 0.f, 0.f}, s1b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const int hb = ks >> 2;
-          const int chunk = ((ks & 3) << 1) + k_chunk_sel;
-          uint32_t r[4];
-          ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
-          mma_16816(s0, qa[ks], r[0], r[1]);
-          mma_16816(s1, qa[ks], r[2], r[3]);
+          for (int kp = 0; kp < D / 32; ++kp) {
+            const int chunk = 2 * kp + k_chunk_sel;
+            uint32_t r[4], b0, b1;
+            ldsm_x4(r, kbase + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+            e4m3x4_to_half2x2(r[0], b0, b1);
+            mma_16816(s0, qa[2 * kp], b0, b1);
+            e4m3x4_to_half2x2(r[1], b0, b1);
+            mma_16816(s0b, qa[2 * kp + 1], b0, b1);
+            e4m3x4_to_half2x2(r[2], b0, b1);
+            mma_16816(s1, qa[2 * kp], b0, b1);
+            e4m3x4_to_half2x2(r[3], b0, b1);
+            mma_16816(s1b, qa[2 * kp + 1], b0, b1);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            s0[e] += s0b[e];
+            s1[e] += s1b[e];
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const int hb = ks >> 2;
+            const int chunk = ((ks & 3) << 1) + k_chunk_sel;
+            uint32_t r[4];
+            ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+            mma_16816(s0, qa[ks], r[0], r[1]);
+            mma_16816(s1, qa[ks], r[2], r[3]);
+          }
         }
         // ---- online softmax (rows g and, when G > 8, g + 8)
         uint32_t pa[4] = {0u, 0u, 0u, 0u};
@@ -224,10 +286,14 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
           }
           l_run[rh] = l_run[rh] * alpha + psum;
           m_run[rh] = m_new;
+          // F8 halves the time per page: skip the 2 * D/8 multiplies while the running maximum stands
+          // (alpha == 1 exactly; warp-uniform vote, so the result is bit-identical either way)
+          if (!F8 || !__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll
-          for (int j = 0; j < D / 8; ++j) {
-            o_acc[j][2 * rh] *= alpha;
-            o_acc[j][2 * rh + 1] *= alpha;
+            for (int j = 0; j < D / 8; ++j) {
+              o_acc[j][2 * rh] *= alpha;
+              o_acc[j][2 * rh + 1] *= alpha;
+            }
           }
           pa[rh] = pack_half2(p[0], p[1]);
           pa[2 + rh] = pack_half2(p[2], p[3]);
@@ -238,18 +304,45 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
                                   (tok_base + 2 * c + 1 < ctx ? 0xFFFF0000u : 0u);
         const uint32_t vmask_hi = (tok_base + 8 + 2 * c < ctx ? 0x0000FFFFu : 0u) |
                                   (tok_base + 9 + 2 * c < ctx ? 0xFFFF0000u : 0u);
+        if (F8) {
+          // transposed 8x8 b16 matrices of the byte tile: lane (g, c) gets the byte pairs (d = 2g, 2g+1)
+          // of tokens 2c and 2c+1.  prmt gathers {tok 2c, 2c+1, 2c+8, 2c+9} for d even / d odd.
+          const uint32_t vmask8 = ((vmask_lo & 0xFFu) ? 0x000000FFu : 0u) | ((vmask_lo >> 16) ? 0x0000FF00u : 0u) |
+                                  ((vmask_hi & 0xFFu) ? 0x00FF0000u : 0u) | ((vmask_hi >> 16) ? 0xFF000000u : 0u);
 #pragma unroll
-        for (int jj = 0; jj < D / 16; ++jj) {
-          const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
-          const int hb = chunk >> 3, c16 = chunk & 7;
-          uint32_t r[4];
-          ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
-          if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
-            r[0] &= vmask_lo; r[2] &= vmask_lo;
-            r[1] &= vmask_hi; r[3] &= vmask_hi;
+          for (int jp = 0; jp < D / 32; ++jp) {
+            const int chunk = 2 * jp + v_chunk_sel;     // 16-byte chunk along d (0..7)
+            uint32_t r[4];
+            ldsm_x4_t(r, vbase + v_tok * 128 + ((chunk ^ (v_tok & 7)) << 4));
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {            // chunk 2 jp + hc: r[2 hc] = tokens 0-7, r[2 hc + 1] = 8-15
+              uint32_t ev = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x6420);
+              uint32_t od = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x7531);
+              if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
+                ev &= vmask8;
+                od &= vmask8;
+              }
+              uint32_t b0, b1;
+              e4m3x4_to_half2x2(ev, b0, b1);
+              mma_16816(o_acc[4 * jp + 2 * hc], pa, b0, b1);        // columns d = 16 chunk + 2 n
+              e4m3x4_to_half2x2(od, b0, b1);
+              mma_16816(o_acc[4 * jp + 2 * hc + 1], pa, b0, b1);    // columns d = 16 chunk + 2 n + 1
+            }
           }
-          mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
-          mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < D / 16; ++jj) {
+            const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
+            const int hb = chunk >> 3, c16 = chunk & 7;
+            uint32_t r[4];
+            ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
+            if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
+              r[0] &= vmask_lo; r[2] &= vmask_lo;
+              r[1] &= vmask_hi; r[3] &= vmask_hi;
+            }
+            mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
+            mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
+          }
         }
       }
       __syncwarp();
@@ -278,10 +371,20 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
 #pragma unroll
         for (int w = 0; w < kConsumerWarps; ++w) m_tot = fmaxf(m_tot, sm_ml[(w * 16 + row) * 2]);
         const float f = exp2f(m_run[rh] - m_tot);   // m_tot finite: the CTA saw >= 1 token
+        if (F8) {
+          // tiles 2 ch / 2 ch + 1 hold the even / odd columns of 16-wide chunk ch: d = 16 ch + 4c + {0..3}
 #pragma unroll
-        for (int j = 0; j < D / 8; ++j) {
-          float2 v = make_float2(o_acc[j][2 * rh] * f, o_acc[j][2 * rh + 1] * f);
-          *reinterpret_cast<float2*>(&sm_o[(warp * G + row) * D + j * 8 + 2 * c]) = v;
+          for (int ch = 0; ch < D / 16; ++ch) {
+            float4 v = make_float4(o_acc[2 * ch][2 * rh] * f, o_acc[2 * ch + 1][2 * rh] * f,
+                                   o_acc[2 * ch][2 * rh + 1] * f, o_acc[2 * ch + 1][2 * rh + 1] * f);
+            *reinterpret_cast<float4*>(&sm_o[(warp * G + row) * D + ch * 16 + 4 * c]) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < D / 8; ++j) {
+            float2 v = make_float2(o_acc[j][2 * rh] * f, o_acc[j][2 * rh + 1] * f);
+            *reinterpret_cast<float2*>(&sm_o[(warp * G + row) * D + j * 8 + 2 * c]) = v;
+          }
         }
       }
     }
@@ -310,6 +413,28 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap,
       }
     }
   }
+}
+
+#define B200_ATTN_DECODE_PARAMS                                                                      \
+  const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,                \
+      const __half *__restrict__ q, __half *__restrict__ out, const uint32_t *__restrict__ block_tables, \
+      const uint32_t *__restrict__ context_lens, float *__restrict__ part_o, float *__restrict__ part_ml, \
+      unsigned *__restrict__ counters, int q_stride, int H, int Hkv, int max_blocks, int pages_per_split, \
+      int max_splits, float scale_log2, float softcap, int window
+#define B200_ATTN_DECODE_ARGS                                                                         \
+  kmap, vmap, q, out, block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks, \
+      pages_per_split, max_splits, scale_log2, softcap, window
+
+// fp16 cache: 2 CTAs per SM (96 KB of stages each)
+template <int D, bool F8, bool HI>
+__global__ void __launch_bounds__(kThreads, 2) paged_attn_decode_kernel(B200_ATTN_DECODE_PARAMS) {
+  paged_attn_decode_body<D, F8, HI>(B200_ATTN_DECODE_ARGS);
+}
+// e4m3 cache: 3 CTAs per SM.  136 registers x 160 threads x 3 = 65 280 of the SM's 65 536 (the min-blocks form
+// of __launch_bounds__ made ptxas stop at 128 and spill inside the page loop).
+template <int D, bool HI>
+__global__ void __maxnreg__(136) paged_attn_decode_fp8_kernel(B200_ATTN_DECODE_PARAMS) {
+  paged_attn_decode_body<D, true, HI>(B200_ATTN_DECODE_ARGS);
 }
 
 // Split merge: one CTA per (head, sequence).  Launched with PDL right behind the main kernel, so
@@ -351,8 +476,8 @@ struct SplitPlan {
 // waves of 2 CTAs per SM, a CTA costs p pages plus about one page of fixed work (prologue,
 // partial store).  Picks the p that minimises waves * (p + 1): e.g. 32 x 8 x 65 pages on 148 SMs
 // -> p = 9 (8 splits, 6.9 waves) rather than p = 10 (7 splits, 6.05 -> 7 waves).
-static SplitPlan plan_splits(int batch, int num_kv_heads, int max_blocks) {
-  const long slots = static_cast<long>(sm_count()) * 2;
+static SplitPlan plan_splits(int batch, int num_kv_heads, int max_blocks, int ctas_per_sm = 2) {
+  const long slots = static_cast<long>(sm_count()) * ctas_per_sm;
   const long heads = static_cast<long>(batch) * num_kv_heads;
   int hi = max_blocks < kMaxPagesPerSplit ? max_blocks : kMaxPagesPerSplit;
   if (hi < 1) hi = 1;
@@ -382,43 +507,47 @@ static SplitPlan plan_splits(int batch, int num_kv_heads, int max_blocks) {
   return r;
 }
 
-static bool make_cache_map(CUtensorMap* map, const void* cache, int num_blocks, int Hkv, int D) {
+static bool make_cache_map(CUtensorMap* map, const void* cache, int num_blocks, int Hkv, int D, bool fp8) {
+  const uint64_t es_bytes = fp8 ? 1 : 2;
   const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(Hkv), kTok,
                             static_cast<uint64_t>(num_blocks)};
-  const uint64_t strides[3] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(Hkv) * D * 2,
-                               static_cast<uint64_t>(kTok) * Hkv * D * 2};
-  const uint32_t box[4] = {64, 1, kTok, 1};
+  const uint64_t strides[3] = {static_cast<uint64_t>(D) * es_bytes, static_cast<uint64_t>(Hkv) * D * es_bytes,
+                               static_cast<uint64_t>(kTok) * Hkv * D * es_bytes};
+  const uint32_t box[4] = {fp8 ? 128u : 64u, 1, kTok, 1};      // 128-byte rows either way
   const uint32_t es[4] = {1, 1, 1, 1};
-  return encode_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(cache),
-                           dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+  return encode_tensor_map(map, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                           const_cast<void*>(cache), dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
 }
 
 bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks,
-                    int Hkv, int D) {
-  return make_cache_map(&m->k, k_cache, num_blocks, Hkv, D) &&
-         make_cache_map(&m->v, v_cache, num_blocks, Hkv, D);
+                    int Hkv, int D, bool fp8) {
+  m->fp8 = fp8;
+  if (fp8 && D != 128) return false;
+  return make_cache_map(&m->k, k_cache, num_blocks, Hkv, D, fp8) &&
+         make_cache_map(&m->v, v_cache, num_blocks, Hkv, D, fp8);
 }
 
-template <int D>
+template <int D, bool F8 = false, bool HI = true>
 static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                           const uint32_t* block_tables, const uint32_t* context_lens, int B,
                           int H, int Hkv, int max_blocks, float scale, float softcap, int window,
                           void* workspace, cudaStream_t st) {
-  const SplitPlan sp = plan_splits(B, Hkv, max_blocks);
+  const SplitPlan sp = plan_splits(B, Hkv, max_blocks, AttnSmem<D, F8>::kCtasPerSm);
   // workspace: [arrival counters B*Hkv u32, zero at rest][partial O fp32][partial (m, l)]
   unsigned* counters = reinterpret_cast<unsigned*>(workspace);
   float* part_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
                                            ((static_cast<size_t>(B) * Hkv * 4 + 255) / 256) * 256);
   float* part_ml = part_o + static_cast<size_t>(B) * H * sp.max_splits * D;
+  auto kern = paged_attn_decode_kernel<D, false, HI>;
+  if constexpr (F8) kern = paged_attn_decode_fp8_kernel<D, HI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(paged_attn_decode_kernel<D>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D>::kAlloc);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D, F8>::kAlloc);
     attr_set = true;
   }
   dim3 grid(sp.max_splits, Hkv, B);
-  launch_pdl(paged_attn_decode_kernel<D>, grid, dim3(kThreads), AttnSmem<D>::kAlloc, st,
+  launch_pdl(kern, grid, dim3(kThreads), AttnSmem<D, F8>::kAlloc, st,
       maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
       block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
@@ -433,7 +562,13 @@ void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, in
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
                               int window, void* workspace, cudaStream_t st) {
-  if (D == 128)
+  if (maps.fp8 && H / Hkv <= 8)
+    launch_decode<128, true, false>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
+                                    scale, softcap, window, workspace, st);
+  else if (maps.fp8)
+    launch_decode<128, true, true>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
+                                   scale, softcap, window, workspace, st);
+  else if (D == 128)
     launch_decode<128>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
                        scale, softcap, window, workspace, st);
   else
@@ -449,12 +584,39 @@ int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_
                                         int32_t max_blocks_per_seq) {
   // worst case over kv-head counts: plan with Hkv = 1 gives the most splits per sequence
   int max_splits = 1;
-  for (int hkv = 1; hkv <= num_heads; hkv <<= 1) {
-    b200::SplitPlan sp = b200::plan_splits(batch, hkv, max_blocks_per_seq);
-    if (sp.max_splits > max_splits) max_splits = sp.max_splits;
-  }
+  for (int hkv = 1; hkv <= num_heads; hkv <<= 1)
+    for (int occ = 2; occ <= 3; ++occ) {       // fp16 cache: 2 CTAs per SM, fp8 cache: 3
+      b200::SplitPlan sp = b200::plan_splits(batch, hkv, max_blocks_per_seq, occ);
+      if (sp.max_splits > max_splits) max_splits = sp.max_splits;
+    }
   return static_cast<int64_t>(batch) * num_heads * max_splits * (head_dim + 2) * 4 +
          static_cast<int64_t>(batch) * num_heads * 4 + 1024;
+}
+
+static void paged_attn_decode_any(void* out, const void* q, const void* k_cache,
+                                const void* v_cache, const uint32_t* block_tables,
+                                const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                float softcap, int32_t window, void* workspace,
+                                int64_t stream, bool fp8) {
+  using namespace b200;
+  B200_CHECK_ARG(!fp8 || head_dim == 128, "paged_attn_decode: the fp8 KV cache needs head_dim 128");
+  B200_CHECK_ARG(block_size == kTok, "paged_attn_decode: block_size must be 64");
+  B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "paged_attn_decode: head_dim must be 64/128");
+  B200_CHECK_ARG(num_kv_heads > 0 && num_heads % num_kv_heads == 0 &&
+                     num_heads / num_kv_heads <= 16,
+                 "paged_attn_decode: H/Hkv must be an integer <= 16");
+  B200_CHECK_ARG(batch > 0 && max_blocks_per_seq > 0 && num_blocks > 0 && workspace != nullptr,
+                 "paged_attn_decode: bad sizes or NULL workspace");
+  AttnMaps maps;
+  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim, fp8)) {
+    set_error(2, "paged_attn_decode: cuTensorMapEncodeTiled failed");
+    return;
+  }
+  launch_paged_attn_decode(maps, out, q, num_heads * head_dim, block_tables, context_lens, batch,
+                           num_heads, num_kv_heads, head_dim, max_blocks_per_seq, scale, softcap,
+                           window, workspace, reinterpret_cast<cudaStream_t>(stream));
 }
 
 void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
@@ -464,22 +626,21 @@ void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
                                 float softcap, int32_t window, void* workspace,
                                 int64_t stream) {
-  using namespace b200;
-  B200_CHECK_ARG(block_size == kTok, "paged_attn_decode: block_size must be 64");
-  B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "paged_attn_decode: head_dim must be 64/128");
-  B200_CHECK_ARG(num_kv_heads > 0 && num_heads % num_kv_heads == 0 &&
-                     num_heads / num_kv_heads <= 16,
-                 "paged_attn_decode: H/Hkv must be an integer <= 16");
-  B200_CHECK_ARG(batch > 0 && max_blocks_per_seq > 0 && num_blocks > 0 && workspace != nullptr,
-                 "paged_attn_decode: bad sizes or NULL workspace");
-  AttnMaps maps;
-  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim)) {
-    set_error(2, "paged_attn_decode: cuTensorMapEncodeTiled failed");
-    return;
-  }
-  launch_paged_attn_decode(maps, out, q, num_heads * head_dim, block_tables, context_lens, batch,
-                           num_heads, num_kv_heads, head_dim, max_blocks_per_seq, scale, softcap,
-                           window, workspace, reinterpret_cast<cudaStream_t>(stream));
+  paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
+                        num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
+                        window, workspace, stream, false);
+}
+
+void b200_paged_attn_decode_fp8kv_f16(void* out, const void* q, const void* k_cache,
+                                      const void* v_cache, const uint32_t* block_tables,
+                                      const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                      int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                      int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                      float softcap, int32_t window, void* workspace,
+                                      int64_t stream) {
+  paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
+                        num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
+                        window, workspace, stream, true);
 }
 
 }  // extern "C"

@@ -9,6 +9,8 @@
 //         qzeros  i32 [K/G, N/8] same nibble order, no +1
 //   w = (q - z) * s, rounded once to fp16.
 #pragma once
+#include <cuda_fp8.h>
+
 #include "../../include/b200_vllm.h"
 #include "common.cuh"
 
@@ -129,6 +131,7 @@ struct FusedEpi {
   __half* k_cache;
   __half* v_cache;
   int H, Hkv, D;
+  int kv_fp8;      // caches hold e4m3 bytes (--fp8-kvcache): K/V rows are rounded to fp16, then to e4m3
   // kEpiPushPeers: rank r's receive slot for THIS rank's partial [M, N] and its tile counter
   __half* push[kMaxTpRanks];
   uint32_t* push_cnt[kMaxTpRanks];
@@ -312,7 +315,15 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
         const bool is_k = hh < fe.H + fe.Hkv;
         __half* cache = is_k ? fe.k_cache : fe.v_cache;
         const int kvh = hh - fe.H - (is_k ? 0 : fe.Hkv);
-        store_half4(cache + (static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d, out);
+        const size_t ci = (static_cast<size_t>(r.sl) * fe.Hkv + kvh) * D + d;
+        if (fe.kv_fp8) {
+          __half2_raw a = __floats2half2_rn(out[0], out[1]), b = __floats2half2_rn(out[2], out[3]);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(cache) + ci) =
+              static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(a, __NV_SATFINITE, __NV_E4M3)) |
+              (static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(b, __NV_SATFINITE, __NV_E4M3)) << 16);
+        } else {
+          store_half4(cache + ci, out);
+        }
       }
     }
   } else if (epi == kEpiPushPeers) {

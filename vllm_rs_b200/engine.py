@@ -239,7 +239,7 @@ class ModelRunner:
     def __init__(self, *, hidden, num_layers, num_heads, num_kv_heads, head_dim, inter, vocab,
                  num_blocks, max_blocks_per_seq, max_batch, bits=4, group_size=128,
                  qfmt=ops.QFMT_AWQ, rms_eps=1e-5, qkv_bias=False, max_pos=8192,
-                 max_prefill_tokens=0, device="cuda"):
+                 max_prefill_tokens=0, device="cuda", kv_fp8=False):
         self._l = _lib.lib()
         self.device = torch.device(device)
         self.cfg = ModelConfig(
@@ -248,14 +248,15 @@ class ModelRunner:
             qfmt=qfmt, block_size=64, num_blocks=num_blocks, max_blocks_per_seq=max_blocks_per_seq,
             max_batch=max_batch, max_pos=max_pos, qkv_bias=int(qkv_bias), cos_sin_f32=0,
             rms_eps=rms_eps, attn_scale=1.0 / float(np.sqrt(head_dim)), tp_rank=0, tp_size=1,
-            max_prefill_tokens=max_prefill_tokens)
+            max_prefill_tokens=max_prefill_tokens, kv_fp8=int(kv_fp8))
         self._h = self._l.b200_runner_new(C.byref(self.cfg))
         _lib.check()
         self._keep = []            # tensors whose pointers the runner holds
         shape = (num_blocks, 64, num_kv_heads, head_dim)
-        self.k_cache = [torch.zeros(shape, dtype=torch.float16, device=self.device)
+        cache_dtype = torch.uint8 if kv_fp8 else torch.float16   # kvcache_allocator.rs:776
+        self.k_cache = [torch.zeros(shape, dtype=cache_dtype, device=self.device)
                         for _ in range(num_layers)]
-        self.v_cache = [torch.zeros(shape, dtype=torch.float16, device=self.device)
+        self.v_cache = [torch.zeros(shape, dtype=cache_dtype, device=self.device)
                         for _ in range(num_layers)]
         nbytes = self._l.b200_runner_workspace_bytes(self._h)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
@@ -397,9 +398,11 @@ class LLMEngine:
     (filter_prefill_finished / postprocess / clear_finished).  Greedy sampling."""
 
     def __init__(self, runner: ModelRunner, num_blocks, max_num_seqs, eos_token_ids=(),
-                 chunk_size=8192):
+                 chunk_size=8192, prefix_cache=False, prefix_cache_max_tokens=None):
         self.runner = runner
         self.sched = Scheduler(num_blocks, 64, max_num_seqs, 0, chunk_size, eos_token_ids)
+        if prefix_cache:                    # EngineConfig.prefix_cache / prefix_cache_max_tokens
+            self.sched.enable_prefix_cache(prefix_cache_max_tokens)
         self.max_blocks = runner.cfg.max_blocks_per_seq
         self.outputs = {}
 

@@ -104,7 +104,9 @@ def rope_kv_write(q, k, v, cos, sin, positions, slot_mapping=None, k_cache=None,
     T, H, D = q.shape
     Hkv = k.shape[1]
     bs = k_cache.shape[1] if k_cache is not None else 64
-    _lib.lib().b200_rope_kv_write_f16(
+    fp8 = k_cache is not None and k_cache.dtype == torch.uint8        # --fp8-kvcache: e4m3 bytes
+    fn = _lib.lib().b200_rope_kv_write_fp8kv_f16 if fp8 else _lib.lib().b200_rope_kv_write_f16
+    fn(
         _p(q), _p(k), _p(v), _p(cos), _p(sin), _p(positions), _p(slot_mapping), _p(k_cache),
         _p(v_cache), T, H, Hkv, D, rot_dim or D, bs, int(interleaved),
         int(cos.dtype == torch.float32), _stream())
@@ -136,10 +138,10 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
         workspace = paged_attn_workspace(B, H, D, mb, q.device)
     if out is None:
         out = torch.empty_like(q)
-    _lib.lib().b200_paged_attn_decode_f16(_p(out), _p(q), _p(k_cache), _p(v_cache),
-                                          _p(block_tables), _p(context_lens), B, H, Hkv, D, bs,
-                                          mb, nb, float(scale), float(softcap), int(window),
-                                          _p(workspace), _stream())
+    fp8 = k_cache.dtype == torch.uint8                                # --fp8-kvcache: e4m3 bytes
+    fn = _lib.lib().b200_paged_attn_decode_fp8kv_f16 if fp8 else _lib.lib().b200_paged_attn_decode_f16
+    fn(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(block_tables), _p(context_lens), B, H, Hkv, D, bs,
+       mb, nb, float(scale), float(softcap), int(window), _p(workspace), _stream())
     _lib.check()
     return out
 

@@ -49,7 +49,7 @@ def _fused_awq_device(gen, K, Ns, group, device):
 
 def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_batch, seed=0,
                      group=128, num_layers=None, tp_size=1, device="cuda",
-                     max_prefill_tokens=0) -> ModelRunner:
+                     max_prefill_tokens=0, kv_fp8=False) -> ModelRunner:
     """Random AWQ-int4 model of the named architecture (optionally one TP shard of it:
     q/k/v/gate/up column-sharded, o/down row-sharded, attention.rs:445-530, mlp.rs:367-442)."""
     hidden, L, H, Hkv, D, inter, vocab, theta = SHAPES[name]
@@ -59,7 +59,7 @@ def build_awq_runner(name="llama3-8b", *, num_blocks, max_blocks_per_seq, max_ba
                     inter=interl, vocab=vocab, num_blocks=num_blocks,
                     max_blocks_per_seq=max_blocks_per_seq, max_batch=max_batch, bits=4,
                     group_size=group, qfmt=ops.QFMT_AWQ, device=device,
-                    max_prefill_tokens=max_prefill_tokens)
+                    max_prefill_tokens=max_prefill_tokens, kv_fp8=kv_fp8)
     gen = torch.Generator(device=device).manual_seed(seed)
 
     def norm_w():
@@ -84,11 +84,16 @@ def fill_kv_random(r: ModelRunner, seed=1):
     """KV cache ~ N(0,1) fp16 without a huge temporary."""
     gen = torch.Generator(device=r.device).manual_seed(seed)
     for kc, vc in zip(r.k_cache, r.v_cache):
+        if kc.dtype == torch.uint8:          # --fp8-kvcache: e4m3 bytes of the same N(0,1) values
+            for c in (kc, vc):
+                c.copy_(torch.randn(c.shape, generator=gen, device=r.device, dtype=torch.float16)
+                        .to(torch.float8_e4m3fn).view(torch.uint8))
+            continue
         kc.normal_(generator=gen)
         vc.normal_(generator=gen)
 
 
-def decode_algorithmic_bytes(shape: dict, batch: int, ctx: int, bits=4) -> dict:
+def decode_algorithmic_bytes(shape: dict, batch: int, ctx: int, bits=4, kv_bytes=2) -> dict:
     """Algorithmic HBM bytes of one decode step (SURVEY.md 8(d) / BASELINE.md section 4)."""
     h, L, H, Hkv, D, inter, V, G = (shape[k] for k in
                                     ("hidden", "L", "H", "Hkv", "D", "inter", "vocab", "group"))
@@ -96,7 +101,7 @@ def decode_algorithmic_bytes(shape: dict, batch: int, ctx: int, bits=4) -> dict:
     W = L * per_layer_kn * bits // 8
     S = L * per_layer_kn // G * (2 + bits / 8)
     LM = V * h * 2
-    KV = batch * ctx * L * 2 * Hkv * D * 2
-    KV_new = batch * L * 2 * Hkv * D * 2
+    KV = batch * ctx * L * 2 * Hkv * D * kv_bytes
+    KV_new = batch * L * 2 * Hkv * D * kv_bytes
     return dict(weights=W, scales_zeros=int(S), lm_head=LM, kv_read=KV, kv_write=KV_new,
                 total=int(W + S + LM + KV + KV_new))
