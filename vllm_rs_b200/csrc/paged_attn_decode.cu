@@ -36,6 +36,7 @@
 //     regroups them into the {token 2c, 2c+1, 2c+8, 2c+9} bytes of an even-d and an odd-d n-tile, whose
 //     output columns are un-permuted when O is written out.
 #include <cuda_fp8.h>
+#include <cstdio>
 #include <cstdlib>
 #include "../../include/b200_vllm.h"
 #include "attn.cuh"
@@ -48,12 +49,12 @@ constexpr int kConsumerWarps = 4;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxPagesPerSplit = 128;
 
-template <int D, bool F8 = false>
+// NS = ring depth.  fp16: 3 stages x 32 KB, 2 CTAs per SM.  F8 (16 KB stages): 6 stages, 2 CTAs per SM -- the same
+// 192 KB in flight per SM.  (4 stages with 3 CTAs per SM was measured slower: 128 registers spill inside the
+// page loop, 136 do not fit three CTAs -- profiles/r1_v7_attn_fp8_variants.txt.)
+template <int D, bool F8 = false, int NS = kStages>
 struct AttnSmem {
-  // F8: 4 stages x 16 KB and 3 CTAs per SM keep the same 192 KB in flight per SM as 3 x 32 KB x 2 CTAs, with
-  // 12 instead of 8 consumer warps to hide the (now twice as frequent) ldmatrix -> cvt -> mma -> softmax chain
-  static constexpr int kNumStages = F8 ? 4 : kStages;
-  static constexpr int kCtasPerSm = F8 ? 3 : 2;
+  static constexpr int kNumStages = NS;
   static constexpr int kTileBytes = kTok * D * (F8 ? 1 : 2);      // one K (or V) page tile
   static constexpr int kStageBytes = 2 * kTileBytes;
   static constexpr int kDataBytes = kNumStages * kStageBytes;
@@ -80,7 +81,7 @@ __device__ __forceinline__ int first_page_of(int ctx, int window) {
 
 // HI = false promises H / Hkv <= 8: rows 8..15 of every A fragment are the constant 0, which frees the 16
 // registers the fp8 instantiation needs to fit 3 CTAs per SM without spilling.
-template <int D, bool F8, bool HI>
+template <int D, bool F8, bool HI, int NS>
 __device__ __forceinline__ void
 paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
                        const __half* __restrict__ q, __half* __restrict__ out,
@@ -90,7 +91,7 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
                        int q_stride, int H, int Hkv, int max_blocks,
                        int pages_per_split, int max_splits, float scale_log2, float softcap,
                        int window) {
-  using SM = AttnSmem<D, F8>;
+  using SM = AttnSmem<D, F8, NS>;
   constexpr int kNS = SM::kNumStages;
   static_assert(!F8 || D == 128, "fp8 tiles are one 128-byte row per token");
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
@@ -425,18 +426,11 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
   kmap, vmap, q, out, block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks, \
       pages_per_split, max_splits, scale_log2, softcap, window
 
-// fp16 cache: 2 CTAs per SM (96 KB of stages each)
+// 2 CTAs per SM (96 KB of stages each) for both cache formats
 template <int D, bool F8, bool HI>
 __global__ void __launch_bounds__(kThreads, 2) paged_attn_decode_kernel(B200_ATTN_DECODE_PARAMS) {
-  paged_attn_decode_body<D, F8, HI>(B200_ATTN_DECODE_ARGS);
+  paged_attn_decode_body<D, F8, HI, F8 ? 6 : kStages>(B200_ATTN_DECODE_ARGS);
 }
-// e4m3 cache: 3 CTAs per SM.  136 registers x 160 threads x 3 = 65 280 of the SM's 65 536 (the min-blocks form
-// of __launch_bounds__ made ptxas stop at 128 and spill inside the page loop).
-template <int D, bool HI>
-__global__ void __maxnreg__(136) paged_attn_decode_fp8_kernel(B200_ATTN_DECODE_PARAMS) {
-  paged_attn_decode_body<D, true, HI>(B200_ATTN_DECODE_ARGS);
-}
-
 // Split merge: one CTA per (head, sequence).  Launched with PDL right behind the main kernel, so
 // its launch latency hides under the main kernel's tail (a fused last-CTA merge was measured
 // slower: it serialises two L2 round trips behind the last wave).
@@ -533,21 +527,26 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
                           const uint32_t* block_tables, const uint32_t* context_lens, int B,
                           int H, int Hkv, int max_blocks, float scale, float softcap, int window,
                           void* workspace, cudaStream_t st) {
-  const SplitPlan sp = plan_splits(B, Hkv, max_blocks, AttnSmem<D, F8>::kCtasPerSm);
+  constexpr int NS = F8 ? 6 : kStages;
+  using SM = AttnSmem<D, F8, NS>;
+  auto kern = paged_attn_decode_kernel<D, F8, HI>;
+  // resident CTAs per SM as the driver computes them (registers are allocated in per-warp units): the
+  // wave model of the split planner must use the real number
+  static int occ = 0;
+  if (occ == 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kAlloc);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, SM::kAlloc) != cudaSuccess || occ < 1)
+      occ = 1;
+    if (getenv("B200_ATTN_DEBUG")) fprintf(stderr, "paged_attn_decode<%d,%d,%d>: %d CTAs/SM\n", D, F8, HI, occ);
+  }
+  const SplitPlan sp = plan_splits(B, Hkv, max_blocks, occ > 3 ? 3 : occ);
   // workspace: [arrival counters B*Hkv u32, zero at rest][partial O fp32][partial (m, l)]
   unsigned* counters = reinterpret_cast<unsigned*>(workspace);
   float* part_o = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
                                            ((static_cast<size_t>(B) * Hkv * 4 + 255) / 256) * 256);
   float* part_ml = part_o + static_cast<size_t>(B) * H * sp.max_splits * D;
-  auto kern = paged_attn_decode_kernel<D, false, HI>;
-  if constexpr (F8) kern = paged_attn_decode_fp8_kernel<D, HI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D, F8>::kAlloc);
-    attr_set = true;
-  }
   dim3 grid(sp.max_splits, Hkv, B);
-  launch_pdl(kern, grid, dim3(kThreads), AttnSmem<D, F8>::kAlloc, st,
+  launch_pdl(kern, grid, dim3(kThreads), SM::kAlloc, st,
       maps.k, maps.v, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out),
       block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
@@ -585,7 +584,7 @@ int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_
   // worst case over kv-head counts: plan with Hkv = 1 gives the most splits per sequence
   int max_splits = 1;
   for (int hkv = 1; hkv <= num_heads; hkv <<= 1)
-    for (int occ = 2; occ <= 3; ++occ) {       // fp16 cache: 2 CTAs per SM, fp8 cache: 3
+    for (int occ = 1; occ <= 3; ++occ) {       // whatever occupancy the launcher will find (it caps at 3)
       b200::SplitPlan sp = b200::plan_splits(batch, hkv, max_blocks_per_seq, occ);
       if (sp.max_splits > max_splits) max_splits = sp.max_splits;
     }
