@@ -37,6 +37,7 @@
 //     output columns are un-permuted when O is written out.
 #include <cuda_fp8.h>
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 #include "../../include/b200_vllm.h"
 #include "attn.cuh"
@@ -73,6 +74,13 @@ __device__ __forceinline__ void e4m3x4_to_half2x2(uint32_t w, uint32_t& lo, uint
       "cvt.rn.f16x2.e4m3x2 %1, h;\n\t}\n"
       : "=r"(lo), "=r"(hi)
       : "r"(w));
+}
+
+// 2^x in one MUFU (exp2f without fast-math wraps it in a denormal-range rescale); ex2.approx(-inf) = +0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ int first_page_of(int ctx, int window) {
@@ -213,6 +221,142 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
     const int v_tok = t0 + ((lane >> 3) & 1) * 8 + (lane & 7);
     const int v_chunk_sel = lane >> 4;
 
+    if constexpr (F8) {
+      // ---------------------------------------------------------------- e4m3 cache
+      // Half the bytes per page means half the time per page: the ldmatrix -> cvt -> mma -> softmax -> mma
+      // chain of ONE page no longer hides under the stream with two warps per scheduler.  Pages are
+      // therefore processed in PAIRS: both pages' S = Q K^T run as four independent accumulation chains,
+      // one online-softmax update (one max, one rescale of O) covers the 32 tokens, then both P V.
+      auto process = [&](auto np_tag, int i) {
+        constexpr int NP = decltype(np_tag)::value;
+        int st[NP], tok_base[NP];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          st[p] = (i + p) % kNS;
+          mbar_wait(&full_bar[st[p]], ((i + p) / kNS) & 1);
+          tok_base[p] = (page0 + i + p) * kTok + t0;
+          any = any || (tok_base[p] < ctx && tok_base[p] + 16 > win_lo);
+        }
+        if (any) {
+          // ---- S = Q K^T: one 16-byte chunk of a token row = one whole k-step; matrices = (token half) x (chunk pair)
+          float sc[NP][2][4];
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sc[p][0][e] = sc[p][1][e] = 0.f;
+#pragma unroll
+          for (int kp = 0; kp < D / 32; ++kp) {
+            const int chunk = 2 * kp + k_chunk_sel;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              uint32_t r[4], b0, b1;
+              ldsm_x4(r, smem_u32(smem + st[p] * SM::kStageBytes) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+              e4m3x4_to_half2x2(r[0], b0, b1);
+              mma_16816(sc[p][0], qa[2 * kp], b0, b1);
+              e4m3x4_to_half2x2(r[1], b0, b1);
+              mma_16816(sc[p][0], qa[2 * kp + 1], b0, b1);
+              e4m3x4_to_half2x2(r[2], b0, b1);
+              mma_16816(sc[p][1], qa[2 * kp], b0, b1);
+              e4m3x4_to_half2x2(r[3], b0, b1);
+              mma_16816(sc[p][1], qa[2 * kp + 1], b0, b1);
+            }
+          }
+          // ---- online softmax over the NP x 16 tokens (rows g and, when G > 8, g + 8)
+          uint32_t pa[NP][4];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) pa[p][0] = pa[p][1] = pa[p][2] = pa[p][3] = 0u;
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            if (rh == 1 && !hi_rows) break;
+            float t[NP][4];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              t[p][0] = sc[p][0][2 * rh]; t[p][1] = sc[p][0][2 * rh + 1];
+              t[p][2] = sc[p][1][2 * rh]; t[p][3] = sc[p][1][2 * rh + 1];
+              const int tk[4] = {tok_base[p] + 2 * c, tok_base[p] + 2 * c + 1, tok_base[p] + 8 + 2 * c,
+                                 tok_base[p] + 9 + 2 * c};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v = softcap > 0.f ? softcap * tanhf(t[p][e] * scale_nat * inv_cap) * LOG2E
+                                        : t[p][e] * scale_log2;
+                v = (tk[e] < ctx && tk[e] >= win_lo) ? v : -INFINITY;
+                t[p][e] = v;
+                mx = fmaxf(mx, v);
+              }
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[rh], mx);
+            const float base = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = ex2_approx(m_run[rh] - base);
+            float psum = 0.f;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              float pe[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pe[e] = ex2_approx(t[p][e] - base);
+                psum += pe[e];
+              }
+              pa[p][rh] = pack_half2(pe[0], pe[1]);
+              pa[p][2 + rh] = pack_half2(pe[2], pe[3]);
+            }
+            l_run[rh] = l_run[rh] * alpha + psum;
+            m_run[rh] = m_new;
+            // skip the 2 * D/8 multiplies while the running maximum stands (alpha == 1 exactly; the vote is
+            // warp-uniform, so the result is bit-identical either way)
+            if (!__all_sync(0xffffffffu, alpha == 1.f)) {
+#pragma unroll
+              for (int j = 0; j < D / 8; ++j) {
+                o_acc[j][2 * rh] *= alpha;
+                o_acc[j][2 * rh + 1] *= alpha;
+              }
+            }
+          }
+          // ---- O += P V.  Transposed 8x8 b16 matrices of the byte tile: lane (g, c) gets the byte pairs
+          // (d = 2g, 2g+1) of tokens 2c and 2c+1; prmt gathers {tok 2c, 2c+1, 2c+8, 2c+9} for d even / d odd.
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const uint32_t vbase = smem_u32(smem + st[p] * SM::kStageBytes) + SM::kTileBytes;
+            const bool partial = tok_base[p] + 16 > ctx;       // never let stale cache rows (possibly NaN) meet p == 0
+            const uint32_t vmask8 = (tok_base[p] + 2 * c < ctx ? 0x000000FFu : 0u) |
+                                    (tok_base[p] + 2 * c + 1 < ctx ? 0x0000FF00u : 0u) |
+                                    (tok_base[p] + 8 + 2 * c < ctx ? 0x00FF0000u : 0u) |
+                                    (tok_base[p] + 9 + 2 * c < ctx ? 0xFF000000u : 0u);
+#pragma unroll
+            for (int jp = 0; jp < D / 32; ++jp) {
+              const int chunk = 2 * jp + v_chunk_sel;     // 16-byte chunk along d (0..7)
+              uint32_t r[4];
+              ldsm_x4_t(r, vbase + v_tok * 128 + ((chunk ^ (v_tok & 7)) << 4));
+#pragma unroll
+              for (int hc = 0; hc < 2; ++hc) {            // chunk 2 jp + hc: r[2 hc] = tokens 0-7, r[2 hc + 1] = 8-15
+                uint32_t ev = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x6420);
+                uint32_t od = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x7531);
+                if (partial) {
+                  ev &= vmask8;
+                  od &= vmask8;
+                }
+                uint32_t b0, b1;
+                e4m3x4_to_half2x2(ev, b0, b1);
+                mma_16816(o_acc[4 * jp + 2 * hc], pa[p], b0, b1);        // columns d = 16 chunk + 2 n
+                e4m3x4_to_half2x2(od, b0, b1);
+                mma_16816(o_acc[4 * jp + 2 * hc + 1], pa[p], b0, b1);    // columns d = 16 chunk + 2 n + 1
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) mbar_arrive(&empty_bar[st[p]]);
+        }
+      };
+      int i = 0;
+      for (; i + 1 < n_cta_pages; i += 2) process(std::integral_constant<int, 2>{}, i);
+      if (i < n_cta_pages) process(std::integral_constant<int, 1>{}, i);
+    } else {
     for (int i = 0; i < n_cta_pages; ++i) {
       const int s = i % kNS;
       const uint32_t ph = (i / kNS) & 1;
@@ -223,39 +367,14 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
         const uint32_t vbase = kbase + SM::kTileBytes;
         // ---- S = Q K^T for 16 tokens
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-        if (F8) {
-          // one 16-byte chunk of a token row = one whole k-step; matrices = (token half) x (chunk pair)
-          // even / odd k-steps accumulate separately: 4 dependent MMAs per chain instead of 8
-          float s0b[4] = {0.f, 0.f, 0.f, 0.f}, s1b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int kp = 0; kp < D / 32; ++kp) {
-            const int chunk = 2 * kp + k_chunk_sel;
-            uint32_t r[4], b0, b1;
-            ldsm_x4(r, kbase + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
-            e4m3x4_to_half2x2(r[0], b0, b1);
-            mma_16816(s0, qa[2 * kp], b0, b1);
-            e4m3x4_to_half2x2(r[1], b0, b1);
-            mma_16816(s0b, qa[2 * kp + 1], b0, b1);
-            e4m3x4_to_half2x2(r[2], b0, b1);
-            mma_16816(s1, qa[2 * kp], b0, b1);
-            e4m3x4_to_half2x2(r[3], b0, b1);
-            mma_16816(s1b, qa[2 * kp + 1], b0, b1);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            s0[e] += s0b[e];
-            s1[e] += s1b[e];
-          }
-        } else {
-#pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const int hb = ks >> 2;
-            const int chunk = ((ks & 3) << 1) + k_chunk_sel;
-            uint32_t r[4];
-            ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
-            mma_16816(s0, qa[ks], r[0], r[1]);
-            mma_16816(s1, qa[ks], r[2], r[3]);
-          }
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const int hb = ks >> 2;
+          const int chunk = ((ks & 3) << 1) + k_chunk_sel;
+          uint32_t r[4];
+          ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+          mma_16816(s0, qa[ks], r[0], r[1]);
+          mma_16816(s1, qa[ks], r[2], r[3]);
         }
         // ---- online softmax (rows g and, when G > 8, g + 8)
         uint32_t pa[4] = {0u, 0u, 0u, 0u};
@@ -287,14 +406,10 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
           }
           l_run[rh] = l_run[rh] * alpha + psum;
           m_run[rh] = m_new;
-          // F8 halves the time per page: skip the 2 * D/8 multiplies while the running maximum stands
-          // (alpha == 1 exactly; warp-uniform vote, so the result is bit-identical either way)
-          if (!F8 || !__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll
-            for (int j = 0; j < D / 8; ++j) {
-              o_acc[j][2 * rh] *= alpha;
-              o_acc[j][2 * rh + 1] *= alpha;
-            }
+          for (int j = 0; j < D / 8; ++j) {
+            o_acc[j][2 * rh] *= alpha;
+            o_acc[j][2 * rh + 1] *= alpha;
           }
           pa[rh] = pack_half2(p[0], p[1]);
           pa[2 + rh] = pack_half2(p[2], p[3]);
@@ -305,49 +420,23 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
                                   (tok_base + 2 * c + 1 < ctx ? 0xFFFF0000u : 0u);
         const uint32_t vmask_hi = (tok_base + 8 + 2 * c < ctx ? 0x0000FFFFu : 0u) |
                                   (tok_base + 9 + 2 * c < ctx ? 0xFFFF0000u : 0u);
-        if (F8) {
-          // transposed 8x8 b16 matrices of the byte tile: lane (g, c) gets the byte pairs (d = 2g, 2g+1)
-          // of tokens 2c and 2c+1.  prmt gathers {tok 2c, 2c+1, 2c+8, 2c+9} for d even / d odd.
-          const uint32_t vmask8 = ((vmask_lo & 0xFFu) ? 0x000000FFu : 0u) | ((vmask_lo >> 16) ? 0x0000FF00u : 0u) |
-                                  ((vmask_hi & 0xFFu) ? 0x00FF0000u : 0u) | ((vmask_hi >> 16) ? 0xFF000000u : 0u);
 #pragma unroll
-          for (int jp = 0; jp < D / 32; ++jp) {
-            const int chunk = 2 * jp + v_chunk_sel;     // 16-byte chunk along d (0..7)
-            uint32_t r[4];
-            ldsm_x4_t(r, vbase + v_tok * 128 + ((chunk ^ (v_tok & 7)) << 4));
-#pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {            // chunk 2 jp + hc: r[2 hc] = tokens 0-7, r[2 hc + 1] = 8-15
-              uint32_t ev = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x6420);
-              uint32_t od = __byte_perm(r[2 * hc], r[2 * hc + 1], 0x7531);
-              if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
-                ev &= vmask8;
-                od &= vmask8;
-              }
-              uint32_t b0, b1;
-              e4m3x4_to_half2x2(ev, b0, b1);
-              mma_16816(o_acc[4 * jp + 2 * hc], pa, b0, b1);        // columns d = 16 chunk + 2 n
-              e4m3x4_to_half2x2(od, b0, b1);
-              mma_16816(o_acc[4 * jp + 2 * hc + 1], pa, b0, b1);    // columns d = 16 chunk + 2 n + 1
-            }
+        for (int jj = 0; jj < D / 16; ++jj) {
+          const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
+          const int hb = chunk >> 3, c16 = chunk & 7;
+          uint32_t r[4];
+          ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
+          if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
+            r[0] &= vmask_lo; r[2] &= vmask_lo;
+            r[1] &= vmask_hi; r[3] &= vmask_hi;
           }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < D / 16; ++jj) {
-            const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
-            const int hb = chunk >> 3, c16 = chunk & 7;
-            uint32_t r[4];
-            ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
-            if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
-              r[0] &= vmask_lo; r[2] &= vmask_lo;
-              r[1] &= vmask_hi; r[3] &= vmask_hi;
-            }
-            mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
-            mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
-          }
+          mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
+          mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
     }
     // quad-reduce the row sums, publish (m, l) per warp
 #pragma unroll
