@@ -11,7 +11,8 @@ import re
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libb200_vllm.so"
+# B200_LIB_PATH: load an instrumented build instead (tools/dec_trace.py builds one with -DB200_DEC_TRACE)
+LIB_PATH = Path(os.environ["B200_LIB_PATH"]) if os.environ.get("B200_LIB_PATH") else PKG / "libb200_vllm.so"
 HEADER = PKG.parent / "include" / "b200_vllm.h"
 
 _lib = None

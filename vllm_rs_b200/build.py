@@ -17,8 +17,10 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-BUILD = ROOT / "build" / "obj"
-LIB = PKG / "libb200_vllm.so"
+# B200_BUILD_TAG=<name>: a side build (objects under build/obj-<name>, library build/<name>/libb200_vllm.so)
+_TAG = os.environ.get("B200_BUILD_TAG", "")
+BUILD = ROOT / "build" / ("obj-" + _TAG if _TAG else "obj")
+LIB = (ROOT / "build" / _TAG / "libb200_vllm.so") if _TAG else PKG / "libb200_vllm.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = [
@@ -62,6 +64,7 @@ def _compile(src: Path, force: bool) -> Path:
 
 def build(force: bool = False, verbose: bool = True) -> Path:
     BUILD.mkdir(parents=True, exist_ok=True)
+    LIB.parent.mkdir(parents=True, exist_ok=True)
     srcs = sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force), srcs))

@@ -640,10 +640,12 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
       block_tables, context_lens, part_o, part_ml, counters, q_stride, H, Hkv, max_blocks,
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
   B200_CUDA_LAUNCH_CHECK();
-  launch_pdl(paged_attn_reduce_kernel<D>, dim3(H, B), dim3(D), 0, st, reinterpret_cast<__half*>(out),
-             static_cast<const float*>(part_o), static_cast<const float*>(part_ml), context_lens, H,
-             sp.pages_per_split, sp.max_splits, window);
-  B200_CUDA_LAUNCH_CHECK();
+  if (sp.max_splits > 1) {      // one split per sequence: every CTA wrote its fp16 rows itself
+    launch_pdl(paged_attn_reduce_kernel<D>, dim3(H, B), dim3(D), 0, st, reinterpret_cast<__half*>(out),
+               static_cast<const float*>(part_o), static_cast<const float*>(part_ml), context_lens, H,
+               sp.pages_per_split, sp.max_splits, window);
+    B200_CUDA_LAUNCH_CHECK();
+  }
 }
 
 void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
