@@ -141,6 +141,15 @@ void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cach
                        const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
                        int32_t head_dim, int32_t block_size, int64_t stream);
 
+/* attention_rs::cache::swap_blocks as called for CPU swap (runner.rs:1626-1645: once per layer for K and for
+ * V, mapping = HashMap<src block, dst block>) and PD transfer (transfer/mod.rs:260-311): copies whole cache
+ * blocks src[pairs[i][0]] -> dst[pairs[i][1]] in ONE launch.  block_bytes = bytes of one block of this cache
+ * (block_size * Hkv * D * element size; multiple of 16).  pairs_dev: int64 [num_pairs][2] in DEVICE memory.
+ * src / dst: device memory, pinned host memory (read / written by the kernel through UVA) or a peer GPU's
+ * cache with peer access enabled.  Blocks must not overlap between src and dst ranges of one call.        */
+void b200_swap_blocks(const void* src_cache, void* dst_cache, const int64_t* pairs_dev, int32_t num_pairs,
+                      int64_t block_bytes, int64_t stream);
+
 /* ------------------------------------------------- paged attention, decode
  * Replaces the decode branch of PagedAttention::forward (attention.rs:808-820).
  * out/q [B,H,D] fp16; block_tables u32 [B, max_blocks_per_seq] (zero padded);

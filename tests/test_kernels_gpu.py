@@ -358,3 +358,37 @@ def test_wna16_gemm_prefill_sizes(ops, M):
     y = ops.wna16_gemm(x.cuda(), packed, torch.from_numpy(s).cuda(), torch.from_numpy(qz).cuda(), ws,
                        k=K, n=N, variant=2)
     _close(y, om.linear(x, W), 2e-3, 2e-3)
+
+
+# ---------------------------------------------------------------- cache::swap_blocks (data path)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.uint8])
+def test_swap_blocks_gpu_cpu_round_trip(ops, dtype):
+    """swap_kvcache (runner.rs:1626-1645): GPU -> pinned CPU swap space -> other GPU blocks, whole blocks by
+    a {src: dst} mapping in one launch per cache tensor; byte-exact, untouched blocks stay untouched."""
+    g = torch.Generator().manual_seed(5)
+    nb_gpu, nb_cpu, Hkv, D = 24, 16, 8, 128
+    gpu = torch.randint(0, 255, (nb_gpu, 64, Hkv, D), generator=g, dtype=torch.uint8)
+    if dtype == torch.float16:
+        gpu = torch.randn(nb_gpu, 64, Hkv, D, generator=g).to(dtype)
+    ref_gpu = gpu.clone()
+    ref_cpu = torch.zeros(nb_cpu, 64, Hkv, D, dtype=dtype)
+    cpu = torch.zeros(nb_cpu, 64, Hkv, D, dtype=dtype).pin_memory()
+    dgpu = gpu.cuda()
+    out_map = {3: 7, 20: 0, 11: 15, 0: 1}                      # swap out: GPU block -> CPU block
+    keep = ops.swap_blocks(dgpu, cpu, out_map)
+    torch.cuda.synchronize()
+    for s, d in out_map.items():
+        ref_cpu[d] = ref_gpu[s]
+    assert torch.equal(cpu, ref_cpu)
+    in_map = {7: 22, 0: 5, 15: 3, 1: 9}                        # swap in: CPU block -> (different) GPU block
+    keep = ops.swap_blocks(cpu, dgpu, in_map)
+    torch.cuda.synchronize()
+    for s, d in in_map.items():
+        ref_gpu[d] = ref_cpu[s]
+    assert torch.equal(dgpu.cpu(), ref_gpu)
+    # device to device (the PD transfer path uses the same call between two GPU caches)
+    dst = torch.zeros_like(dgpu)
+    keep = ops.swap_blocks(dgpu, dst, [(i, nb_gpu - 1 - i) for i in range(nb_gpu)])
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), ref_gpu.flip(0))
+    del keep

@@ -73,6 +73,7 @@ _SIGS = {
     "b200_rope_kv_write_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_rope_kv_write_fp8kv_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
+    "b200_swap_blocks": (None, [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_decode_fp8kv_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),

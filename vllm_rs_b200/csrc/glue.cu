@@ -164,6 +164,33 @@ __global__ void scratch_block_table_kernel(uint32_t* __restrict__ bt, int n) {
   if (i < n) bt[i] = static_cast<uint32_t>(i);
 }
 
+// ------------------------------------------------------------------ cache::swap_blocks
+// One launch moves every mapped KV block (runner.rs:1626-1645 CPU swap, transfer/mod.rs:260-311 PD transfer):
+// grid = (16 KB pieces of a block, mapped pairs).  Either side may be pinned host memory (UVA: the kernel
+// reads / writes it over PCIe / C2C directly) or a peer GPU's cache (peer access enabled): no per-block
+// cudaMemcpy calls, no staging.
+__global__ void __launch_bounds__(256)
+swap_blocks_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                   const int64_t* __restrict__ pairs, int64_t block_bytes) {
+  const int64_t sb = pairs[2 * blockIdx.y], db = pairs[2 * blockIdx.y + 1];
+  const uint4* s = reinterpret_cast<const uint4*>(src + sb * block_bytes);
+  uint4* d = reinterpret_cast<uint4*>(dst + db * block_bytes);
+  const int64_t n16 = block_bytes >> 4;
+  const int64_t lo = static_cast<int64_t>(blockIdx.x) * 1024;
+  const int64_t hi = lo + 1024 < n16 ? lo + 1024 : n16;
+  uint4 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t i = lo + threadIdx.x + j * 256;
+    if (i < hi) v[j] = s[i];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t i = lo + threadIdx.x + j * 256;
+    if (i < hi) d[i] = v[j];
+  }
+}
+
 void launch_kv_fp8_gather(const void* k8, const void* v8, void* ks, void* vs, uint32_t* scratch_bt,
                           const uint32_t* block_tables, const uint32_t* context_lens, const uint32_t* cu_q,
                           int B, int max_blocks, int Hkv, int D, cudaStream_t st) {
@@ -439,6 +466,18 @@ void b200_rope_kv_write_fp8kv_f16(void* q, void* k, const void* v, const void* c
                        num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
                        v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
                        interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream), 1);
+}
+
+void b200_swap_blocks(const void* src_cache, void* dst_cache, const int64_t* pairs_dev, int32_t num_pairs,
+                      int64_t block_bytes, int64_t stream) {
+  if (num_pairs <= 0) return;
+  B200_CHECK_ARG(src_cache && dst_cache && pairs_dev, "swap_blocks: NULL pointer");
+  B200_CHECK_ARG(block_bytes > 0 && block_bytes % 16 == 0, "swap_blocks: block bytes must be a multiple of 16");
+  B200_CHECK_ARG(num_pairs <= 65535, "swap_blocks: at most 65535 blocks per call");
+  const unsigned pieces = static_cast<unsigned>((block_bytes / 16 + 1023) / 1024);
+  swap_blocks_kernel<<<dim3(pieces, num_pairs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(src_cache), static_cast<uint8_t*>(dst_cache), pairs_dev, block_bytes);
+  B200_CUDA_LAUNCH_CHECK();
 }
 
 void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cache,

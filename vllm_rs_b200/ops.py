@@ -121,6 +121,23 @@ def kv_write(k, v, k_cache, v_cache, slot_mapping):
     _lib.check()
 
 
+def swap_blocks(src_cache, dst_cache, mapping):
+    """attention_rs::cache::swap_blocks (runner.rs:1626-1645): dst[d] = src[s] for every (s, d) of `mapping`
+    (dict or list of pairs).  Caches are [num_blocks, ...] tensors on the GPU or in PINNED host memory."""
+    pairs = list(mapping.items()) if isinstance(mapping, dict) else list(mapping)
+    if not pairs:
+        return
+    for t in (src_cache, dst_cache):
+        assert t.is_contiguous() and (t.is_cuda or t.is_pinned()), "caches must be CUDA or pinned host tensors"
+    block_bytes = src_cache[0].numel() * src_cache.element_size()
+    assert block_bytes == dst_cache[0].numel() * dst_cache.element_size()
+    dev = src_cache.device if src_cache.is_cuda else dst_cache.device
+    pd = torch.tensor(pairs, dtype=torch.int64).to(dev)
+    _lib.lib().b200_swap_blocks(_p(src_cache), _p(dst_cache), _p(pd), len(pairs), block_bytes, _stream())
+    _lib.check()
+    return pd            # keep alive until the stream has run the copy
+
+
 def paged_attn_workspace(batch, num_heads, head_dim, max_blocks, device="cuda"):
     n = _lib.lib().b200_paged_attn_workspace_bytes(batch, num_heads, head_dim, max_blocks)
     return torch.zeros(n, dtype=torch.uint8, device=device)     # arrival counters start at rest
