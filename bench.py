@@ -13,6 +13,8 @@ One "step" = one decode step of the whole model (32 layers + lm_head + greedy sa
          loop drives it (engine.rs:1693-1757).
   roofline       dominant kernel (paged attention decode), timed alone with CUDA events across
                  all 32 layer caches (17 GB >> L2), algorithmic bytes / duration vs measured HBM.
+  fp8_kv         the same decode step with the e4m3 KV cache (`--fp8-kvcache`); reported beside the headline,
+                 which stays the reference's default fp16 cache.
   cpu_baseline   oracle/c/decode_ref.c (C + OpenMP port of the same step; the reference has no
                  CPU path for AWQ) on a bounded sample: 2 of 32 layers + lm_head.
 
@@ -433,7 +435,9 @@ def run_b200(args):
                       "kv_format": "e4m3, scale 1 (library-defined; parity unpinned)",
                       "attention": {"kernel": "paged_attn_decode_kernel<128, fp8>", "ms_per_launch": a8_ms,
                                     "bytes_per_launch": a8_bytes, "achieved": a8_bytes / (a8_ms * 1e-3) / 1e9,
-                                    "peak": peak, "unit": "GB/s", "frac": a8_bytes / (a8_ms * 1e-3) / 1e9 / peak},
+                                    "peak": peak, "unit": "GB/s", "frac": a8_bytes / (a8_ms * 1e-3) / 1e9 / peak,
+                                    # dram read + write of one launch, profiles/r1_v7_attn_decode_fp8_ncu_full.txt
+                                    "traffic": 274544384 if (B, ctx, L) == (32, 4096, 32) else None},
                       "step_roofline": {"algorithmic_bytes": alg8["total"],
                                         "achieved": alg8["total"] / (ms8 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                         "frac": alg8["total"] / (ms8 * 1e-3) / 1e9 / peak}}
