@@ -142,6 +142,13 @@ def cpu_baseline(batch, ctx, steps=2, layers_sample=2):
     pos = np.full(batch, ctx - 1, np.int64)
     slots = bt[:, (ctx - 1) // 64].astype(np.int64) * 64 + (ctx - 1) % 64
     cl = np.full(batch, ctx, np.uint32)
+    # every host core the process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers; under
+    # torchrun only rank 0 runs this, the other ranks have exited or are idle)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    cref.lib().ref_set_num_threads(ncores)
     threads = cref.lib().ref_num_threads()
     t_layers, t_head = [], []
     for _ in range(steps):

@@ -210,6 +210,11 @@ void ref_decode_layers(f16* x, const ref_layer* layers, int num_layers, const f1
   free(xn); free(q); free(k); free(v); free(a); free(o); free(g); free(u);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the timed baseline asks for the host's cores itself */
+void ref_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 int ref_num_threads(void) {
   int n = 1;
 #pragma omp parallel

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         build()
         _lib = C.CDLL(str(OUT))
         _lib.ref_num_threads.restype = C.c_int
+        _lib.ref_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
