@@ -44,8 +44,11 @@ __device__ uint32_t* g_dec_trace = nullptr;
 #define DEC_TRE(k) do { } while (0)
 #endif
 
-constexpr int kGroups = 4;
-constexpr int kDqWarps = 16;
+#ifndef B200_DEC_GROUPS
+#define B200_DEC_GROUPS 4          // dequant groups (experiment: -DB200_DEC_GROUPS=5 via B200_NVCC_EXTRA)
+#endif
+constexpr int kGroups = B200_DEC_GROUPS;
+constexpr int kDqWarps = 4 * kGroups;
 constexpr int kDqThreads = kDqWarps * 32;
 constexpr int kThreads = (kDqWarps + 2 + kGroups) * 32;   // + weight producer, activation producer, one MMA issuer warp per group
 constexpr int kSZGroups = 64;        // quantisation groups of the CTA's K range staged in smem
@@ -72,7 +75,7 @@ struct Cfg {
   static constexpr int kAlloc = kTmemPtrOff + 16 + 1024;
   static_assert(kAlloc <= 227 * 1024, "shared memory budget");
   static constexpr int kDCols = NT < 32 ? 32 : NT;                        // per-group accumulator
-  static constexpr int kAS = NT <= 32 ? 3 : 2;                            // A stages per group (32 columns each)
+  static constexpr int kAS = (NT <= 32 && kGroups <= 4) ? 3 : 2;          // A stages per group (32 columns each)
   static constexpr int kACol0 = kGroups * kDCols;
   static constexpr int kTmemCols = 512;
   static_assert(kACol0 + kGroups * kAS * 32 <= 512, "TMEM budget");
@@ -526,6 +529,11 @@ bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
   if (groups_per_cta > dec::kSZGroups) return false;
   if (p.epilogue == B200_EPI_SILU_MUL && ((p.N / kTileN) & 1)) return false;
   if (p.epilogue == kEpiRopeKv && p.fe && (kTileN % p.fe->D) != 0) return false;
+#if B200_DEC_GROUPS > 4
+  if (p.M > 32 || p.bits != 4) return false;   // five groups: TMEM / shared memory only fit the 4-bit, 32-token tiles
+  if (p.M <= 16) return dec::launch_nt<4, 16>(p, st);
+  return dec::launch_nt<4, 32>(p, st);
+#else
   if (p.bits == 4) {
     if (p.M <= 16) return dec::launch_nt<4, 16>(p, st);
     if (p.M <= 32) return dec::launch_nt<4, 32>(p, st);
@@ -534,6 +542,7 @@ bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
   if (p.M <= 16) return dec::launch_nt<8, 16>(p, st);
   if (p.M <= 32) return dec::launch_nt<8, 32>(p, st);
   return dec::launch_nt<8, 64>(p, st);
+#endif
 }
 
 }  // namespace b200
