@@ -183,7 +183,7 @@ def run_reference(args):
     v = args.batch / step_s
     base["value"] = v
     print(json.dumps({
-        "impl": "reference", "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",
+        "impl": "reference", "metric": f"decode tokens/s (Llama-3-8B AWQ-int4, b={args.batch}, ctx={args.ctx})",
         "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
@@ -230,7 +230,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B, ctx, K, W = args.batch, args.ctx, args.steps, max(args.warmup, 3)
     blocks_per_seq = (ctx + K + W + 64) // 64 + 1
-    num_blocks = B * blocks_per_seq
+    # + 2: the reference's can_append rule wants two free blocks while a sequence is inside a block
+    # (block_manager.rs:233-239); with one sequence the per-sequence slack alone is a single block
+    num_blocks = B * blocks_per_seq + 2
     hidden, L, H, Hkv, D, inter, vocab, _ = synthetic.SHAPES[MODEL]
     if args.layers:
         L = args.layers
@@ -250,7 +252,7 @@ def run_b200(args):
     # ---------------- device-resident value: graph replays of one step at ctx
     g = torch.Generator(device=dev).manual_seed(1)
     perm = torch.randperm(num_blocks, device=dev, generator=g).to(torch.int32)
-    bt = perm.reshape(B, blocks_per_seq).contiguous()
+    bt = perm[:B * blocks_per_seq].reshape(B, blocks_per_seq).contiguous()
     ids = torch.randint(0, vocab, (B,), device=dev, generator=g, dtype=torch.int32)
     pos = torch.full((B,), ctx - 1, dtype=torch.int64, device=dev)
     cl = torch.full((B,), ctx, dtype=torch.int32, device=dev)
@@ -454,7 +456,7 @@ def run_b200(args):
         _trace("fp8 KV leg done")
 
     out_line = {
-        "metric": "decode tokens/s (Llama-3-8B AWQ-int4, b=32, ctx=4096)",
+        "metric": f"decode tokens/s (Llama-3-8B AWQ-int4, b={B}, ctx={ctx})",
         "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16",

@@ -366,3 +366,58 @@ def test_engine_loop_with_prefix_cache(lib):
             assert a == b, f"seq {sid} step {t}: oracle {a} vs gpu {b} (margin {o_margin[sid][t]})"
             checked += 1
     assert checked >= 12
+
+
+@pytest.mark.parametrize("nseq", [1, 2, 4])
+@pytest.mark.parametrize("plan", ["fused", "classic"])
+def test_decode_small_batches(lib, nseq, plan):
+    """Batches of 1-4 sequences (BASELINE: "batch 1-64") run the tcgen05 decode GEMM with a 16-token tile since
+    the GEMV lost its M <= 4 slot (B200_GEMV_MAX_M): same parity bars as the larger batches, two steps."""
+    from vllm_rs_b200 import engine
+    cfg = _toy_cfg()
+    NB, MAXB, MAXBLK = 32, 4, 8
+    oracle, runner = _build(cfg, "awq", seed=40 + nseq, num_blocks=NB, max_batch=MAXB, max_blocks=MAXBLK)
+    if plan == "classic":
+        runner.set_allreduce(lambda buf, n, st: None)
+    with om.exact_mode():
+        exact = om.LlamaOracle(cfg, oracle.w, NB)
+    osch, csch = osched.Scheduler(NB, 64, MAXB), engine.Scheduler(NB, 64, MAXB)
+    rng = np.random.default_rng(nseq)
+    for L in (37, 64, 130, 65)[:nseq]:
+        toks = rng.integers(0, cfg.vocab, size=L).tolist()
+        osch.add(osched.Sequence(toks, 64, max_tokens=8))
+        csch.add(toks, 8)
+    ids, _ = osch.schedule()
+    csch.schedule()
+    pmeta = osched.prepare_prefill([osch.running[i] for i in ids], 64)
+    first = oracle.prefill(pmeta).argmax(-1).tolist()
+    with om.exact_mode():
+        exact.prefill(pmeta)
+    for s in (osch, csch):
+        _, fin = s.filter_prefill_finished(ids)
+        s.postprocess(fin, first)
+    _sync_cache_to_gpu(oracle, runner)
+    for step in range(2):
+        ids, _ = osch.schedule()
+        csch.schedule()
+        mo = osched.prepare_decode([osch.running[i] for i in ids], 64)
+        mc = csch.prepare_decode(ids, max_blocks_cap=MAXBLK)
+        ref = oracle.decode(mo)
+        with om.exact_mode():
+            truth = exact.decode(mo)
+        B = len(ids)
+        assert B == nseq
+        bt = torch.zeros(B, MAXBLK, dtype=torch.int32)
+        bt[:, :mc["max_blocks"]] = torch.from_numpy(mc["block_tables"].astype(np.int32))
+        got, _ = runner.decode_device(
+            torch.from_numpy(mc["input_ids"].astype(np.int32)).cuda(),
+            torch.from_numpy(mc["positions"]).cuda(), torch.from_numpy(mc["slot_mapping"]).cuda(),
+            bt.cuda(), torch.from_numpy(mc["context_lens"].astype(np.int32)).cuda())
+        got = got.cpu()
+        noise = (ref - truth).abs().max().item()
+        assert (got - truth).abs().max().item() <= 3 * noise + 2e-3
+        assert (got - ref).abs().max().item() <= 3 * noise + 2e-3
+        toks = ref.argmax(-1).tolist()
+        osch.postprocess(ids, toks)
+        csch.postprocess(ids, toks)
+        _sync_cache_to_gpu(oracle, runner)

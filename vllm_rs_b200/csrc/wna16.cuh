@@ -459,5 +459,9 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported
 bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st);   // decode shapes (M <= 64)
+// Largest M the automatic dispatch still gives to the flat GEMV (env B200_GEMV_MAX_M, default 0: the tcgen05
+// decode kernel streams the weights faster than the GEMV even for one token, profiles/r1_v7_batch_sweep.txt;
+// the GEMV stays as `variant 1` and as the fallback for shapes the tensor-core kernels do not take).
+int gemv_max_m();
 
 }  // namespace b200

@@ -13,6 +13,8 @@
 // partials; the last CTA of a tile sums them in split order and applies bias / SiLU*mul.  HBM-bound only for M <= 4; larger M goes to the tcgen05 path.
 #include <cstring>
 
+#include <cstdlib>
+
 #include "wna16.cuh"
 
 namespace b200 {
@@ -222,6 +224,18 @@ static bool check_wna(const WnaParams& p, const char** why) {
 
 }  // namespace b200
 
+namespace b200 {
+int gemv_max_m() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMV_MAX_M");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+}  // namespace b200
+
 extern "C" {
 using namespace b200;
 
@@ -280,7 +294,7 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (variant == 2 || variant == 3 || variant == 4 || (variant == 0 && m > 4)) {
+  if (variant == 2 || variant == 3 || variant == 4 || (variant == 0 && m > gemv_max_m())) {
     if (variant != 4 && launch_wna16_tc_dec(p, st)) return;    // latency-optimised decode kernel
     if (launch_wna16_tc(p, st)) return;
     if (variant >= 2) { set_error(1, "wna16: shape unsupported by the tcgen05 variant"); return; }
