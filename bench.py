@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalid as a bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp8-kv", action="store_true", help="skip the extra FP8-KV-cache decode leg")
+    ap.add_argument("--py-step", action="store_true",
+                    help="e2e: drive the step from Python over the individual C symbols instead of b200_engine_step")
     ap.add_argument("--prefill-tokens", type=int, default=8192,
                     help="also time one prefill chunk of this many tokens (0 = skip)")
     return ap.parse_args()
@@ -344,16 +346,33 @@ def run_b200(args):
     runner.capture([B])
     _trace("runner graph captured")
 
+    # the step loop itself is one native call (b200_engine_step: schedule -> prepare_decode into pinned staging
+    # -> b200_runner_decode_host -> postprocess -> clear_finished); --py-step spells it out over the single symbols
+    import ctypes as C
+    eh = None
+    if not args.py_step:
+        eh = l.b200_engine_new(sched._h, runner._h, B, blocks_per_seq)
+        _lib.check()
+        e_idx = np.zeros(max(B, 5), np.int32)
+        e_tok = np.zeros(max(B, 5), np.uint32)
+        e_npf = C.c_int32(0)
+        e_stream = runner._graph_stream.cuda_stream
+
     def engine_step():
+        if eh is not None:
+            n = l.b200_engine_step(eh, e_idx.ctypes.data, None, e_tok.ctypes.data, C.byref(e_npf), e_stream)
+            if n != B:
+                _lib.check()
+                raise RuntimeError(f"engine_step returned {n}")
+            return
         ii, pf = sched.schedule()
         meta = sched.prepare_decode(ii, max_blocks_cap=blocks_per_seq, pinned=runner.pinned)
         toks = runner.run_decode(meta)
         sched.postprocess(ii, toks)
-        return meta
 
     for _ in range(W):
-        meta = engine_step()
-    h2d = B * (4 + 8 + 8 + 4) + B * int(meta["max_blocks"]) * 4
+        engine_step()
+    h2d = B * (4 + 8 + 8 + 4) + B * len(sched.block_table(0)) * 4
     d2h = B * 4
     if world > 1:
         dist.barrier()
@@ -368,6 +387,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = B * 1e3 / e2e_ms
+    if eh is not None:
+        l.b200_engine_free(eh)
+        eh = None
     _trace("e2e done")
 
     # ---------------- prefill chunk (second half of BASELINE's metric: "prefill TFLOPS")

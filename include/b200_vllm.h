@@ -400,6 +400,21 @@ int64_t b200_runner_launches_per_step(const b200_runner*);
 void b200_runner_set_sampling(b200_runner*, int32_t top_k, float top_p, float temperature);
 void b200_runner_set_step_seed(b200_runner*, uint64_t seed, int64_t stream);
 
+/* ------------------------------------------------- engine step (engine.rs:1693-1757)
+ * prepare_step -> run_forward -> finish_step of a DECODE batch in one native call: schedule(),
+ * prepare_decode into pinned staging owned by the handle, b200_runner_decode_host, postprocess,
+ * clear_finished.  b200_engine_step returns the number of sequences decoded (running indices at schedule
+ * time, sequence ids and new tokens in the three output arrays, each sized >= max(max_batch, 5), any may be
+ * NULL); 0 = nothing schedulable; -2 = the scheduler produced a PREFILL batch: *num_prefill indices are in
+ * indices_out and the caller runs that step (b200_prepare_prefill / b200_runner_prefill_device /
+ * filter_prefill_finished / postprocess); -1 = error.  The handle borrows the scheduler and the runner. */
+typedef struct b200_engine b200_engine;
+b200_engine* b200_engine_new(b200_scheduler* sched, b200_runner* runner, int32_t max_batch,
+                             int32_t max_blocks_per_seq);
+void b200_engine_free(b200_engine*);
+int32_t b200_engine_step(b200_engine*, int32_t* indices_out, int64_t* seq_ids_out, uint32_t* tokens_out,
+                         int32_t* num_prefill, int64_t stream);
+
 /* ------------------------------------------------- tensor-parallel communicator
  * One process per GPU (runner/runner.rs:73-240).  NCCL communicator from a 128-byte unique id
  * (engine.rs:263, runner/mod.rs:33-58) + an optional one-shot NVLink all-reduce over

@@ -248,6 +248,16 @@ def test_prefill_step_and_engine_loop(lib):
             checked += 1
         assert len(g_out[sid]) == len(o_out[sid]) == 7    # prefill token + 6 decode tokens
     assert checked >= 15
+    # the loop above ran its decode steps through b200_engine_step (one native call per step); the same loop
+    # spelled out over the individual C symbols must produce identical tokens
+    for l in range(cfg.num_layers):
+        runner.k_cache[l].zero_()
+        runner.v_cache[l].zero_()
+    eng2 = engine.LLMEngine(runner, NB, MAXB, chunk_size=CH, native_step=False)
+    for p in prompts:
+        eng2.add_request(p, 6)
+    g2 = eng2.run_to_completion()
+    assert {k: v for k, v in g2.items()} == {k: v for k, v in g_out.items()}
 
 
 @pytest.mark.parametrize("fmt", ["awq", "gptq8"])

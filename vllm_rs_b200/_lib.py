@@ -129,6 +129,9 @@ _SIGS = {
     "b200_runner_capture": (c_i32, [c_vp, c_vp, c_i32, c_i64]),
     "b200_runner_prefill_device": (None, [c_vp] * 8 + [c_i32] * 4 + [c_vp, c_vp, c_i64]),
     "b200_runner_launches_per_step": (c_i64, [c_vp]),
+    "b200_engine_new": (c_vp, [c_vp, c_vp, c_i32, c_i32]),
+    "b200_engine_free": (None, [c_vp]),
+    "b200_engine_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "b200_runner_set_comm": (None, [c_vp, c_vp]),
     "b200_runner_set_tp_fused": (None, [c_vp, c_i32]),
     "b200_nccl_unique_id": (c_i32, [c_vp]),

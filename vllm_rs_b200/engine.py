@@ -398,13 +398,30 @@ class LLMEngine:
     (filter_prefill_finished / postprocess / clear_finished).  Greedy sampling."""
 
     def __init__(self, runner: ModelRunner, num_blocks, max_num_seqs, eos_token_ids=(),
-                 chunk_size=8192, prefix_cache=False, prefix_cache_max_tokens=None):
+                 chunk_size=8192, prefix_cache=False, prefix_cache_max_tokens=None, native_step=True):
         self.runner = runner
         self.sched = Scheduler(num_blocks, 64, max_num_seqs, 0, chunk_size, eos_token_ids)
         if prefix_cache:                    # EngineConfig.prefix_cache / prefix_cache_max_tokens
             self.sched.enable_prefix_cache(prefix_cache_max_tokens)
+        # native_step: schedule -> prepare_decode -> run -> postprocess of a decode batch is ONE C call
+        # (b200_engine_step); False keeps the same loop spelled out over the individual C symbols
+        self._l = _lib.lib()
+        self._eh = None
+        if native_step:
+            self._eh = self._l.b200_engine_new(self.sched._h, runner._h, runner.cfg.max_batch,
+                                               runner.cfg.max_blocks_per_seq)
+            _lib.check()
+            cap = max(runner.cfg.max_batch, 5)
+            self._idx = np.zeros(cap, np.int32)
+            self._sid = np.zeros(cap, np.int64)
+            self._tok = np.zeros(cap, np.uint32)
         self.max_blocks = runner.cfg.max_blocks_per_seq
         self.outputs = {}
+
+    def __del__(self):
+        if getattr(self, "_eh", None):
+            self._l.b200_engine_free(self._eh)
+            self._eh = None
 
     def add_request(self, token_ids, max_tokens):
         sid = self.sched.add(token_ids, max_tokens)
@@ -419,8 +436,27 @@ class LLMEngine:
             bt[r, :len(t)] = t
         return bt
 
+    def _stream(self):
+        st = getattr(self.runner, "_graph_stream", None)
+        return st.cuda_stream if st is not None else torch.cuda.current_stream().cuda_stream
+
     def step(self):
-        ids, is_prefill = self.sched.schedule()
+        if self._eh:
+            npf = C.c_int32(0)
+            n = self._l.b200_engine_step(self._eh, self._idx.ctypes.data, self._sid.ctypes.data,
+                                         self._tok.ctypes.data, C.byref(npf), self._stream())
+            _lib.check()
+            if n == -1:
+                raise _lib.B200Error("engine_step failed")
+            if n == 0:
+                return False
+            if n > 0:
+                for sid, t in zip(self._sid[:n].tolist(), self._tok[:n].tolist()):
+                    self.outputs[sid].append(int(t))
+                return True
+            ids, is_prefill = self._idx[:npf.value].tolist(), True       # n == -2: a prefill batch was scheduled
+        else:
+            ids, is_prefill = self.sched.schedule()
         if not ids:
             return False
         if is_prefill:
