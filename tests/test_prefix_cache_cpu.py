@@ -287,3 +287,67 @@ def test_property_shared_prefix_traces(lib, reqs, num_blocks, max_seqs, cap_bloc
         assert len(bm.free_block_ids) == sum(1 for x in bm.ref_count if x == 0)
         if r is None and not pending:
             break
+
+
+# ------------------------------------------------------------------------------------ committed golden vectors
+def test_golden_hash_chain_and_trace(eng, lib):
+    """tests/golden/prefix_cache.json (made by tests/golden/make_prefix_golden.py from the pinned oracle): the chain
+    hashes and a three-wave scheduler trace with prefix hits must be reproduced by the oracle AND by the C++
+    mirror -- a drift of both at once would otherwise go unnoticed."""
+    import json
+    from pathlib import Path
+    doc = json.loads((Path(__file__).parent / "golden" / "prefix_cache.json").read_text())
+    toks = doc["tokens"]
+    for rec in doc["hash_chain"]:
+        parent, n, want = int(rec["parent"]), rec["n"], int(rec["hash"])
+        assert osched.hash_block(parent, toks[:n]) == want
+        arr = np.asarray(toks[:n], dtype=np.uint32)
+        assert lib.b200_prefix_hash_block(parent, arr.ctypes.data, n) == want
+    # replay the trace on both sides
+    o, c = _mk(eng, 24, max_num_seqs=8)
+    base = [(i * 7919 + 13) % 32000 for i in range(400)]
+    waves = [[(base[:150], 3)], [(base[:150] + [5, 6, 7], 2), (base[:128], 2), (base[:70] + base[200:300], 4)],
+             [(base[:330], 2), (base[:64], 1)]]
+    it = iter(doc["trace"])
+    steps = 0
+    for wave in waves:
+        for t, mx in wave:
+            _add(o, c, t, mx)
+        for _ in range(64):
+            if not (o.running or o.waiting):
+                break
+            ids, pf = o.schedule()
+            if not ids:
+                c.schedule()
+                break
+            seqs_before = [(o.running[i].id, list(o.running[i].block_table), o.running[i].num_cached_tokens) for i in ids]
+            cids, cpf = c.schedule()
+            rec = next(it)
+            assert (ids, pf) == (cids, cpf) == (rec["ids"], rec["prefill"])
+            assert [s[0] for s in seqs_before] == rec["seq_ids"]
+            assert [s[1] for s in seqs_before] == rec["block_tables"] == [c.block_table(i) for i in cids]
+            assert [s[2] for s in seqs_before] == rec["num_cached_tokens"]
+            seqs = [o.running[i] for i in ids]
+            if pf:
+                m = osched.prepare_prefill(seqs, BS, o.chunk_size)
+                mc = c.prepare_prefill(cids)
+                assert m["cu_seqlens_q"] == rec["cu_seqlens_q"] == list(mc["cu_seqlens_q"])
+                assert m["cu_seqlens_k"] == rec["cu_seqlens_k"] == list(mc["cu_seqlens_k"])
+                assert m["slot_mapping"][:4] == rec["slot_head"] == list(mc["slot_mapping"][:4])
+                pos, fin = o.filter_prefill_finished(ids)
+                c.filter_prefill_finished(cids)
+                o.postprocess(fin, [11] * len(fin))
+                c.postprocess(fin, [11] * len(fin))
+            else:
+                m = osched.prepare_decode(seqs, BS)
+                mc = c.prepare_decode(cids)
+                assert m["slot_mapping"] == rec["slot_mapping"] == list(mc["slot_mapping"])
+                o.postprocess(ids, [11] * len(ids))
+                c.postprocess(cids, [11] * len(ids))
+            o.clear_finished()
+            c.clear_finished()
+            assert list(o.block_manager.free_block_ids) == rec["free_block_ids"] == c.free_block_ids()
+            assert o.block_manager.ref_count == rec["ref_count"]
+            assert o.block_manager.prefix_cache_blocks() == rec["cached_blocks"] == c.prefix_cache_blocks
+            steps += 1
+    assert steps == len(doc["trace"]) and steps >= 10
