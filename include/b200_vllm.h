@@ -283,6 +283,20 @@ int32_t b200_scheduler_block_ref_count(const b200_scheduler*, int32_t block_id);
 /* free_block_ids in pop order; returns the count, copies up to cap */
 int32_t b200_scheduler_free_block_ids(const b200_scheduler*, uint32_t* out, int32_t cap);
 uint64_t b200_prefix_hash_block(uint64_t parent_hash, const uint32_t* tokens, int32_t n);
+/* CPU swap of running sequences (block_manager.rs:69-78,255-272,878-1000; scheduler.rs:303-337,830-954), the
+ * bookkeeping: enable with the number of CPU blocks (kvcache plan: num_cpu_blocks).  schedule() then swaps the
+ * OLDEST sequence that cannot append out to CPU blocks when there is no prefix cache left to evict (and
+ * another sequence keeps running), and brings ONE swapped sequence back per call once it has cooled down
+ * 5 s, nothing is preempted and the cache has room.  The reference reads the wall clock; here the host sets it
+ * (set_time_ms) before schedule().  The block copies themselves are NOT done here: after schedule() drain
+ * pop_swap_op -- (src, dst) block pairs, GPU->CPU or CPU->GPU -- and run b200_swap_blocks per layer cache
+ * before the step's forward.  Session ("Cached") sequences are out of scope.                              */
+void b200_scheduler_enable_cpu_swap(b200_scheduler*, int32_t num_cpu_blocks);
+void b200_scheduler_set_time_ms(b200_scheduler*, int64_t now_ms);
+int32_t b200_scheduler_num_swapped(const b200_scheduler*);
+int64_t b200_scheduler_swapped_seq_id(const b200_scheduler*, int32_t i);
+int32_t b200_scheduler_free_cpu_block_ids(const b200_scheduler*, uint32_t* out, int32_t cap);
+int32_t b200_scheduler_pop_swap_op(b200_scheduler*, int64_t* pairs, int32_t cap_pairs, int32_t* swap_in);
 /* inspect a running sequence: returns token count; copies up to cap entries */
 int32_t b200_scheduler_seq_info(const b200_scheduler*, int32_t running_idx, int64_t* seq_id,
                                 int32_t* num_cached_tokens, int32_t* status,

@@ -18,7 +18,9 @@ from __future__ import annotations
 from collections import deque
 from dataclasses import dataclass, field
 
-WAITING, RUNNING, FINISHED = 0, 1, 2
+WAITING, RUNNING, FINISHED, CACHED, SWAPPED, FINISH_SWAPPED = 0, 1, 2, 3, 4, 5    # sequence.rs:8-15
+SWAP_COOLING_PERIOD = 5000               # ms, scheduler.rs:49
+MIN_KVCACHE_TOKENS_LEFT_FOR_SWAP = 1000  # scheduler.rs:50
 MIN_NUM_SCHEDULED_REQS = 5        # scheduler.rs:44
 KVCACHE_SWAP_THRESHOLD = 0.95     # scheduler.rs:48
 PREFIX_CACHE_RATIO_NORMAL = 0.65  # scheduler.rs:55
@@ -46,6 +48,7 @@ class Sequence:
     block_table: list = field(default_factory=list)
     num_cached_tokens: int = 0
     last_token: int = 0
+    swapped_time: object = None      # ms since the epoch of the last swap, sequence.rs
 
     def __post_init__(self):
         self.token_ids = list(self.token_ids)
@@ -75,6 +78,7 @@ class Sequence:
         c.block_table = list(self.block_table)
         c.num_cached_tokens = self.num_cached_tokens
         c.last_token = self.last_token
+        c.swapped_time = self.swapped_time
         return c
 
 
@@ -254,6 +258,68 @@ class BlockManager:
         self.num_blocks = num_blocks
         # :80-84: the cache exists only when enabled with a positive capacity
         self.prefix_cache = PrefixCache(block_size, prefix_cache_blocks) if prefix_cache_blocks > 0 else None
+        # CPU swap space (block_manager.rs:69-78): ids 0..n-1, FIFO; swapped_map: seq id -> its CPU block ids
+        self.free_cpu_block_ids = deque()
+        self.swapped_map = {}
+        self.swap_ops = []          # (swap_in, [(src, dst), ...]) for the host to execute with swap_blocks
+
+    def enable_cpu_swap(self, num_cpu_blocks):
+        self.free_cpu_block_ids = deque(range(num_cpu_blocks))
+
+    # ---- CPU swap (block_manager.rs:255-272, 878-1000)
+    def ensure_allocate(self, seq):                            # :255-272
+        for _ in range(len(seq.block_table), seq.num_blocks()):
+            if not self.free_block_ids:
+                raise RuntimeError("No free blocks available, retry later!")
+            b = self.free_block_ids.popleft()
+            self._allocate_block(b)
+            seq.block_table.append(b)
+
+    def can_swap_out(self, seq):                               # :878-894
+        if any(self.ref_count[b] > 1 for b in seq.block_table):
+            return False
+        return len(self.free_cpu_block_ids) > seq.num_blocks()
+
+    def can_swap_in(self, seq):                                # :898-906
+        return len(self.free_block_ids) > seq.num_blocks()
+
+    def swap_out(self, seq, now_ms):                           # :910-957
+        n = len(seq.block_table)
+        if len(self.free_cpu_block_ids) < n:
+            raise RuntimeError("Not enough CPU swap blocks")
+        cpu_ids = [self.free_cpu_block_ids.popleft() for _ in range(n)]
+        self.swap_ops.append((False, list(zip(seq.block_table, cpu_ids))))
+        seq.swapped_time = now_ms
+        self.swapped_map[seq.id] = cpu_ids
+
+    def free_cpu_swap_for_seq(self, seq_id):                   # :993-1000
+        for b in self.swapped_map.pop(seq_id, []):
+            self.free_cpu_block_ids.append(b)
+
+    def swap_in(self, seq):                                    # :959-990
+        if seq.id not in self.swapped_map:
+            raise RuntimeError("No CPU-swap entry for seq")
+        cpu_ids = self.swapped_map.pop(seq.id)
+        if len(cpu_ids) > len(seq.block_table):
+            self.swapped_map[seq.id] = cpu_ids
+            self.free_cpu_swap_for_seq(seq.id)
+            raise RuntimeError("Insufficient GPU blocks to swap in sequence")
+        self.swap_ops.append((True, [(c, seq.block_table[i]) for i, c in enumerate(cpu_ids)]))
+        for c in cpu_ids:
+            self.free_cpu_block_ids.append(c)
+
+    def evict_prefix_cache_until_free(self, min_free_blocks):  # :674-697
+        total = 0
+        while len(self.free_block_ids) < min_free_blocks:
+            if self.prefix_cache is None:
+                break
+            evicted = self.prefix_cache.evict_blocks(1)
+            if not evicted:
+                break
+            total += len(evicted)
+            for b in evicted:
+                self._decrement_block_ref(b)
+        return total
 
     def _allocate_block(self, block_id):                       # block_manager.rs:113-120
         assert self.ref_count[block_id] == 0
@@ -367,6 +433,8 @@ class Scheduler:
         self.waiting = deque()
         self.running = []
         self.block_manager = BlockManager(num_blocks, block_size, prefix_cache_blocks)
+        self.cached = []            # swapped-out sequences (scheduler.rs `cached`; session caching is out of scope)
+        self.now_ms = 0             # the host's clock (SystemTime::now() in the reference), set before schedule()
         self.next_seq_id = 0
         self.eos_token_id = list(eos_token_ids)
         self.block_size = block_size
@@ -407,20 +475,29 @@ class Scheduler:
         if scheduled_ids:
             self.is_last_prefill = True
             return scheduled_ids, True
-        # :288-337 without CPU swap: sequences that cannot append are "preempt" candidates; when there are
-        # any, or the cache is over 95 % full, 10 % of the prefix cache (at least one block) is evicted
+        # :288-337: sequences that cannot append are "preempt" candidates.  With nothing to preempt and room
+        # in the cache, ONE swapped-out sequence may come back (try_swap_in); otherwise, under pressure, 10 % of
+        # the prefix cache (at least one block) is evicted, and if there is nothing to evict the oldest
+        # preempt candidate is swapped out to CPU memory (only when another sequence keeps running).
         import numpy as _np
         f32 = _np.float32
-        preempt = [i for i, q in enumerate(self.running) if not self.block_manager.can_append(q)]
+        preempt = [i for i, q in enumerate(self.running)
+                   if not self.block_manager.can_append(q) and q.status not in (SWAPPED, FINISH_SWAPPED)]
         bm = self.block_manager
         usage = f32(1.0) - (f32(len(bm.free_block_ids)) * f32(1.0) / f32(bm.num_blocks))        # :1255-1259
         swap_in = (not preempt) and (usage < f32(KVCACHE_SWAP_THRESHOLD) * f32(0.9)
                                      or (not self.running and usage <= f32(0.3)))
-        if not swap_in and (preempt or usage > f32(KVCACHE_SWAP_THRESHOLD)):
+        if swap_in:
+            self.try_swap_in()
+        elif preempt or usage > f32(KVCACHE_SWAP_THRESHOLD):
+            evicted = 0
             cached = bm.prefix_cache_blocks()                                                   # :1167-1175
             if cached > 0:
                 blocks = max(int(_np.ceil(f32(cached) * f32(PREFIX_CACHE_PRESSURE_EVICT_PERCENT))), 1)
-                bm.evict_prefix_cache_blocks(blocks)
+                evicted = bm.evict_prefix_cache_blocks(blocks)
+            if evicted == 0 and preempt and len(self.running) > 1:
+                idx = min(preempt, key=lambda i: self.running[i].id)                            # the oldest
+                self.try_swap_out(idx)
         decode_ids = []
         decode_max_seqs = max(self.max_num_seqs, MIN_NUM_SCHEDULED_REQS)
         for idx, seq in enumerate(self.running):
@@ -432,6 +509,63 @@ class Scheduler:
             decode_ids.append(idx)
         self.is_last_prefill = False
         return decode_ids, False
+
+    def try_swap_out(self, idx):                               # scheduler.rs:904-954 (running sequences only)
+        if idx >= len(self.running):
+            return False
+        seq = self.running[idx]
+        bm = self.block_manager
+        if seq.block_table and seq.status == RUNNING and bm.can_swap_out(seq):
+            try:
+                bm.ensure_allocate(seq)         # same number of blocks when it comes back
+            except RuntimeError:
+                return False
+            try:
+                bm.swap_out(seq, self.now_ms)
+            except RuntimeError:
+                return False
+            seq = self.running.pop(idx)
+            seq.status = SWAPPED
+            bm.deallocate(seq)
+            self.cached.append(seq.clone())     # the block table is rebuilt at swap-in
+            return True
+        return False
+
+    def try_swap_in(self):                                     # scheduler.rs:830-901
+        cur = self.now_ms
+        bm = self.block_manager
+        i = 0
+        while i < len(self.cached):
+            seq = self.cached[i]
+            st = seq.swapped_time if seq.swapped_time is not None else cur
+            if seq.status != SWAPPED or cur - st < SWAP_COOLING_PERIOD:
+                i += 1
+                continue
+            available = len(bm.free_block_ids) * self.block_size
+            if not bm.can_swap_in(seq) or available - len(seq) < MIN_KVCACHE_TOKENS_LEFT_FOR_SWAP:
+                if self.running:
+                    i += 1
+                    continue                    # wait for a later step
+                if bm.evict_prefix_cache_until_free(seq.num_blocks() + 1) > 0:
+                    break
+                seq = self.cached.pop(i)
+                seq.status = FINISHED           # "No KvCache left for swap in"
+                self.running.append(seq)
+                break
+            seq = self.cached.pop(i)
+            seq.swapped_time = cur
+            seq.block_table = []
+            try:
+                bm.ensure_allocate(seq)
+            except RuntimeError:
+                continue                        # (the reference drops the sequence here as well)
+            try:
+                bm.swap_in(seq)
+                seq.status = RUNNING
+            except RuntimeError:
+                seq.status = FINISHED
+            self.running.append(seq)
+            break
 
     def filter_prefill_finished(self, scheduled_ids):          # scheduler.rs:718-785
         finished_seqs, remove_ids = [], []

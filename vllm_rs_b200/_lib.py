@@ -111,6 +111,12 @@ _SIGS = {
     "b200_scheduler_block_ref_count": (c_i32, [c_vp, c_i32]),
     "b200_scheduler_free_block_ids": (c_i32, [c_vp, c_vp, c_i32]),
     "b200_prefix_hash_block": (C.c_uint64, [C.c_uint64, c_vp, c_i32]),
+    "b200_scheduler_enable_cpu_swap": (None, [c_vp, c_i32]),
+    "b200_scheduler_set_time_ms": (None, [c_vp, c_i64]),
+    "b200_scheduler_num_swapped": (c_i32, [c_vp]),
+    "b200_scheduler_swapped_seq_id": (c_i64, [c_vp, c_i32]),
+    "b200_scheduler_free_cpu_block_ids": (c_i32, [c_vp, c_vp, c_i32]),
+    "b200_scheduler_pop_swap_op": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
     "b200_scheduler_seq_info": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200_scheduler_seq_block_table": (c_i32, [c_vp, c_i32, c_vp, c_i32]),
     "b200_scheduler_seq_tokens": (c_i32, [c_vp, c_i32, c_vp, c_i32]),

@@ -11,7 +11,9 @@
 //   /root/reference/src/core/prefix_cache.rs (hash chain of full blocks + leaf LRU) and
 //   block_manager.rs:179-221,275-299,346-442,552-604,657-672 (allocate_with_prefix, cache_sequence,
 //        reference-counted sharing, eviction); scheduler.rs:288-337,1167-1175 (eviction under pressure)
-// Out of scope here: CPU swap, PD transfer, mamba state, image seeds,
+//   CPU swap of running sequences (block_manager.rs:255-272,878-1000; scheduler.rs:303-337,830-954): the
+//        bookkeeping only -- the block copies are handed to the host as (src, dst) lists for b200_swap_blocks
+// Out of scope here: session ("Cached") sequences, PD transfer, mamba state, image seeds,
 // tool-call / stop-sequence detection (EOS and max_tokens are handled).
 #include <algorithm>
 #include <cstdint>
@@ -32,7 +34,9 @@ void set_error(int code, const char* msg);
 
 namespace {
 
-enum class Status : int32_t { Waiting = 0, Running = 1, Finished = 2 };
+enum class Status : int32_t { Waiting = 0, Running = 1, Finished = 2, Cached = 3, Swapped = 4, FinishSwapped = 5 };  // sequence.rs:8-15
+constexpr int64_t kSwapCoolingPeriodMs = 5000;            // scheduler.rs:49
+constexpr size_t kMinKvTokensLeftForSwap = 1000;          // scheduler.rs:50
 
 struct Sequence {
   int64_t id = 0;
@@ -44,6 +48,8 @@ struct Sequence {
   uint32_t last_token = 0;
   size_t block_size = 64;
   size_t max_tokens = 16384;   // sampling_params.max_tokens.unwrap_or(16384), scheduler.rs:605
+  bool has_swapped_time = false;
+  int64_t swapped_time = 0;    // ms, set by swap_out / swap-in
 
   size_t len() const { return token_ids.size(); }
   size_t num_blocks() const { return (len() + block_size - 1) / block_size; }
@@ -326,6 +332,95 @@ class BlockManager {
     for (size_t id : evicted) decrement_ref(id);
     return evicted.size();
   }
+  // ---- CPU swap space (block_manager.rs:69-78, 255-272, 878-1000)
+  struct SwapOp {
+    bool swap_in;
+    std::vector<std::pair<int64_t, int64_t>> pairs;     // (src block, dst block)
+  };
+  void enable_cpu_swap(size_t n) {
+    free_cpu_.clear();
+    for (size_t i = 0; i < n; ++i) free_cpu_.push_back(i);
+  }
+  int32_t copy_free_cpu(uint32_t* out, int32_t cap) const {
+    int32_t i = 0;
+    for (size_t id : free_cpu_) {
+      if (out && i < cap) out[i] = static_cast<uint32_t>(id);
+      ++i;
+    }
+    return i;
+  }
+  bool ensure_allocate(Sequence& s) {                                    // :255-272
+    for (size_t i = s.block_table.size(); i < s.num_blocks(); ++i) {
+      if (free_.empty()) return false;
+      const size_t id = free_.front();
+      free_.pop_front();
+      take(id);
+      s.block_table.push_back(static_cast<uint32_t>(id));
+    }
+    return true;
+  }
+  bool can_swap_out(const Sequence& s) const {                           // :878-894
+    for (uint32_t id : s.block_table)
+      if (ref_[id] > 1) return false;
+    return free_cpu_.size() > s.num_blocks();
+  }
+  bool can_swap_in(const Sequence& s) const { return free_.size() > s.num_blocks(); }   // :898-906
+  bool swap_out(Sequence& s, int64_t now_ms) {                           // :910-957
+    const size_t n = s.block_table.size();
+    if (free_cpu_.size() < n) return false;
+    SwapOp op;
+    op.swap_in = false;
+    std::vector<size_t> cpu_ids;
+    for (size_t i = 0; i < n; ++i) {
+      const size_t c = free_cpu_.front();
+      free_cpu_.pop_front();
+      cpu_ids.push_back(c);
+      op.pairs.emplace_back(static_cast<int64_t>(s.block_table[i]), static_cast<int64_t>(c));
+    }
+    swap_ops.push_back(std::move(op));
+    s.has_swapped_time = true;
+    s.swapped_time = now_ms;
+    swapped_map_[s.id] = std::move(cpu_ids);
+    return true;
+  }
+  void free_cpu_swap_for_seq(int64_t seq_id) {                           // :993-1000
+    auto it = swapped_map_.find(seq_id);
+    if (it == swapped_map_.end()) return;
+    for (size_t c : it->second) free_cpu_.push_back(c);
+    swapped_map_.erase(it);
+  }
+  bool swap_in(Sequence& s) {                                            // :959-990
+    auto it = swapped_map_.find(s.id);
+    if (it == swapped_map_.end()) return false;
+    std::vector<size_t> cpu_ids = std::move(it->second);
+    swapped_map_.erase(it);
+    if (cpu_ids.size() > s.block_table.size()) {
+      swapped_map_[s.id] = std::move(cpu_ids);
+      free_cpu_swap_for_seq(s.id);
+      return false;
+    }
+    SwapOp op;
+    op.swap_in = true;
+    for (size_t i = 0; i < cpu_ids.size(); ++i)
+      op.pairs.emplace_back(static_cast<int64_t>(cpu_ids[i]), static_cast<int64_t>(s.block_table[i]));
+    swap_ops.push_back(std::move(op));
+    for (size_t c : cpu_ids) free_cpu_.push_back(c);
+    return true;
+  }
+  size_t evict_prefix_cache_until_free(size_t min_free) {                // :674-697
+    size_t total = 0;
+    while (free_.size() < min_free) {
+      if (!prefix_) break;
+      std::vector<size_t> evicted;
+      prefix_->evict_blocks(1, &evicted);
+      if (evicted.empty()) break;
+      total += evicted.size();
+      for (size_t id : evicted) decrement_ref(id);
+    }
+    return total;
+  }
+  std::deque<SwapOp> swap_ops;      // pending block copies, oldest first
+
   // block_manager.rs:233-239
   bool can_append(const Sequence& s) const {
     size_t need = 1;
@@ -370,6 +465,8 @@ class BlockManager {
   std::deque<size_t> free_;
   std::unordered_set<size_t> used_;
   std::unique_ptr<PrefixCache> prefix_;
+  std::deque<size_t> free_cpu_;
+  std::unordered_map<int64_t, std::vector<size_t>> swapped_map_;
 };
 
 constexpr size_t kMinNumScheduledReqs = 5;   // scheduler.rs:44
@@ -379,6 +476,8 @@ constexpr size_t kMinNumScheduledReqs = 5;   // scheduler.rs:44
 struct b200_scheduler {
   std::deque<Sequence> waiting;
   std::vector<Sequence> running;
+  std::vector<Sequence> cached;        // swapped-out sequences (scheduler.rs `cached`)
+  int64_t now_ms = 0;                  // the host's clock (SystemTime::now() in the reference)
   BlockManager bm;
   int64_t next_seq_id = 0;
   std::vector<uint32_t> eos;
@@ -390,6 +489,57 @@ struct b200_scheduler {
       : bm(nb, bs), block_size(bs), max_num_seqs(mns), max_num_batched_tokens(mnbt),
         chunk_size(cs) {}
 };
+
+// try_swap_out (scheduler.rs:904-954), running sequences only
+static bool try_swap_out(b200_scheduler* s, size_t idx) {
+  if (idx >= s->running.size()) return false;
+  Sequence& seq = s->running[idx];
+  if (seq.block_table.empty() || seq.status != Status::Running || !s->bm.can_swap_out(seq)) return false;
+  if (!s->bm.ensure_allocate(seq)) return false;        // same number of blocks when it comes back
+  if (!s->bm.swap_out(seq, s->now_ms)) return false;
+  Sequence out = std::move(s->running[idx]);
+  s->running.erase(s->running.begin() + static_cast<std::ptrdiff_t>(idx));
+  out.status = Status::Swapped;
+  s->bm.deallocate(out);
+  s->cached.push_back(std::move(out));                  // the block table is rebuilt at swap-in
+  return true;
+}
+
+// try_swap_in (scheduler.rs:830-901): at most one sequence per schedule() call
+static void try_swap_in(b200_scheduler* s) {
+  const int64_t cur = s->now_ms;
+  size_t i = 0;
+  while (i < s->cached.size()) {
+    Sequence& c = s->cached[i];
+    const int64_t st = c.has_swapped_time ? c.swapped_time : cur;
+    if (c.status != Status::Swapped || cur - st < kSwapCoolingPeriodMs) {
+      ++i;
+      continue;
+    }
+    const size_t available = s->bm.num_free() * s->block_size;
+    if (!s->bm.can_swap_in(c) || available - c.len() < kMinKvTokensLeftForSwap) {
+      if (!s->running.empty()) {
+        ++i;
+        continue;                                       // wait for a later step
+      }
+      if (s->bm.evict_prefix_cache_until_free(c.num_blocks() + 1) > 0) break;
+      Sequence seq = std::move(s->cached[i]);
+      s->cached.erase(s->cached.begin() + static_cast<std::ptrdiff_t>(i));
+      seq.status = Status::Finished;                    // "No KvCache left for swap in"
+      s->running.push_back(std::move(seq));
+      break;
+    }
+    Sequence seq = std::move(s->cached[i]);
+    s->cached.erase(s->cached.begin() + static_cast<std::ptrdiff_t>(i));
+    seq.has_swapped_time = true;
+    seq.swapped_time = cur;
+    seq.block_table.clear();
+    if (!s->bm.ensure_allocate(seq)) continue;          // (the reference drops the sequence here as well)
+    seq.status = s->bm.swap_in(seq) ? Status::Running : Status::Finished;
+    s->running.push_back(std::move(seq));
+    break;
+  }
+}
 
 extern "C" {
 
@@ -467,18 +617,32 @@ int32_t b200_scheduler_schedule(b200_scheduler* s, int32_t* indices, int32_t cap
   // ---- decode phase (scheduler.rs:285-378); swap / preemption is out of scope: a
   // sequence that cannot append is skipped this step exactly as the reference's filter does
   {
-    // scheduler.rs:288-337 without CPU swap: when some sequence cannot append, or the cache is over
-    // 95 % full, 10 % of the prefix cache (at least one block) is evicted (scheduler.rs:1167-1175)
-    bool any_preempt = false;
-    for (const Sequence& q : s->running) any_preempt = any_preempt || !s->bm.can_append(q);
+    // scheduler.rs:288-337: with nothing to preempt and room in the cache ONE swapped-out sequence may come
+    // back; otherwise, under pressure, 10 % of the prefix cache (at least one block) is evicted
+    // (scheduler.rs:1167-1175) and, if there was nothing to evict, the oldest sequence that cannot append is
+    // swapped out to CPU memory (only while another one keeps running)
+    std::vector<size_t> preempt;
+    for (size_t i = 0; i < s->running.size(); ++i) {
+      const Sequence& q = s->running[i];
+      if (!s->bm.can_append(q) && q.status != Status::Swapped && q.status != Status::FinishSwapped) preempt.push_back(i);
+    }
     const float usage = 1.0f - (static_cast<float>(s->bm.num_free()) * 1.0f / static_cast<float>(s->bm.num_total()));
-    const bool swap_in = !any_preempt && (usage < 0.95f * 0.9f || (s->running.empty() && usage <= 0.3f));
-    if (!swap_in && (any_preempt || usage > 0.95f)) {
+    const bool swap_in = preempt.empty() && (usage < 0.95f * 0.9f || (s->running.empty() && usage <= 0.3f));
+    if (swap_in) {
+      try_swap_in(s);
+    } else if (!preempt.empty() || usage > 0.95f) {
+      size_t evicted = 0;
       const size_t cached = s->bm.prefix_cache_blocks();
       if (cached > 0) {
         size_t blocks = static_cast<size_t>(std::ceil(static_cast<float>(cached) * 0.1f));
         if (blocks < 1) blocks = 1;
-        s->bm.evict_prefix_cache_blocks(blocks);
+        evicted = s->bm.evict_prefix_cache_blocks(blocks);
+      }
+      if (evicted == 0 && !preempt.empty() && s->running.size() > 1) {
+        size_t best = preempt[0];
+        for (size_t i : preempt)
+          if (s->running[i].id < s->running[best].id) best = i;
+        try_swap_out(s, best);
       }
     }
   }
@@ -604,6 +768,34 @@ int32_t b200_scheduler_free_block_ids(const b200_scheduler* s, uint32_t* out, in
 }
 uint64_t b200_prefix_hash_block(uint64_t parent_hash, const uint32_t* tokens, int32_t n) {
   return hash_block(parent_hash, tokens, n > 0 ? n : 0);
+}
+
+// ---- CPU swap (block_manager.rs:69-78: num_cpu_blocks CPU blocks, ids 0..n-1)
+void b200_scheduler_enable_cpu_swap(b200_scheduler* s, int32_t num_cpu_blocks) {
+  s->bm.enable_cpu_swap(num_cpu_blocks > 0 ? static_cast<size_t>(num_cpu_blocks) : 0);
+}
+void b200_scheduler_set_time_ms(b200_scheduler* s, int64_t now_ms) { s->now_ms = now_ms; }
+int32_t b200_scheduler_num_swapped(const b200_scheduler* s) { return static_cast<int32_t>(s->cached.size()); }
+int64_t b200_scheduler_swapped_seq_id(const b200_scheduler* s, int32_t i) {
+  return (i < 0 || static_cast<size_t>(i) >= s->cached.size()) ? -1 : s->cached[i].id;
+}
+int32_t b200_scheduler_free_cpu_block_ids(const b200_scheduler* s, uint32_t* out, int32_t cap) {
+  return s->bm.copy_free_cpu(out, cap);
+}
+// Oldest pending block-copy list: returns its number of (src, dst) pairs (0 = nothing pending, -1 = cap too
+// small) and removes it; *swap_in = 1: CPU -> GPU block ids, 0: GPU -> CPU.
+int32_t b200_scheduler_pop_swap_op(b200_scheduler* s, int64_t* pairs, int32_t cap_pairs, int32_t* swap_in) {
+  if (s->bm.swap_ops.empty()) return 0;
+  const auto& op = s->bm.swap_ops.front();
+  const int32_t n = static_cast<int32_t>(op.pairs.size());
+  if (n > cap_pairs) return -1;
+  for (int32_t i = 0; i < n; ++i) {
+    pairs[2 * i] = op.pairs[i].first;
+    pairs[2 * i + 1] = op.pairs[i].second;
+  }
+  if (swap_in) *swap_in = op.swap_in ? 1 : 0;
+  s->bm.swap_ops.pop_front();
+  return n;
 }
 
 int32_t b200_scheduler_seq_info(const b200_scheduler* s, int32_t i, int64_t* seq_id,

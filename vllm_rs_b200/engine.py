@@ -102,6 +102,35 @@ class Scheduler:
         self._l.b200_scheduler_free_block_ids(self._h, out.ctypes.data, n)
         return out[:n].tolist()
 
+    # ---- CPU swap bookkeeping (scheduler.rs:303-337,830-954)
+    def enable_cpu_swap(self, num_cpu_blocks):
+        self._l.b200_scheduler_enable_cpu_swap(self._h, int(num_cpu_blocks))
+
+    def set_time_ms(self, now_ms):
+        self._l.b200_scheduler_set_time_ms(self._h, int(now_ms))
+
+    @property
+    def num_swapped(self):
+        return self._l.b200_scheduler_num_swapped(self._h)
+
+    def swapped_seq_ids(self):
+        return [self._l.b200_scheduler_swapped_seq_id(self._h, i) for i in range(self.num_swapped)]
+
+    def free_cpu_block_ids(self):
+        n = self._l.b200_scheduler_free_cpu_block_ids(self._h, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._l.b200_scheduler_free_cpu_block_ids(self._h, out.ctypes.data, n)
+        return out[:n].tolist()
+
+    def pop_swap_ops(self):
+        """Pending block copies, oldest first: [(swap_in, [(src, dst), ...]), ...] for ops.swap_blocks."""
+        ops_, buf, flag = [], np.zeros(2 * 4096, np.int64), C.c_int32(0)
+        while True:
+            n = self._l.b200_scheduler_pop_swap_op(self._h, buf.ctypes.data, 4096, C.byref(flag))
+            if n <= 0:
+                return ops_
+            ops_.append((bool(flag.value), [tuple(p) for p in buf[:2 * n].reshape(n, 2).tolist()]))
+
     def seq_info(self, i):
         sid, cached, st, nout = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
         n = self._l.b200_scheduler_seq_info(self._h, i, C.byref(sid), C.byref(cached),
