@@ -178,3 +178,66 @@ def test_property_swap_traces(lib, reqs, num_blocks, num_cpu, max_seqs, prefix_b
         assert len(bm.free_block_ids) == sum(1 for x in bm.ref_count if x == 0)
         if not ids and not pending and not o.cached:
             break
+
+
+def test_swap_copy_lists_preserve_every_sequences_kv():
+    """Semantics of the copy lists, with numpy arrays standing in for the GPU cache and the CPU swap space: every token
+    writes a marker (seq id, position) at its slot; the copy lists of schedule() are applied exactly as the host
+    would (dst[d] = src[s] per pair, runner.rs:1626-1645); at every decode step the pages of each scheduled sequence
+    must hold exactly its own history -- across swap-out, reuse of its old blocks by others, and swap-in."""
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        NB, NCPU = int(rng.integers(10, 22)), int(rng.integers(8, 20))
+        o = osched.Scheduler(NB, BS, 6)
+        o.block_manager.enable_cpu_swap(NCPU)
+        gpu = np.full((NB, BS, 2), -1, dtype=np.int64)
+        cpu = np.full((NCPU, BS, 2), -1, dtype=np.int64)
+        for _ in range(int(rng.integers(3, 7))):
+            L = int(rng.integers(20, 300))
+            o.add(osched.Sequence(rng.integers(0, 1000, size=L).tolist(), BS, max_tokens=int(rng.integers(20, 120))))
+        now, swaps = 0, 0
+        for step in range(600):
+            now += int(rng.choice([100, 700, 2600]))
+            o.now_ms = now
+            ids, pf = o.schedule()
+            for swap_in, pairs in o.block_manager.swap_ops:           # the host runs these before the forward
+                swaps += 1
+                for s_, d_ in pairs:
+                    if swap_in:
+                        gpu[d_] = cpu[s_]
+                    else:
+                        cpu[d_] = gpu[s_]
+            o.block_manager.swap_ops.clear()
+            if not ids:
+                if not o.cached and not o.waiting:
+                    break
+                continue
+            seqs = [o.running[i] for i in ids]
+            flat = gpu.reshape(NB * BS, 2)
+            if pf:
+                m = osched.prepare_prefill(seqs, BS, o.chunk_size)
+                k = 0
+                for s in seqs:
+                    n = m["cu_seqlens_q"][seqs.index(s) + 1] - m["cu_seqlens_q"][seqs.index(s)]
+                    for j in range(n):
+                        flat[m["slot_mapping"][k]] = (s.id, m["positions"][k])
+                        k += 1
+                pos, fin = o.filter_prefill_finished(ids)
+                o.postprocess(fin, [5] * len(fin))
+            else:
+                m = osched.prepare_decode(seqs, BS)
+                for b, s in enumerate(seqs):
+                    if s.status == osched.FINISHED:
+                        # reference quirk, preserved by the mirror (scheduler.rs:872-876): a sequence that can
+                        # never be swapped back in is marked Finished and pushed to `running` INSIDE schedule(),
+                        # so it is scheduled once more with its stale block table.  A host must drop such rows
+                        # (their slot now belongs to someone else); this simulation does.
+                        continue
+                    flat[m["slot_mapping"][b]] = (s.id, m["positions"][b])
+                    ctx = m["context_lens"][b]
+                    pages = gpu[np.asarray(m["block_tables"][b][:-(-ctx // BS)])].reshape(-1, 2)[:ctx]
+                    assert (pages[:, 0] == s.id).all() and (pages[:, 1] == np.arange(ctx)).all(), (trial, step, s.id)
+                o.postprocess(ids, [5] * len(ids))
+            o.clear_finished()
+        assert not o.running or step == 599
+    assert swaps > 0

@@ -102,6 +102,18 @@ int32_t b200_engine_step(b200_engine* e, int32_t* indices_out, int64_t* seq_ids_
     b200::set_error(1, "engine_step: block table wider than max_blocks_per_seq");
     return -1;
   }
+  // Reference quirk (scheduler.rs:872-876): a swapped-out sequence that can never come back is marked Finished and
+  // pushed to `running` inside schedule(), so it is scheduled once more with a STALE block table.  The metadata
+  // mirror stays bit-exact; this loop neutralises the row the way padded graph rows are (graph.rs:741-767):
+  // slot -1 = no cache write, context 0 = no attention, so the stale slot's new owner is not overwritten.
+  for (int32_t i = 0; i < n; ++i) {
+    int32_t status = 0;
+    b200_scheduler_seq_info(e->sched, e->indices[i], nullptr, nullptr, &status, nullptr);
+    if (status == 2) {
+      e->slot_mapping[i] = -1;
+      e->context_lens[i] = 0;
+    }
+  }
   if (b200_runner_decode_host(e->runner, e->input_ids, e->positions, e->slot_mapping, e->block_tables, mb,
                               e->context_lens, n, e->out_ids, stream) != 0)
     return -1;
