@@ -254,6 +254,12 @@ void b200_scheduler_free(b200_scheduler*);
 /* returns seq id (scheduler.rs:186-192) */
 int64_t b200_scheduler_add(b200_scheduler*, const uint32_t* tokens, int32_t num_tokens,
                            int32_t max_tokens);
+/* SamplingParams.stop_token_ids of a sequence that is still WAITING (id from add): num_stops token sequences
+ * back to back in stop_tokens, lengths in stop_lens.  postprocess() then finishes the sequence when the sampled
+ * token completes one of them (scheduler.rs:1309-1341: the head must equal the tail of the GENERATED tokens;
+ * the stop token itself is not appended, like EOS).  Returns 0, -1 if the id is not waiting.             */
+int32_t b200_scheduler_set_stop_sequences(b200_scheduler*, int64_t seq_id, const uint32_t* stop_tokens,
+                                          const int32_t* stop_lens, int32_t num_stops);
 /* schedule(): writes indices into `running` (<= cap); returns count, *is_prefill set.
  * Returns -1 on error (e.g. out of blocks).  (scheduler.rs:200-380)               */
 int32_t b200_scheduler_schedule(b200_scheduler*, int32_t* indices, int32_t cap,

@@ -49,6 +49,7 @@ class Sequence:
     num_cached_tokens: int = 0
     last_token: int = 0
     swapped_time: object = None      # ms since the epoch of the last swap, sequence.rs
+    stop_token_ids: object = None    # sampling_params.stop_token_ids: list of token sequences (or None)
 
     def __post_init__(self):
         self.token_ids = list(self.token_ids)
@@ -79,6 +80,7 @@ class Sequence:
         c.num_cached_tokens = self.num_cached_tokens
         c.last_token = self.last_token
         c.swapped_time = self.swapped_time
+        c.stop_token_ids = self.stop_token_ids
         return c
 
 
@@ -597,7 +599,8 @@ class Scheduler:
                 continue
             seq = self.running[idx]
             token = output_ids[i]
-            if (token in self.eos_token_id
+            if (stop_sequence_match_index(token, seq) is not None
+                    or token in self.eos_token_id
                     or len(seq.output_ids) >= seq.max_tokens
                     or len(seq) > self.max_num_batched_tokens):
                 seq.status = FINISHED
@@ -609,6 +612,28 @@ class Scheduler:
     def clear_finished(self):                                  # scheduler.rs:631-654
         self.running = [s for s in self.running if s.status != FINISHED]
         self.waiting = deque(s for s in self.waiting if s.status != FINISHED)
+
+
+def stop_sequence_match_index(token, seq):                     # scheduler.rs:1309-1341
+    """Index of the first stop sequence completed by `token`: a one-token stop matches the token itself, a longer
+    one needs its head to equal the tail of the tokens generated so far (output_ids, prompt excluded)."""
+    stops = seq.stop_token_ids
+    if not stops:
+        return None
+    for idx, stop in enumerate(stops):
+        if not stop:
+            continue
+        if len(stop) == 1:
+            if stop[0] == token:
+                return idx
+            continue
+        prior = len(seq.output_ids)
+        if len(stop) - 1 > prior:
+            continue
+        start = prior + 1 - len(stop)
+        if seq.output_ids[start:] == list(stop[:-1]) and stop[-1] == token:
+            return idx
+    return None
 
 
 def prepare_block_tables(seqs):                                # runner.rs:952-974

@@ -249,3 +249,58 @@ def test_kvcache_plan_matches_oracle_randomised():
                 engine.plan_kvcache(avail, **kw, max_num_seqs=user[0], max_model_len=user[1])
             continue
         assert engine.plan_kvcache(avail, **kw, max_num_seqs=user[0], max_model_len=user[1]) == want
+
+
+# ---------------------------------------------------------------- stop sequences (a23: scheduler.rs:1309-1341)
+def test_stop_sequences(eng):
+    """A one-token stop matches the sampled token; a longer one needs its head to equal the tail of the GENERATED
+    tokens (the prompt does not count); the completing token is not appended (like EOS); empty stops are ignored."""
+    o, c = _mk(eng, 64)
+    cases = [([1, 2, 3], [[9]], [4, 9, 5]),                       # single token stop at the 2nd sampled token
+             ([7, 8], [[5, 6, 7]], [5, 6, 7, 1]),                 # three-token stop completed by the 3rd
+             ([5, 6], [[5, 6, 7]], [7, 7, 5, 6, 7, 2]),           # head must come from outputs, not the prompt
+             ([1], [[], [3, 3]], [3, 3, 3]),                      # empty stop ignored; [3, 3] fires on the 2nd 3
+             ([1], None, [4, 4, 4])]                              # no stops
+    for prompt, stops, _ in cases:
+        o.add(osched.Sequence(prompt, 64, max_tokens=5, stop_token_ids=stops))
+        c.add(prompt, 5, stop_token_ids=stops)
+    script = {i: list(toks) for i, (_, _, toks) in enumerate(cases)}
+    produced = {i: [] for i in script}
+    def tok(s):
+        t = script[s.id].pop(0) if script[s.id] else 0
+        produced[s.id].append(t)
+        return t
+    for _ in range(12):
+        if not (o.running or o.waiting):
+            break
+        _step(o, c, tok)
+    # expected generated tokens (output_ids) at finish, derived by hand from the rule above
+    assert produced[0][:2] == [4, 9] and len(produced[0]) == 2
+    assert produced[1][:3] == [5, 6, 7] and len(produced[1]) == 3
+    assert produced[2][:5] == [7, 7, 5, 6, 7] and len(produced[2]) == 5
+    assert produced[3][:2] == [3, 3] and len(produced[3]) == 2
+    assert len(produced[4]) == 6                                   # max_tokens = 5 outputs, the 6th sample finishes it
+    assert not o.running and c.num_running == 0 and c.num_free_blocks == 64
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 90), st.lists(st.lists(st.integers(0, 3), max_size=3), max_size=3)),
+                min_size=1, max_size=6),
+       st.lists(st.integers(0, 3), min_size=8, max_size=40))
+def test_property_stop_sequences(lib, reqs, stream):
+    """Random stop sets over a 4-token alphabet and a random token stream: C++ == oracle at every step."""
+    from vllm_rs_b200 import engine
+    o, c = _mk(engine, 32, max_num_seqs=8)
+    for L, stops in reqs:
+        toks = [(j * 7) % 100 for j in range(L)]
+        o.add(osched.Sequence(toks, 64, max_tokens=12, stop_token_ids=stops or None))
+        c.add(toks, 12, stop_token_ids=stops or None)
+    k = [0]
+    def tok(s):
+        k[0] += 1
+        return stream[(k[0] + s.id) % len(stream)]
+    for _ in range(60):
+        if not (o.running or o.waiting):
+            break
+        if _step(o, c, tok) is None:
+            break

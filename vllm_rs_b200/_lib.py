@@ -98,6 +98,7 @@ _SIGS = {
     "b200_scheduler_new": (c_vp, [c_i32] * 5 + [c_vp, c_i32]),
     "b200_scheduler_free": (None, [c_vp]),
     "b200_scheduler_add": (c_i64, [c_vp, c_vp, c_i32, c_i32]),
+    "b200_scheduler_set_stop_sequences": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32]),
     "b200_scheduler_schedule": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
     "b200_scheduler_filter_prefill_finished": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     "b200_scheduler_postprocess": (None, [c_vp, c_vp, c_i32, c_vp]),

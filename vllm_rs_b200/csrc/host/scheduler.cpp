@@ -14,7 +14,7 @@
 //   CPU swap of running sequences (block_manager.rs:255-272,878-1000; scheduler.rs:303-337,830-954): the
 //        bookkeeping only -- the block copies are handed to the host as (src, dst) lists for b200_swap_blocks
 // Out of scope here: session ("Cached") sequences, PD transfer, mamba state, image seeds,
-// tool-call / stop-sequence detection (EOS and max_tokens are handled).
+// tool-call end detection (EOS, max_tokens and stop_token_ids sequences are handled).
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -50,6 +50,7 @@ struct Sequence {
   size_t max_tokens = 16384;   // sampling_params.max_tokens.unwrap_or(16384), scheduler.rs:605
   bool has_swapped_time = false;
   int64_t swapped_time = 0;    // ms, set by swap_out / swap-in
+  std::vector<std::vector<uint32_t>> stop_token_ids;   // sampling_params.stop_token_ids
 
   size_t len() const { return token_ids.size(); }
   size_t num_blocks() const { return (len() + block_size - 1) / block_size; }
@@ -471,6 +472,25 @@ class BlockManager {
 
 constexpr size_t kMinNumScheduledReqs = 5;   // scheduler.rs:44
 
+// stop_sequence_match_index (scheduler.rs:1309-1341): a one-token stop matches the token itself, a longer one
+// needs its head to equal the tail of the tokens generated so far (output_ids; the prompt does not count)
+bool hits_stop_sequence(uint32_t token, const Sequence& seq) {
+  for (const auto& stop : seq.stop_token_ids) {
+    if (stop.empty()) continue;
+    if (stop.size() == 1) {
+      if (stop[0] == token) return true;
+      continue;
+    }
+    const size_t prior = seq.output_ids.size();
+    if (stop.size() - 1 > prior) continue;
+    const size_t start = prior + 1 - stop.size();
+    if (std::equal(seq.output_ids.begin() + static_cast<std::ptrdiff_t>(start), seq.output_ids.end(), stop.begin()) &&
+        stop.back() == token)
+      return true;
+  }
+  return false;
+}
+
 }  // namespace
 
 struct b200_scheduler {
@@ -576,6 +596,24 @@ int64_t b200_scheduler_add(b200_scheduler* s, const uint32_t* tokens, int32_t nu
   const int64_t id = seq.id;
   s->waiting.push_back(std::move(seq));
   return id;
+}
+
+// SamplingParams.stop_token_ids of a WAITING sequence (by the id add() returned): `num_stops` token sequences
+// stored back to back in stop_tokens, their lengths in stop_lens.  Returns 0, or -1 if the id is not waiting.
+int32_t b200_scheduler_set_stop_sequences(b200_scheduler* s, int64_t seq_id, const uint32_t* stop_tokens,
+                                          const int32_t* stop_lens, int32_t num_stops) {
+  for (Sequence& q : s->waiting) {
+    if (q.id != seq_id) continue;
+    q.stop_token_ids.clear();
+    size_t off = 0;
+    for (int32_t i = 0; i < num_stops; ++i) {
+      const size_t n = stop_lens[i] > 0 ? static_cast<size_t>(stop_lens[i]) : 0;
+      q.stop_token_ids.emplace_back(stop_tokens + off, stop_tokens + off + n);
+      off += n;
+    }
+    return 0;
+  }
+  return -1;
 }
 
 int32_t b200_scheduler_schedule(b200_scheduler* s, int32_t* indices, int32_t cap,
@@ -712,7 +750,7 @@ void b200_scheduler_postprocess(b200_scheduler* s, const int32_t* indices, int32
     Sequence& seq = s->running[idx];
     const uint32_t tok = tokens[i];
     const bool is_eos = std::find(s->eos.begin(), s->eos.end(), tok) != s->eos.end();
-    if (is_eos || seq.output_ids.size() >= seq.max_tokens ||
+    if (hits_stop_sequence(tok, seq) || is_eos || seq.output_ids.size() >= seq.max_tokens ||
         seq.len() > s->max_num_batched_tokens) {
       seq.status = Status::Finished;
       s->bm.cache_sequence(seq);     // scheduler.rs:617-620: the cache takes its references first

@@ -39,10 +39,15 @@ class Scheduler:
             self._l.b200_scheduler_free(self._h)
             self._h = None
 
-    def add(self, token_ids, max_tokens=0) -> int:
+    def add(self, token_ids, max_tokens=0, stop_token_ids=None) -> int:
         arr = np.ascontiguousarray(token_ids, dtype=np.uint32)
         sid = self._l.b200_scheduler_add(self._h, arr.ctypes.data, len(arr), max_tokens)
         _lib.check()
+        if stop_token_ids:                  # SamplingParams.stop_token_ids: a list of token sequences
+            flat = np.ascontiguousarray([t for st_ in stop_token_ids for t in st_], dtype=np.uint32)
+            lens = np.ascontiguousarray([len(st_) for st_ in stop_token_ids], dtype=np.int32)
+            rc = self._l.b200_scheduler_set_stop_sequences(self._h, sid, flat.ctypes.data, lens.ctypes.data, len(lens))
+            assert rc == 0
         return sid
 
     def schedule(self):
