@@ -95,3 +95,37 @@ def test_shard_shapes_and_group_alignment():
     with pytest.raises(AssertionError):
         tp.shard_row(*bad, 0, 2, 128)
     assert tp.kv_head_shard(3, 4, 8) == (3, 4)
+    assert tp.padded_inter(29568, 4, 128) == 29696 and tp.padded_inter(29568, 8, 128) == 29696
+    assert tp.padded_inter(14336, 8, 128) == 14336 and tp.padded_inter(28672, 8, 128) == 28672
+
+
+@pytest.mark.parametrize("fmt", ["awq", "gptq"])
+def test_pad_mlp_for_uneven_groups(fmt):
+    """BASELINE configs[3] (Qwen2-72B GPTQ TP=4): inter / group_size is not divisible by the world size.  Scaled
+    down: inter = 3 groups at TP=4 -> padded to 4 groups with zero scales: the padded MLP computes the SAME
+    output as the original, its down_proj dequantises to the original rows followed by zeros, and it shards."""
+    from vllm_rs_b200 import tp
+    rng = np.random.default_rng(5)
+    hidden, inter, world, G = 256, 3 * 128, 4, 128
+    mk = (lambda K, N: oq.random_awq(rng, K, N)) if fmt == "awq" else (lambda K, N: oq.random_gptq(rng, K, N, G, 4))
+    gate, up, down = mk(hidden, inter), mk(hidden, inter), mk(inter, hidden)
+    inter_to = tp.padded_inter(inter, world, G)
+    assert inter_to == 512
+    pg, pu, pd = tp.pad_mlp(gate, up, down, inter_to, G, fmt)
+    Wd, Wpd = _deq(fmt, down), _deq(fmt, pd)
+    assert Wpd.shape == (inter_to, hidden) and torch.equal(Wpd[:inter], Wd) and not Wpd[inter:].any()
+    Wg, Wpg = _deq(fmt, gate), _deq(fmt, pg)
+    assert torch.equal(Wpg[:, :inter], Wg) and not Wpg[:, inter:].any()
+    x = torch.from_numpy(rng.standard_normal((5, hidden)).astype(np.float16))
+    full = _mlp(fmt, x, gate, up, down)
+    padded = _mlp(fmt, x, pg, pu, pd)
+    # same terms plus exact zeros; only the fp32 summation order of the (longer) K loop may differ
+    assert (full - padded).abs().max() < 1e-4
+    # and now every rank gets whole groups and whole 128-channel tiles
+    acc = torch.zeros_like(full)
+    for r in range(world):
+        g_r, u_r = tp.shard_column(*pg, r, world), tp.shard_column(*pu, r, world)
+        d_r = tp.shard_row(*pd, r, world, G)
+        assert g_r[2].shape[1] % 128 == 0 and d_r[2].shape[0] * G == inter_to // world
+        acc += _mlp(fmt, x, g_r, u_r, d_r)
+    assert (acc - full).abs().max() < 2e-3

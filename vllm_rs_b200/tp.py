@@ -52,6 +52,49 @@ def shard_row(qweight, qzeros, scales, idx, n, group_size):
             _chunk(scales, 0, idx, n))
 
 
+def padded_inter(inter: int, world: int, group_size: int) -> int:
+    """Smallest intermediate size >= inter whose row shards are whole quantisation groups AND whole 128-channel
+    weight tiles per rank: a multiple of world * lcm(group_size, 128).  Qwen2-72B: 29568 -> 29696 at TP=4 (the
+    size Qwen2.5 checkpoints ship with), 231 -> 232 groups."""
+    unit = world * int(np.lcm(group_size, 128))
+    return -(-inter // unit) * unit
+
+
+def pad_mlp(gate, up, down, inter_to: int, group_size: int, fmt: str, bits: int = 4):
+    """Pad a quantised MLP from `inter` to `inter_to` intermediate channels without changing its output.
+    gate / up get extra OUTPUT channels, down gets extra INPUT rows; every added scale is 0, so the added
+    channels compute silu(0) * 0 = 0 and the added down rows dequantise to (q - z) * 0 = 0 whatever the packed
+    bits hold (they are zero-filled).  Each argument is the checkpoint triple (qweight, qzeros, scales):
+      AWQ   qweight [K, N/8],    qzeros [K/G, N/8],    scales [K/G, N]
+      GPTQ  qweight [K/pack, N], qzeros [K/G, N/pack], scales [K/G, N]        (wna16.rs:56-83,127-152)
+    `inter_to - inter` must be a multiple of the group size (added down rows = whole groups)."""
+    pack = 32 // bits
+
+    def pad_cols(t, extra_n):                               # more output channels (tensor dim 1 everywhere)
+        qw, qz, s = t
+        add_packed = extra_n // pack if fmt == "awq" else extra_n
+        qw2 = np.concatenate([qw, np.zeros((qw.shape[0], add_packed), qw.dtype)], axis=1)
+        qz2 = None if qz is None else np.concatenate([qz, np.zeros((qz.shape[0], extra_n // pack), qz.dtype)], axis=1)
+        s2 = np.concatenate([s, np.zeros((s.shape[0], extra_n), s.dtype)], axis=1)
+        return qw2, qz2, s2
+
+    def pad_rows(t, extra_k):                               # more input rows (tensor dim 0 everywhere)
+        qw, qz, s = t
+        add_packed = extra_k if fmt == "awq" else extra_k // pack
+        qw2 = np.concatenate([qw, np.zeros((add_packed, qw.shape[1]), qw.dtype)], axis=0)
+        g = extra_k // group_size
+        qz2 = None if qz is None else np.concatenate([qz, np.zeros((g, qz.shape[1]), qz.dtype)], axis=0)
+        s2 = np.concatenate([s, np.zeros((g, s.shape[1]), s.dtype)], axis=0)
+        return qw2, qz2, s2
+
+    inter = gate[2].shape[1]
+    extra = inter_to - inter
+    assert extra >= 0 and extra % group_size == 0 and extra % pack == 0, (inter, inter_to, group_size)
+    if extra == 0:
+        return gate, up, down
+    return pad_cols(gate, extra), pad_cols(up, extra), pad_rows(down, extra)
+
+
 # ------------------------------------------------------------------ communicator
 class Comm:
     """Comm::from_rank equivalent (runner.rs:81-89): NCCL communicator from a 128-byte id."""
