@@ -217,7 +217,8 @@ void b200_add_bias_f16(void* x, const void* bias, int32_t num_tokens, int32_t n,
 /* ------------------------------------------------- sampling (logits_processor.rs, runner.rs:1390-1570)
  * Device replacement of attention_rs::sampler::Sampler::sample_cuda (logits_processor.rs:226-229):
  * full-vocabulary softmax(logits / temperature) -> top_k (1..256) -> top-p cut on the
- * un-renormalised top-k probabilities -> multinomial; out_ids u32 [batch].  `seed_dev` points to
+ * un-renormalised top-k probabilities -> multinomial (top_k = 0: Sampling::All, the whole vocabulary, no
+ * cut); out_ids u32 [batch].  `seed_dev` points to
  * ONE u64 in device memory (the step seed, LogitsProcessor's rng.next_u64()), so a captured graph
  * changes it with a copy.  Row b draws u = f(seed, b) (this library's definition; the reference
  * kernel's is not source-visible).  Greedy (Sampling::ArgMax) is b200_argmax_f32.          */
@@ -419,6 +420,10 @@ int64_t b200_runner_launches_per_step(const b200_runner*);
  * (call once per step before b200_runner_decode_host / _device; graph-replay safe).          */
 void b200_runner_set_sampling(b200_runner*, int32_t top_k, float top_p, float temperature);
 void b200_runner_set_step_seed(b200_runner*, uint64_t seed, int64_t stream);
+/* The same from b200_sampling_strategy's result (0 ArgMax, 1 All, 2 TopK, 3 TopP, 4 TopKThenTopP) and its
+ * (k, p, t): Sampling::All (temperature only, logits_processor.rs:199-207) draws from the whole vocabulary.
+ * Any change of strategy or parameters drops the captured graphs (the values are kernel arguments).  0 / -1. */
+int32_t b200_runner_set_sampling_strategy(b200_runner*, int32_t strategy, int32_t k, float p, float t);
 
 /* ------------------------------------------------- engine step (engine.rs:1693-1757)
  * prepare_step -> run_forward -> finish_step of a DECODE batch in one native call: schedule(),
@@ -432,6 +437,15 @@ typedef struct b200_engine b200_engine;
 b200_engine* b200_engine_new(b200_scheduler* sched, b200_runner* runner, int32_t max_batch,
                              int32_t max_blocks_per_seq);
 void b200_engine_free(b200_engine*);
+/* CPU swap (scheduler.rs:303-337,830-954; runner.rs:1626-1645): per layer the GPU K / V caches and their
+ * pinned-host mirrors.  b200_engine_step then runs every block copy schedule() queued BEFORE the step's
+ * forward (a victim's GPU blocks may already belong to a sequence of the same batch); with swapping enabled
+ * on the scheduler and no caches registered the step fails instead of decoding stale pages.  0 / -1.       */
+int32_t b200_engine_set_swap_caches(b200_engine*, int32_t num_layers, void* const* gpu_k, void* const* gpu_v,
+                                    void* const* cpu_k, void* const* cpu_v, int64_t block_bytes);
+/* Seed of the sampling stream (StdRng::seed_from_u64, logits_processor.rs:29-30): once set, every decode step
+ * pushes rng.next_u64() to the runner's device seed before the forward (logits_processor.rs:222-225).      */
+void b200_engine_set_seed(b200_engine*, uint64_t seed);
 int32_t b200_engine_step(b200_engine*, int32_t* indices_out, int64_t* seq_ids_out, uint32_t* tokens_out,
                          int32_t* num_prefill, int64_t stream);
 

@@ -87,3 +87,10 @@ if __name__ == "__main__":
                                          rope_theta=500000.0),
          rope_scaling={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0,
                        "high_freq_factor": 4.0, "original_max_position_embeddings": 64}, seed=5)
+    # head_dim 64 / 128: the head sizes the CUDA kernels take, so the GPU path is compared with an implementation
+    # that is independent of oracle/ (tests/test_hf_fixture_gpu.py); dims are multiples of 64 (tcgen05 GEMM K tiles)
+    make("llama_d64_2l", "llama", dict(base, hidden=128, head_dim=64, num_heads=2, num_kv_heads=1, inter=256,
+                                       vocab=128), seed=7, prompts=(37, 64, 65, 130))
+    make("qwen2_d128_bias_2l", "qwen2", dict(base, hidden=256, head_dim=128, num_heads=2, num_kv_heads=1,
+                                             inter=256, vocab=128, qkv_bias=True, rope_theta=1000000.0),
+         seed=9, prompts=(37, 64, 65, 130))

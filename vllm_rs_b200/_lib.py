@@ -95,6 +95,9 @@ _SIGS = {
     "b200_rng_next_u64": (C.c_uint64, [c_vp]),
     "b200_runner_set_sampling": (None, [c_vp, c_i32, c_f32, c_f32]),
     "b200_runner_set_step_seed": (None, [c_vp, C.c_uint64, c_i64]),
+    "b200_runner_set_sampling_strategy": (c_i32, [c_vp, c_i32, c_i32, c_f32, c_f32]),
+    "b200_engine_set_swap_caches": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64]),
+    "b200_engine_set_seed": (None, [c_vp, C.c_uint64]),
     "b200_scheduler_new": (c_vp, [c_i32] * 5 + [c_vp, c_i32]),
     "b200_scheduler_free": (None, [c_vp]),
     "b200_scheduler_add": (c_i64, [c_vp, c_vp, c_i32, c_i32]),

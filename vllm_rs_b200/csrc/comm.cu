@@ -24,7 +24,7 @@ namespace b200 {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat16 = 6, ncclUint8 = 1, ncclSum = 0 };
+enum { ncclFloat16 = 6, ncclUint8 = 1, ncclInt32 = 2, ncclSum = 0, ncclMin = 3 };
 
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
@@ -300,8 +300,11 @@ b200_comm* b200_comm_init_rank(const uint8_t* id128, int32_t rank, int32_t world
 }
 
 /* Enable the one-shot path: allocate the symmetric buffer, exchange cudaIpc handles with
- * ncclAllGather, map every peer.  Returns 0 on success; on failure the communicator keeps
- * working through NCCL only. */
+ * ncclAllGather, map every peer.  Every rank runs the SAME collectives whatever happened locally and the
+ * outcome is agreed with an all-reduce(MIN) of the local ok flags: the path is on for all ranks or for
+ * none (a rank that silently fell back to NCCL would leave its peers spinning on flags that never come).
+ * Returns 0 on success; on failure everything is released and the communicator keeps working through
+ * NCCL only. */
 int32_t b200_comm_enable_oneshot(b200_comm* c, int64_t stream) {
   if (!c || c->world < 2) return -1;
   NcclApi& a = nccl();
@@ -314,41 +317,82 @@ int32_t b200_comm_enable_oneshot(b200_comm* c, int64_t stream) {
   const size_t cnt_off = push_off + push_bytes;
   const size_t pstate_off = cnt_off + 256;
   const size_t total = pstate_off + 256;
-  if (cudaMalloc(&base, total) != cudaSuccess) return -1;
-  cudaMemset(base, 0, total);
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&base, total) != cudaSuccess) {
+    cudaGetLastError();
+    base = nullptr;
+    ok = 0;
+  } else {
+    cudaMemset(base, 0, total);
+    if (cudaIpcGetMemHandle(&mine, base) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // scratch for the two collectives: [world handles][1 int flag]
+  uint8_t* d_x = nullptr;
+  const size_t hbytes = sizeof(cudaIpcMemHandle_t) * static_cast<size_t>(c->world);
+  if (cudaMalloc(&d_x, hbytes + 16) != cudaSuccess) {
+    // without even this scratch the rank cannot take part in the agreement: a hard error, not a fallback
+    cudaGetLastError();
+    if (base) cudaFree(base);
+    set_error(2, "comm_enable_oneshot: cudaMalloc of the exchange scratch failed");
+    return -1;
+  }
+  cudaIpcMemHandle_t* d_all = reinterpret_cast<cudaIpcMemHandle_t*>(d_x);
+  int* d_ok = reinterpret_cast<int*>(d_x + hbytes);
+  cudaMemcpy(d_all + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+  bool coll_ok = a.AllGather(d_all + c->rank, d_all, sizeof(mine), ncclUint8, c->nccl, st) == 0;
+  cudaStreamSynchronize(st);
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  cudaMemcpy(all.data(), d_all, hbytes, cudaMemcpyDeviceToHost);
+  OneShotPeers peers;
+  std::memset(&peers, 0, sizeof(peers));
+  std::vector<void*> opened;
+  if (ok && coll_ok) {
+    for (int r = 0; r < c->world && ok; ++r) {
+      uint8_t* p = base;
+      if (r != c->rank) {
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        opened.push_back(q);
+        p = reinterpret_cast<uint8_t*>(q);
+      }
+      peers.data[r] = p;
+      peers.flags[r] = reinterpret_cast<uint32_t*>(p + data_bytes);
+    }
+  }
+  // agreement: enabled only if EVERY rank mapped every peer
+  int all_ok = ok && coll_ok ? 1 : 0;
+  cudaMemcpy(d_ok, &all_ok, sizeof(int), cudaMemcpyHostToDevice);
+  if (a.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->nccl, st) != 0) all_ok = 0;
+  cudaStreamSynchronize(st);
+  int agreed = 0;
+  cudaMemcpy(&agreed, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_x);
+  if (!all_ok || !agreed) {
+    for (void* q : opened) cudaIpcCloseMemHandle(q);
+    if (base) cudaFree(base);
+    c->oneshot = false;
+    c->my_data = nullptr;
+    c->my_flags = nullptr;
+    c->state = nullptr;
+    return -1;
+  }
   c->push_off = push_off;
   c->cnt_off = cnt_off;
   c->pstate_off = pstate_off;
   c->my_data = base;
   c->my_flags = reinterpret_cast<uint32_t*>(base + data_bytes);
   c->state = reinterpret_cast<uint32_t*>(base + data_bytes + flag_bytes);
-  cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, base) != cudaSuccess) {
-    cudaGetLastError();
-    return -1;
-  }
-  cudaIpcMemHandle_t* d_all = nullptr;
-  cudaMalloc(&d_all, sizeof(cudaIpcMemHandle_t) * c->world);
-  cudaMemcpy(d_all + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
-  if (a.AllGather(d_all + c->rank, d_all, sizeof(mine), ncclUint8, c->nccl, st) != 0) return -1;
-  cudaStreamSynchronize(st);
-  std::vector<cudaIpcMemHandle_t> all(c->world);
-  cudaMemcpy(all.data(), d_all, sizeof(mine) * c->world, cudaMemcpyDeviceToHost);
-  cudaFree(d_all);
-  for (int r = 0; r < c->world; ++r) {
-    uint8_t* p = base;
-    if (r != c->rank) {
-      void* q = nullptr;
-      if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-      }
-      c->opened.push_back(q);
-      p = reinterpret_cast<uint8_t*>(q);
-    }
-    c->peers.data[r] = p;
-    c->peers.flags[r] = reinterpret_cast<uint32_t*>(p + data_bytes);
-  }
+  c->peers = peers;
+  c->opened = opened;
   c->oneshot = true;
   return 0;
 }

@@ -2,9 +2,10 @@
 //   C[m, n] = A[m, k] x W[n, k]^T, fp32 accumulate, fp16 or fp32 output.
 // Reference: Linear::forward -> candle -> cuBLAS (/root/reference/src/models/layers/linear.rs:75-123)
 // and the f32 logits cast in /root/reference/src/models/llama.rs:311-320.
-// Default: the hand-written tcgen05 kernel of dense_gemm_tc.cu.  B200_DENSE=cublas selects the
-// library GEMM the reference itself calls (kept as the A/B baseline and for shapes the kernel does
-// not take: K % 64 != 0, N % 8 != 0); B200_DENSE=tc1 forces single-CTA tiles for M > 128.
+// Default: the hand-written tcgen05 kernel of dense_gemm_tc.cu.  B200_DENSE=cublas (or mode 0) selects the
+// library GEMM the reference itself calls -- ONLY as an explicit A/B arm: a shape the tcgen05 kernel does not
+// take (K % 64 != 0, N % 8 != 0, unaligned pointers) latches an error, there is no silent library fallback.
+// B200_DENSE=tc1 forces single-CTA tiles for M > 128.
 #include <cublas_v2.h>
 
 #include <cstdlib>
@@ -52,9 +53,12 @@ extern "C" void b200_dense_gemm_ex(const void* a, const void* w, const void* bia
   if (m <= 0) return;
   B200_CHECK_ARG(a && w && c && n > 0 && k > 0, "dense_gemm: bad arguments");
   if (mode < 0) mode = dense_mode();
-  if (mode != 0 &&
-      launch_dense_gemm_tc(a, w, c, bias, m, n, k, out_f32, mode, reinterpret_cast<cudaStream_t>(stream)))
+  if (mode != 0) {
+    if (!launch_dense_gemm_tc(a, w, c, bias, m, n, k, out_f32, mode, reinterpret_cast<cudaStream_t>(stream)))
+      set_error(1, "dense_gemm: shape not taken by the tcgen05 kernel (needs K % 64 == 0, N % 8 == 0, 16-byte "
+                   "aligned pointers); the cuBLAS arm must be asked for explicitly (mode 0 / B200_DENSE=cublas)");
     return;
+  }
   cublasHandle_t h = cublas_for_device();
   if (!h) {
     set_error(2, "dense_gemm: cublasCreate failed");

@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "attn.cuh"
+#include "wna16.cuh"
 
 namespace b200 {
 
@@ -288,7 +289,9 @@ __global__ void rowscale_kernel(__half* __restrict__ out, const __half* __restri
   pdl_trigger();
   pdl_wait();
   const int t = blockIdx.x;
-  const float rs = rsqrtf(ssq[t * 32] * inv_dim + eps);   // kSsqStride (wna16.cuh)
+  // per-tile slots summed in the finalisers' order (wna16.cuh: ssq_lane_partial + warp_sum), by every warp
+  const float rs = rsqrtf(warp_sum(ssq_lane_partial(ssq + t * kSsqStride, hidden / kTileN, threadIdx.x & 31)) *
+                              inv_dim + eps);
   const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * hidden);
   uint4* os = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * hidden);
   for (int i = threadIdx.x; i < (hidden >> 3); i += blockDim.x) {

@@ -74,7 +74,8 @@ struct b200_runner {
   int64_t *s_pos = nullptr, *s_slot = nullptr;
   // pinned host staging for padded rows
   uint64_t* s_seed = nullptr;    // step seed of the device sampler
-  int samp_k = 0;                // 0 = greedy
+  int samp_k = 0;                // 0 = greedy (or Sampling::All when samp_all)
+  bool samp_all = false;         // temperature-only multinomial over the whole vocabulary
   float samp_p = 1.f, samp_t = 1.f;
   std::map<int, cudaGraphExec_t> graphs;
   int64_t launches = 0;
@@ -247,9 +248,9 @@ void b200_runner_set_allreduce(b200_runner* r, b200_allreduce_fn fn, void* user)
 
 // ModelRunner::sample (runner.rs:1390-1570) for the cached strategy: greedy argmax or the device sampler
 static void pick_tokens(b200_runner* r, uint32_t* out_ids, const float* logits, int B, int64_t stream) {
-  if (r->samp_k > 0)
-    launch_sample_topk_topp(out_ids, logits, B, r->cfg.vocab, std::min(r->samp_k, r->cfg.vocab), r->samp_p,
-                            r->samp_t, r->s_seed, reinterpret_cast<cudaStream_t>(stream));
+  if (r->samp_k > 0 || r->samp_all)
+    launch_sample_topk_topp(out_ids, logits, B, r->cfg.vocab, r->samp_all ? 0 : std::min(r->samp_k, r->cfg.vocab),
+                            r->samp_p, r->samp_t, r->s_seed, reinterpret_cast<cudaStream_t>(stream));
   else
     b200_argmax_f32(out_ids, logits, B, r->cfg.vocab, stream);
 }
@@ -310,6 +311,8 @@ static bool rope_fusable(const b200_runner* r) {
   return c.bits != 16 && !c.cos_sin_f32 && (kTileN % c.head_dim) == 0 && c.max_batch <= 64;
 }
 static bool fused_plan_enabled(const b200_runner* r) {
+  // one sum-of-squares slot per 128-channel tile of the residual stream (kSsqStride slots per row)
+  if (r->cfg.hidden % kTileN != 0 || r->cfg.hidden / kTileN > kSsqStride) return false;
   return fused_env() == 1 && rope_fusable(r) && r->allreduce == nullptr;
 }
 
@@ -353,7 +356,6 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
   const int qkv_n = (H + 2 * Hkv) * D;
   const float inv_h = 1.f / static_cast<float>(c.hidden);
   const size_t MB = c.max_batch;
-  cudaMemsetAsync(r->ssq, 0, (2 * static_cast<size_t>(L) + 1) * MB * kSsqStride * 4, st);
   b200_embedding_f16(r->x, r->embed, input_ids, B, c.hidden, c.vocab, stream);
   b200_rmsnorm_f16(r->xn, r->x, r->layers[0].input_norm, B, c.hidden, c.rms_eps, stream);
   __half* xw = r->xn;          // GEMM input buffer: x * w_norm (the 1/rms factor rides in ssq)
@@ -361,7 +363,10 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
     const b200_layer_weights& w = r->layers[l];
     FusedEpi fq;
     std::memset(&fq, 0, sizeof(fq));
-    if (l > 0) { fq.ssq_in = r->ssq + (2 * l - 1) * MB * kSsqStride; fq.inv_dim = inv_h; fq.eps = c.rms_eps; }
+    if (l > 0) {
+      fq.ssq_in = r->ssq + (2 * l - 1) * MB * kSsqStride; fq.ssq_tiles = c.hidden / kTileN;
+      fq.inv_dim = inv_h; fq.eps = c.rms_eps;
+    }
     fq.positions = positions; fq.slots = slot_mapping;
     fq.cos = (const __half*)r->cos; fq.sin = (const __half*)r->sin;
     fq.k_cache = (__half*)w.k_cache; fq.v_cache = (__half*)w.v_cache;
@@ -376,7 +381,8 @@ static void decode_fused(b200_runner* r, const uint32_t* input_ids, const int64_
     linear_fused(r, r->attn, w.o_w, w.o_s, w.o_z, nullptr, xw, B, H * D, c.hidden, kEpiResidNorm, fo, st);
     FusedEpi fg;
     std::memset(&fg, 0, sizeof(fg));
-    fg.ssq_in = r->ssq + (2 * l) * MB * kSsqStride; fg.inv_dim = inv_h; fg.eps = c.rms_eps;
+    fg.ssq_in = r->ssq + (2 * l) * MB * kSsqStride; fg.ssq_tiles = c.hidden / kTileN;
+    fg.inv_dim = inv_h; fg.eps = c.rms_eps;
     linear_fused(r, xw, w.gate_up_w, w.gate_up_s, w.gate_up_z, nullptr, r->act, B, c.hidden,
                  2 * c.inter, B200_EPI_SILU_MUL, fg, st);
     FusedEpi fd;
@@ -662,18 +668,39 @@ int32_t b200_runner_capture(b200_runner* r, const int32_t* buckets, int32_t num_
 
 int64_t b200_runner_launches_per_step(const b200_runner* r) { return r->launches; }
 
+static void set_sampling_impl(b200_runner* r, bool all, int32_t top_k, float top_p, float temperature) {
+  // k, p and 1/t are by-value kernel arguments, i.e. baked into captured graphs: ANY change drops them
+  if (top_k != r->samp_k || all != r->samp_all || top_p != r->samp_p || temperature != r->samp_t) {
+    for (auto& g : r->graphs) cudaGraphExecDestroy(g.second);
+    r->graphs.clear();
+  }
+  r->samp_all = all;
+  r->samp_k = top_k;
+  r->samp_p = top_p;
+  r->samp_t = temperature;
+}
+
 void b200_runner_set_sampling(b200_runner* r, int32_t top_k, float top_p, float temperature) {
   if (top_k < 0 || top_k > 256 || (top_k > 0 && !(temperature > 0.f))) {
     set_error(1, "runner_set_sampling: top_k must be 0 (greedy) or 1..256 with a positive temperature");
     return;
   }
-  if (top_k != r->samp_k) {           // graphs captured for the other strategy no longer apply
-    for (auto& g : r->graphs) cudaGraphExecDestroy(g.second);
-    r->graphs.clear();
+  set_sampling_impl(r, false, top_k, top_p, temperature);
+}
+
+// strategy = the return value of b200_sampling_strategy (0 ArgMax, 1 All, 2 TopK, 3 TopP, 4 TopKThenTopP) with
+// its (k, p, t): ArgMax -> greedy, All -> temperature-only multinomial over the whole vocabulary.
+int32_t b200_runner_set_sampling_strategy(b200_runner* r, int32_t strategy, int32_t k, float p, float t) {
+  if (strategy == 0) {
+    set_sampling_impl(r, false, 0, 1.f, 1.f);
+    return 0;
   }
-  r->samp_k = top_k;
-  r->samp_p = top_p;
-  r->samp_t = temperature;
+  if (strategy < 0 || strategy > 4 || !(t > 0.f) || (strategy != 1 && (k < 1 || k > 256))) {
+    set_error(1, "runner_set_sampling_strategy: unknown strategy or parameters out of range");
+    return -1;
+  }
+  set_sampling_impl(r, strategy == 1, strategy == 1 ? 0 : k, p, t);
+  return 0;
 }
 
 void b200_runner_set_step_seed(b200_runner* r, uint64_t seed, int64_t stream) {

@@ -203,6 +203,56 @@ sample_topk_topp_kernel(uint32_t* __restrict__ out_ids, const float* __restrict_
   }
 }
 
+// Sampling::All (logits_processor.rs:199-207: temperature only): multinomial over the FULL softmax(logits / T).
+// A thread owns a contiguous span of the vocabulary; the span sums are scanned in index order, so the draw is
+// the inverse CDF in token-id order (deterministic for a given seed).
+__global__ void __launch_bounds__(kSampThreads)
+sample_all_kernel(uint32_t* __restrict__ out_ids, const float* __restrict__ logits, int V, float inv_t,
+                  const uint64_t* __restrict__ seed_ptr) {
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + static_cast<size_t>(row) * V;
+  __shared__ float red_f[32];
+  __shared__ double part[kSampThreads];
+  __shared__ double s_total;
+  __shared__ int s_pick;
+  pdl_trigger();
+  pdl_wait();
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += kSampThreads) mx = fmaxf(mx, x[i]);
+  mx = block_reduce(mx, [](float a, float b) { return fmaxf(a, b); }, red_f, -INFINITY);
+  const int span = (V + kSampThreads - 1) / kSampThreads;
+  const int i0 = min(V, tid * span), i1 = min(V, i0 + span);
+  double local = 0.0;
+  for (int i = i0; i < i1; ++i) local += static_cast<double>(__expf((x[i] - mx) * inv_t));
+  part[tid] = local;
+  if (tid == 0) s_pick = V - 1;
+  __syncthreads();
+  if (tid == 0) {                                     // 1024 adds: exclusive prefix in place
+    double run = 0.0;
+    for (int t = 0; t < kSampThreads; ++t) {
+      const double v = part[t];
+      part[t] = run;
+      run += v;
+    }
+    s_total = run;
+  }
+  __syncthreads();
+  const double total = s_total;
+  const double target = static_cast<double>(row_uniform(*seed_ptr, row)) * total;
+  const double before = part[tid];
+  if (i0 < i1 && target >= before && target < before + local) {
+    double cum = before;
+    int pick = i1 - 1;
+    for (int i = i0; i < i1; ++i) {
+      cum += static_cast<double>(__expf((x[i] - mx) * inv_t));
+      if (cum > target) { pick = i; break; }
+    }
+    s_pick = pick;                                    // exactly one span contains the target
+  }
+  __syncthreads();
+  if (tid == 0) out_ids[row] = static_cast<uint32_t>(s_pick);
+}
+
 // logits[b, tok] -= count * frequency + (count > 0) * presence over the row's penalty window
 // (<= 128 tokens, logits_processor.rs:286-306); windows shorter than 2 tokens are no-ops (:325).
 __global__ void __launch_bounds__(128)
@@ -238,6 +288,11 @@ penalties_kernel(float* __restrict__ logits, int V, const uint32_t* __restrict__
 
 void launch_sample_topk_topp(uint32_t* out_ids, const float* logits, int B, int V, int k, float p, float t,
                              const uint64_t* seed_dev, cudaStream_t st) {
+  if (k <= 0) {                                        // Sampling::All
+    launch_pdl(sample_all_kernel, dim3(B), dim3(kSampThreads), 0, st, out_ids, logits, V, 1.f / t, seed_dev);
+    B200_CUDA_LAUNCH_CHECK();
+    return;
+  }
   launch_pdl(sample_topk_topp_kernel, dim3(B), dim3(kSampThreads), 0, st, out_ids, logits, V, k, p, 1.f / t,
              seed_dev);
   B200_CUDA_LAUNCH_CHECK();
@@ -253,7 +308,7 @@ void b200_sample_topk_topp_f32(uint32_t* out_ids, const float* logits, int32_t b
   using namespace b200;
   if (batch <= 0) return;
   B200_CHECK_ARG(out_ids && logits && seed_dev && vocab > 0, "sample: null pointer");
-  B200_CHECK_ARG(top_k >= 1 && top_k <= kMaxK, "sample: top_k must be in [1, 256]");
+  B200_CHECK_ARG(top_k >= 0 && top_k <= kMaxK, "sample: top_k must be in [1, 256], or 0 = Sampling::All (temperature only)");
   B200_CHECK_ARG(temperature > 0.f, "sample: temperature must be positive (greedy is b200_argmax_f32)");
   launch_sample_topk_topp(out_ids, logits, batch, vocab, top_k < vocab ? top_k : vocab, top_p, temperature,
                           seed_dev, reinterpret_cast<cudaStream_t>(stream));

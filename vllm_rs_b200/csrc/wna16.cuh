@@ -103,9 +103,10 @@ constexpr int kCounterBytes = 16384;
 constexpr int kMaxSplitCols = 148 * 128 * 2;     // launchers keep splits * N below this
 
 // internal epilogue kinds beyond the public B200_EPI_* flags (used by the fused decode plan)
-constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m] += sum x^2
-constexpr int kSsqStride = 32;    // floats between two rows' sums of squares: one 128 B line per row, so the
-                                  // finalisers' atomics spread over L2 slices instead of serialising on one line
+constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m][tile] = sum x^2 over the tile
+constexpr int kSsqStride = 64;    // floats per row of sums of squares: one slot per 128-channel tile (hidden <=
+                                  // 8192).  Tile finalisers STORE their slot (no atomics, nothing to zero) and the
+                                  // consumer adds the slots in a fixed butterfly order: run-to-run deterministic
 constexpr int kEpiRopeKv = 3;      // fused q|k|v: RoPE(q, k), K/V rows written to the paged cache
 constexpr int kEpiPushPeers = 4;   // row-parallel GEMM of a TP rank: the fp16 partial tile is stored into
                                    // EVERY rank's receive buffer over NVLink and a per-source tile counter is
@@ -118,6 +119,7 @@ struct FusedEpi {
   // consumer side of a folded RMSNorm: row m of the accumulators is scaled by
   // rsqrt(ssq_in[m] * inv_dim + eps) (the per-token factor commutes with the GEMM)
   const float* ssq_in;
+  int ssq_tiles;       // slots written per row of ssq_in (= producer N / 128)
   float inv_dim, eps;
   // kEpiResidNorm: residual stream (in/out), weight of the NEXT norm, its sum-of-squares target
   __half* resid;
@@ -183,6 +185,14 @@ __device__ __forceinline__ void store_half4(void* p, const float (&f)[4]) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// lane's share of a row's sum of squares (slots lane, lane + 32); warp_sum() of it is the row's total, added in
+// the same order wherever it is consumed (GEMM finalisers, rowscale_kernel)
+__device__ __forceinline__ float ssq_lane_partial(const float* __restrict__ row, int tiles, int lane) {
+  float v = lane < tiles ? row[lane] : 0.f;
+  if (lane + 32 < tiles) v += row[lane + 32];
+  return v;
+}
+
 template <int EPI>
 __device__ __forceinline__ EpiCol epi_col(const SplitOut& o, int nt, int ch) {
   const FusedEpi& fe = o.fe;
@@ -229,7 +239,7 @@ __device__ __forceinline__ void epi_row_prefetch(const SplitOut& o, const EpiCol
     r.e1[e] = 0.f;
   }
   if (!valid) return;
-  if (fe.ssq_in) r.rs = fe.ssq_in[m * kSsqStride];
+  if (fe.ssq_in) r.rs = ssq_lane_partial(fe.ssq_in + m * kSsqStride, fe.ssq_tiles, (c.n0 >> 2) & 31);
   if (EPI == kEpiResidNorm) {
     half4_to_float(fe.resid + static_cast<size_t>(m) * o.N + c.n0, r.e0);
   } else if (EPI == kEpiRopeKv) {
@@ -261,7 +271,7 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
   const FusedEpi& fe = o.fe;
   const int N = o.N;
   constexpr int epi = EPI;
-  const float scale = fe.ssq_in ? rsqrtf(r.rs * fe.inv_dim + fe.eps) : 1.f;
+  const float scale = fe.ssq_in ? rsqrtf(warp_sum(r.rs) * fe.inv_dim + fe.eps) : 1.f;
   float v0[4], v1[4], out[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -294,8 +304,8 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
       store_half4(fe.resid + idx, xn);
       store_half4(o.c + idx, out);
     }
-    sq = warp_sum(sq);
-    if (lane == 0 && valid) atomicAdd(fe.ssq_out + m * kSsqStride, sq);
+    sq = warp_sum(sq);            // the warp holds the whole 128-channel row of this tile
+    if (lane == 0 && valid) fe.ssq_out[m * kSsqStride + (c.n0 >> 7)] = sq;
   } else if (epi == kEpiRopeKv) {
     if (valid) {
       const int D = fe.D, hd = D >> 1;

@@ -32,6 +32,7 @@ class Scheduler:
                                              len(eos_token_ids))
         _lib.check()
         self.block_size = block_size
+        self.chunk_size = chunk_size
         self.cap = 4096
 
     def __del__(self):
@@ -432,9 +433,14 @@ class LLMEngine:
     (filter_prefill_finished / postprocess / clear_finished).  Greedy sampling."""
 
     def __init__(self, runner: ModelRunner, num_blocks, max_num_seqs, eos_token_ids=(),
-                 chunk_size=8192, prefix_cache=False, prefix_cache_max_tokens=None, native_step=True):
+                 chunk_size=8192, prefix_cache=False, prefix_cache_max_tokens=None, native_step=True,
+                 max_num_batched_tokens=0, seed=None, num_cpu_blocks=0):
         self.runner = runner
-        self.sched = Scheduler(num_blocks, 64, max_num_seqs, 0, chunk_size, eos_token_ids)
+        # the scheduler hands out up to max(max_num_seqs, 5) sequences per step (scheduler.rs:44); the runner
+        # must be able to take such a decode batch, and one chunk of one sequence as a prefill step
+        if max(max_num_seqs, 5) > runner.cfg.max_batch:
+            raise ValueError(f"runner max_batch {runner.cfg.max_batch} < max(max_num_seqs, 5) = {max(max_num_seqs, 5)}")
+        self.sched = Scheduler(num_blocks, 64, max_num_seqs, max_num_batched_tokens, chunk_size, eos_token_ids)
         if prefix_cache:                    # EngineConfig.prefix_cache / prefix_cache_max_tokens
             self.sched.enable_prefix_cache(prefix_cache_max_tokens)
         # native_step: schedule -> prepare_decode -> run -> postprocess of a decode batch is ONE C call
@@ -449,13 +455,66 @@ class LLMEngine:
             self._idx = np.zeros(cap, np.int32)
             self._sid = np.zeros(cap, np.int64)
             self._tok = np.zeros(cap, np.uint32)
+            if seed is not None:            # SamplingParams.seed -> the engine's StdRng (logits_processor.rs:48-70)
+                self._l.b200_engine_set_seed(self._eh, int(seed) & ((1 << 64) - 1))
+        self._rng = None
+        if seed is not None and not native_step:
+            self._rng = self._l.b200_rng_new(int(seed) & ((1 << 64) - 1))
         self.max_blocks = runner.cfg.max_blocks_per_seq
         self.outputs = {}
+        self.cpu_k = self.cpu_v = None
+        if num_cpu_blocks > 0:              # CPU swap: pinned-host mirrors of the layer caches (kvcache plan)
+            self.sched.enable_cpu_swap(num_cpu_blocks)
+            shp = (num_cpu_blocks,) + tuple(runner.k_cache[0].shape[1:])
+            dt = runner.k_cache[0].dtype
+            self.cpu_k = [torch.zeros(shp, dtype=dt).pin_memory() for _ in runner.k_cache]
+            self.cpu_v = [torch.zeros(shp, dtype=dt).pin_memory() for _ in runner.v_cache]
+            if self._eh:
+                L = len(runner.k_cache)
+                arr = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])      # noqa: E731
+                bb = runner.k_cache[0][0].numel() * runner.k_cache[0].element_size()
+                rc = self._l.b200_engine_set_swap_caches(self._eh, L, arr(runner.k_cache), arr(runner.v_cache),
+                                                         arr(self.cpu_k), arr(self.cpu_v), bb)
+                _lib.check()
+                assert rc == 0
 
     def __del__(self):
         if getattr(self, "_eh", None):
             self._l.b200_engine_free(self._eh)
             self._eh = None
+        if getattr(self, "_rng", None):
+            self._l.b200_rng_free(self._rng)
+            self._rng = None
+
+    def _drain_swaps(self):
+        """Python-step twin of the native drain: every queued block copy runs before the forward."""
+        for swap_in, pairs in self.sched.pop_swap_ops():
+            if self.cpu_k is None:
+                raise _lib.B200Error("the scheduler queued KV swap copies but the engine has no CPU caches")
+            keep = []
+            for gk, gv, ck, cv in zip(self.runner.k_cache, self.runner.v_cache, self.cpu_k, self.cpu_v):
+                keep.append(ops.swap_blocks(ck if swap_in else gk, gk if swap_in else ck, pairs))
+                keep.append(ops.swap_blocks(cv if swap_in else gv, gv if swap_in else cv, pairs))
+            torch.cuda.synchronize()
+
+    def _prefill_batches(self, ids):
+        """Split a scheduled prefill batch at sequence boundaries so every runner call fits the runner's
+        max_prefill_tokens / max_batch (the scheduler's budget is max_num_batched_tokens, scheduler.rs:258-260)."""
+        cap_t, cap_b = self.runner.cfg.max_prefill_tokens, self.runner.cfg.max_batch
+        out, cur, tok = [], [], 0
+        for i in ids:
+            info = self.sched.seq_info(i)
+            eff = min(self.sched.chunk_size, info["len"] - info["num_cached_tokens"])
+            if eff > cap_t:
+                raise _lib.B200Error(f"a prefill chunk of {eff} tokens exceeds the runner's max_prefill_tokens {cap_t}")
+            if cur and (tok + eff > cap_t or len(cur) >= cap_b):
+                out.append(cur)
+                cur, tok = [], 0
+            cur.append(i)
+            tok += eff
+        if cur:
+            out.append(cur)
+        return out
 
     def add_request(self, token_ids, max_tokens):
         sid = self.sched.add(token_ids, max_tokens)
@@ -475,6 +534,7 @@ class LLMEngine:
         return st.cuda_stream if st is not None else torch.cuda.current_stream().cuda_stream
 
     def step(self):
+        self.last_kind, self.last_prefill_tokens = "decode", 0
         if self._eh:
             npf = C.c_int32(0)
             n = self._l.b200_engine_step(self._eh, self._idx.ctypes.data, self._sid.ctypes.data,
@@ -491,15 +551,21 @@ class LLMEngine:
             ids, is_prefill = self._idx[:npf.value].tolist(), True       # n == -2: a prefill batch was scheduled
         else:
             ids, is_prefill = self.sched.schedule()
+            self._drain_swaps()
         if not ids:
             return False
         if is_prefill:
-            meta = self.sched.prepare_prefill(ids, token_cap=self.runner.cfg.max_prefill_tokens,
-                                              max_blocks_cap=self.max_blocks)
-            if meta["block_tables"] is None:            # the CUDA path always reads the paged cache
-                meta["block_tables"] = self._all_block_tables(ids)
-            _, toks = self.runner.prefill_device(meta, want_logits=False)
-            toks = toks.cpu().numpy().astype(np.uint32)
+            parts = []
+            self.last_kind = "prefill"
+            for sub in self._prefill_batches(ids):
+                meta = self.sched.prepare_prefill(sub, token_cap=self.runner.cfg.max_prefill_tokens,
+                                                  max_blocks_cap=self.max_blocks)
+                self.last_prefill_tokens += len(meta["input_ids"])
+                if meta["block_tables"] is None:            # the CUDA path always reads the paged cache
+                    meta["block_tables"] = self._all_block_tables(sub)
+                _, t = self.runner.prefill_device(meta, want_logits=False)
+                parts.append(t)
+            toks = torch.cat(parts).cpu().numpy().astype(np.uint32)
             pos, fin = self.sched.filter_prefill_finished(ids)
             sel = toks[pos] if len(pos) else toks[:0]
             for i, t in zip(fin, sel):
@@ -508,6 +574,8 @@ class LLMEngine:
         else:
             meta = self.sched.prepare_decode(ids, max_blocks_cap=self.max_blocks,
                                              pinned=self.runner.pinned)
+            if self._rng:
+                self.runner.set_step_seed(self._l.b200_rng_next_u64(self._rng), self._stream())
             toks = self.runner.run_decode(meta)
             for i, t in zip(ids, toks):
                 self.outputs[self.sched.seq_info(i)["id"]].append(int(t))
@@ -519,6 +587,8 @@ class LLMEngine:
         n = 0
         while (self.sched.num_running or self.sched.num_waiting) and n < max_steps:
             if not self.step():
-                break
+                raise _lib.B200Error(
+                    f"engine stalled: nothing schedulable with {self.sched.num_running} running / "
+                    f"{self.sched.num_waiting} waiting sequences and {self.sched.num_free_blocks} free blocks")
             n += 1
         return self.outputs
