@@ -309,8 +309,8 @@ __global__ void rowscale_kernel(__half* __restrict__ out, const __half* __restri
 // ------------------------------------------------------------------ SiLU(gate) * up
 __global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restrict__ gate_up,
                                 int inter) {
-  const int t = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index of an 8-half vector
+  const int t = blockIdx.x;                              // tokens on grid.x: a prefill step may hold > 65535 of them
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;   // index of an 8-half vector
   if (i * 8 >= inter) return;
   const uint4 gv = reinterpret_cast<const uint4*>(gate_up + static_cast<size_t>(t) * 2 * inter)[i];
   const uint4 uv =
@@ -342,8 +342,8 @@ __global__ void gather_rows_kernel(__half* __restrict__ out, const __half* __res
 }
 
 __global__ void add_bias_kernel(__half* __restrict__ x, const __half* __restrict__ bias, int n) {
-  const int t = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
   if (i * 2 >= n) return;
   __half2* p = reinterpret_cast<__half2*>(x + static_cast<size_t>(t) * n) + i;
   *p = __hadd2(*p, reinterpret_cast<const __half2*>(bias)[i]);
@@ -519,7 +519,7 @@ void b200_silu_mul_f16(void* out, const void* gate_up, int32_t num_tokens, int32
                        int64_t stream) {
   if (num_tokens <= 0) return;
   B200_CHECK_ARG(inter % 8 == 0, "silu_mul: inter % 8 != 0");
-  dim3 grid((inter / 8 + 255) / 256, num_tokens);
+  dim3 grid(num_tokens, (inter / 8 + 255) / 256);
   silu_mul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (__half*)out, (const __half*)gate_up, inter);
   B200_CUDA_LAUNCH_CHECK();
@@ -547,7 +547,7 @@ void b200_add_bias_f16(void* x, const void* bias, int32_t num_tokens, int32_t n,
                        int64_t stream) {
   if (num_tokens <= 0) return;
   B200_CHECK_ARG(n % 2 == 0, "add_bias: n % 2 != 0");
-  dim3 grid((n / 2 + 255) / 256, num_tokens);
+  dim3 grid(num_tokens, (n / 2 + 255) / 256);
   add_bias_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (__half*)x, (const __half*)bias, n);
   B200_CUDA_LAUNCH_CHECK();

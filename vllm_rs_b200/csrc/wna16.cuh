@@ -77,10 +77,20 @@ __device__ __forceinline__ void dequant4_word(uint32_t x, const DqConst& d, uint
   __half2 v1 = u32_as_h2(lop3_or_and(x, 0x00F000F0u, 0x64006400u));
   __half2 v2 = u32_as_h2(lop3_or_and(y, 0x000F000Fu, 0x64006400u));
   __half2 v3 = u32_as_h2(lop3_or_and(y, 0x00F000F0u, 0x64006400u));
+#if defined(B200_DQ_EXPERIMENT) && B200_DQ_EXPERIMENT == 2
+  // TIMING EXPERIMENT ONLY (side builds, wrong values): the lop3-only core of a bias-folded dequant
+  out[0] = h2_as_u32(v0); out[1] = h2_as_u32(v1); out[2] = h2_as_u32(v2); out[3] = h2_as_u32(v3);
+  return;
+#endif
   v0 = __hsub2(v0, d.zlo);
   v1 = __hfma2(v1, sixteenth, __hneg2(d.zhi));
   v2 = __hsub2(v2, d.zlo);
   v3 = __hfma2(v3, sixteenth, __hneg2(d.zhi));
+#if defined(B200_DQ_EXPERIMENT) && B200_DQ_EXPERIMENT == 1
+  // TIMING EXPERIMENT ONLY (side builds, unscaled values): the exact (q - z) core of a post-MMA-scaled dequant
+  out[0] = h2_as_u32(v0); out[1] = h2_as_u32(v1); out[2] = h2_as_u32(v2); out[3] = h2_as_u32(v3);
+  return;
+#endif
   out[0] = h2_as_u32(__hmul2(v0, d.s2));
   out[1] = h2_as_u32(__hmul2(v1, d.s2));
   out[2] = h2_as_u32(__hmul2(v2, d.s2));
