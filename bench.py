@@ -290,6 +290,9 @@ def graph_time(cx: Ctx, fn, K, W, prof=None, sample_clocks=False):
     import torch
     stream = cx.stream
     clocks = None
+    # inputs and caches were produced on the default stream (decode_inputs, fill_kv_random): the step stream must
+    # not start before they exist (the FP8-KV leg read unwritten positions -> wild cos / sin rows -> illegal address)
+    stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(stream):
         for _ in range(2):
             fn()
@@ -358,6 +361,7 @@ def attention_roofline(cx: Ctx, runner, B, ctx, blocks_per_seq, bt, cl, peak, pe
     out = torch.empty_like(q)
     scale = 1.0 / float(np.sqrt(D))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(cx.stream):
         for rep in range(2):      # first pass warms up, second is timed
             e0.record(cx.stream)
@@ -571,6 +575,7 @@ def run_prefill_leg(args, cx: Ctx, fmt, seqs, tokens_per_seq, reps=2):
                 cu_seqlens_q=(np.arange(seqs + 1) * tokens_per_seq).astype(np.uint32), context_lens=None,
                 block_tables=bt, max_seqlen_q=tokens_per_seq)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.stream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(cx.stream):
         runner.prefill_device(meta, want_logits=False)          # warm-up
         cx.stream.synchronize()

@@ -83,8 +83,17 @@ void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const ui
                                 const void* scales, const int32_t* g_idx, void* c, int32_t m,
                                 int32_t n, int32_t k, int32_t group_size, const void* workspace,
                                 int64_t stream);
+/* gemm_half_q_half_alt with the reference's EXACT signature (gptq.rs:183-195 call site, 316-324 declaration):
+ * `qweight` is the checkpoint-format GPTQ tensor [k / (32/bits), n] as the loader leaves it on this path, no
+ * group size, no workspace.  The group size is derived from g_idx (required; one cached 8-byte read), the
+ * tile-major copy of the weight is made on first use and kept, the workspace is library-owned.  The first call
+ * per tensor synchronises the stream; later calls do not.  b200_gemm_half_q_half_alt_release() frees all of it. */
+void b200_gemm_half_q_half_alt(const void* a, const uint32_t* qweight, const uint32_t* qzeros,
+                               const void* scales, const int32_t* g_idx, void* c, int32_t m, int32_t n,
+                               int32_t k, int32_t bits, int64_t stream);
+void b200_gemm_half_q_half_alt_release(void);
 /* General entry: bits in {4,8}, qfmt AWQ/GPTQ, optional bias[n] (fp16, may be NULL),
- * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05,
+ * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05 (round-1 decode kernel for m <= 64),
  * 3 = tcgen05 with a single K split (direct store, workspace untouched; prefill),
  * 4 = the general tcgen05 kernel even for decode shapes (A/B testing).                 */
 void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,

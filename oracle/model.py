@@ -107,6 +107,27 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     return h(xf * inv * w.to(F32))
 
 
+def normx(x: torch.Tensor, w: torch.Tensor, eps: float, norm_dtype=None) -> torch.Tensor:
+    """NormX::forward (/root/reference/src/models/layers/others.rs:11-30) with the norm weight loaded by
+    rms_norm_sharded (others.rs:43-66).  llama.rs builds its norms in the model dtype (norm_dtype None): the fused
+    RmsNorm runs on the fp16 tensor -- fp32 inside, ONE rounding of x * rsqrt(mean(x^2) + eps) * w to fp16.
+    qwen3.rs:83,95,261 (Qwen2 / Qwen3) builds them with DType::F32: the weight is cast to f32 at load (exact:
+    every fp16 is an f32), the input is cast fp16 -> f32 (exact), the norm runs in f32 and the result is cast
+    back to the input dtype -- again ONE rounding of the same f32 product.  The two branches are therefore the
+    same function of (x, w) up to the f32 association order of the three factors, which the final fp16 rounding
+    absorbs except on exact ties; tests/test_oracle_cpu.py::test_normx_f32_round_trip_is_the_fp16_norm pins that
+    on 1e6 random elements, and the CUDA kernels (glue.cu rmsnorm_kernel, the folded norms of the GEMM finalisers)
+    are compared against this one definition for both model families."""
+    if norm_dtype is None or norm_dtype == x.dtype:
+        return rmsnorm(x, w, eps)
+    in_dtype = x.dtype
+    conv = x.to(norm_dtype)                                   # others.rs:15
+    wf = w.to(norm_dtype)                                     # others.rs:53-55
+    inv = torch.rsqrt(conv.pow(2).mean(-1, keepdim=True) + eps)
+    out = conv * inv * wf                                     # RmsNorm on the converted tensor (others.rs:17)
+    return out.to(F32) if _EXACT else out.to(in_dtype)        # others.rs:20
+
+
 def apply_rope(q, k, cos, sin, positions, interleaved=False):
     """q [T,H,D], k [T,Hkv,D] fp16; NeoX (rotate-half) unless interleaved.  fp32 math."""
     c = cos[positions].to(F32).unsqueeze(1)      # [T,1,D/2]

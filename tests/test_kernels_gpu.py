@@ -198,7 +198,8 @@ def _wna_case(K, N, M, fmt, bits, seed, group=128):
     return qw, qz, s, torch.from_numpy(W), x
 
 
-@pytest.mark.parametrize("variant", [1, 2, 4])   # flat GEMV / tcgen05 (decode kernel for M<=64) / general tcgen05
+# flat GEMV / round-1 tcgen05 decode kernel (M <= 64) / general tcgen05 / stream-K tcgen05 decode kernel (M <= 32)
+@pytest.mark.parametrize("variant", [1, 2, 4, 5])
 @pytest.mark.parametrize("fmt,bits,K,N,M", [
     ("awq", 4, 4096, 1024, 1), ("awq", 4, 4096, 6144, 32), ("awq", 4, 14336, 4096, 5),
     ("gptq", 4, 2048, 256, 3), ("gptq_sym", 4, 1024, 512, 16), ("gptq", 8, 2048, 512, 7),
@@ -207,6 +208,8 @@ def _wna_case(K, N, M, fmt, bits, seed, group=128):
 def test_wna16_gemm(ops, fmt, bits, K, N, M, variant):
     if variant >= 2 and not _tc_available(ops):
         pytest.skip("tcgen05 variant not built yet")
+    if variant == 5 and M > 32:
+        pytest.skip("the stream-K decode kernel takes M <= 32")
     qw, qz, s, W, x = _wna_case(K, N, M, fmt, bits, seed=K + N + M)
     qwd = torch.from_numpy(qw).cuda()
     packed = ops.awq_prepack(qwd) if fmt == "awq" else ops.gptq_prepack(qwd, bits)
@@ -227,6 +230,54 @@ def test_wna16_gemm(ops, fmt, bits, K, N, M, variant):
     assert torch.equal(y2, y)                   # split-K partials are reduced in a fixed order
 
 
+@pytest.mark.parametrize("fmt,bits,K,N,M,group,epi", [
+    ("awq", 4, 4096, 28672, 32, 128, "silu"),      # gate|up of Llama-3-8B: 3 tile segments per CTA, gate / up pairs
+    ("awq", 4, 14336, 4096, 17, 128, "none"),      # down: every tile cut 4-5 ways
+    ("gptq", 4, 4096, 4096, 32, 4096, "none"),     # one group per channel
+    ("gptq_sym", 4, 2048, 1536, 8, 256, "bias"),   # groups of two units, bias in the finaliser / direct store
+    ("gptq", 8, 4096, 1024, 32, 128, "none"),      # W8A16
+    ("awq", 4, 256, 128, 1, 128, "none"),          # one tile, two units, one CTA
+    ("awq", 4, 8192, 7168, 32, 128, "silu"),       # Llama-3-70B gate|up shard at TP = 8
+])
+def test_wna16_streamk_decode(ops, fmt, bits, K, N, M, group, epi):
+    """wna16_sk.cu (variant 5): CTA ranges that cut tiles anywhere, per-CTA partial slots, every epilogue the
+    public entry exposes; and the post-MMA scale is at least as close to the fp32 truth as the fp16-rounded
+    weights the reference multiplies with."""
+    qw, qz, s, W, x = _wna_case(K, N, M, fmt, bits, seed=K + N + M + group, group=group)
+    qwd = torch.from_numpy(qw).cuda()
+    packed = ops.awq_prepack(qwd) if fmt == "awq" else ops.gptq_prepack(qwd, bits)
+    ws = ops.wna16_workspace(max(M, 16), N)
+    sd = torch.from_numpy(s).cuda()
+    zd = None if qz is None else torch.from_numpy(qz).cuda()
+    qf = ops.QFMT_AWQ if fmt == "awq" else ops.QFMT_GPTQ
+    bias = torch.randn(N).to(F16) if epi == "bias" else None
+    kw = dict(k=K, n=N, bits=bits, group_size=group, qfmt=qf,
+              epilogue=ops.EPI_SILU_MUL if epi == "silu" else ops.EPI_NONE,
+              bias=None if bias is None else bias.cuda())
+    y = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=5, **kw)
+    full = om.linear(x, W, bias)
+    ref = om.silu_mul(full[:, :N // 2], full[:, N // 2:]) if epi == "silu" else full
+    _close(y, ref, 2e-3, 4e-3 if epi == "silu" else 2e-3)
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0      # arrival counters back at rest
+    y2 = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=5, **kw)
+    assert torch.equal(y2, y)                                      # contributor-ordered sums: deterministic
+    if epi == "none":
+        # the exact product x @ ((q - z) * s), no fp16 rounding of the weights: the post-MMA scale must be at least
+        # as close to it as the round-1 kernel, which multiplies with the reference's fp16-rounded weights
+        q = oq.unpack_awq(qw) if fmt == "awq" else oq.unpack_gptq(qw, bits)
+        if qz is None:
+            z = np.full((K // group, N), 1 << (bits - 1), dtype=np.int32)
+        else:
+            z = oq.unpack_awq(qz).astype(np.int32) if fmt == "awq" else oq.unpack_gptq_zeros(qz, bits)
+        gi = np.arange(K) // group
+        wexact = (q.astype(np.float64) - z[gi]) * s[gi].astype(np.float64)
+        truth = torch.from_numpy(x.numpy().astype(np.float64) @ wexact)
+        y_old = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=2, **kw)
+        e_new = (y.cpu().double() - truth).abs().max().item()
+        e_old = (y_old.cpu().double() - truth).abs().max().item()
+        assert e_new <= e_old + 5e-4, (e_new, e_old)
+
+
 def _tc_available(ops):
     from vllm_rs_b200 import _lib
     rng = np.random.default_rng(0)
@@ -240,6 +291,29 @@ def _tc_available(ops):
         return True
     except _lib.B200Error:
         return False
+
+
+@pytest.mark.parametrize("bits,K,N,M,group", [(8, 2048, 512, 7, 128), (4, 4096, 1024, 32, 128), (4, 1024, 256, 200, 64)])
+def test_gemm_half_q_half_alt_exact_signature(ops, bits, K, N, M, group):
+    """The reference's own argument list (gptq.rs:183-195): checkpoint-format qweight, g_idx, no group size, no
+    workspace.  Second call hits the cached tile-major copy and must agree bit for bit."""
+    from vllm_rs_b200 import _lib
+    l = _lib.lib()
+    qw, qz, s, W, x = _wna_case(K, N, M, "gptq", bits, seed=K + N + M + bits, group=group)
+    qwd, qzd, sd = (torch.from_numpy(t).cuda() for t in (qw, qz, s))
+    xd = x.cuda()
+    g_idx = (torch.arange(K, dtype=torch.int32) // group + 5).cuda()       # a TP shard's g_idx starts at its first group
+    outs = []
+    for _ in range(2):
+        y = torch.empty(M, N, dtype=F16, device="cuda")
+        l.b200_gemm_half_q_half_alt(xd.data_ptr(), qwd.data_ptr(), qzd.data_ptr(), sd.data_ptr(), g_idx.data_ptr(),
+                                    y.data_ptr(), M, N, K, bits, torch.cuda.current_stream().cuda_stream)
+        _lib.check()
+        outs.append(y)
+    _close(outs[0], om.linear(x, W), 2e-3, 2e-3)
+    assert torch.equal(outs[0], outs[1])
+    l.b200_gemm_half_q_half_alt_release()
+    _lib.check()
 
 
 def test_prepack_bit_exact(ops):

@@ -65,6 +65,8 @@ _SIGS = {
     "b200_marlin_awq_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
     "b200_marlin_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
     "b200_gemm_half_q_half_8bit": (None, [c_vp] * 6 + [c_i32] * 4 + [c_vp, c_i64]),
+    "b200_gemm_half_q_half_alt": (None, [c_vp] * 6 + [c_i32] * 4 + [c_i64]),
+    "b200_gemm_half_q_half_alt_release": (None, []),
     "b200_wna16_gemm_ex": (None, [c_vp] * 6 + [c_i32] * 8 + [c_vp, c_i64]),
     "b200_wna16_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "b200_wna16_dequant_f16": (None, [c_vp] * 4 + [c_i32] * 5 + [c_i64]),

@@ -289,6 +289,7 @@ static void linear_fused(b200_runner* r, const __half* in, const void* w, const 
   p.bias = (const __half*)bias; p.c = out; p.M = M; p.K = K; p.N = N; p.bits = c.bits;
   p.group_size = c.group_size <= 0 ? K : c.group_size; p.qfmt = c.qfmt; p.epilogue = epilogue;
   p.no_split = 0; p.workspace = r->wna_ws; p.fe = &fe;
+  if (M > gemv_max_m() && launch_wna16_sk(p, st)) return;
   if (M > gemv_max_m() && launch_wna16_tc_dec(p, st)) return;
   if (M > gemv_max_m() && launch_wna16_tc(p, st)) return;
   launch_wna16_gemv(p, st);

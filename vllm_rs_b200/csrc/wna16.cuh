@@ -111,6 +111,7 @@ __device__ __forceinline__ void dequant8_word(uint32_t x, const DqConst& d, uint
 // and self-resetting; then fp32 partials [splits][M][N] with no invariant (nothing to zero).
 constexpr int kCounterBytes = 16384;
 constexpr int kMaxSplitCols = 148 * 128 * 2;     // launchers keep splits * N below this
+constexpr int kSkSlotCols = 148 * 128 * 4;       // stream-K kernel (wna16_sk.cu): per-CTA partial slots, [M][128] fp32 each
 
 // internal epilogue kinds beyond the public B200_EPI_* flags (used by the fused decode plan)
 constexpr int kEpiResidNorm = 2;   // x += y (fp16), out = x * w_next, ssq_out[m][tile] = sum x^2 over the tile
@@ -479,6 +480,7 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported
 bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st);   // decode shapes (M <= 64)
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force = false);   // stream-K decode kernel (M <= 32)
 // Largest M the automatic dispatch still gives to the flat GEMV (env B200_GEMV_MAX_M, default 0: the tcgen05
 // decode kernel streams the weights faster than the GEMV even for one token, profiles/r1_v7_batch_sweep.txt;
 // the GEMV stays as `variant 1` and as the fallback for shapes the tensor-core kernels do not take).

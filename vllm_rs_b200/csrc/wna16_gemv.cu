@@ -15,6 +15,9 @@
 
 #include <cstdlib>
 
+#include <map>
+#include <mutex>
+
 #include "wna16.cuh"
 
 namespace b200 {
@@ -270,7 +273,7 @@ int64_t b200_wna16_workspace_bytes(int32_t max_m, int32_t max_n) {
   // [16 KB arrival counters][fp32 split-K partials]: launchers keep splits * N <= kMaxSplitCols
   // unless splits == 1, so max(max_n, kMaxSplitCols) columns always suffice.
   const int64_t m = max_m < 16 ? 16 : max_m;
-  const int64_t cols = max_n > kMaxSplitCols ? max_n : kMaxSplitCols;
+  const int64_t cols = max_n > kSkSlotCols ? max_n : kSkSlotCols;
   return kCounterBytes + m * cols * 4 + 256;
 }
 
@@ -294,8 +297,14 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (variant == 5) {
+    if (launch_wna16_sk(p, st, true)) return;
+    set_error(1, "wna16: shape unsupported by the stream-K decode kernel");
+    return;
+  }
   if (variant == 2 || variant == 3 || variant == 4 || (variant == 0 && m > gemv_max_m())) {
-    if (variant != 4 && launch_wna16_tc_dec(p, st)) return;    // latency-optimised decode kernel
+    if (variant == 0 && launch_wna16_sk(p, st)) return;        // persistent stream-K decode kernel (M <= 32)
+    if (variant != 4 && launch_wna16_tc_dec(p, st)) return;    // round-1 decode kernel (M <= 64; A/B arm: variant 2)
     if (launch_wna16_tc(p, st)) return;
     if (variant >= 2) { set_error(1, "wna16: shape unsupported by the tcgen05 variant"); return; }
   }
@@ -326,6 +335,89 @@ void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const ui
   (void)g_idx;
   b200_wna16_gemm_ex(a, qweight, scales, qzeros, nullptr, c, m, k, n, 8, group_size,
                      B200_QFMT_GPTQ, B200_EPI_NONE, 0, const_cast<void*>(workspace), stream);
+}
+
+// ---- gemm_half_q_half_alt with the reference's EXACT signature (gptq.rs:183-195, 316-324): the caller hands over
+// the checkpoint-format GPTQ tensor [K/pack, N] (no repack at load on this path), no group size and no workspace.
+// The group size is what the reference kernel derives from g_idx (one 8-byte read, cached per tensor); the B200
+// tile-major copy of the weight is made on first use and kept (the repack the Marlin path does at load,
+// wna16.rs:127-152, deferred); the split-K workspace is library-owned and grows on demand.
+namespace {
+struct AltEntry { uint32_t* packed; int group_size; };
+struct AltKey {
+  const void* qw; int k, n, bits;
+  bool operator<(const AltKey& o) const {
+    if (qw != o.qw) return qw < o.qw;
+    if (k != o.k) return k < o.k;
+    if (n != o.n) return n < o.n;
+    return bits < o.bits;
+  }
+};
+std::mutex g_alt_mu;
+std::map<AltKey, AltEntry> g_alt;
+void* g_alt_ws = nullptr;
+int64_t g_alt_ws_bytes = 0;
+}  // namespace
+
+void b200_gemm_half_q_half_alt(const void* a, const uint32_t* qweight, const uint32_t* qzeros, const void* scales,
+                               const int32_t* g_idx, void* c, int32_t m, int32_t n, int32_t k, int32_t bits,
+                               int64_t stream) {
+  if (m <= 0) return;
+  B200_CHECK_ARG(bits == 4 || bits == 8, "gemm_half_q_half_alt: bits must be 4 or 8");
+  B200_CHECK_ARG(a && qweight && scales && c, "gemm_half_q_half_alt: NULL pointer");
+  B200_CHECK_ARG(k % kChunkK == 0 && n % kTileN == 0, "gemm_half_q_half_alt: need K % 64 == 0, N % 128 == 0");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_alt_mu);
+  const AltKey key{qweight, k, n, bits};
+  auto it = g_alt.find(key);
+  if (it == g_alt.end()) {
+    B200_CHECK_ARG(g_idx != nullptr, "gemm_half_q_half_alt: g_idx is required (the group size is derived from it)");
+    int32_t first = 0, last = 0;
+    if (cudaMemcpyAsync(&first, g_idx, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(&last, g_idx + (k - 1), 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error(2, "gemm_half_q_half_alt: reading g_idx failed");
+      return;
+    }
+    const int groups = last - first + 1;           // a TP shard's g_idx starts at its first global group
+    if (groups <= 0 || k % groups != 0 || (k / groups) % 32 != 0) {
+      set_error(1, "gemm_half_q_half_alt: g_idx is not k / group_size (act-order checkpoints are rejected by the loader)");
+      return;
+    }
+    AltEntry e;
+    e.group_size = k / groups;
+    if (cudaMalloc(&e.packed, static_cast<size_t>(k) * n * bits / 8) != cudaSuccess) {
+      set_error(2, "gemm_half_q_half_alt: cudaMalloc of the tile-major weight copy failed");
+      return;
+    }
+    b200_gptq_prepack(qweight, e.packed, k * bits / 32, n, bits, stream);
+    it = g_alt.emplace(key, e).first;
+  }
+  const int64_t need = b200_wna16_workspace_bytes(m, n);
+  if (need > g_alt_ws_bytes) {
+    cudaStreamSynchronize(st);                      // a previous call may still be using the old block
+    if (g_alt_ws) cudaFree(g_alt_ws);
+    g_alt_ws = nullptr;
+    g_alt_ws_bytes = 0;
+    if (cudaMalloc(&g_alt_ws, need) != cudaSuccess || cudaMemsetAsync(g_alt_ws, 0, need, st) != cudaSuccess) {
+      set_error(2, "gemm_half_q_half_alt: workspace allocation failed");
+      return;
+    }
+    g_alt_ws_bytes = need;
+  }
+  b200_wna16_gemm_ex(a, it->second.packed, scales, qzeros, nullptr, c, m, k, n, bits, it->second.group_size,
+                     B200_QFMT_GPTQ, B200_EPI_NONE, 0, g_alt_ws, stream);
+}
+
+// Drop the tile-major copies and the workspace b200_gemm_half_q_half_alt made (model unload).
+void b200_gemm_half_q_half_alt_release(void) {
+  std::lock_guard<std::mutex> lock(g_alt_mu);
+  cudaDeviceSynchronize();
+  for (auto& kv : g_alt) cudaFree(kv.second.packed);
+  g_alt.clear();
+  if (g_alt_ws) cudaFree(g_alt_ws);
+  g_alt_ws = nullptr;
+  g_alt_ws_bytes = 0;
 }
 
 }  // extern "C"

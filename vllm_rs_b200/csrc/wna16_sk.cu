@@ -1,0 +1,764 @@
+// W4A16 / W8A16 GEMM on tcgen05 for DECODE batches (M <= 32): persistent stream-K variant.
+//
+// Replaces marlin_*_4bit_f16 / gemm_half_q_half_alt for decode shapes (/root/reference/src/utils/gptq.rs:118-195,
+// wna16.rs:263-306).  Same data layout, epilogues and split meeting point as wna16_tc_dec.cu; what changes is how
+// the work is cut and who does what.  Motivation (round-2 measurements of the round-1 kernel,
+// profiles/r2_b_dec_gemm_diet_experiments.txt, r2_c_dec_gemm_sass_histogram.txt): two thirds of its issued
+// instructions are pipeline bookkeeping, gate|up runs 1.51 waves, ~4 us of serial epilogue per launch.
+// Outcome (profiles/r2_j_sk_vs_dec.txt, six measured iterations): bit-reproducible and inside the same tolerances
+// on every shape / epilogue (tests/test_kernels_gpu.py::test_wna16_streamk_decode), FASTER than the round-1 kernel
+// only for small batches on big-N projections (gate|up at one token: 24.0 vs 30.0 us, 2.44 TB/s), SLOWER at 32
+// tokens (86-108 vs 65.9 us per layer) -- so the automatic dispatch uses it only there (sk_mode below) and the
+// round-1 kernel stays the batch-32 path.
+//
+//   * WORK = units of 128 K (two 64-K chunks) of one 128-channel tile.  The tile-major weight layout makes
+//     the flattened (tile, unit) list ONE contiguous byte range, so CTA b of a one-CTA-per-SM grid simply
+//     streams bytes [b*share, (b+1)*share) * unit_bytes: no wave tail, every SM busy on every shape.
+//     A tile cut by a CTA boundary is finished by the split meeting point (per-CTA partial slots, arrival
+//     counter, last arriver reduces in contributor order: deterministic).
+//   * the dequant threads write the EXACT integers (q - z) to TMEM as fp16 (lop3 magic numbers + one
+//     hsub2; no multiply).  Each 128-K unit accumulates into a fresh TMEM accumulator (two per dequant group, so
+//     the MMAs of the group's next unit run meanwhile); the SAME four warps drain it one unit later
+//     (tcgen05.ld) and fold the group scale in fp32: acc[m] += s[n, g] * sum_k (q - z) x.  This is
+//     the reference's w = (q - z) * s without the intermediate fp16 rounding of w (closer to the fp32
+//     truth, well inside the 1e-3 bar); it needs group_size = 128 * 2^k (or one group), else the round-1
+//     kernel runs.  The running sums live in registers for a whole tile segment.  (A first version drained
+//     every unit through four dedicated scale warps: one serial 170-instruction chain per unit, 1 640 cycles
+//     per unit.)
+//   * at the end of a tile segment the three groups leave their sums in shared memory; two EPILOGUE warps
+//     add them (fixed order), write the CTA's partial tile to L2, meet the other contributors at the arrival
+//     counter and, if last, run the fused tile finaliser of wna16.cuh -- while dequant / MMA are already on the
+//     CTA's next tile.
+//   * zero points and scales are read straight from global memory three units ahead (a 4-byte + 2-byte load
+//     per thread per 128 K): no staging ring, no extra barriers.
+//   * what still limits it (ncu source view of v4-v6): ~380 issued instructions per unit per dequant warp against
+//     176 of arithmetic, ~10 cycles per instruction per warp with three dequant warps per scheduler, and a
+//     ~2.3 us dequant -> MMA -> drain chain per unit and group that small shapes (10 units per CTA on qkv) cannot hide.
+#include <cstdlib>
+#include <cstring>
+
+#include "wna16.cuh"
+
+namespace b200 {
+namespace sk {
+
+constexpr int kDG = 3;                          // dequant groups (4 warps = 128 channels each)
+constexpr int kDqWarps = 4 * kDG;               // warps 0 .. 11 (warp % 4 == TMEM lane quarter)
+constexpr int kEpiWarps = 2;                    // (four would push the CTA past 20 warps = below 96 registers per thread)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kEpiWarp0 = kDqWarps;             // 12 .. 13
+constexpr int kWProdWarp = kEpiWarp0 + kEpiWarps;   // 14
+constexpr int kXProdWarp = kWProdWarp + 1;      // 15: activations, up to kDG * kSXS units ahead of the MMAs (fetching
+                                                // them from the issuers, two units ahead, left the kernel bound by the
+                                                // TMA latency: gate|up 25.5 us at one token, 37.2 us at 32)
+constexpr int kIssWarp0 = kXProdWarp + 1;       // 16 .. 18 (one MMA issuer per dequant group)
+constexpr int kWarps = kIssWarp0 + kDG;
+constexpr int kThreads = kWarps * 32;           // 608: 19 warps leave 96 registers per thread
+constexpr int kAS = 3;                          // A stages (one 64-K chunk = 32 TMEM columns) per dequant group
+constexpr int kDB = 2;                          // accumulators per dequant group (unit i + 1 runs while unit i is drained)
+constexpr int kMaxSeg = 8;                      // tile segments per CTA (one-shot barriers)
+constexpr int kUnitK = 2 * kChunkK;             // 128
+constexpr int kPF = 3;                          // zero-point / scale prefetch depth (units of one dequant group)
+
+template <int BITS, int NT>
+struct Cfg {
+  static constexpr int kWBytes = kTileN * kChunkK * BITS / 8;   // one (tile, 64-K chunk): 4 KB / 8 KB
+  static constexpr int kUnitW = 2 * kWBytes;
+  static constexpr int kWStage = kDG * kUnitW;                  // one bulk copy: 24 KB / 48 KB
+  static constexpr int kSWS = BITS == 4 ? 4 : 2;
+  static constexpr int kXBytes = NT * kChunkK * 2;              // activations of one chunk: [NT][128 B] swizzled
+  static constexpr int kXUnit = 2 * kXBytes;
+  static constexpr int kSXS = 3;                                // activation slots per dequant group
+  static constexpr int kXOff = 0;
+  static constexpr int kWOff = kDG * kSXS * kXUnit;
+  static constexpr int kHOff = kWOff + kSWS * kWStage;          // segment sums of the three groups: [group][NT][128] fp32
+  static constexpr int kHBytes = NT * kTileN * 4;
+  static constexpr int kBarOff = kHOff + kDG * kHBytes;
+  static constexpr int kNumBars = 2 * kSWS + 2 * kDG * kSXS + 2 * kDG * kAS + 2 * kDG * kDB + 2 * kMaxSeg;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kFlagOff = kTmemPtrOff + 16;
+  static constexpr int kTidOff = kFlagOff + 16;                 // one word per thread (see the kernel prologue)
+  static constexpr int kAlloc = kTidOff + kThreads * 4 + 1024;
+  static_assert(kAlloc <= 227 * 1024, "shared memory budget");
+  static_assert(kXBytes % 1024 == 0, "SWIZZLE_128B tiles are 1024-byte aligned");
+  static constexpr int kDCol0 = 0;                              // accumulator (g, buf): columns [32 (2 g + buf), + NT)
+  static constexpr int kACol0 = kDG * kDB * 32;
+  static constexpr int kTmemCols = 512;
+  static_assert(NT <= 32 && kACol0 + kDG * kAS * 32 <= 512, "TMEM budget");
+};
+
+struct Args {
+  const uint32_t* bp;
+  const __half* scales;
+  const uint32_t* qzeros;
+  const __half* bias;
+  __half* c;
+  float* partials;       // [cta][S_max][M][128] fp32
+  uint32_t* counters;
+  int M, K, N, gshift, qfmt, KP, units, share, smax;   // quantisation group of unit `pair`: pair >> gshift
+  FusedEpi fe;
+};
+
+struct Pos { int tile, pair; };
+__device__ __forceinline__ Pos pos_of(int u, int KP) {
+  Pos p;
+  p.tile = u / KP;
+  p.pair = u - p.tile * KP;
+  return p;
+}
+__device__ __forceinline__ void pos_advance(Pos& p, int d, int KP) {
+  p.pair += d;
+  while (p.pair >= KP) { p.pair -= KP; ++p.tile; }
+}
+
+// Which CTAs hold a piece of tile t, and where their partial tiles live.
+struct Contrib { int first, cnt, slot0; };
+__device__ __forceinline__ Contrib contrib_of(int t, int KP, int share, int smax) {
+  Contrib c;
+  c.first = (t * KP) / share;
+  const int last = ((t + 1) * KP - 1) / share;
+  c.cnt = last - c.first + 1;
+  c.slot0 = c.first * smax + (t - (c.first * share) / KP);     // the first contributor may hold t as a later segment
+  return c;
+}
+__device__ __forceinline__ const float* part_ptr(const float* partials, const Contrib& c, int s, int smax,
+                                                 size_t slot_floats) {
+  const int slot = s == 0 ? c.slot0 : (c.first + s) * smax;    // every later contributor STARTS inside t
+  return partials + static_cast<size_t>(slot) * slot_floats;
+}
+
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) __trap();        // ~2 s: a protocol bug fails the launch, never hangs
+  } while (!ok);
+}
+// long waits of warps that are off the critical path (epilogue warps): back off instead of competing for issue slots
+__device__ __forceinline__ void wait_bar_sleepy(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(1000);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void arrive_bar(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// exact (q - z) as fp16 pairs: nibbles at mantissa bits 0..3 read as 1024 + q, at bits 4..7 as 64 + q
+__device__ __forceinline__ void dq4_exact(uint32_t x, __half2 zlo, __half2 zhi, uint32_t (&out)[4]) {
+  const uint32_t y = x >> 8;
+  out[0] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(x, 0x000F000Fu, 0x64006400u)), zlo));
+  out[1] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(x, 0x00F000F0u, 0x54005400u)), zhi));
+  out[2] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(y, 0x000F000Fu, 0x64006400u)), zlo));
+  out[3] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(y, 0x00F000F0u, 0x54005400u)), zhi));
+}
+__device__ __forceinline__ void dq8_exact(uint32_t x, __half2 zlo, uint32_t (&out)[2]) {
+  uint32_t lo, hi;
+  asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(lo) : "r"(x), "r"(0x64646464u));
+  asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(hi) : "r"(x), "r"(0x64646464u));
+  out[0] = h2_as_u32(__hsub2(u32_as_h2(lo), zlo));
+  out[1] = h2_as_u32(__hsub2(u32_as_h2(hi), zlo));
+}
+
+// ---- tile finaliser over per-CTA partial slots (the row / column logic is wna16.cuh's; only the addressing of
+// the partials differs from split_reduce_rows).  kEpiThreads threads: lane = 4 channels, warp = row phase.
+template <int EPI>
+__device__ __forceinline__ void reduce_tile(const Args& a, const SplitOut& o, int nt, int tid) {
+  const int M = a.M, KP = a.KP;
+  const int lane = tid & 31, phase = tid >> 5;
+  constexpr int nphase = kEpiWarps, R = 2;
+  constexpr bool kSilu = EPI == B200_EPI_SILU_MUL;
+  constexpr bool kMayPair = kSilu || EPI == kEpiRopeKv;
+  constexpr int U = kMayPair ? 2 : 4;
+  const EpiCol c = epi_col<EPI>(o, nt, lane * 4);
+  const size_t slot_floats = static_cast<size_t>(M) * kTileN;
+  const int half_tiles = (a.N / kTileN) >> 1;
+  const int t0 = kSilu ? nt % half_tiles : nt;
+  const Contrib k0 = contrib_of(t0, KP, a.share, a.smax);
+  const Contrib k1 = kSilu ? contrib_of(t0 + half_tiles, KP, a.share, a.smax) : k0;
+  const int c0 = lane * 4;
+  const int c1 = kSilu ? c0 : (c.pair ? c.n1 - nt * kTileN : c0);
+  const int smaxc = k0.cnt > k1.cnt ? k0.cnt : k1.cnt;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int mb = phase; mb < M; mb += R * nphase) {
+    float a0[R][4], a1[R][4];
+    EpiRow er[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a0[j][e] = 0.f;
+        a1[j][e] = 0.f;
+      }
+      epi_row_prefetch<EPI>(o, c, mb + j * nphase, mb + j * nphase < M, er[j]);
+    }
+    for (int s0 = 0; s0 < smaxc; s0 += U) {
+      float4 v0[U][R], v1[U][R];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        const float* p0 = part_ptr(a.partials, k0, s, a.smax, slot_floats);
+        const float* p1 = kSilu ? part_ptr(a.partials, k1, s, a.smax, slot_floats) : p0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int m = mb + j * nphase;
+          const bool ok0 = s < k0.cnt && m < M;
+          const bool ok1 = s < k1.cnt && m < M && c.pair;
+          v0[u][j] = ok0 ? ld_cg_f4(p0 + m * kTileN + c0) : zero4;
+          if (kMayPair) v1[u][j] = ok1 ? ld_cg_f4(p1 + m * kTileN + c1) : zero4;
+        }
+      }
+      if (s0 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) epi_row_prefetch2<EPI>(o, c, mb + j * nphase < M, er[j]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          a0[j][0] += v0[u][j].x; a0[j][1] += v0[u][j].y; a0[j][2] += v0[u][j].z; a0[j][3] += v0[u][j].w;
+          if (kMayPair) {
+            a1[j][0] += v1[u][j].x; a1[j][1] += v1[u][j].y; a1[j][2] += v1[u][j].z; a1[j][3] += v1[u][j].w;
+          }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      epi_row_apply<EPI>(o, c, mb + j * nphase, mb + j * nphase < M, a0[j], a1[j], er[j], lane);
+  }
+}
+
+template <int BITS, int NT, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+  using C = Cfg<BITS, NT>;
+  const int b = blockIdx.x;
+  const int KP = a.KP, N = a.N, M = a.M;
+  const int u0 = b * a.share;
+  const int n = min(a.share, a.units - u0);            // units of this CTA (>= 1 by construction of the grid)
+
+  extern __shared__ uint8_t smem_raw[];
+  // The 1024-aligned shared-space base as ONE pinned 32-bit register: left to itself the compiler rebuilds it
+  // (S2R CgaCtaId / SWINHI + align, ~10 instructions) at every barrier of the hot loops (seen in the ncu source
+  // view of the first versions).  Every shared address below is s_base + offset.
+  const uint32_t s_raw = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  uint32_t s_base = (s_raw + 1023u) & ~1023u;
+  asm volatile("" : "+r"(s_base));
+  uint8_t* smem = smem_raw + (s_base - s_raw);
+  // The thread index makes a round trip through shared memory: ptxas otherwise re-derives warp / lane / TMEM lane
+  // offsets from S2R SR_TID.X (long, variable latency) at every use inside the hot loops instead of keeping them.
+  uint32_t tid_o = threadIdx.x;
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(s_base + C::kTidOff + tid_o * 4), "r"(tid_o) : "memory");
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tid_o) : "r"(s_base + C::kTidOff + threadIdx.x * 4) : "memory");
+  const int warp = static_cast<int>(tid_o >> 5), lane = static_cast<int>(tid_o & 31);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* wfull = bars;
+  uint64_t* wempty = wfull + C::kSWS;
+  uint64_t* xfull = wempty + C::kSWS;                  // [unit % (kDG * kSXS)]
+  uint64_t* xempty = xfull + kDG * C::kSXS;
+  uint64_t* afree = xempty + kDG * C::kSXS;            // [group][stage]
+  uint64_t* stored = afree + kDG * kAS;                // [group][stage]
+  uint64_t* dfull = stored + kDG * kAS;                // [group][buf]: the unit's eight MMAs are complete
+  uint64_t* dfree = dfull + kDG * kDB;                 // [group][buf]: the dequant warps have read the accumulator
+  uint64_t* segdone = dfree + kDG * kDB;               // [segment]: all twelve dequant warps left their sums in smem
+  uint64_t* hfree = segdone + kMaxSeg;                 // [segment]: the epilogue warps have read them
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kTmemPtrOff);
+  volatile int* s_flag = reinterpret_cast<volatile int*>(smem + C::kFlagOff);
+  // the same barriers as shared-space addresses
+  const uint32_t s_wfull = s_base + C::kBarOff, s_wempty = s_wfull + C::kSWS * 8;
+  const uint32_t s_xfull = s_wempty + C::kSWS * 8, s_xempty = s_xfull + kDG * C::kSXS * 8;
+  const uint32_t s_afree = s_xempty + kDG * C::kSXS * 8;
+  const uint32_t s_stored = s_afree + kDG * kAS * 8, s_dfull = s_stored + kDG * kAS * 8;
+  const uint32_t s_dfree = s_dfull + kDG * kDB * 8, s_segdone = s_dfree + kDG * kDB * 8;
+  const uint32_t s_hfree = s_segdone + kMaxSeg * 8;
+
+  if (tid_o == 0) {
+    for (int i = 0; i < C::kSWS; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], kDqWarps);
+    }
+    for (int i = 0; i < kDG * C::kSXS; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    for (int i = 0; i < kDG * kAS; ++i) {
+      mbar_init(&afree[i], 1);
+      mbar_init(&stored[i], 4);
+    }
+    for (int i = 0; i < kDG * kDB; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dfree[i], 4);
+    }
+    for (int i = 0; i < kMaxSeg; ++i) {
+      mbar_init(&segdone[i], kDqWarps);
+      mbar_init(&hfree[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kWProdWarp) {
+    tmem_alloc(tmem_ptr, C::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == kXProdWarp && lane == 0) prefetch_tmap(&xmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kWProdWarp) {
+    // ------------------------------------------------------------ weight producer: one contiguous stream
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.bp) + static_cast<size_t>(u0) * C::kUnitW;
+      const int nst = (n + kDG - 1) / kDG;
+      for (int s = 0; s < nst; ++s) {
+        const int slot = s % C::kSWS;
+        wait_bar(s_wempty + slot * 8, ((s / C::kSWS) & 1) ^ 1);
+        const int left = n - s * kDG;
+        const uint32_t bytes = static_cast<uint32_t>(left < kDG ? left : kDG) * C::kUnitW;
+        mbar_arrive_expect_tx(&wfull[slot], bytes);
+        bulk_load_1d(smem + C::kWOff + slot * C::kWStage, src + static_cast<size_t>(s) * C::kWStage, bytes,
+                     &wfull[slot]);
+      }
+    }
+  } else if (warp == kXProdWarp) {
+    // ------------------------------------------------------------ activation producer (ring of kDG * kSXS units)
+    if (lane == 0) {
+      pdl_wait();      // activations are the previous kernel's output; weights are not
+      constexpr int R = kDG * C::kSXS;
+      Pos p = pos_of(u0, KP);
+      int slot = 0;
+      uint32_t ph = 1;                                 // xempty: the first round passes
+      for (int j = 0; j < n; ++j) {
+        wait_bar(s_xempty + slot * 8, ph);
+        mbar_arrive_expect_tx(&xfull[slot], C::kXUnit);          // TMA zero-fills rows >= M
+        tma_load_3d(smem + C::kXOff + slot * C::kXUnit, &xmap, &xfull[slot], 0, 0, 2 * p.pair);
+        pos_advance(p, 1, KP);
+        if (++slot == R) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= kIssWarp0) {
+    // ------------------------------------------------------------ MMA issuers (one per dequant group)
+    if (lane == 0) {
+      const int grp = warp - kIssWarp0;
+      const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
+      int ai = 0;
+      uint32_t aphase = 0;
+      int it = 0;
+      for (int j = grp; j < n; j += kDG, ++it) {
+        const int xs = (it % C::kSXS) * kDG + grp;               // unit j lives in ring slot j % (kDG * kSXS)
+        const int db = it & 1;
+        const uint32_t d_tmem = tmem_base + C::kDCol0 + (grp * kDB + db) * 32;
+        wait_bar(s_xfull + xs * 8, (it / C::kSXS) & 1);
+        // accumulator `db` was last used by this group's unit it - 2: it must have been drained
+        wait_bar(s_dfree + (grp * kDB + db) * 8, ((it >> 1) & 1) ^ 1);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int as = grp * kAS + ai;
+          wait_bar(s_stored + as * 8, aphase);
+          tc_fence_after();
+          const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
+          const uint64_t bdesc = make_smem_desc_sw128(s_base + C::kXOff + xs * C::kXUnit + cc * C::kXBytes);
+#pragma unroll
+          for (int ks = 0; ks < kChunkK / 16; ++ks)
+            tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
+                      (cc > 0 || ks > 0) ? 1u : 0u);
+          tc_commit(&afree[as]);
+          if (++ai == kAS) { ai = 0; aphase ^= 1; }
+        }
+        tc_commit(&xempty[xs]);
+        tc_commit(&dfull[grp * kDB + db]);
+      }
+    }
+  } else if (warp < kDqWarps) {
+    // ------------------------------------------------------------ dequant groups (dequantise, then drain one unit later)
+    const int grp = warp >> 2, q4 = warp & 3;
+    const int ch = q4 * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    constexpr int W = 2 * BITS;                        // packed words per thread per chunk (8 / 16)
+    constexpr int ZWN = kTileN * BITS / 32;            // zero-point words per tile row
+    const int zword = BITS == 4 ? (ch >> 3) : (ch >> 2);
+    const int zshift = BITS == 4 ? ((a.qfmt == B200_QFMT_AWQ) ? 4 * awq_nibble_of(ch & 7) : 4 * (ch & 7))
+                                 : 8 * (ch & 3);
+    const uint32_t zadd = (a.qfmt == B200_QFMT_AWQ && BITS == 4) ? 0u : 1u;
+    const uint32_t zmask = (1u << BITS) - 1;
+    const uint32_t zrow = static_cast<uint32_t>(N) * BITS / 32;      // 32-bit indices: the tensors are far below 2^31 elements
+    const bool has_z = a.qzeros != nullptr;
+    uint32_t s_h = s_base + C::kHOff + grp * C::kHBytes + ch * 4;
+    uint32_t s_w = s_base + C::kWOff + grp * C::kUnitW + ch * 16;        // this thread's words of (stage 0, chunk 0)
+    uint32_t lane0 = lane == 0 ? 1u : 0u;
+    asm volatile("" : "+r"(s_h), "+r"(s_w), "+r"(lane0));
+    const unsigned short* scales_u16 = reinterpret_cast<const unsigned short*>(a.scales);
+    // zero word (low half... no: full word) and scale bits of a unit, read from global memory
+    auto zload = [&](const Pos& q) -> uint32_t {
+      if (!has_z) return 0u;
+      return __ldg(a.qzeros + (static_cast<uint32_t>(q.pair >> a.gshift) * zrow + q.tile * ZWN + zword));
+    };
+    auto sload = [&](const Pos& q) -> uint32_t {
+      return __ldg(scales_u16 + (static_cast<uint32_t>(q.pair >> a.gshift) * N + q.tile * kTileN + ch));
+    };
+    auto load_chunk = [&](uint32_t (&dst)[W], int wslot, int cc) {
+      const uint32_t addr = s_w + wslot * C::kWStage + cc * C::kWBytes;
+#pragma unroll
+      for (int sub = 0; sub < W / 4; ++sub)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(dst[sub * 4]), "=r"(dst[sub * 4 + 1]), "=r"(dst[sub * 4 + 2]), "=r"(dst[sub * 4 + 3])
+                     : "r"(addr + sub * kTileN * 16));
+    };
+    float acc[NT];
+#pragma unroll
+    for (int m = 0; m < NT; ++m) acc[m] = 0.f;
+    const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
+    int acc_tile = t_first;                            // the tile segment `acc` belongs to
+    // leave the sums of segments [acc_tile, upto) in shared memory (zeros for segments this group has no unit in)
+    auto flush_until = [&](int upto) {
+      while (acc_tile < upto) {
+        const int seg = acc_tile - t_first;
+        if (seg >= 1) wait_bar(s_hfree + (seg - 1) * 8, 0);      // the previous segment's sums have been read
+#pragma unroll
+        for (int m = 0; m < NT; ++m) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_h + m * (kTileN * 4)), "f"(acc[m]) : "memory");
+          acc[m] = 0.f;
+        }
+        __syncwarp();
+        if (lane0) arrive_bar(s_segdone + seg * 8);
+        ++acc_tile;
+      }
+    };
+    // accumulator of this group's unit `itp` (position q, scale bits sb): acc += s * D, then hand the buffer back
+    auto drain = [&](const Pos& q, int itp, uint32_t sb) {
+      flush_until(q.tile);
+      const float sc = __half2float(__ushort_as_half(static_cast<unsigned short>(sb)));
+      const int gb = grp * kDB + (itp & 1);
+      wait_bar(s_dfull + gb * 8, (itp >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[16];
+      const uint32_t d_addr = tmem_base + C::kDCol0 + gb * 32 + lane_base;
+      tmem_ld_x16(d_addr, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int m = 0; m < 16; ++m) acc[m] = fmaf(sc, __uint_as_float(v[m]), acc[m]);
+      if constexpr (NT == 32) {
+        tmem_ld_x16(d_addr + 16, v);
+        tc_wait_ld();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane0) arrive_bar(s_dfree + gb * 8);
+      if constexpr (NT == 32) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) acc[16 + m] = fmaf(sc, __uint_as_float(v[m]), acc[16 + m]);
+      }
+    };
+    if (grp < n) {
+      Pos p = pos_of(u0 + grp, KP);
+      uint32_t zq[kPF], sq[kPF];                       // zero words / scale bits of this group's next kPF units
+      Pos pz = p;
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        zq[k] = 0;
+        sq[k] = 0;
+        if (grp + k * kDG < n) {
+          zq[k] = zload(pz);
+          sq[k] = sload(pz);
+          pos_advance(pz, kDG, KP);
+        }
+      }
+      int wslot = 0;
+      uint32_t wphase = 0;
+      int ai = 0;
+      uint32_t aphase = 1;                             // afree: the first round passes
+      int pending = -1;
+      uint32_t cur[W];
+      Pos p_prev = p;
+      uint32_t s_prev = 0;
+      wait_bar(s_wfull, 0);
+      load_chunk(cur, 0, 0);
+      int it = 0;
+      for (int j = grp; j < n; j += kDG, ++it) {
+        const uint32_t z = has_z ? ((zq[0] >> zshift) & zmask) + zadd : (1u << (BITS - 1));
+        const __half2 zlo = u32_as_h2((0x6400u | z) * 0x00010001u);                // 1024 + z
+        const __half2 zhi = u32_as_h2((0x5400u | (z << 4)) * 0x00010001u);         // 64 + z (4-bit path)
+        const uint32_t s_cur = sq[0];
+        const bool more = j + kDG < n;
+#pragma unroll
+        for (int k = 0; k + 1 < kPF; ++k) {
+          zq[k] = zq[k + 1];
+          sq[k] = sq[k + 1];
+        }
+        if (j + kPF * kDG < n) {
+          zq[kPF - 1] = zload(pz);
+          sq[kPF - 1] = sload(pz);
+          pos_advance(pz, kDG, KP);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t lo[16], hi[16];
+          // ---- first half of the chunk (K 0..31)
+          if (BITS == 4) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              uint32_t o4[4];
+              dq4_exact(cur[w], zlo, zhi, o4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) lo[w * 4 + e] = o4[e];
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              uint32_t o2[2];
+              dq8_exact(cur[w], zlo, o2);
+              lo[w * 2] = o2[0];
+              lo[w * 2 + 1] = o2[1];
+            }
+          }
+          if (pending >= 0) {
+            // deferred completion of the previous chunk's TMEM stores: their latency ran under the ALU work above
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane0) arrive_bar(s_stored + pending * 8);
+          }
+          const int as = grp * kAS + ai;
+          const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32 + lane_base;
+          wait_bar(s_afree + as * 8, aphase);
+          tc_fence_after();
+          tmem_st_x16(a_tmem, lo);
+          // ---- second half (K 32..63)
+          if (BITS == 4) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              uint32_t o4[4];
+              dq4_exact(cur[4 + w], zlo, zhi, o4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hi[w * 4 + e] = o4[e];
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              uint32_t o2[2];
+              dq8_exact(cur[8 + w], zlo, o2);
+              hi[w * 2] = o2[0];
+              hi[w * 2 + 1] = o2[1];
+            }
+          }
+          // ---- packed words of the next chunk (cur is consumed)
+          if (cc == 0) {
+            load_chunk(cur, wslot, 1);
+          } else {
+            __syncwarp();
+            if (lane0) arrive_bar(s_wempty + wslot * 8);   // this warp's quarter of the stage is in registers
+            if (++wslot == C::kSWS) { wslot = 0; wphase ^= 1; }
+            if (more) {
+              wait_bar(s_wfull + wslot * 8, wphase);
+              load_chunk(cur, wslot, 0);
+            }
+          }
+          tmem_st_x16(a_tmem + 16, hi);
+          pending = as;
+          if (++ai == kAS) { ai = 0; aphase ^= 1; }
+        }
+        // ---- the PREVIOUS unit of this group: its MMAs were issued a unit ago
+        if (it >= 1) drain(p_prev, it - 1, s_prev);
+        p_prev = p;
+        s_prev = s_cur;
+        pos_advance(p, kDG, KP);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane0) arrive_bar(s_stored + pending * 8);
+      drain(p_prev, it - 1, s_prev);
+    }
+    flush_until(t_last + 1);
+  } else {
+    // ------------------------------------------------------------ epilogue warps: group sums -> partial tile -> meeting point
+    const int tid = static_cast<int>(tid_o) - kEpiWarp0 * 32;
+    const int ewarp = tid >> 5;
+    constexpr bool kPlain = EPI == B200_EPI_NONE;
+    constexpr bool kSilu = EPI == B200_EPI_SILU_MUL;
+    pdl_wait();
+    SplitOut o;
+    o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
+    o.M = M; o.N = N; o.splits = 1; o.epilogue = EPI; o.fe = a.fe;
+    const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
+    const int half_tiles = (N / kTileN) >> 1;
+    const uint32_t s_h = s_base + C::kHOff + lane * 16;
+    for (int t = t_first; t <= t_last; ++t) {
+      const int seg = t - t_first;
+      const Contrib k = contrib_of(t, KP, a.share, a.smax);
+      const bool direct = kPlain && a.fe.ssq_in == nullptr && k.cnt == 1;
+      wait_bar_sleepy(s_segdone + seg * 8, 0);
+      // rows ewarp, ewarp + kEpiWarps, ...: lane = 4 channels; the three groups' sums are added in group order
+      float* P = a.partials + (static_cast<size_t>(b) * a.smax + seg) * (static_cast<size_t>(M) * kTileN);
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (direct && a.bias) half4_to_float(a.bias + t * kTileN + lane * 4, bv);
+      for (int m = ewarp; m < M; m += kEpiWarps) {
+        float4 v[kDG];
+#pragma unroll
+        for (int g = 0; g < kDG; ++g)
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[g].x), "=f"(v[g].y), "=f"(v[g].z), "=f"(v[g].w)
+                       : "r"(s_h + g * C::kHBytes + m * (kTileN * 4)));
+        float sum[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+        for (int g = 1; g < kDG; ++g) {
+          sum[0] += v[g].x; sum[1] += v[g].y; sum[2] += v[g].z; sum[3] += v[g].w;
+        }
+        if (direct) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sum[e] += bv[e];
+          store_half4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
+        } else {
+          *reinterpret_cast<float4*>(P + m * kTileN + lane * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) arrive_bar(s_hfree + seg * 8);
+      if (direct) continue;
+      named_bar_sync(1, kEpiThreads);                            // every epilogue warp's rows are stored
+      if (tid == 0) {
+        int cidx = t;
+        unsigned target = static_cast<unsigned>(k.cnt);
+        if (kSilu) {
+          cidx = t % half_tiles;
+          const Contrib kg = contrib_of(cidx, KP, a.share, a.smax);
+          const Contrib ku = contrib_of(cidx + half_tiles, KP, a.share, a.smax);
+          target = static_cast<unsigned>(kg.cnt + ku.cnt);
+        }
+        // acq_rel RMW at gpu scope: releases this CTA's partial tile (the barrier above orders the other
+        // threads' stores before it), acquires the other contributors'
+        unsigned old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.counters + cidx) : "memory");
+        const int last = (old == target - 1) ? 1 : 0;
+        if (last) a.counters[cidx] = 0;                 // self-reset (graph replay safe)
+        *s_flag = last;
+      }
+      named_bar_sync(1, kEpiThreads);
+      const bool last = *s_flag != 0;
+      if (last) {
+        reduce_tile<EPI>(a, o, t, tid);
+        if (EPI == kEpiPushPeers) push_signal(o.fe, tid, kEpiThreads, 2);
+      }
+      named_bar_sync(1, kEpiThreads);                            // s_flag is rewritten by the next segment
+    }
+  }
+  __syncthreads();
+  if (warp == kWProdWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// B200_DEC_SK: 0 = never, 1 = every shape the kernel takes (M <= 32), 2 (default) = where it measured faster than the
+// round-1 kernel on B200 (profiles/r2_j_sk_vs_dec.txt): at most four tokens AND at least 32 units per CTA, i.e. the
+// big-N projections (gate|up) of small decode batches.  At M = 32 the round-1 kernel stays ahead (65.9 vs 86-108 us per
+// layer): a unit's dequant -> MMA -> drain chain is ~2.3 us long, so shapes with few units per CTA are latency-bound,
+// and the 32-row epilogue runs on two warps instead of sixteen.
+static int sk_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_DEC_SK");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
+template <int BITS, int NT, int EPI>
+static bool launch_epi(const WnaParams& p, cudaStream_t st) {
+  using C = Cfg<BITS, NT>;
+  const int KC = p.K / kChunkK, KP = p.K / kUnitK;
+  const int tiles = p.N / kTileN;
+  const long units = static_cast<long>(tiles) * KP;
+  // one CTA per SM; never less than two units (four chunks) per CTA, as in the round-1 split rule
+  long G = sm_count();
+  if (G > units / 2) G = units / 2 > 0 ? units / 2 : 1;
+  const int share = static_cast<int>((units + G - 1) / G);
+  G = (units + share - 1) / share;
+  const int smax = (share + KP - 2) / KP + 1;            // tiles a range of `share` units can touch
+  if (smax > kMaxSeg) return false;
+  if (G * smax * kTileN > kSkSlotCols) return false;     // partial slots must fit b200_wna16_workspace_bytes
+  CUtensorMap xmap;
+  {
+    const uint64_t dims[3] = {kChunkK, static_cast<uint64_t>(p.M), static_cast<uint64_t>(KC)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(p.K) * 2, kChunkK * 2};
+    const uint32_t box[3] = {kChunkK, static_cast<uint32_t>(NT), 2};
+    const uint32_t es[3] = {1, 1, 1};
+    if (encode_tensor_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(p.a), dims, strides,
+                          box, es, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS) {
+      set_error(2, "wna16_sk: cuTensorMapEncodeTiled (activations) failed");
+      return true;
+    }
+  }
+  Args a;
+  a.bp = p.bp; a.scales = p.scales; a.qzeros = p.qzeros; a.bias = p.bias; a.c = p.c;
+  a.counters = reinterpret_cast<uint32_t*>(p.workspace);
+  a.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kCounterBytes);
+  a.M = p.M; a.K = p.K; a.N = p.N; a.qfmt = p.qfmt;
+  a.gshift = 30;                                          // one group: every unit reads row 0
+  if (p.group_size < p.K)
+    for (int sft = 0; sft < 24; ++sft)
+      if ((kUnitK << sft) == p.group_size) a.gshift = sft;
+  a.KP = KP; a.units = static_cast<int>(units); a.share = share; a.smax = smax;
+  if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wna16_sk_kernel<BITS, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kAlloc);
+    attr_set = true;
+  }
+  launch_pdl(wna16_sk_kernel<BITS, NT, EPI>, dim3(static_cast<unsigned>(G)), dim3(kThreads), C::kAlloc, st, xmap, a);
+  B200_CUDA_LAUNCH_CHECK();
+  return true;
+}
+
+template <int BITS, int NT>
+static bool launch_nt(const WnaParams& p, cudaStream_t st) {
+  switch (p.epilogue) {
+    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL>(p, st);
+    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm>(p, st);
+    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv>(p, st);
+    case kEpiPushPeers: return launch_epi<BITS, NT, kEpiPushPeers>(p, st);
+    default: return launch_epi<BITS, NT, B200_EPI_NONE>(p, st);
+  }
+}
+
+}  // namespace sk
+
+// Decode-shape entry (M <= 32): false when the shape needs another kernel.  `force` skips the B200_DEC_SK switch
+// (b200_wna16_gemm_ex variant 5).
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force) {
+  if (!force && sk::sk_mode() == 0) return false;
+  if (p.M > 32) return false;
+  if (!force && sk::sk_mode() == 2) {
+    const long units = static_cast<long>(p.N / kTileN) * (p.K / sk::kUnitK);
+    if (p.M > 4 || units < 32L * sm_count()) return false;
+  }
+  if (p.K % sk::kUnitK != 0) return false;
+  if (p.group_size < p.K) {                             // a 128-K unit must lie inside one quantisation group,
+    bool ok = false;                                    // and the group of a unit is a shift of its index
+    for (int sft = 0; sft < 24; ++sft) ok = ok || (sk::kUnitK << sft) == p.group_size;
+    if (!ok) return false;
+  }
+  if (p.epilogue == B200_EPI_SILU_MUL && ((p.N / kTileN) & 1)) return false;
+  if (p.epilogue == kEpiRopeKv && p.fe && (kTileN % p.fe->D) != 0) return false;
+  if (p.bits == 4) return p.M <= 16 ? sk::launch_nt<4, 16>(p, st) : sk::launch_nt<4, 32>(p, st);
+  return p.M <= 16 ? sk::launch_nt<8, 16>(p, st) : sk::launch_nt<8, 32>(p, st);
+}
+
+}  // namespace b200
