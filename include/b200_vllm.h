@@ -77,6 +77,17 @@ void b200_marlin_awq_4bit_f16(const void* a, const int32_t* b, const void* scale
 void b200_marlin_4bit_f16(const void* a, const int32_t* b, const void* scales,
                           const void* qzeros, const void* g_idx, void* c, int32_t m, int32_t k,
                           int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+/* bf16 flavour (replace marlin_awq_4bit_bf16 / marlin_4bit_bf16, gptq.rs:150-178; bf16 is the reference's
+ * default dtype, utils/mod.rs:1919-1925): a, scales and c are bf16, same argument order and workspace.  Needs
+ * k % 128 == 0 and group_size = 128 * 2^j (or <= 0 / >= k: one group per channel).  Decode-shaped calls
+ * (m <= 32) are one launch of the stream-K tcgen05 kernel; larger m runs 32 rows per launch.            */
+void b200_marlin_awq_4bit_bf16(const void* a, const int32_t* b, const void* scales,
+                               const void* qzeros, const void* g_idx, void* c, int32_t m,
+                               int32_t k, int32_t n, const void* workspace, int32_t group_size,
+                               int64_t stream);
+void b200_marlin_4bit_bf16(const void* a, const int32_t* b, const void* scales,
+                           const void* qzeros, const void* g_idx, void* c, int32_t m, int32_t k,
+                           int32_t n, const void* workspace, int32_t group_size, int64_t stream);
 /* 8-bit GPTQ path (reference: gemm_half_q_half_alt, bits == 8).  Unlike the reference
  * symbol this takes the prepacked weight, an explicit group_size and a workspace.  */
 void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const uint32_t* qzeros,
@@ -95,7 +106,8 @@ void b200_gemm_half_q_half_alt_release(void);
 /* General entry: bits in {4,8}, qfmt AWQ/GPTQ, optional bias[n] (fp16, may be NULL),
  * epilogue flag.  variant: 0 = auto by m, 1 = flat GEMV (CUDA cores), 2 = tcgen05 (round-1 decode kernel for m <= 64),
  * 3 = tcgen05 with a single K split (direct store, workspace untouched; prefill),
- * 4 = the general tcgen05 kernel even for decode shapes (A/B testing).                 */
+ * 4 = the general tcgen05 kernel even for decode shapes (A/B testing),
+ * 5 = the stream-K tcgen05 decode kernel (m <= 32, k % 128 == 0, group_size = 128 * 2^j). */
 void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
                         const void* qzeros, const void* bias, void* c, int32_t m, int32_t k,
                         int32_t n, int32_t bits, int32_t group_size, int32_t qfmt,
@@ -158,6 +170,42 @@ void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cach
  * cache with peer access enabled.  Blocks must not overlap between src and dst ranges of one call.        */
 void b200_swap_blocks(const void* src_cache, void* dst_cache, const int64_t* pairs_dev, int32_t num_pairs,
                       int64_t block_bytes, int64_t stream);
+
+/* ------------------------------------------------- PD (prefill / decode) KV hand-off: wire frames + block movement
+ * transfer/mod.rs:82-125 (KVTransferHandle / FinishedPrefillData / TransferMessage), comm.rs:384-410 (u32 LE length +
+ * bincode 1.3.1 body) and the data legs of transfer/mod.rs:260-311,370-470.  A KV frame is built in place in a PINNED
+ * host buffer: _frame_begin writes every field but the payloads and returns where layer l's K and V bytes go;
+ * _export_blocks lets the copy kernel write them there from the paged caches (pairs = (server block, i));
+ * _frame_parse gives the same offsets of a received frame and _import_blocks copies (i, local block) out of it.
+ * _copy_blocks_peer is the LocalIpc leg: (server block, local block) between two GPUs' caches over NVLink.      */
+typedef struct b200_pd_kv_header {
+  uint64_t seq_id;
+  uint32_t first_token;
+  int32_t num_layers;
+  uint64_t layer_bytes;        /* bytes of ONE layer's K (= V) payload: num_blocks * block bytes */
+  uint64_t num_blocks;
+  uint64_t sending_time;       /* ms since the epoch (mod.rs:383-386) */
+  uint64_t num_cached_tokens;
+} b200_pd_kv_header;
+int64_t b200_pd_kv_frame_bytes(int32_t num_layers, int64_t layer_bytes);
+int64_t b200_pd_kv_frame_begin(uint8_t* frame, int64_t cap, const b200_pd_kv_header* h, int64_t* k_off,
+                               int64_t* v_off);
+int32_t b200_pd_kv_frame_parse(const uint8_t* frame, int64_t len, b200_pd_kv_header* h, int64_t* k_off,
+                               int64_t* v_off, int32_t max_layers);
+/* kind 1 = AvailableTokenResponse(value), 3 = ReleaseKvCache(value); returns the frame length (16) */
+int64_t b200_pd_frame_small(uint8_t* out, int64_t cap, int32_t kind, uint64_t value);
+/* TransferMessage variant of a frame (0..3), -1 if malformed; *value for kinds 1 and 3 */
+int32_t b200_pd_frame_kind(const uint8_t* frame, int64_t len, uint64_t* value);
+void b200_pd_export_blocks(const void* const* k_caches, const void* const* v_caches, int32_t num_layers,
+                           const int64_t* pairs_dev, int32_t n, int64_t block_bytes, uint8_t* frame,
+                           const int64_t* k_off, const int64_t* v_off, int64_t stream);
+void b200_pd_import_blocks(void* const* k_caches, void* const* v_caches, int32_t num_layers,
+                           const int64_t* pairs_dev, int32_t n, int64_t block_bytes, const uint8_t* frame,
+                           const int64_t* k_off, const int64_t* v_off, int64_t stream);
+void b200_pd_copy_blocks_peer(const void* const* remote_k, const void* const* remote_v, void* const* local_k,
+                              void* const* local_v, int32_t num_layers, const int64_t* pairs_dev, int32_t n,
+                              int64_t block_bytes, int64_t stream);
+int32_t b200_enable_peer_access(int32_t dev, int32_t peer);
 
 /* ------------------------------------------------- paged attention, decode
  * Replaces the decode branch of PagedAttention::forward (attention.rs:808-820).

@@ -316,6 +316,47 @@ def test_gemm_half_q_half_alt_exact_signature(ops, bits, K, N, M, group):
     _lib.check()
 
 
+@pytest.mark.parametrize("fmt,K,N,M,group", [("awq", 4096, 6144, 32, 128), ("gptq", 2048, 1024, 5, 128),
+                                             ("gptq_sym", 1024, 512, 70, 256), ("awq", 4096, 14336, 1, 128)])
+def test_marlin_bf16_entry_points(ops, fmt, K, N, M, group):
+    """marlin_awq_4bit_bf16 / marlin_4bit_bf16 (gptq.rs:150-178) with the reference's argument list: bf16 activations,
+    bf16 scales, bf16 output.  Checked against the exact product of the bf16 inputs (fp64) within bf16 output
+    rounding, and against the reference-style pipeline (weights rounded to bf16 first) within its own error."""
+    from vllm_rs_b200 import _lib
+    l = _lib.lib()
+    BF = torch.bfloat16
+    qw, qz, s, W, x = _wna_case(K, N, M, fmt, 4, seed=K + N + M + 1, group=group)
+    s_bf = torch.from_numpy(s.astype(np.float32)).to(BF)              # the loader casts the scales to the model dtype
+    x_bf = x.to(BF)
+    q = oq.unpack_awq(qw) if fmt == "awq" else oq.unpack_gptq(qw, 4)
+    if qz is None:
+        z = np.full((K // group, N), 8, dtype=np.int32)
+    else:
+        z = oq.unpack_awq(qz).astype(np.int32) if fmt == "awq" else oq.unpack_gptq_zeros(qz, 4)
+    gi = np.arange(K) // group
+    d = torch.from_numpy((q.astype(np.int32) - z[gi]).astype(np.float64))
+    sg = s_bf.double()[torch.from_numpy(gi)]
+    truth = x_bf.double() @ (d * sg)
+    w_ref = (d * sg).to(BF)                                           # Marlin bf16: the weight is rounded to bf16
+    ref = (x_bf.double() @ w_ref.double()).to(BF)
+    qwd = torch.from_numpy(qw).cuda()
+    packed = ops.awq_prepack(qwd) if fmt == "awq" else ops.gptq_prepack(qwd, 4)
+    ws = ops.wna16_workspace(max(M, 16), N)
+    zd = None if qz is None else torch.from_numpy(qz).cuda()
+    xd, sd = x_bf.cuda(), s_bf.cuda()
+    y = torch.empty(M, N, dtype=BF, device="cuda")
+    fn = l.b200_marlin_awq_4bit_bf16 if fmt == "awq" else l.b200_marlin_4bit_bf16
+    fn(xd.data_ptr(), packed.data_ptr(), sd.data_ptr(), 0 if zd is None else zd.data_ptr(), 0, y.data_ptr(),
+       M, K, N, ws.data_ptr(), group, torch.cuda.current_stream().cuda_stream)
+    _lib.check()
+    e_new = (y.cpu().double() - truth).abs().max().item()
+    e_ref = (ref.double() - truth).abs().max().item()
+    scale = truth.abs().max().item()
+    assert e_new <= 2.0 ** -8 * scale + 1e-3, (e_new, scale)          # half a bf16 ulp of the largest output, + slack
+    assert e_new <= e_ref + 2.0 ** -9 * scale, (e_new, e_ref)         # never worse than the reference-style pipeline
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0
+
+
 def test_prepack_bit_exact(ops):
     """Prepacked words decode back to the checkpoint nibbles (layout in include/b200_vllm.h)."""
     rng = np.random.default_rng(5)

@@ -51,6 +51,14 @@ class KvCachePlan(C.Structure):
                                      "max_model_len", "kvcache_memory_bytes", "max_num_batched_tokens")]
 
 
+class PdKvHeader(C.Structure):
+    """b200_pd_kv_header (include/b200_vllm.h)."""
+
+    _fields_ = [("seq_id", C.c_uint64), ("first_token", C.c_uint32), ("num_layers", c_i32),
+                ("layer_bytes", C.c_uint64), ("num_blocks", C.c_uint64), ("sending_time", C.c_uint64),
+                ("num_cached_tokens", C.c_uint64)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, c_vp, c_i64, c_vp, c_i64)
 
 # name -> (restype, argtypes)
@@ -64,6 +72,8 @@ _SIGS = {
     "b200_gptq_prepack": (None, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64]),
     "b200_marlin_awq_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
     "b200_marlin_4bit_f16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
+    "b200_marlin_awq_4bit_bf16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
+    "b200_marlin_4bit_bf16": (None, [c_vp] * 6 + [c_i32] * 3 + [c_vp, c_i32, c_i64]),
     "b200_gemm_half_q_half_8bit": (None, [c_vp] * 6 + [c_i32] * 4 + [c_vp, c_i64]),
     "b200_gemm_half_q_half_alt": (None, [c_vp] * 6 + [c_i32] * 4 + [c_i64]),
     "b200_gemm_half_q_half_alt_release": (None, []),
@@ -76,6 +86,15 @@ _SIGS = {
     "b200_rope_kv_write_fp8kv_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
     "b200_swap_blocks": (None, [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64]),
+    "b200_pd_kv_frame_bytes": (c_i64, [c_i32, c_i64]),
+    "b200_pd_kv_frame_begin": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b200_pd_kv_frame_parse": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32]),
+    "b200_pd_frame_small": (c_i64, [c_vp, c_i64, c_i32, C.c_uint64]),
+    "b200_pd_frame_kind": (c_i32, [c_vp, c_i64, c_vp]),
+    "b200_pd_export_blocks": (None, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_i64]),
+    "b200_pd_import_blocks": (None, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_i64]),
+    "b200_pd_copy_blocks_peer": (None, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_i64]),
+    "b200_enable_peer_access": (c_i32, [c_i32, c_i32]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_decode_fp8kv_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),

@@ -149,6 +149,7 @@ struct FusedEpi {
   __half* push[kMaxTpRanks];
   uint32_t* push_cnt[kMaxTpRanks];
   int push_world;
+  int out_bf16;    // plain epilogue only: C (and the bias) are bf16 (b200_marlin_*_bf16, wna16_sk.cu)
 };
 
 struct SplitOut {
@@ -188,6 +189,17 @@ __device__ __forceinline__ void half4_to_float(const void* p, float (&f)[4]) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
   const float2 lo = __half22float2(u32_as_h2(u.x)), hi = __half22float2(u32_as_h2(u.y));
   f[0] = lo.x; f[1] = lo.y; f[2] = hi.x; f[3] = hi.y;
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void store_bf16x4(void* p, const float (&f)[4]) {
+  uint2 u;
+  u.x = bf16x2_bits(f[0], f[1]);
+  u.y = bf16x2_bits(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = u;
 }
 __device__ __forceinline__ void store_half4(void* p, const float (&f)[4]) {
   uint2 u;
@@ -353,7 +365,10 @@ __device__ __forceinline__ void epi_row_apply(const SplitOut& o, const EpiCol& c
       for (int p = 0; p < fe.push_world; ++p) store_half4(fe.push[p] + idx, v0);   // peer-mapped (NVLink) stores
     }
   } else if (valid) {
-    store_half4(o.c + static_cast<size_t>(m) * N + c.n0, v0);
+    if (fe.out_bf16)
+      store_bf16x4(o.c + static_cast<size_t>(m) * N + c.n0, v0);
+    else
+      store_half4(o.c + static_cast<size_t>(m) * N + c.n0, v0);
   }
 }
 
@@ -480,7 +495,8 @@ __device__ __forceinline__ void split_arrive_and_reduce(const SplitOut& o, int n
 void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported
 bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st);   // decode shapes (M <= 64)
-bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force = false);   // stream-K decode kernel (M <= 32)
+// stream-K decode kernel (M <= 32); bf16: A, scales and C are bf16 (plain epilogue, 4-bit only)
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force = false, bool bf16 = false);
 // Largest M the automatic dispatch still gives to the flat GEMV (env B200_GEMV_MAX_M, default 0: the tcgen05
 // decode kernel streams the weights faster than the GEMV even for one token, profiles/r1_v7_batch_sweep.txt;
 // the GEMV stays as `variant 1` and as the fallback for shapes the tensor-core kernels do not take).

@@ -328,6 +328,55 @@ void b200_marlin_4bit_f16(const void* a, const int32_t* b, const void* scales,
                      B200_EPI_NONE, 0, const_cast<void*>(workspace), stream);
 }
 
+// bf16 flavour of the Marlin entry points (gptq.rs:150-178; bf16 is the reference's default dtype,
+// utils/mod.rs:1919-1925): A, scales and C are bf16.  The stream-K tcgen05 kernel (wna16_sk.cu) does the work:
+// exact (q - z) as bf16 into TMEM, kind::f16 MMA with bf16 operands, fp32 group scale after the MMA, bf16 output.
+// It takes 32 token rows per launch; larger m runs as consecutive 32-row launches on the stream (a prefill-sized
+// bf16 call therefore re-streams the weight once per 32 rows: correct, not fast -- the fp16 entry points are the
+// tuned path).
+static void marlin_bf16(const void* a, const int32_t* b, const void* scales, const void* qzeros, void* c, int32_t m,
+                        int32_t k, int32_t n, const void* workspace, int32_t group_size, int32_t qfmt,
+                        int64_t stream) {
+  if (m <= 0) return;
+  WnaParams p;
+  p.bp = (const uint32_t*)b;
+  p.scales = (const __half*)scales;
+  p.qzeros = (const uint32_t*)qzeros;
+  p.bias = nullptr;
+  p.K = k; p.N = n; p.bits = 4;
+  p.group_size = group_size <= 0 ? k : group_size;
+  p.qfmt = qfmt; p.epilogue = B200_EPI_NONE; p.workspace = const_cast<void*>(workspace);
+  p.no_split = 0;
+  p.fe = nullptr;
+  p.a = (const __half*)a; p.c = (__half*)c; p.M = m < 32 ? m : 32;
+  const char* why = nullptr;
+  if (!check_wna(p, &why)) { set_error(1, why); return; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int m0 = 0; m0 < m; m0 += 32) {
+    p.a = reinterpret_cast<const __half*>(a) + static_cast<size_t>(m0) * k;      // 2-byte elements either way
+    p.c = reinterpret_cast<__half*>(c) + static_cast<size_t>(m0) * n;
+    p.M = m - m0 < 32 ? m - m0 : 32;
+    if (!launch_wna16_sk(p, st, true, true)) {
+      set_error(1, "marlin bf16: needs K % 128 == 0 and group_size = 128 * 2^j (or one group per channel)");
+      return;
+    }
+  }
+}
+
+void b200_marlin_awq_4bit_bf16(const void* a, const int32_t* b, const void* scales, const void* qzeros,
+                               const void* g_idx, void* c, int32_t m, int32_t k, int32_t n, const void* workspace,
+                               int32_t group_size, int64_t stream) {
+  (void)g_idx;
+  marlin_bf16(a, b, scales, qzeros, c, m, k, n, workspace, group_size, B200_QFMT_AWQ, stream);
+}
+
+void b200_marlin_4bit_bf16(const void* a, const int32_t* b, const void* scales, const void* qzeros,
+                           const void* g_idx, void* c, int32_t m, int32_t k, int32_t n, const void* workspace,
+                           int32_t group_size, int64_t stream) {
+  (void)g_idx;
+  marlin_bf16(a, b, scales, qzeros, c, m, k, n, workspace, group_size, B200_QFMT_GPTQ, stream);
+}
+
 void b200_gemm_half_q_half_8bit(const void* a, const uint32_t* qweight, const uint32_t* qzeros,
                                 const void* scales, const int32_t* g_idx, void* c, int32_t m,
                                 int32_t n, int32_t k, int32_t group_size, const void* workspace,

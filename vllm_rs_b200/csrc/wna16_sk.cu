@@ -58,6 +58,7 @@ constexpr int kAS = 3;                          // A stages (one 64-K chunk = 32
 constexpr int kDB = 2;                          // accumulators per dequant group (unit i + 1 runs while unit i is drained)
 constexpr int kMaxSeg = 8;                      // tile segments per CTA (one-shot barriers)
 constexpr int kUnitK = 2 * kChunkK;             // 128
+constexpr int kEpiNoneBf16 = 5;                  // template-only: plain epilogue with bf16 activations / scales / output
 constexpr int kPF = 3;                          // zero-point / scale prefetch depth (units of one dequant group)
 
 template <int BITS, int NT>
@@ -168,6 +169,15 @@ __device__ __forceinline__ void dq4_exact(uint32_t x, __half2 zlo, __half2 zhi, 
   out[2] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(y, 0x000F000Fu, 0x64006400u)), zlo));
   out[3] = h2_as_u32(__hsub2(u32_as_h2(lop3_or_and(y, 0x00F000F0u, 0x54005400u)), zhi));
 }
+// bf16 flavour (b200_marlin_*_bf16): 7 mantissa bits hold a nibble only at bits 0..3, so every pair is shifted down
+// first; 128 + q and 128 + z are exact in bf16, and so is their difference
+__device__ __forceinline__ void dq4_exact_bf16(uint32_t x, uint32_t zb, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const uint32_t v = lop3_or_and(x >> (4 * p), 0x000F000Fu, 0x43004300u);
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(out[p]) : "r"(v), "r"(zb));
+  }
+}
 __device__ __forceinline__ void dq8_exact(uint32_t x, __half2 zlo, uint32_t (&out)[2]) {
   uint32_t lo, hi;
   asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(lo) : "r"(x), "r"(0x64646464u));
@@ -248,6 +258,9 @@ template <int BITS, int NT, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   using C = Cfg<BITS, NT>;
+  constexpr bool kBf16 = EPI == kEpiNoneBf16;
+  constexpr int EPX = kBf16 ? B200_EPI_NONE : EPI;     // the epilogue the finaliser templates see
+  static_assert(!kBf16 || BITS == 4, "bf16 entry points are 4-bit only (gptq.rs:150-178)");
   const int b = blockIdx.x;
   const int KP = a.KP, N = a.N, M = a.M;
   const int u0 = b * a.share;
@@ -357,7 +370,8 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     // ------------------------------------------------------------ MMA issuers (one per dequant group)
     if (lane == 0) {
       const int grp = warp - kIssWarp0;
-      const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT);
+      // kind::f16 takes bf16 operands with a_format = b_format = 1 (bits [7,10) and [10,13))
+      const uint32_t idesc = make_idesc_f16(128, NT < 16 ? 16 : NT) | (kBf16 ? ((1u << 7) | (1u << 10)) : 0u);
       int ai = 0;
       uint32_t aphase = 0;
       int it = 0;
@@ -444,7 +458,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     // accumulator of this group's unit `itp` (position q, scale bits sb): acc += s * D, then hand the buffer back
     auto drain = [&](const Pos& q, int itp, uint32_t sb) {
       flush_until(q.tile);
-      const float sc = __half2float(__ushort_as_half(static_cast<unsigned short>(sb)));
+      const float sc = kBf16 ? __uint_as_float(sb << 16) : __half2float(__ushort_as_half(static_cast<unsigned short>(sb)));
       const int gb = grp * kDB + (itp & 1);
       wait_bar(s_dfull + gb * 8, (itp >> 1) & 1);
       tc_fence_after();
@@ -495,6 +509,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         const uint32_t z = has_z ? ((zq[0] >> zshift) & zmask) + zadd : (1u << (BITS - 1));
         const __half2 zlo = u32_as_h2((0x6400u | z) * 0x00010001u);                // 1024 + z
         const __half2 zhi = u32_as_h2((0x5400u | (z << 4)) * 0x00010001u);         // 64 + z (4-bit path)
+        const uint32_t zb16 = (0x4300u | z) * 0x00010001u;                          // bf16 128 + z
         const uint32_t s_cur = sq[0];
         const bool more = j + kDG < n;
 #pragma unroll
@@ -515,7 +530,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
               uint32_t o4[4];
-              dq4_exact(cur[w], zlo, zhi, o4);
+              if constexpr (kBf16) dq4_exact_bf16(cur[w], zb16, o4); else dq4_exact(cur[w], zlo, zhi, o4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) lo[w * 4 + e] = o4[e];
             }
@@ -545,7 +560,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
               uint32_t o4[4];
-              dq4_exact(cur[4 + w], zlo, zhi, o4);
+              if constexpr (kBf16) dq4_exact_bf16(cur[4 + w], zb16, o4); else dq4_exact(cur[4 + w], zlo, zhi, o4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) hi[w * 4 + e] = o4[e];
             }
@@ -591,12 +606,12 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     // ------------------------------------------------------------ epilogue warps: group sums -> partial tile -> meeting point
     const int tid = static_cast<int>(tid_o) - kEpiWarp0 * 32;
     const int ewarp = tid >> 5;
-    constexpr bool kPlain = EPI == B200_EPI_NONE;
-    constexpr bool kSilu = EPI == B200_EPI_SILU_MUL;
+    constexpr bool kPlain = EPX == B200_EPI_NONE;
+    constexpr bool kSilu = EPX == B200_EPI_SILU_MUL;
     pdl_wait();
     SplitOut o;
     o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-    o.M = M; o.N = N; o.splits = 1; o.epilogue = EPI; o.fe = a.fe;
+    o.M = M; o.N = N; o.splits = 1; o.epilogue = EPX; o.fe = a.fe;
     const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
     const int half_tiles = (N / kTileN) >> 1;
     const uint32_t s_h = s_base + C::kHOff + lane * 16;
@@ -608,7 +623,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       // rows ewarp, ewarp + kEpiWarps, ...: lane = 4 channels; the three groups' sums are added in group order
       float* P = a.partials + (static_cast<size_t>(b) * a.smax + seg) * (static_cast<size_t>(M) * kTileN);
       float bv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (direct && a.bias) half4_to_float(a.bias + t * kTileN + lane * 4, bv);
+      if (direct && a.bias && !kBf16) half4_to_float(a.bias + t * kTileN + lane * 4, bv);
       for (int m = ewarp; m < M; m += kEpiWarps) {
         float4 v[kDG];
 #pragma unroll
@@ -624,7 +639,10 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         if (direct) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) sum[e] += bv[e];
-          store_half4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
+          if constexpr (kBf16)
+            store_bf16x4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
+          else
+            store_half4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
         } else {
           *reinterpret_cast<float4*>(P + m * kTileN + lane * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
         }
@@ -653,8 +671,8 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       named_bar_sync(1, kEpiThreads);
       const bool last = *s_flag != 0;
       if (last) {
-        reduce_tile<EPI>(a, o, t, tid);
-        if (EPI == kEpiPushPeers) push_signal(o.fe, tid, kEpiThreads, 2);
+        reduce_tile<EPX>(a, o, t, tid);
+        if (EPX == kEpiPushPeers) push_signal(o.fe, tid, kEpiThreads, 2);
       }
       named_bar_sync(1, kEpiThreads);                            // s_flag is rewritten by the next segment
     }
@@ -700,7 +718,8 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
     const uint64_t strides[2] = {static_cast<uint64_t>(p.K) * 2, kChunkK * 2};
     const uint32_t box[3] = {kChunkK, static_cast<uint32_t>(NT), 2};
     const uint32_t es[3] = {1, 1, 1};
-    if (encode_tensor_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(p.a), dims, strides,
+    if (encode_tensor_map(&xmap, EPI == kEpiNoneBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                          3, const_cast<__half*>(p.a), dims, strides,
                           box, es, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS) {
       set_error(2, "wna16_sk: cuTensorMapEncodeTiled (activations) failed");
       return true;
@@ -717,6 +736,7 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
       if ((kUnitK << sft) == p.group_size) a.gshift = sft;
   a.KP = KP; a.units = static_cast<int>(units); a.share = share; a.smax = smax;
   if (p.fe) a.fe = *p.fe; else memset(&a.fe, 0, sizeof(a.fe));
+  if (EPI == kEpiNoneBf16) a.fe.out_bf16 = 1;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(wna16_sk_kernel<BITS, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kAlloc);
@@ -741,8 +761,8 @@ static bool launch_nt(const WnaParams& p, cudaStream_t st) {
 }  // namespace sk
 
 // Decode-shape entry (M <= 32): false when the shape needs another kernel.  `force` skips the B200_DEC_SK switch
-// (b200_wna16_gemm_ex variant 5).
-bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force) {
+// (b200_wna16_gemm_ex variant 5, the bf16 entry points).
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16) {
   if (!force && sk::sk_mode() == 0) return false;
   if (p.M > 32) return false;
   if (!force && sk::sk_mode() == 2) {
@@ -757,6 +777,10 @@ bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force) {
   }
   if (p.epilogue == B200_EPI_SILU_MUL && ((p.N / kTileN) & 1)) return false;
   if (p.epilogue == kEpiRopeKv && p.fe && (kTileN % p.fe->D) != 0) return false;
+  if (bf16) {
+    if (p.bits != 4 || p.epilogue != B200_EPI_NONE || p.bias || p.fe) return false;
+    return p.M <= 16 ? sk::launch_epi<4, 16, sk::kEpiNoneBf16>(p, st) : sk::launch_epi<4, 32, sk::kEpiNoneBf16>(p, st);
+  }
   if (p.bits == 4) return p.M <= 16 ? sk::launch_nt<4, 16>(p, st) : sk::launch_nt<4, 32>(p, st);
   return p.M <= 16 ? sk::launch_nt<8, 16>(p, st) : sk::launch_nt<8, 32>(p, st);
 }
