@@ -170,16 +170,17 @@ __global__ void scratch_block_table_kernel(uint32_t* __restrict__ bt, int n) {
 // grid = (16 KB pieces of a block, mapped pairs).  Either side may be pinned host memory (UVA: the kernel
 // reads / writes it over PCIe / C2C directly) or a peer GPU's cache (peer access enabled): no per-block
 // cudaMemcpy calls, no staging.
+template <typename V>
 __global__ void __launch_bounds__(256)
 swap_blocks_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                    const int64_t* __restrict__ pairs, int64_t block_bytes) {
   const int64_t sb = pairs[2 * blockIdx.y], db = pairs[2 * blockIdx.y + 1];
-  const uint4* s = reinterpret_cast<const uint4*>(src + sb * block_bytes);
-  uint4* d = reinterpret_cast<uint4*>(dst + db * block_bytes);
-  const int64_t n16 = block_bytes >> 4;
+  const V* s = reinterpret_cast<const V*>(src + sb * block_bytes);
+  V* d = reinterpret_cast<V*>(dst + db * block_bytes);
+  const int64_t nv = block_bytes / static_cast<int64_t>(sizeof(V));
   const int64_t lo = static_cast<int64_t>(blockIdx.x) * 1024;
-  const int64_t hi = lo + 1024 < n16 ? lo + 1024 : n16;
-  uint4 v[4];
+  const int64_t hi = lo + 1024 < nv ? lo + 1024 : nv;
+  V v[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int64_t i = lo + threadIdx.x + j * 256;
@@ -477,9 +478,20 @@ void b200_swap_blocks(const void* src_cache, void* dst_cache, const int64_t* pai
   B200_CHECK_ARG(src_cache && dst_cache && pairs_dev, "swap_blocks: NULL pointer");
   B200_CHECK_ARG(block_bytes > 0 && block_bytes % 16 == 0, "swap_blocks: block bytes must be a multiple of 16");
   B200_CHECK_ARG(num_pairs <= 65535, "swap_blocks: at most 65535 blocks per call");
-  const unsigned pieces = static_cast<unsigned>((block_bytes / 16 + 1023) / 1024);
-  swap_blocks_kernel<<<dim3(pieces, num_pairs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(src_cache), static_cast<uint8_t*>(dst_cache), pairs_dev, block_bytes);
+  // 16-byte accesses when both sides allow it; the payloads of a PD wire frame sit at 8 (mod 16) -- the bincode
+  // length fields in front of them are 8 bytes -- and take the 8-byte flavour
+  const uintptr_t both = reinterpret_cast<uintptr_t>(src_cache) | reinterpret_cast<uintptr_t>(dst_cache);
+  B200_CHECK_ARG((both & 7) == 0, "swap_blocks: caches must be 8-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((both & 15) == 0) {
+    const unsigned pieces = static_cast<unsigned>((block_bytes / 16 + 1023) / 1024);
+    swap_blocks_kernel<uint4><<<dim3(pieces, num_pairs), 256, 0, st>>>(
+        static_cast<const uint8_t*>(src_cache), static_cast<uint8_t*>(dst_cache), pairs_dev, block_bytes);
+  } else {
+    const unsigned pieces = static_cast<unsigned>((block_bytes / 8 + 1023) / 1024);
+    swap_blocks_kernel<uint2><<<dim3(pieces, num_pairs), 256, 0, st>>>(
+        static_cast<const uint8_t*>(src_cache), static_cast<uint8_t*>(dst_cache), pairs_dev, block_bytes);
+  }
   B200_CUDA_LAUNCH_CHECK();
 }
 
