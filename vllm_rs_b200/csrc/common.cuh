@@ -200,19 +200,59 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// B200_MBAR_HINT_NS (compile time, experiment): suspend-time hint of try_wait.  Without a hint a waiting thread
+// comes back after ~20 cycles and re-polls: the single-lane producer / issuer warps of the decode GEMMs then
+// spend a measurable share of the SM's issue slots spinning (profiles/r2_c_dec_gemm_sass_histogram.txt).
+#ifndef B200_MBAR_HINT_NS
+#define B200_MBAR_HINT_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if B200_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(B200_MBAR_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  return mbar_try_wait_addr(smem_u32(bar), parity);
+}
+// Non-suspending probe (mbarrier.test_wait): issued EARLY, its ~200-cycle round trip to the barrier runs under
+// independent ALU work; the result is consumed later (a false answer falls back to the try_wait loop).
+__device__ __forceinline__ uint32_t mbar_probe_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// B200_MBAR_SPIN_SLEEP_NS (compile time, experiment): back-off between polls of the pointer flavour (the single-lane
+// producer / issuer roles use it; the dequant warps poll through mbar_try_wait_addr directly)
+#ifndef B200_MBAR_SPIN_SLEEP_NS
+#define B200_MBAR_SPIN_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+#if B200_MBAR_SPIN_SLEEP_NS > 0
+    __nanosleep(B200_MBAR_SPIN_SLEEP_NS);
+#endif
   }
 }
 

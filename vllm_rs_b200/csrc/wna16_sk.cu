@@ -129,16 +129,11 @@ __device__ __forceinline__ const float* part_ptr(const float* partials, const Co
 }
 
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-               "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  if (ok) return;
+  if (mbar_try_wait_addr(bar, parity)) return;
   const long long t0 = clock64();
-  do {
-    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && clock64() - t0 > 4000000000LL) __trap();        // ~2 s: a protocol bug fails the launch, never hangs
-  } while (!ok);
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();               // ~2 s: a protocol bug fails the launch, never hangs
+  }
 }
 // long waits of warps that are off the critical path (epilogue warps): back off instead of competing for issue slots
 __device__ __forceinline__ void wait_bar_sleepy(uint32_t bar, uint32_t parity) {

@@ -44,6 +44,18 @@ __device__ uint32_t* g_dec_trace = nullptr;
 #define DEC_TRE(k) do { } while (0)
 #endif
 
+#ifndef B200_DEC_EXP
+#define B200_DEC_EXP 0            // timing experiments (side builds only; results are wrong on purpose): bit 0 no TMEM
+#endif                            // stores, bit 1 no MMAs, bit 2 no activation loads
+#ifndef B200_DEC_PROBE
+#define B200_DEC_PROBE 0          // 1 = early non-blocking probes of afree / wfull: measured neutral (profiles/r2_v_*)
+#endif
+#ifndef B200_DEC_UNROLL
+#define B200_DEC_UNROLL 0         // 1 = ring-unrolled dequant loop: -5 % in tools/gemm_bench.py, nothing in the decode
+#endif                            // step (cold instruction fetch of a 50 % larger kernel): the round-1 loop stays the default
+#ifndef B200_DEC_SXS
+#define B200_DEC_SXS 3            // activation super-stages
+#endif
 #ifndef B200_DEC_GROUPS
 #define B200_DEC_GROUPS 4          // dequant groups (experiment: -DB200_DEC_GROUPS=5 via B200_NVCC_EXTRA)
 #endif
@@ -64,7 +76,7 @@ struct Cfg {
   static constexpr int kWSBytes = kSuper * kWBytes;                       // 16 KB (4-bit) / 32 KB
   static constexpr int kXSBytes = kSuper * kXBytes;
   static constexpr int kSWS = 96 * 1024 / kWSBytes;                       // weight super-stages (96 KB)
-  static constexpr int kSXS = 3;                                          // activation super-stages
+  static constexpr int kSXS = NT <= 32 ? B200_DEC_SXS : 3;                // activation super-stages
   static constexpr int kXOff = 0;
   static constexpr int kWOff = kSXS * kXSBytes;
   static constexpr int kScaleOff = kWOff + kSWS * kWSBytes;               // [groups][128] fp16
@@ -189,8 +201,12 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const int xs = j % C::kSXS;
         mbar_wait(&xempty[xs], ((j / C::kSXS) & 1) ^ 1);
         DEC_TR(6, j * C::kSuper);
+#if B200_DEC_EXP & 4           // TIMING EXPERIMENT bit 2: the stage is declared full without loading anything
+        mbar_arrive(&xfull[xs]);
+#else
         mbar_arrive_expect_tx(&xfull[xs], C::kXSBytes);       // TMA zero-fills rows >= M / chunks >= KC
         tma_load_3d(smem + C::kXOff + xs * C::kXSBytes, &xmap, &xfull[xs], 0, 0, c0 + j * C::kSuper);
+#endif
       }
     }
   } else if (warp >= kDqWarps + 2) {
@@ -207,17 +223,24 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const int as = grp * kAS + (it % kAS);
         const int xs = it % C::kSXS;                 // chunk i = 4 * it + grp: slot grp of super-chunk it
         DEC_TR(7, i);
+#if B200_DEC_PROBE
+        mbar_wait(&xfull[xs], (it / C::kSXS) & 1);   // long since complete: its round trip runs before the dequant
+        mbar_wait(&stored[as], (it / kAS) & 1);      // warps arrive, not after
+#else
         mbar_wait(&stored[as], (it / kAS) & 1);
         mbar_wait(&xfull[xs], (it / C::kSXS) & 1);
+#endif
         tc_fence_after();
         DEC_TR(5, i);
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
         const uint64_t bdesc =
             make_smem_desc_sw128(smem_u32(smem + C::kXOff + xs * C::kXSBytes + grp * C::kXBytes));
+#if !(B200_DEC_EXP & 2)      // TIMING EXPERIMENT bit 1 (side builds): no MMAs (commits only)
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
           tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
                     (it > 0 || ks > 0) ? 1u : 0u);
+#endif
         tc_commit(&xempty[xs]);
         tc_commit(&afree[as]);
         if (i + kGroups >= nchunks) tc_commit(&gdone[grp]);      // the group's last chunk
@@ -240,20 +263,17 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const uint32_t s_wfull = smem_u32(wfull), s_wempty = smem_u32(wempty);
     const uint32_t s_afree = smem_u32(afree), s_stored = smem_u32(stored);
     auto bar_wait = [](uint32_t bar, uint32_t parity) {
-      uint32_t ok;
-      do {
-        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-      } while (!ok);
+      while (!mbar_try_wait_addr(bar, parity)) {
+      }
     };
     auto bar_arrive = [](uint32_t bar) {
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
     };
     int ss = 0;                         // weight super-stage of the group's current chunk
     uint32_t ss_phase = 0;
-    auto load_words = [&](uint32_t (&dst)[W], int ci) {
+    auto load_words = [&](uint32_t (&dst)[W], int ci, uint32_t probed = 0) {
       if (q4 == 0 && lane == 0) DEC_TR(1, ci);
-      bar_wait(s_wfull + ss * 8, ss_phase);
+      if (!probed) bar_wait(s_wfull + ss * 8, ss_phase);
       if (q4 == 0 && lane == 0) DEC_TR(2, ci);
       const uint32_t addr = s_base + C::kWOff + ss * C::kWSBytes + grp * C::kWBytes + ch * 16;
 #pragma unroll
@@ -307,6 +327,124 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         }
       }
     };
+#if B200_DEC_UNROLL
+    {
+      // Ring-unrolled form of the loop below (round 2).  The ncu source view says the loop is bound by its serial
+      // bookkeeping, not by the dequant arithmetic (removing 60 % of the arithmetic bought 10 %): ring-stage indices,
+      // barrier addresses, phase bits and TMEM columns recomputed per chunk with dependent ISETP / SEL / IMAD chains.
+      // Unrolling by P = lcm(weight stages, A stages) chunks makes every one of them a compile-time constant of the
+      // unrolled copy; what is left per chunk is the waits, the loads, the stores and the arithmetic.
+      constexpr int kP = (C::kSWS % kAS == 0) ? C::kSWS : C::kSWS * kAS;       // lcm for (6,3) (3,3) (6,2) (3,2)
+      static_assert(kP % C::kSWS == 0 && kP % kAS == 0, "ring period");
+      const uint32_t s_wq = s_base + C::kWOff + grp * C::kWBytes + ch * 16;    // this thread's words of stage 0
+      const uint32_t a_tq = tmem_base + C::kACol0 + grp * kAS * 32 + lane_base;
+      const uint32_t s_af = s_afree + grp * kAS * 8, s_st = s_stored + grp * kAS * 8;
+      const bool lane0 = lane == 0;
+      uint32_t wpar = 0;                // parity of wfull for the stages of this pass over the ring
+      uint32_t apar = 1;                // parity of afree (the first round passes)
+      uint32_t zlo = 0, zhi = 0, s2 = 0;
+      auto set_group = [&](int g) {
+        cur_g = g;
+        uint32_t sbits;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sbits) : "r"(s_scale + g * (kTileN * 2)));
+        uint32_t z = 1u << (BITS - 1);
+        if (a.qzeros) {
+          uint32_t zw;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(s_zero + g * (ZW * 4)));
+          z = ((zw >> zshift) & zmask) + static_cast<uint32_t>(zadd);
+        }
+        // the constants of make_dq as bit patterns (no int -> half conversions): 1024 + z, 64 + z, (s, s)
+        s2 = sbits * 0x00010001u;
+        zlo = (0x6400u | z) * 0x00010001u;
+        zhi = (0x5400u | (z << 4)) * 0x00010001u;
+        dq.s2 = u32_as_h2(s2);
+        dq.zlo = u32_as_h2(zlo);
+        dq.zhi = u32_as_h2(zhi);
+      };
+      auto dq_half = [&](int hf, uint32_t (&dst)[16]) {
+        if (BITS == 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            uint32_t o4[4];
+            dequant4_word(cur[hf * 4 + w], dq, o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[w * 4 + e] = o4[e];
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            uint32_t o2[2];
+            dequant8_word(cur[(hf * 8 + w) % W], dq, o2);
+            dst[w * 2] = o2[0];
+            dst[w * 2 + 1] = o2[1];
+          }
+        }
+      };
+      const bool per_half = a.g_shift == 5;            // 32-wide groups: the two halves of a chunk differ
+      bool have_pending = false;
+      bool running = grp < nchunks;
+      int i = grp;
+      while (running) {
+#pragma unroll
+        for (int u = 0; u < kP; ++u) {
+          if (i >= nchunks) { running = false; break; }
+          // every index below is a constant of this unrolled copy
+          const int ssn = (u + 1) % C::kSWS;                                   // stage of the group's NEXT chunk
+          const uint32_t wphn = wpar ^ static_cast<uint32_t>(((u + 1) / C::kSWS) & 1);
+          const int asl = u % kAS, aslp = (u + kAS - 1) % kAS;
+          const uint32_t aph = apar ^ static_cast<uint32_t>((u / kAS) & 1);
+          const bool more = i + kGroups < nchunks;
+          uint32_t lo[16], hi[16];
+          const uint32_t af_ok = mbar_probe_addr(s_af + asl * 8, aph);
+          const int g = a.g_shift >= 0 ? (((c0 + i) * kChunkK) >> a.g_shift) - g_first : 0;
+          if (g != cur_g) set_group(g);
+          dq_half(0, lo);
+          if (have_pending) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane0) bar_arrive(s_st + aslp * 8);
+            if (q4 == 0 && lane0) DEC_TR(4, i - kGroups);
+          }
+          if (!af_ok) bar_wait(s_af + asl * 8, aph);
+          tc_fence_after();
+          if (q4 == 0 && lane0) DEC_TR(3, i);
+          tmem_st_x16(a_tq + asl * 32, lo);
+          const uint32_t wf_ok = more ? mbar_probe_addr(s_wfull + ssn * 8, wphn) : 0u;
+          if (per_half) {
+            const int g1 = (((c0 + i) * kChunkK + 32) >> 5) - g_first;
+            if (g1 != cur_g) set_group(g1);
+          }
+          dq_half(1, hi);
+          if (more) {
+            if (q4 == 0 && lane0) DEC_TR(1, i + kGroups);
+            if (!wf_ok) bar_wait(s_wfull + ssn * 8, wphn);
+            if (q4 == 0 && lane0) DEC_TR(2, i + kGroups);
+#pragma unroll
+            for (int sub = 0; sub < W / 4; ++sub)
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(cur[sub * 4]), "=r"(cur[sub * 4 + 1]), "=r"(cur[sub * 4 + 2]), "=r"(cur[sub * 4 + 3])
+                           : "r"(s_wq + ssn * C::kWSBytes + sub * kTileN * 16));
+            __syncwarp();
+            if (lane0) bar_arrive(s_wempty + ssn * 8);
+          }
+          tmem_st_x16(a_tq + asl * 32 + 16, hi);
+          have_pending = true;
+          i += kGroups;
+        }
+        wpar ^= static_cast<uint32_t>((kP / C::kSWS) & 1);
+        apar ^= static_cast<uint32_t>((kP / kAS) & 1);
+      }
+      if (have_pending) {
+        // the last chunk's stage: chunk ordinal (count - 1) % kAS
+        const int cnt = (nchunks - grp + kGroups - 1) / kGroups;
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane0) bar_arrive(s_st + ((cnt - 1) % kAS) * 8);
+      }
+    }
+#else
     {
       // Deferred completion: the TMEM stores of chunk i are awaited (and the issuer signalled)
       // only after the first half of chunk i+1 has been dequantised, so tcgen05.st latency
@@ -314,6 +452,14 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       int pending_as = -1;
       for (int i = grp; i < nchunks; i += kGroups) {
         uint32_t lo[16], hi[16];
+        const int as = grp * kAS + as_l;
+#if B200_DEC_PROBE
+        // is the A stage free?  Asked before the ALU work whose result goes there (a passing mbarrier wait costs a
+        // ~200-cycle round trip: profiles/r2_t_dec_trace_floor.txt)
+        const uint32_t af_ok = mbar_probe_addr(s_afree + as * 8, as_phase);
+#else
+        const uint32_t af_ok = 0;
+#endif
         dequant_half(i, 0, lo);
         if (pending_as >= 0) {
           tc_wait_st();
@@ -322,15 +468,27 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           if (lane == 0) bar_arrive(s_stored + pending_as * 8);
           if (q4 == 0 && lane == 0) DEC_TR(4, i - kGroups);
         }
-        const int as = grp * kAS + as_l;
         const uint32_t a_tmem = tmem_base + C::kACol0 + as * 32;
-        bar_wait(s_afree + as * 8, as_phase);
+        if (!af_ok) bar_wait(s_afree + as * 8, as_phase);
         tc_fence_after();
         if (q4 == 0 && lane == 0) DEC_TR(3, i);
+#if !(B200_DEC_EXP & 1)      // TIMING EXPERIMENT bit 0 (side builds): no TMEM stores
         tmem_st_x16(a_tmem + lane_base, lo);
+#else
+        asm volatile("" ::"r"(lo[0]), "r"(lo[5]), "r"(lo[10]), "r"(lo[15]));
+#endif
+#if B200_DEC_PROBE
+        const uint32_t wf_ok = (i + kGroups < nchunks) ? mbar_probe_addr(s_wfull + ss * 8, ss_phase) : 0;
+#else
+        const uint32_t wf_ok = 0;
+#endif
         dequant_half(i, 1, hi);
-        if (i + kGroups < nchunks) load_words(cur, i + kGroups);
+        if (i + kGroups < nchunks) load_words(cur, i + kGroups, wf_ok);
+#if !(B200_DEC_EXP & 1)
         tmem_st_x16(a_tmem + lane_base + 16, hi);
+#else
+        asm volatile("" ::"r"(hi[0]), "r"(hi[5]), "r"(hi[10]), "r"(hi[15]));
+#endif
         pending_as = as;
         if (++as_l == kAS) { as_l = 0; as_phase ^= 1; }
       }
@@ -341,6 +499,7 @@ wna16_tc_dec_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         if (lane == 0) bar_arrive(s_stored + pending_as * 8);
       }
     }
+#endif
     // ------------------------------------------------------------ epilogue
     // (the kernel is templated on the epilogue kind: one lean finaliser per kernel -- code
     // size and register allocation of this tail were measured to move the whole GEMM by 2-5 us)
