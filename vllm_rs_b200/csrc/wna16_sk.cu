@@ -5,11 +5,11 @@
 // the work is cut and who does what.  Motivation (round-2 measurements of the round-1 kernel,
 // profiles/r2_b_dec_gemm_diet_experiments.txt, r2_c_dec_gemm_sass_histogram.txt): two thirds of its issued
 // instructions are pipeline bookkeeping, gate|up runs 1.51 waves, ~4 us of serial epilogue per launch.
-// Outcome (profiles/r2_j_sk_vs_dec.txt, six measured iterations): bit-reproducible and inside the same tolerances
+// Outcome (profiles/r2_j_sk_vs_dec.txt, nine measured iterations): bit-reproducible and inside the same tolerances
 // on every shape / epilogue (tests/test_kernels_gpu.py::test_wna16_streamk_decode), FASTER than the round-1 kernel
-// only for small batches on big-N projections (gate|up at one token: 24.0 vs 30.0 us, 2.44 TB/s), SLOWER at 32
-// tokens (86-108 vs 65.9 us per layer) -- so the automatic dispatch uses it only there (sk_mode below) and the
-// round-1 kernel stays the batch-32 path.
+// for small batches on big-N projections (gate|up at one token: 25.5 vs 30.0 us, 2.3 TB/s; at 16 tokens 28.8 vs
+// 30.7), slower at 32 tokens (73.9 vs 65.7 us per layer) -- so the automatic dispatch uses it only there (sk_mode
+// below) and the round-1 kernel stays the batch-32 path.
 //
 //   * WORK = units of 128 K (two 64-K chunks) of one 128-channel tile.  The tile-major weight layout makes
 //     the flattened (tile, unit) list ONE contiguous byte range, so CTA b of a one-CTA-per-SM grid simply
@@ -78,7 +78,8 @@ struct Cfg {
   static constexpr int kNumBars = 2 * kSWS + 2 * kDG * kSXS + 2 * kDG * kAS + 2 * kDG * kDB + 2 * kMaxSeg;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kFlagOff = kTmemPtrOff + 16;
-  static constexpr int kTidOff = kFlagOff + 16;                 // one word per thread (see the kernel prologue)
+  static constexpr int kPendOff = kFlagOff + 16;                // finaliser runs deferred to the end: count + tile ids
+  static constexpr int kTidOff = kPendOff + 16 + kMaxSeg * 4;   // one word per thread (see the kernel prologue)
   static constexpr int kAlloc = kTidOff + kThreads * 4 + 1024;
   static_assert(kAlloc <= 227 * 1024, "shared memory budget");
   static_assert(kXBytes % 1024 == 0, "SWIZZLE_128B tiles are 1024-byte aligned");
@@ -182,12 +183,12 @@ __device__ __forceinline__ void dq8_exact(uint32_t x, __half2 zlo, uint32_t (&ou
 }
 
 // ---- tile finaliser over per-CTA partial slots (the row / column logic is wna16.cuh's; only the addressing of
-// the partials differs from split_reduce_rows).  kEpiThreads threads: lane = 4 channels, warp = row phase.
+// the partials differs from split_reduce_rows).  nphase warps: lane = 4 channels, warp = row phase.
 template <int EPI>
-__device__ __forceinline__ void reduce_tile(const Args& a, const SplitOut& o, int nt, int tid) {
+__device__ __forceinline__ void reduce_tile(const Args& a, const SplitOut& o, int nt, int tid, int nphase) {
   const int M = a.M, KP = a.KP;
   const int lane = tid & 31, phase = tid >> 5;
-  constexpr int nphase = kEpiWarps, R = 2;
+  constexpr int R = 2;
   constexpr bool kSilu = EPI == B200_EPI_SILU_MUL;
   constexpr bool kMayPair = kSilu || EPI == kEpiRopeKv;
   constexpr int U = kMayPair ? 2 : 4;
@@ -288,6 +289,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   uint64_t* hfree = segdone + kMaxSeg;                 // [segment]: the epilogue warps have read them
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kTmemPtrOff);
   volatile int* s_flag = reinterpret_cast<volatile int*>(smem + C::kFlagOff);
+  volatile int* s_pend = reinterpret_cast<volatile int*>(smem + C::kPendOff);      // [0] = count, [1 ..] = tiles
   // the same barriers as shared-space addresses
   const uint32_t s_wfull = s_base + C::kBarOff, s_wempty = s_wfull + C::kSWS * 8;
   const uint32_t s_xfull = s_wempty + C::kSWS * 8, s_xempty = s_xfull + kDG * C::kSXS * 8;
@@ -297,6 +299,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   const uint32_t s_hfree = s_segdone + kMaxSeg * 8;
 
   if (tid_o == 0) {
+    s_pend[0] = 0;
     for (int i = 0; i < C::kSWS; ++i) {
       mbar_init(&wfull[i], 1);
       mbar_init(&wempty[i], kDqWarps);
@@ -330,6 +333,98 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   pdl_trigger();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // ---- one tile segment's epilogue, run by `nw` cooperating warps (warp `wid`, thread `tid_c` of them, named barrier
+  // `bar_id`): add the three groups' sums (fixed order), store the CTA's partial tile (or the output itself when
+  // the CTA holds the whole tile and the epilogue is plain), meet the other contributors at the arrival counter and,
+  // if last, run the fused finaliser.  Intermediate segments are done by the two epilogue warps while the next tile
+  // streams; the CTA's LAST segment is done by the dequant and producer warps as well (16 warps: they are idle by then,
+  // and a 32-row finaliser on two warps was the longest piece of the kernel's tail).
+  constexpr int EPXL = kBf16 ? B200_EPI_NONE : EPI;
+  auto segment_epilogue = [&](int t, int seg, int wid, int nw, int tid_c, int bar_id, bool free_slots) {
+    constexpr bool kPlainL = EPXL == B200_EPI_NONE;
+    constexpr bool kSiluL = EPXL == B200_EPI_SILU_MUL;
+    SplitOut o;
+    o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
+    o.M = M; o.N = N; o.splits = 1; o.epilogue = EPXL; o.fe = a.fe;
+    const int half_tiles = (N / kTileN) >> 1;
+    const uint32_t s_hl = s_base + C::kHOff + lane * 16;
+    const Contrib k = contrib_of(t, KP, a.share, a.smax);
+    const bool direct = kPlainL && a.fe.ssq_in == nullptr && k.cnt == 1;
+    if (free_slots) wait_bar_sleepy(s_segdone + seg * 8, 0); else wait_bar(s_segdone + seg * 8, 0);
+    float* P = a.partials + (static_cast<size_t>(b) * a.smax + seg) * (static_cast<size_t>(M) * kTileN);
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (direct && a.bias && !kBf16) half4_to_float(a.bias + t * kTileN + lane * 4, bv);
+    for (int m = wid; m < M; m += nw) {
+      float4 v[kDG];
+#pragma unroll
+      for (int g = 0; g < kDG; ++g)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[g].x), "=f"(v[g].y), "=f"(v[g].z), "=f"(v[g].w)
+                     : "r"(s_hl + g * C::kHBytes + m * (kTileN * 4)));
+      float sum[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+      for (int g = 1; g < kDG; ++g) {
+        sum[0] += v[g].x; sum[1] += v[g].y; sum[2] += v[g].z; sum[3] += v[g].w;
+      }
+      if (direct) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sum[e] += bv[e];
+        if constexpr (kBf16)
+          store_bf16x4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
+        else
+          store_half4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
+      } else {
+        *reinterpret_cast<float4*>(P + m * kTileN + lane * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+      }
+    }
+    if (free_slots) {
+      __syncwarp();
+      if (lane == 0) arrive_bar(s_hfree + seg * 8);
+    }
+    if (direct) return;
+    named_bar_sync(bar_id, nw * 32);                     // every cooperating warp's rows are stored
+    if (tid_c == 0) {
+      int cidx = t;
+      unsigned target = static_cast<unsigned>(k.cnt);
+      if (kSiluL) {
+        cidx = t % half_tiles;
+        const Contrib kg = contrib_of(cidx, KP, a.share, a.smax);
+        const Contrib ku = contrib_of(cidx + half_tiles, KP, a.share, a.smax);
+        target = static_cast<unsigned>(kg.cnt + ku.cnt);
+      }
+      // acq_rel RMW at gpu scope: releases this CTA's partial tile (the barrier above orders the other
+      // threads' stores before it), acquires the other contributors'
+      unsigned old;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.counters + cidx) : "memory");
+      const int last = (old == target - 1) ? 1 : 0;
+      if (last) a.counters[cidx] = 0;                   // self-reset (graph replay safe)
+      *s_flag = last;
+    }
+    named_bar_sync(bar_id, nw * 32);
+    const bool last = *s_flag != 0;
+    if (free_slots) {
+      // intermediate segment (two warps): a finaliser run here would hold them for 32 rows x L2 round trips while
+      // later segments queue up behind; note the tile and let all sixteen warps run it at the end
+      if (last && tid_c == 0) {
+        const int np = s_pend[0];
+        s_pend[1 + np] = t;
+        s_pend[0] = np + 1;
+      }
+      named_bar_sync(bar_id, nw * 32);                   // s_flag is rewritten by the next segment
+      return;
+    }
+    if (last) reduce_tile<EPXL>(a, o, t, tid_c, nw);
+    const int np = s_pend[0];                            // written before the epilogue warps joined this barrier
+    for (int q = 0; q < np; ++q) reduce_tile<EPXL>(a, o, s_pend[1 + q], tid_c, nw);
+    if (EPXL == kEpiPushPeers && (last || np > 0)) {
+      // one signal per finished tile: the consumer counts tiles (comm.cu), so bump once per tile
+      const int bumps = (last ? 1 : 0) + np;
+      for (int q = 0; q < bumps; ++q) push_signal(o.fe, tid_c, nw * 32, bar_id + 1);
+    }
+  };
+  constexpr int kAllEpiWarps = kIssWarp0;              // the CTA's last segment: warps 0 .. 15 (dequant, epilogue, the two producers)
+  static_assert(kAllEpiWarps == 16, "32 token rows = one pass of the finaliser (2 rows per warp)");
+
   if (warp == kWProdWarp) {
     // ------------------------------------------------------------ weight producer: one contiguous stream
     if (lane == 0) {
@@ -344,6 +439,12 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         bulk_load_1d(smem + C::kWOff + slot * C::kWStage, src + static_cast<size_t>(s) * C::kWStage, bytes,
                      &wfull[slot]);
       }
+    }
+    __syncwarp();
+    {
+      const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
+      pdl_wait();
+      segment_epilogue(t_last, t_last - t_first, warp, kAllEpiWarps, warp * 32 + lane, 3, false);
     }
   } else if (warp == kXProdWarp) {
     // ------------------------------------------------------------ activation producer (ring of kDG * kSXS units)
@@ -360,6 +461,12 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         pos_advance(p, 1, KP);
         if (++slot == R) { slot = 0; ph ^= 1; }
       }
+    }
+    __syncwarp();
+    {
+      const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
+      pdl_wait();
+      segment_epilogue(t_last, t_last - t_first, warp, kAllEpiWarps, warp * 32 + lane, 3, false);
     }
   } else if (warp >= kIssWarp0) {
     // ------------------------------------------------------------ MMA issuers (one per dequant group)
@@ -597,80 +704,16 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       drain(p_prev, it - 1, s_prev);
     }
     flush_until(t_last + 1);
+    pdl_wait();                                          // first global writes of this role
+    segment_epilogue(t_last, t_last - t_first, warp, kAllEpiWarps, warp * 32 + lane, 3, false);
   } else {
     // ------------------------------------------------------------ epilogue warps: group sums -> partial tile -> meeting point
     const int tid = static_cast<int>(tid_o) - kEpiWarp0 * 32;
     const int ewarp = tid >> 5;
-    constexpr bool kPlain = EPX == B200_EPI_NONE;
-    constexpr bool kSilu = EPX == B200_EPI_SILU_MUL;
     pdl_wait();
-    SplitOut o;
-    o.partials = a.partials; o.counters = a.counters; o.bias = a.bias; o.c = a.c;
-    o.M = M; o.N = N; o.splits = 1; o.epilogue = EPX; o.fe = a.fe;
     const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
-    const int half_tiles = (N / kTileN) >> 1;
-    const uint32_t s_h = s_base + C::kHOff + lane * 16;
-    for (int t = t_first; t <= t_last; ++t) {
-      const int seg = t - t_first;
-      const Contrib k = contrib_of(t, KP, a.share, a.smax);
-      const bool direct = kPlain && a.fe.ssq_in == nullptr && k.cnt == 1;
-      wait_bar_sleepy(s_segdone + seg * 8, 0);
-      // rows ewarp, ewarp + kEpiWarps, ...: lane = 4 channels; the three groups' sums are added in group order
-      float* P = a.partials + (static_cast<size_t>(b) * a.smax + seg) * (static_cast<size_t>(M) * kTileN);
-      float bv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (direct && a.bias && !kBf16) half4_to_float(a.bias + t * kTileN + lane * 4, bv);
-      for (int m = ewarp; m < M; m += kEpiWarps) {
-        float4 v[kDG];
-#pragma unroll
-        for (int g = 0; g < kDG; ++g)
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(v[g].x), "=f"(v[g].y), "=f"(v[g].z), "=f"(v[g].w)
-                       : "r"(s_h + g * C::kHBytes + m * (kTileN * 4)));
-        float sum[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
-#pragma unroll
-        for (int g = 1; g < kDG; ++g) {
-          sum[0] += v[g].x; sum[1] += v[g].y; sum[2] += v[g].z; sum[3] += v[g].w;
-        }
-        if (direct) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sum[e] += bv[e];
-          if constexpr (kBf16)
-            store_bf16x4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
-          else
-            store_half4(a.c + static_cast<size_t>(m) * N + t * kTileN + lane * 4, sum);
-        } else {
-          *reinterpret_cast<float4*>(P + m * kTileN + lane * 4) = make_float4(sum[0], sum[1], sum[2], sum[3]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) arrive_bar(s_hfree + seg * 8);
-      if (direct) continue;
-      named_bar_sync(1, kEpiThreads);                            // every epilogue warp's rows are stored
-      if (tid == 0) {
-        int cidx = t;
-        unsigned target = static_cast<unsigned>(k.cnt);
-        if (kSilu) {
-          cidx = t % half_tiles;
-          const Contrib kg = contrib_of(cidx, KP, a.share, a.smax);
-          const Contrib ku = contrib_of(cidx + half_tiles, KP, a.share, a.smax);
-          target = static_cast<unsigned>(kg.cnt + ku.cnt);
-        }
-        // acq_rel RMW at gpu scope: releases this CTA's partial tile (the barrier above orders the other
-        // threads' stores before it), acquires the other contributors'
-        unsigned old;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.counters + cidx) : "memory");
-        const int last = (old == target - 1) ? 1 : 0;
-        if (last) a.counters[cidx] = 0;                 // self-reset (graph replay safe)
-        *s_flag = last;
-      }
-      named_bar_sync(1, kEpiThreads);
-      const bool last = *s_flag != 0;
-      if (last) {
-        reduce_tile<EPX>(a, o, t, tid);
-        if (EPX == kEpiPushPeers) push_signal(o.fe, tid, kEpiThreads, 2);
-      }
-      named_bar_sync(1, kEpiThreads);                            // s_flag is rewritten by the next segment
-    }
+    for (int t = t_first; t < t_last; ++t) segment_epilogue(t, t - t_first, ewarp, kEpiWarps, tid, 1, true);
+    segment_epilogue(t_last, t_last - t_first, kDqWarps + ewarp, kAllEpiWarps, kDqWarps * 32 + tid, 3, false);
   }
   __syncthreads();
   if (warp == kWProdWarp) {
@@ -680,10 +723,10 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
 }
 
 // B200_DEC_SK: 0 = never, 1 = every shape the kernel takes (M <= 32), 2 (default) = where it measured faster than the
-// round-1 kernel on B200 (profiles/r2_j_sk_vs_dec.txt): at most four tokens AND at least 32 units per CTA, i.e. the
-// big-N projections (gate|up) of small decode batches.  At M = 32 the round-1 kernel stays ahead (65.9 vs 86-108 us per
-// layer): a unit's dequant -> MMA -> drain chain is ~2.3 us long, so shapes with few units per CTA are latency-bound,
-// and the 32-row epilogue runs on two warps instead of sixteen.
+// round-1 kernel on B200 (profiles/r2_j_sk_vs_dec.txt, last block): at most 16 tokens AND at least 32 units per CTA,
+// i.e. the big-N projections (gate|up) of small decode batches: 25.5 vs 30.0 us at one token, 28.8 vs 30.7 us at 16.
+// At 32 tokens the round-1 kernel stays ahead (65.7 vs 73.9 us per layer): the 32-column accumulator drain and the
+// 32-row epilogue cost more than the wave tail the stream-K grid removes.
 static int sk_mode() {
   static int v = -1;
   if (v < 0) {
@@ -702,7 +745,17 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   // one CTA per SM; never less than two units (four chunks) per CTA, as in the round-1 split rule
   long G = sm_count();
   if (G > units / 2) G = units / 2 > 0 ? units / 2 : 1;
-  const int share = static_cast<int>((units + G - 1) / G);
+  int share = static_cast<int>((units + G - 1) / G);
+  // Small-N projections (qkv, o, down): cut every tile into the SAME s <= 4 aligned pieces (s | KP), as the round-1
+  // kernel does -- the last arriver then sums at most four partial tiles, one load batch of the finaliser; a free-
+  // running share cut `o` into six and `down` into five or six.  Big-N projections keep the pure stream-K share.
+  if (static_cast<long>(tiles) * 4 <= sm_count() + sm_count() / 8) {
+    for (int sp = 4; sp >= 1; --sp)
+      if (KP % sp == 0 && static_cast<long>(tiles) * sp <= sm_count() && KP / sp >= 2) {
+        share = KP / sp;
+        break;
+      }
+  }
   G = (units + share - 1) / share;
   const int smax = (share + KP - 2) / KP + 1;            // tiles a range of `share` units can touch
   if (smax > kMaxSeg) return false;
@@ -762,7 +815,7 @@ bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16)
   if (p.M > 32) return false;
   if (!force && sk::sk_mode() == 2) {
     const long units = static_cast<long>(p.N / kTileN) * (p.K / sk::kUnitK);
-    if (p.M > 4 || units < 32L * sm_count()) return false;
+    if (p.M > 16 || units < 32L * sm_count()) return false;
   }
   if (p.K % sk::kUnitK != 0) return false;
   if (p.group_size < p.K) {                             // a 128-K unit must lie inside one quantisation group,
@@ -776,7 +829,8 @@ bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16)
     if (p.bits != 4 || p.epilogue != B200_EPI_NONE || p.bias || p.fe) return false;
     return p.M <= 16 ? sk::launch_epi<4, 16, sk::kEpiNoneBf16>(p, st) : sk::launch_epi<4, 32, sk::kEpiNoneBf16>(p, st);
   }
-  if (p.bits == 4) return p.M <= 16 ? sk::launch_nt<4, 16>(p, st) : sk::launch_nt<4, 32>(p, st);
+  static const bool force_nt32 = getenv("B200_SK_FORCE_NT32") != nullptr;      // experiment: 32-column tiles for any M
+  if (p.bits == 4) return (p.M <= 16 && !force_nt32) ? sk::launch_nt<4, 16>(p, st) : sk::launch_nt<4, 32>(p, st);
   return p.M <= 16 ? sk::launch_nt<8, 16>(p, st) : sk::launch_nt<8, 32>(p, st);
 }
 
