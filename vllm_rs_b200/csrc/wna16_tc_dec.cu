@@ -576,6 +576,12 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   int splits = sm_count() / tiles;
   if (splits < 1) splits = 1;
   if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  {
+    // more than eight K pieces per tile cost more at the meeting point than they save in the main loop (TP-rank
+    // shapes, profiles/r2_ad_tp_shape_splits.txt: qkv at TP = 8, 6 tiles x 16 pieces 7.7 us -> x 8 pieces 6.5 us)
+    static const int cap = getenv("B200_DEC_MAX_SPLITS") ? atoi(getenv("B200_DEC_MAX_SPLITS")) : 8;
+    if (cap > 0 && splits > cap) splits = cap;
+  }
   while (splits > 1 && static_cast<long>(splits) * p.N > kMaxSplitCols) --splits;
   if (p.no_split) splits = 1;
   int cps = (KC + splits - 1) / splits;
@@ -682,6 +688,7 @@ bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st) {
   int splits = sm_count() / (p.N / kTileN);
   if (splits < 1) splits = 1;
   if (splits > KC / 4) splits = KC / 4 > 0 ? KC / 4 : 1;
+  if (splits > 8) splits = 8;                 // same cap as launch_epi
   if (p.no_split) splits = 1;
   const int cps = (KC + splits - 1) / splits;
   const int groups_per_cta = p.group_size >= p.K ? 1 : (cps * kChunkK + p.group_size - 1) / p.group_size + 1;
