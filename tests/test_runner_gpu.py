@@ -431,3 +431,20 @@ def test_decode_small_batches(lib, nseq, plan):
         osch.postprocess(ids, toks)
         csch.postprocess(ids, toks)
         _sync_cache_to_gpu(oracle, runner)
+
+
+def test_runner_parity_with_the_streamk_gemm_forced():
+    """The automatic dispatch gives the stream-K decode GEMM (wna16_sk.cu) only big-N projections of small batches,
+    which the toy / TP-rank shapes of this file never are.  B200_DEC_SK=1 routes EVERY decode GEMM with M <= 32
+    through it -- the fused RoPE + KV-write, residual + norm and SiLU.mul finalisers included -- and the same
+    oracle comparisons must hold.  The switch is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B200_DEC_SK="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "test_decode_steps_match_oracle or test_decode_small_batches or "
+                              "test_run_decode_host_path_and_graphs"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

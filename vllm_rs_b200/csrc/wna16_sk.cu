@@ -5,35 +5,38 @@
 // the work is cut and who does what.  Motivation (round-2 measurements of the round-1 kernel,
 // profiles/r2_b_dec_gemm_diet_experiments.txt, r2_c_dec_gemm_sass_histogram.txt): two thirds of its issued
 // instructions are pipeline bookkeeping, gate|up runs 1.51 waves, ~4 us of serial epilogue per launch.
-// Outcome (profiles/r2_j_sk_vs_dec.txt, nine measured iterations): bit-reproducible and inside the same tolerances
-// on every shape / epilogue (tests/test_kernels_gpu.py::test_wna16_streamk_decode), FASTER than the round-1 kernel
-// for small batches on big-N projections (gate|up at one token: 25.5 vs 30.0 us, 2.3 TB/s; at 16 tokens 28.8 vs
-// 30.7), slower at 32 tokens (73.9 vs 65.7 us per layer) -- so the automatic dispatch uses it only there (sk_mode
-// below) and the round-1 kernel stays the batch-32 path.
+// Outcome (profiles/r2_j_sk_vs_dec.txt, ten measured iterations): bit-reproducible, the SAME weight arithmetic as
+// the reference and the round-1 kernel (w = fp16((q - z) * s), one rounding, before the MMA), parity green on every
+// shape / epilogue at kernel level and through the whole runner with every decode GEMM forced onto it
+// (tests/test_runner_gpu.py::test_runner_parity_with_the_streamk_gemm_forced).  FASTER than the round-1 kernel on
+// big-N projections in isolation (gate|up: 25.6 vs 30.0 us at one token, 31.2 vs 32.4 us at 32), slower on the
+// small-N ones (whole layer at 32 tokens 68.4 vs 65.7 us); in the decode step it wins up to 16 tokens -- the
+// automatic dispatch uses it there (sk_mode below).
 //
 //   * WORK = units of 128 K (two 64-K chunks) of one 128-channel tile.  The tile-major weight layout makes
 //     the flattened (tile, unit) list ONE contiguous byte range, so CTA b of a one-CTA-per-SM grid simply
 //     streams bytes [b*share, (b+1)*share) * unit_bytes: no wave tail, every SM busy on every shape.
 //     A tile cut by a CTA boundary is finished by the split meeting point (per-CTA partial slots, arrival
-//     counter, last arriver reduces in contributor order: deterministic).
-//   * the dequant threads write the EXACT integers (q - z) to TMEM as fp16 (lop3 magic numbers + one
-//     hsub2; no multiply).  Each 128-K unit accumulates into a fresh TMEM accumulator (two per dequant group, so
-//     the MMAs of the group's next unit run meanwhile); the SAME four warps drain it one unit later
-//     (tcgen05.ld) and fold the group scale in fp32: acc[m] += s[n, g] * sum_k (q - z) x.  This is
-//     the reference's w = (q - z) * s without the intermediate fp16 rounding of w (closer to the fp32
-//     truth, well inside the 1e-3 bar); it needs group_size = 128 * 2^k (or one group), else the round-1
-//     kernel runs.  The running sums live in registers for a whole tile segment.  (A first version drained
-//     every unit through four dedicated scale warps: one serial 170-instruction chain per unit, 1 640 cycles
-//     per unit.)
-//   * at the end of a tile segment the three groups leave their sums in shared memory; two EPILOGUE warps
-//     add them (fixed order), write the CTA's partial tile to L2, meet the other contributors at the arrival
-//     counter and, if last, run the fused tile finaliser of wna16.cuh -- while dequant / MMA are already on the
-//     CTA's next tile.
-//   * zero points and scales are read straight from global memory three units ahead (a 4-byte + 2-byte load
-//     per thread per 128 K): no staging ring, no extra barriers.
-//   * what still limits it (ncu source view of v4-v6): ~380 issued instructions per unit per dequant warp against
-//     176 of arithmetic, ~10 cycles per instruction per warp with three dequant warps per scheduler, and a
-//     ~2.3 us dequant -> MMA -> drain chain per unit and group that small shapes (10 units per CTA on qkv) cannot hide.
+//     counter, last arriver reduces in contributor order: deterministic).  Small-N projections are cut into the
+//     same <= 4 aligned pieces per tile as the round-1 kernel, so a finaliser sums at most four partial tiles.
+//   * three dequant groups (4 warps = 128 channels each) take the units round robin; a group dequantises a unit
+//     in registers (zero point and scale of the unit read from global memory three units ahead: no staging ring),
+//     tcgen05.st's the fp16 weights to TMEM, and its own issuer warp runs the eight tcgen05.mma of the unit into
+//     the group's accumulator of the current tile segment (two per group, alternating between segments).
+//   * at the end of a tile segment each group reads its accumulator out (tcgen05.ld, one unit later so the MMAs
+//     have finished) into shared memory; two EPILOGUE warps add the three groups' sums (fixed order), write the
+//     CTA's partial tile to L2 and meet the other contributors at the arrival counter -- while dequant / MMA are
+//     already on the CTA's next tile.  The fused finalisers of wna16.cuh (run by the last arriver of a tile) are
+//     deferred to the CTA's last segment, where sixteen warps (dequant, epilogue and producer warps, idle by
+//     then) run them: 32 token rows in one pass.
+//   * history (each step measured, profiles/r2_j_sk_vs_dec.txt): the first versions kept EXACT integers (q - z) in
+//     TMEM and folded the scale in fp32 after the MMA with a per-unit accumulator drain -- closer to the fp32 truth
+//     than the reference, but not the reference's arithmetic (one runner parity case fell outside the bar) and the
+//     drain chain cost more than the multiplies it saved; ptxas re-derived the shared-memory base and the thread
+//     index from S2R at every barrier until both were pinned; a 32-row finaliser on two warps was the longest
+//     piece of the tail.
+//   * what still limits it (ncu source view): ~10 cycles per instruction per dequant warp with three dequant warps
+//     per scheduler and a ~2 us dequant -> MMA chain per unit and group that small shapes cannot hide.
 #include <cstdlib>
 #include <cstring>
 
@@ -172,6 +175,16 @@ __device__ __forceinline__ void dq4_exact_bf16(uint32_t x, uint32_t zb, uint32_t
   for (int p = 0; p < 4; ++p) {
     const uint32_t v = lop3_or_and(x >> (4 * p), 0x000F000Fu, 0x43004300u);
     asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(out[p]) : "r"(v), "r"(zb));
+  }
+}
+// bf16 flavour of the reference arithmetic: w = bf16((q - z) * s), the difference exact, one rounding in the multiply
+__device__ __forceinline__ void dequant4_word_bf16(uint32_t x, uint32_t zb, uint32_t sb, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const uint32_t v = lop3_or_and(x >> (4 * p), 0x000F000Fu, 0x43004300u);
+    uint32_t d;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(zb));
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(out[p]) : "r"(d), "r"(sb));
   }
 }
 __device__ __forceinline__ void dq8_exact(uint32_t x, __half2 zlo, uint32_t (&out)[2]) {
@@ -477,13 +490,26 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       int ai = 0;
       uint32_t aphase = 0;
       int it = 0;
+      int k = -1;                                      // this group's tile segments so far (those it has units in)
+      Pos p = pos_of(u0 + grp, KP);
+      int tile_prev = -1;
+      uint32_t d_tmem = 0;
       for (int j = grp; j < n; j += kDG, ++it) {
         const int xs = (it % C::kSXS) * kDG + grp;               // unit j lives in ring slot j % (kDG * kSXS)
-        const int db = it & 1;
-        const uint32_t d_tmem = tmem_base + C::kDCol0 + (grp * kDB + db) * 32;
+        bool first = false;
+        if (p.tile != tile_prev) {
+          // a new tile segment of this group: fresh accumulator (two per group, alternating); the one it takes
+          // was last used by the group's segment k - 2 and must have been read out by the dequant warps
+          ++k;
+          tile_prev = p.tile;
+          d_tmem = tmem_base + C::kDCol0 + (grp * kDB + (k & 1)) * 32;
+          wait_bar(s_dfree + (grp * kDB + (k & 1)) * 8, ((k >> 1) & 1) ^ 1);
+          first = true;
+        }
+        Pos pn = p;
+        pos_advance(pn, kDG, KP);
+        const bool seg_last = j + kDG >= n || pn.tile != p.tile;
         wait_bar(s_xfull + xs * 8, (it / C::kSXS) & 1);
-        // accumulator `db` was last used by this group's unit it - 2: it must have been drained
-        wait_bar(s_dfree + (grp * kDB + db) * 8, ((it >> 1) & 1) ^ 1);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int as = grp * kAS + ai;
@@ -494,16 +520,17 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
 #pragma unroll
           for (int ks = 0; ks < kChunkK / 16; ++ks)
             tc_mma_ts(d_tmem, a_tmem + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), idesc,
-                      (cc > 0 || ks > 0) ? 1u : 0u);
+                      (first && cc == 0 && ks == 0) ? 0u : 1u);
           tc_commit(&afree[as]);
           if (++ai == kAS) { ai = 0; aphase ^= 1; }
         }
         tc_commit(&xempty[xs]);
-        tc_commit(&dfull[grp * kDB + db]);
+        if (seg_last) tc_commit(&dfull[grp * kDB + (k & 1)]);    // the group's sums of this tile are complete
+        p = pn;
       }
     }
   } else if (warp < kDqWarps) {
-    // ------------------------------------------------------------ dequant groups (dequantise, then drain one unit later)
+    // ------------------------------------------------------------ dequant groups
     const int grp = warp >> 2, q4 = warp & 3;
     const int ch = q4 * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
@@ -521,7 +548,6 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     uint32_t lane0 = lane == 0 ? 1u : 0u;
     asm volatile("" : "+r"(s_h), "+r"(s_w), "+r"(lane0));
     const unsigned short* scales_u16 = reinterpret_cast<const unsigned short*>(a.scales);
-    // zero word (low half... no: full word) and scale bits of a unit, read from global memory
     auto zload = [&](const Pos& q) -> uint32_t {
       if (!has_z) return 0u;
       return __ldg(a.qzeros + (static_cast<uint32_t>(q.pair >> a.gshift) * zrow + q.tile * ZWN + zword));
@@ -537,51 +563,37 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
                      : "=r"(dst[sub * 4]), "=r"(dst[sub * 4 + 1]), "=r"(dst[sub * 4 + 2]), "=r"(dst[sub * 4 + 3])
                      : "r"(addr + sub * kTileN * 16));
     };
-    float acc[NT];
-#pragma unroll
-    for (int m = 0; m < NT; ++m) acc[m] = 0.f;
     const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
-    int acc_tile = t_first;                            // the tile segment `acc` belongs to
-    // leave the sums of segments [acc_tile, upto) in shared memory (zeros for segments this group has no unit in)
-    auto flush_until = [&](int upto) {
-      while (acc_tile < upto) {
-        const int seg = acc_tile - t_first;
-        if (seg >= 1) wait_bar(s_hfree + (seg - 1) * 8, 0);      // the previous segment's sums have been read
+    // ---- a tile segment's sums of this group go to shared memory: read out of the group's accumulator (its
+    // segment ordinal kk picks the buffer and the barrier phase), or zeros when the group had no unit in the segment
+    auto flush = [&](int seg, int kk) {
+      if (seg >= 1) wait_bar(s_hfree + (seg - 1) * 8, 0);        // the previous segment's sums have been read
+      if (kk >= 0) {
+        const int gb = grp * kDB + (kk & 1);
+        wait_bar(s_dfull + gb * 8, (kk >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + C::kDCol0 + gb * 32 + lane_base;
 #pragma unroll
-        for (int m = 0; m < NT; ++m) {
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_h + m * (kTileN * 4)), "f"(acc[m]) : "memory");
-          acc[m] = 0.f;
+        for (int h0 = 0; h0 < NT; h0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(d_addr + h0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int m = 0; m < 16; ++m)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_h + (h0 + m) * (kTileN * 4)), "r"(v[m]) : "memory");
         }
+        tc_fence_before();
         __syncwarp();
-        if (lane0) arrive_bar(s_segdone + seg * 8);
-        ++acc_tile;
-      }
-    };
-    // accumulator of this group's unit `itp` (position q, scale bits sb): acc += s * D, then hand the buffer back
-    auto drain = [&](const Pos& q, int itp, uint32_t sb) {
-      flush_until(q.tile);
-      const float sc = kBf16 ? __uint_as_float(sb << 16) : __half2float(__ushort_as_half(static_cast<unsigned short>(sb)));
-      const int gb = grp * kDB + (itp & 1);
-      wait_bar(s_dfull + gb * 8, (itp >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[16];
-      const uint32_t d_addr = tmem_base + C::kDCol0 + gb * 32 + lane_base;
-      tmem_ld_x16(d_addr, v);
-      tc_wait_ld();
+        if (lane0) arrive_bar(s_dfree + gb * 8);
+      } else {
 #pragma unroll
-      for (int m = 0; m < 16; ++m) acc[m] = fmaf(sc, __uint_as_float(v[m]), acc[m]);
-      if constexpr (NT == 32) {
-        tmem_ld_x16(d_addr + 16, v);
-        tc_wait_ld();
+        for (int m = 0; m < NT; ++m)
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_h + m * (kTileN * 4)), "r"(0u) : "memory");
+        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane0) arrive_bar(s_dfree + gb * 8);
-      if constexpr (NT == 32) {
-#pragma unroll
-        for (int m = 0; m < 16; ++m) acc[16 + m] = fmaf(sc, __uint_as_float(v[m]), acc[16 + m]);
-      }
+      if (lane0) arrive_bar(s_segdone + seg * 8);
     };
+    int next_seg = 0;                                  // segments [0, next_seg) have been flushed by this warp
     if (grp < n) {
       Pos p = pos_of(u0 + grp, KP);
       uint32_t zq[kPF], sq[kPF];                       // zero words / scale bits of this group's next kPF units
@@ -602,17 +614,28 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
       uint32_t aphase = 1;                             // afree: the first round passes
       int pending = -1;
       uint32_t cur[W];
-      Pos p_prev = p;
-      uint32_t s_prev = 0;
+      int kk = -1;                                     // ordinal of the group's current segment (as the issuer counts)
+      int cur_seg = -1;
+      int pend_seg = -1, pend_kk = -1;                 // a finished segment whose read-out is deferred by one unit
+      while (next_seg < p.tile - t_first) flush(next_seg++, -1);   // segments before this group's first unit
       wait_bar(s_wfull, 0);
       load_chunk(cur, 0, 0);
-      int it = 0;
-      for (int j = grp; j < n; j += kDG, ++it) {
+      for (int j = grp; j < n; j += kDG) {
+        const int seg = p.tile - t_first;
+        if (seg != cur_seg) {
+          if (cur_seg >= 0) { pend_seg = cur_seg; pend_kk = kk; }
+          cur_seg = seg;
+          ++kk;
+        }
         const uint32_t z = has_z ? ((zq[0] >> zshift) & zmask) + zadd : (1u << (BITS - 1));
-        const __half2 zlo = u32_as_h2((0x6400u | z) * 0x00010001u);                // 1024 + z
-        const __half2 zhi = u32_as_h2((0x5400u | (z << 4)) * 0x00010001u);         // 64 + z (4-bit path)
+        // the constants of make_dq (wna16.cuh) as bit patterns: 1024 + z, 64 + z, (s, s) -- the SAME arithmetic as
+        // the round-1 kernel and the reference: w = fp16((q - z) * s), one rounding
+        DqConst dq;
+        dq.s2 = u32_as_h2(sq[0] * 0x00010001u);
+        dq.zlo = u32_as_h2((0x6400u | z) * 0x00010001u);
+        dq.zhi = u32_as_h2((0x5400u | (z << 4)) * 0x00010001u);
         const uint32_t zb16 = (0x4300u | z) * 0x00010001u;                          // bf16 128 + z
-        const uint32_t s_cur = sq[0];
+        const uint32_t sb16 = sq[0] * 0x00010001u;                                  // bf16 (s, s)
         const bool more = j + kDG < n;
 #pragma unroll
         for (int k = 0; k + 1 < kPF; ++k) {
@@ -624,27 +647,30 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
           sq[kPF - 1] = sload(pz);
           pos_advance(pz, kDG, KP);
         }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t lo[16], hi[16];
-          // ---- first half of the chunk (K 0..31)
+        auto dq_half = [&](int hf, uint32_t (&dst)[16]) {
           if (BITS == 4) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
               uint32_t o4[4];
-              if constexpr (kBf16) dq4_exact_bf16(cur[w], zb16, o4); else dq4_exact(cur[w], zlo, zhi, o4);
+              if constexpr (kBf16) dequant4_word_bf16(cur[hf * 4 + w], zb16, sb16, o4);
+              else dequant4_word(cur[hf * 4 + w], dq, o4);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) lo[w * 4 + e] = o4[e];
+              for (int e = 0; e < 4; ++e) dst[w * 4 + e] = o4[e];
             }
           } else {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
               uint32_t o2[2];
-              dq8_exact(cur[w], zlo, o2);
-              lo[w * 2] = o2[0];
-              lo[w * 2 + 1] = o2[1];
+              dequant8_word(cur[hf * 8 + w], dq, o2);
+              dst[w * 2] = o2[0];
+              dst[w * 2 + 1] = o2[1];
             }
           }
+        };
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t lo[16], hi[16];
+          dq_half(0, lo);
           if (pending >= 0) {
             // deferred completion of the previous chunk's TMEM stores: their latency ran under the ALU work above
             tc_wait_st();
@@ -657,24 +683,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
           wait_bar(s_afree + as * 8, aphase);
           tc_fence_after();
           tmem_st_x16(a_tmem, lo);
-          // ---- second half (K 32..63)
-          if (BITS == 4) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              uint32_t o4[4];
-              if constexpr (kBf16) dq4_exact_bf16(cur[4 + w], zb16, o4); else dq4_exact(cur[4 + w], zlo, zhi, o4);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) hi[w * 4 + e] = o4[e];
-            }
-          } else {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-              uint32_t o2[2];
-              dq8_exact(cur[8 + w], zlo, o2);
-              hi[w * 2] = o2[0];
-              hi[w * 2 + 1] = o2[1];
-            }
-          }
+          dq_half(1, hi);
           // ---- packed words of the next chunk (cur is consumed)
           if (cc == 0) {
             load_chunk(cur, wslot, 1);
@@ -691,19 +700,26 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
           pending = as;
           if (++ai == kAS) { ai = 0; aphase ^= 1; }
         }
-        // ---- the PREVIOUS unit of this group: its MMAs were issued a unit ago
-        if (it >= 1) drain(p_prev, it - 1, s_prev);
-        p_prev = p;
-        s_prev = s_cur;
+        // ---- a segment that ended one unit ago: its MMAs have had a unit's time to finish
+        if (pend_seg >= 0) {
+          flush(pend_seg, pend_kk);
+          next_seg = pend_seg + 1;
+          pend_seg = -1;
+          // segments between that one and the current one hold no unit of this group: their zeros go out NOW (a
+          // group that sat on them until its next crossing could stall the others' flushes behind hfree)
+          while (next_seg < cur_seg) flush(next_seg++, -1);
+        }
         pos_advance(p, kDG, KP);
       }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane0) arrive_bar(s_stored + pending * 8);
-      drain(p_prev, it - 1, s_prev);
+      while (next_seg < cur_seg) flush(next_seg++, -1);
+      flush(cur_seg, kk);
+      next_seg = cur_seg + 1;
     }
-    flush_until(t_last + 1);
+    while (next_seg <= t_last - t_first) flush(next_seg++, -1);
     pdl_wait();                                          // first global writes of this role
     segment_epilogue(t_last, t_last - t_first, warp, kAllEpiWarps, warp * 32 + lane, 3, false);
   } else {
@@ -723,10 +739,12 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
 }
 
 // B200_DEC_SK: 0 = never, 1 = every shape the kernel takes (M <= 32), 2 (default) = where it measured faster than the
-// round-1 kernel on B200 (profiles/r2_j_sk_vs_dec.txt, last block): at most 16 tokens AND at least 32 units per CTA,
-// i.e. the big-N projections (gate|up) of small decode batches: 25.5 vs 30.0 us at one token, 28.8 vs 30.7 us at 16.
-// At 32 tokens the round-1 kernel stays ahead (65.7 vs 73.9 us per layer): the 32-column accumulator drain and the
-// 32-row epilogue cost more than the wave tail the stream-K grid removes.
+// round-1 kernel on B200 IN THE DECODE STEP (profiles/r2_ai_sk_policy_ab.txt, same-box A/B): at most 16 tokens on
+// projections with at least 32 units per CTA (gate|up): b=1 2.55 -> 2.44 ms per step.  At 32 tokens the kernel is
+// faster in isolation (gate|up 31.2 vs 32.4 us) but the step gets SLOWER (5.05 -> 5.20 ms): a persistent grid ends on
+// all SMs at once, while the round-1 kernel's half-empty second wave lets the next GEMM's CTAs start streaming their
+// weights early under programmatic dependent launch.  The small-N projections (qkv, o, down: 10-25 units per CTA)
+// stay on the round-1 kernel at every batch: 12.4 / 8.7 / 16.2 vs 9.6 / 8.2 / 15.4 us at 32 tokens.
 static int sk_mode() {
   static int v = -1;
   if (v < 0) {
