@@ -207,6 +207,40 @@ void b200_pd_copy_blocks_peer(const void* const* remote_k, const void* const* re
                               int64_t block_bytes, int64_t stream);
 int32_t b200_enable_peer_access(int32_t dev, int32_t peer);
 
+/* ------------------------------------------------- engine <-> runner-process frames of the decode step
+ * runner/mod.rs:168-295 (MessageType; u32 LE length + bincode 1.3.1; every frame is answered by ONE ack byte 0x01),
+ * core/sequence.rs:52-83 (DecodeSequence), utils/config.rs:504-537 (SamplingParams).  A runner process built on this
+ * library reads RunDecode, derives the step metadata (core/runner.rs:1243-1264), runs b200_runner_decode_host and
+ * answers RunResponse; KVCacheSwap yields the (src, dst) pairs b200_swap_blocks takes.  MessageType variant indices:
+ * RunDecode 4, RunResponse 5, FinishDecode 8, Heartbeat 14, KVCacheSwap 21, KVCacheSwapResponse 22, ClearBlocks 31,
+ * ClearBlocksResponse 32, Shutdown 34.  Init / RunPrefill / RunEmbed carry whole Sequence / EngineConfig structs and
+ * stay with the Rust host.                                                                                          */
+typedef struct b200_wire_sampling {          /* the numeric fields of SamplingParams; has_* = Option is Some */
+  int32_t has_temperature, has_max_tokens, ignore_eos, has_top_k, has_top_p, has_frequency_penalty,
+      has_presence_penalty, reserved;
+  float temperature, top_p, frequency_penalty, presence_penalty;
+  int64_t max_tokens, top_k;
+} b200_wire_sampling;
+int32_t b200_wire_kind(const uint8_t* frame, int64_t len);
+int32_t b200_wire_parse_run_decode(const uint8_t* frame, int64_t len, int32_t max_seqs, int32_t max_blocks,
+                                   uint64_t* seq_ids, uint32_t* last_tokens, uint64_t* lens,
+                                   uint64_t* last_block_tokens, uint32_t* block_table_last, uint32_t* block_tables,
+                                   int32_t* num_blocks, b200_wire_sampling* sampling, int32_t* is_prefill);
+int64_t b200_wire_frame_run_decode(uint8_t* out, int64_t cap, int32_t n, const uint64_t* seq_ids,
+                                   const uint32_t* last_tokens, const uint64_t* lens,
+                                   const uint64_t* last_block_tokens, const uint32_t* block_table_last,
+                                   const uint32_t* block_tables, int32_t max_blocks, const int32_t* num_blocks,
+                                   const b200_wire_sampling* sampling, int32_t is_prefill);
+int64_t b200_wire_frame_run_response(uint8_t* out, int64_t cap, const uint32_t* ids, int32_t n);
+int32_t b200_wire_parse_run_response(const uint8_t* frame, int64_t len, uint32_t* ids, int32_t cap);
+int32_t b200_wire_parse_kv_swap(const uint8_t* frame, int64_t len, int64_t* pairs, int32_t cap, int32_t* swap_in);
+int64_t b200_wire_frame_kv_swap(uint8_t* out, int64_t cap, const int64_t* pairs, int32_t n, int32_t swap_in);
+int64_t b200_wire_frame_simple(uint8_t* out, int64_t cap, int32_t kind, int32_t payload_bytes, uint64_t value);
+void b200_wire_decode_metadata(int32_t n, const uint32_t* last_tokens, const uint64_t* lens,
+                               const uint64_t* last_block_tokens, const uint32_t* block_table_last,
+                               int32_t block_size, uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,
+                               uint32_t* context_lens);
+
 /* ------------------------------------------------- paged attention, decode
  * Replaces the decode branch of PagedAttention::forward (attention.rs:808-820).
  * out/q [B,H,D] fp16; block_tables u32 [B, max_blocks_per_seq] (zero padded);

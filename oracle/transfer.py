@@ -66,3 +66,67 @@ def parse_kv_remote_frame(buf: bytes):
     assert off + 24 == len(buf)
     return dict(seq_id=seq_id, first_token=first_token, layer_data=layers, num_blocks=num_blocks,
                 sending_time=sending_time, num_cached_tokens=cached)
+
+
+# ---------------------------------------------------------------- engine <-> runner frames of the decode step
+# /root/reference/src/runner/mod.rs:168-295 (MessageType variant order), core/sequence.rs:52-83 (DecodeSequence),
+# utils/config.rs:504-537 (SamplingParams: stop_token_ids is #[serde(skip)]; grammar travels as Option<String>).
+MT_RUN_DECODE, MT_RUN_RESPONSE, MT_FINISH_DECODE, MT_HEARTBEAT, MT_KV_SWAP, MT_KV_SWAP_RESPONSE = 4, 5, 8, 14, 21, 22
+MT_CLEAR_BLOCKS, MT_CLEAR_BLOCKS_RESPONSE, MT_SHUTDOWN = 31, 32, 34
+
+
+def _opt(fmt, v):
+    return b"\x00" if v is None else b"\x01" + struct.pack(fmt, v)
+
+
+def _opt_str(v):
+    return b"\x00" if v is None else b"\x01" + struct.pack("<Q", len(v)) + v
+
+
+def sampling_params(temperature=None, max_tokens=None, ignore_eos=False, top_k=None, top_p=None, session_id=None,
+                    frequency_penalty=None, presence_penalty=None, stop_sequences=None, thinking=None, mcp_mode=None,
+                    grammar=None, grammar_json=None, reasoning_effort=None) -> bytes:
+    b = _opt("<f", temperature) + _opt("<Q", max_tokens) + struct.pack("<B", 1 if ignore_eos else 0)
+    b += _opt("<q", top_k) + _opt("<f", top_p) + _opt_str(session_id)
+    b += _opt("<f", frequency_penalty) + _opt("<f", presence_penalty)
+    if stop_sequences is None:
+        b += b"\x00"
+    else:
+        b += b"\x01" + struct.pack("<Q", len(stop_sequences)) + b"".join(
+            struct.pack("<Q", len(x)) + x for x in stop_sequences)
+    b += _opt("<B", thinking) + _opt("<B", mcp_mode) + _opt_str(grammar) + _opt_str(grammar_json)
+    b += _opt("<I", reasoning_effort)
+    return b
+
+
+def run_decode_frame(seqs, is_prefill=False) -> bytes:
+    """seqs: dicts with id, last_token, len, last_block_tokens, block_table_last, block_tables, sampling (bytes)."""
+    b = struct.pack("<IQ", MT_RUN_DECODE, len(seqs))
+    for q in seqs:
+        b += struct.pack("<QIQQI", q["id"], q["last_token"], q["len"], q["last_block_tokens"], q["block_table_last"])
+        b += struct.pack("<Q", len(q["block_tables"])) + struct.pack(f"<{len(q['block_tables'])}I", *q["block_tables"])
+        b += q.get("sampling", sampling_params())
+    b += struct.pack("<B", 1 if is_prefill else 0)
+    return frame(b)
+
+
+def run_response_frame(ids) -> bytes:
+    return frame(struct.pack("<IQ", MT_RUN_RESPONSE, len(ids)) + struct.pack(f"<{len(ids)}I", *ids))
+
+
+def kv_swap_frame(pairs, swap_in) -> bytes:
+    b = struct.pack("<IQ", MT_KV_SWAP, len(pairs))
+    for s, d in pairs:
+        b += struct.pack("<QQ", s, d)
+    return frame(b + struct.pack("<B", 1 if swap_in else 0))
+
+
+def simple_frame(kind, payload=b"") -> bytes:
+    return frame(struct.pack("<I", kind) + payload)
+
+
+def decode_metadata(seqs, block_size=64):
+    """core/runner.rs:1248-1264."""
+    return dict(input_ids=[q["last_token"] for q in seqs], positions=[q["len"] - 1 for q in seqs],
+                context_lens=[q["len"] for q in seqs],
+                slot_mapping=[(q["block_table_last"] * block_size + q["last_block_tokens"] - 1) & 0xFFFFFFFF for q in seqs])

@@ -59,6 +59,15 @@ class PdKvHeader(C.Structure):
                 ("num_cached_tokens", C.c_uint64)]
 
 
+class WireSampling(C.Structure):
+    """b200_wire_sampling (include/b200_vllm.h)."""
+
+    _fields_ = [(n, c_i32) for n in ("has_temperature", "has_max_tokens", "ignore_eos", "has_top_k", "has_top_p",
+                                     "has_frequency_penalty", "has_presence_penalty", "reserved")] + \
+               [(n, c_f32) for n in ("temperature", "top_p", "frequency_penalty", "presence_penalty")] + \
+               [("max_tokens", c_i64), ("top_k", c_i64)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, c_vp, c_i64, c_vp, c_i64)
 
 # name -> (restype, argtypes)
@@ -95,6 +104,15 @@ _SIGS = {
     "b200_pd_import_blocks": (None, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_i64]),
     "b200_pd_copy_blocks_peer": (None, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_i64]),
     "b200_enable_peer_access": (c_i32, [c_i32, c_i32]),
+    "b200_wire_kind": (c_i32, [c_vp, c_i64]),
+    "b200_wire_parse_run_decode": (c_i32, [c_vp, c_i64, c_i32, c_i32] + [c_vp] * 9),
+    "b200_wire_frame_run_decode": (c_i64, [c_vp, c_i64, c_i32] + [c_vp] * 6 + [c_i32, c_vp, c_vp, c_i32]),
+    "b200_wire_frame_run_response": (c_i64, [c_vp, c_i64, c_vp, c_i32]),
+    "b200_wire_parse_run_response": (c_i32, [c_vp, c_i64, c_vp, c_i32]),
+    "b200_wire_parse_kv_swap": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp]),
+    "b200_wire_frame_kv_swap": (c_i64, [c_vp, c_i64, c_vp, c_i32, c_i32]),
+    "b200_wire_frame_simple": (c_i64, [c_vp, c_i64, c_i32, c_i32, C.c_uint64]),
+    "b200_wire_decode_metadata": (None, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_decode_fp8kv_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
