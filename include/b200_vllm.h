@@ -146,6 +146,14 @@ void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, co
                             int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
                             int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
                             int64_t stream);
+/* bf16 flavour (the reference's default dtype, utils/mod.rs:1919-1925): q / k / v, the caches and -- unless
+ * cos_sin_f32 -- the cos / sin tables are bf16; same arithmetic (fp32 rotation, one rounding on store).            */
+void b200_rope_kv_write_bf16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                             const int64_t* positions, const int64_t* slot_mapping,
+                             void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                             int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                             int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                             int64_t stream);
 /* Same with an FP8 KV cache (`--fp8-kvcache`; kvcache_allocator.rs:188-193,776 allocates the caches as
  * U8 in the same [num_blocks, block_size, Hkv, D] shape): the rotated fp16 K row and the V row are
  * stored as e4m3 bytes (round to nearest even, saturating at +-448, scale 1 -- attention-rs's own
@@ -255,6 +263,14 @@ void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
                                 int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
                                 float softcap, int32_t window, void* workspace, int64_t stream);
+/* bf16 flavour: q / out and both caches are bf16; S = Q K^T and P V run as bf16 x bf16 -> fp32 MMAs (P rounded
+ * to bf16), softmax in fp32.  Same workspace.                                                                      */
+void b200_paged_attn_decode_bf16(void* out, const void* q, const void* k_cache,
+                                 const void* v_cache, const uint32_t* block_tables,
+                                 const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                 int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                 float softcap, int32_t window, void* workspace, int64_t stream);
 int64_t b200_paged_attn_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim,
                                         int32_t max_blocks_per_seq);
 /* Decode attention over an FP8 (e4m3, scale 1) KV cache: same arguments, k_cache / v_cache are
@@ -288,6 +304,13 @@ void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k_cache, con
                               int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
                               int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
                               int32_t num_tokens, int32_t mode, float scale, int64_t stream);
+/* bf16 flavour (q / out / caches bf16; tcgen05 kind::f16 with bf16 operand formats, or the bf16 mma.sync kernel). */
+void b200_attn_prefill_ex_bf16(void* out, const void* q, const void* k_cache, const void* v_cache,
+                               const uint32_t* cu_seqlens_q, const uint32_t* context_lens,
+                               const uint32_t* block_tables, int32_t batch, int32_t num_heads,
+                               int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                               int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
+                               int32_t num_tokens, int32_t mode, float scale, int64_t stream);
 
 /* ------------------------------------------------- glue kernels (others.rs, mlp.rs, llama.rs) */
 void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
@@ -297,6 +320,15 @@ void b200_add_rmsnorm_f16(void* out, void* residual, const void* x, const void* 
                           int32_t num_tokens, int32_t hidden, float eps, int64_t stream);
 void b200_silu_mul_f16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
                        int64_t stream);
+/* bf16 flavours of the three (x / weight / residual / out bf16, fp32 math, the residual add rounds to bf16).
+ * b200_embedding_f16, b200_gather_rows_f16, b200_kv_write_f16 and b200_swap_blocks move 16-bit elements without
+ * arithmetic and serve bf16 tensors as they are.                                                                */
+void b200_rmsnorm_bf16(void* out, const void* x, const void* weight, int32_t num_tokens,
+                       int32_t hidden, float eps, int64_t stream);
+void b200_add_rmsnorm_bf16(void* out, void* residual, const void* x, const void* weight,
+                           int32_t num_tokens, int32_t hidden, float eps, int64_t stream);
+void b200_silu_mul_bf16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
+                        int64_t stream);
 void b200_embedding_f16(void* out, const void* table, const uint32_t* ids, int32_t num_tokens,
                         int32_t hidden, int32_t vocab, int64_t stream);
 void b200_gather_rows_f16(void* out, const void* x, const uint32_t* rows, int32_t num_rows,

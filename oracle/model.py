@@ -30,6 +30,7 @@ F16, F32 = torch.float16, torch.float32
 # tensor.  `exact_mode()` turns those roundings off (fp32 everywhere, fp32 KV cache) to give the
 # "infinitely precise" result of the same weights -- used by tests to size the fp16 noise floor.
 _EXACT = False
+_DT = F16          # the model dtype h() rounds to: fp16 (the north-star dtype) or bf16 (the reference's default)
 
 
 class exact_mode:
@@ -42,12 +43,28 @@ class exact_mode:
         _EXACT = self._old
 
 
+class model_dtype:
+    """`with model_dtype(torch.bfloat16):` -- the same rounding model with bf16 as the materialised dtype
+    (utils/mod.rs:1919-1925: bf16 is what the reference picks unless the user asks for f16)."""
+
+    def __init__(self, dt):
+        self.dt = dt
+
+    def __enter__(self):
+        global _DT
+        self._old, _DT = _DT, self.dt
+
+    def __exit__(self, *a):
+        global _DT
+        _DT = self._old
+
+
 def h(x: torch.Tensor) -> torch.Tensor:
-    return x.to(F32) if _EXACT else x.to(F16)
+    return x.to(F32) if _EXACT else x.to(_DT)
 
 
 def store_dtype():
-    return F32 if _EXACT else F16
+    return F32 if _EXACT else _DT
 
 
 @dataclass

@@ -507,3 +507,118 @@ def test_swap_blocks_gpu_cpu_round_trip(ops, dtype):
     torch.cuda.synchronize()
     assert torch.equal(dst.cpu(), ref_gpu.flip(0))
     del keep
+
+
+# ---------------------------------------------------------------- bf16 flavours (the reference's default dtype)
+BF16 = torch.bfloat16
+# one bf16 ulp is 8 fp16 ulps: the fp16 bars above, times 8
+
+
+def test_bf16_glue(ops):
+    g = torch.Generator().manual_seed(3)
+    with om.model_dtype(BF16):
+        T, hidden = 9, 4096
+        x = torch.randn(T, hidden, generator=g).to(BF16)
+        w = (1 + 0.1 * torch.randn(hidden, generator=g)).to(BF16)
+        out = ops.rmsnorm(x.cuda(), w.cuda(), 1e-5)
+        assert out.dtype == BF16
+        _close(out, om.rmsnorm(x, w, 1e-5), 1.6e-2, 8e-3)
+        res = torch.randn(T, hidden, generator=g).to(BF16)
+        res_d = res.cuda().clone()
+        out2 = ops.add_rmsnorm(res_d, x.cuda(), w.cuda(), 1e-5)
+        new_res = (res.float() + x.float()).to(BF16)              # the add rounds once, to bf16
+        assert torch.equal(res_d.cpu(), new_res)
+        _close(out2, om.rmsnorm(new_res, w, 1e-5), 1.6e-2, 8e-3)
+        gu = torch.randn(5, 2 * 5632, generator=g).to(BF16)
+        _close(ops.silu_mul(gu.cuda()), om.silu_mul(gu[:, :5632], gu[:, 5632:]), 8e-3, 1.6e-2)
+        table = torch.randn(1000, 256, generator=g).to(BF16)
+        ids = torch.randint(0, 1000, (17,), generator=g, dtype=torch.int32)
+        assert torch.equal(ops.embedding(table.cuda(), ids.cuda()).cpu(), table[ids.long()])
+
+
+@pytest.mark.parametrize("H,Hkv,D,f32_tables", [(32, 8, 128, False), (32, 4, 64, True)])
+def test_bf16_rope_kv_write(ops, H, Hkv, D, f32_tables):
+    cfg = om.ModelConfig(H * D, 1, H, Hkv, D, 64, 64, rope_theta=500000.0, max_pos=4096)
+    cos, sin = om.rope_tables(cfg, dtype=torch.float32 if f32_tables else BF16)
+    g = torch.Generator().manual_seed(1)
+    T, nb = 19, 8
+    q = torch.randn(T, H, D, generator=g).to(BF16)
+    k = torch.randn(T, Hkv, D, generator=g).to(BF16)
+    v = torch.randn(T, Hkv, D, generator=g).to(BF16)
+    pos = torch.randint(0, 4096, (T,), generator=g)
+    slots = torch.randperm(nb * 64, generator=g)[:T]
+    slots[4] = -1
+    kc = torch.zeros(nb, 64, Hkv, D, dtype=BF16)
+    vc = torch.zeros_like(kc)
+    with om.model_dtype(BF16):
+        q_ref, k_ref = om.apply_rope(q, k, cos, sin, pos)
+    om.kv_write(k_ref, v, kc, vc, slots)
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    kcd, vcd = torch.zeros_like(kc).cuda(), torch.zeros_like(vc).cuda()
+    ops.rope_kv_write(qd, kd, vd, cos.cuda(), sin.cuda(), pos.cuda(), slots.cuda(), kcd, vcd)
+    _close(qd, q_ref, 1.6e-2, 8e-3)
+    _close(kd, k_ref, 1.6e-2, 8e-3)
+    exp_k = torch.zeros_like(kc)
+    om.kv_write(kd.cpu(), v, exp_k, torch.zeros_like(vc), slots)
+    assert torch.equal(kcd.cpu(), exp_k)
+    assert torch.equal(vcd.cpu(), vc)
+
+
+@pytest.mark.parametrize("H,Hkv,D,ctxs", [
+    (32, 8, 128, [1, 63, 64, 65, 127, 129, 700, 4096]),
+    (32, 4, 64, [37, 1, 500, 0, 2048]),
+    (16, 1, 128, [130]),
+])
+def test_bf16_paged_attention_decode(ops, H, Hkv, D, ctxs):
+    B = len(ctxs)
+    q, kc, vc, bt, cl = (t.to(BF16) if t.dtype == F16 else t for t in _paged_case(B, H, Hkv, D, ctxs, seed=H + D))
+    scale = 1.0 / math.sqrt(D)
+    with om.model_dtype(BF16):
+        ref = om.paged_attention_decode(q, kc, vc, bt.tolist(), cl.tolist(), scale)
+    out = ops.paged_attention_decode(q.cuda(), kc.cuda(), vc.cuda(), bt.cuda(), cl.cuda(), scale)
+    assert out.dtype == BF16
+    _close(out, ref, 1.6e-2, 1.6e-2)
+    # the fp16 kernel on the same (bf16-representable) values agrees to the bf16 rounding of the output
+    out16 = ops.paged_attention_decode(q.to(F16).cuda(), kc.to(F16).cuda(), vc.to(F16).cuda(), bt.cuda(), cl.cuda(),
+                                       scale)
+    _close(out, out16, 1.6e-2, 1.6e-2)
+
+
+@pytest.mark.parametrize("H,Hkv,D,cases,mode", [
+    (32, 8, 128, [(37, 0), (64, 0), (65, 0), (130, 64), (1, 0), (200, 128)], -1),     # tcgen05 kernel
+    (32, 8, 128, [(70, 0), (5, 192)], 0),                                             # mma.sync kernel
+    (32, 4, 64, [(300, 0), (5, 192)], -1),
+])
+def test_bf16_attention_prefill_paged(ops, H, Hkv, D, cases, mode):
+    g = torch.Generator().manual_seed(H * D + len(cases))
+    B = len(cases)
+    ctxs = [n + c for n, c in cases]
+    nblk = [-(-c // 64) for c in ctxs]
+    nb = sum(nblk) + 3
+    perm = torch.randperm(nb, generator=g).tolist()
+    kc = torch.randn(nb, 64, Hkv, D, generator=g).to(BF16)
+    vc = torch.randn(nb, 64, Hkv, D, generator=g).to(BF16)
+    bt = torch.zeros(B, max(nblk), dtype=torch.int32)
+    off = 0
+    for b, n in enumerate(nblk):
+        bt[b, :n] = torch.tensor(perm[off:off + n], dtype=torch.int32)
+        off += n
+    cu = [0]
+    for n, _ in cases:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    q = torch.randn(T, H, D, generator=g).to(BF16)
+    scale = 1.0 / math.sqrt(D)
+    dummy = torch.zeros(T, Hkv, D, dtype=BF16)
+    with om.model_dtype(BF16):
+        ref = om.attention_prefill(q, dummy, dummy, cu, kc, vc, bt.tolist(), ctxs, scale)
+    for b, n in enumerate(nblk):
+        last = ctxs[b] % 64
+        if last:
+            kc[bt[b, n - 1], last:] = float("nan")
+            vc[bt[b, n - 1], last:] = float("nan")
+    out = ops.attention_prefill(q.cuda(), kc.cuda(), vc.cuda(), torch.tensor(cu, dtype=torch.int32).cuda(),
+                                torch.tensor(ctxs, dtype=torch.int32).cuda(), bt.cuda(),
+                                max(n for n, _ in cases), scale, mode=mode)
+    assert out.dtype == BF16 and not torch.isnan(out).any()
+    _close(out, ref, 1.6e-2, 1.6e-2)

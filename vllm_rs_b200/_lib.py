@@ -92,6 +92,7 @@ _SIGS = {
     "b200_dense_gemm_f16": (None, [c_vp] * 3 + [c_i32] * 4 + [c_i64]),
     "b200_dense_gemm_ex": (None, [c_vp] * 4 + [c_i32] * 5 + [c_i64]),
     "b200_rope_kv_write_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
+    "b200_rope_kv_write_bf16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_rope_kv_write_fp8kv_f16": (None, [c_vp] * 9 + [c_i32] * 8 + [c_i64]),
     "b200_kv_write_f16": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
     "b200_swap_blocks": (None, [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64]),
@@ -114,13 +115,18 @@ _SIGS = {
     "b200_wire_frame_simple": (c_i64, [c_vp, c_i64, c_i32, c_i32, C.c_uint64]),
     "b200_wire_decode_metadata": (None, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
+    "b200_paged_attn_decode_bf16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_decode_fp8kv_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_workspace_bytes": (c_i64, [c_i32] * 4),
     "b200_attn_prefill_f16": (None, [c_vp] * 7 + [c_i32] * 8 + [c_f32, c_i64]),
     "b200_attn_prefill_ex_f16": (None, [c_vp] * 7 + [c_i32] * 10 + [c_f32, c_i64]),
+    "b200_attn_prefill_ex_bf16": (None, [c_vp] * 7 + [c_i32] * 10 + [c_f32, c_i64]),
     "b200_rmsnorm_f16": (None, [c_vp] * 3 + [c_i32, c_i32, c_f32, c_i64]),
+    "b200_rmsnorm_bf16": (None, [c_vp] * 3 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_add_rmsnorm_f16": (None, [c_vp] * 4 + [c_i32, c_i32, c_f32, c_i64]),
+    "b200_add_rmsnorm_bf16": (None, [c_vp] * 4 + [c_i32, c_i32, c_f32, c_i64]),
     "b200_silu_mul_f16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
+    "b200_silu_mul_bf16": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),
     "b200_embedding_f16": (None, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64]),
     "b200_gather_rows_f16": (None, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64]),
     "b200_argmax_f32": (None, [c_vp, c_vp, c_i32, c_i32, c_i64]),

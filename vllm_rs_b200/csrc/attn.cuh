@@ -13,24 +13,24 @@ bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int n
 void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
-                              int window, void* workspace, cudaStream_t st);
+                              int window, void* workspace, cudaStream_t st, bool bf16 = false);
 void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_stride,
                          const uint32_t* cu_q, const uint32_t* ctx_lens,
                          const uint32_t* block_tables, int B, int H, int Hkv, int D, int max_blocks,
-                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows = 0, int mode = -1);
+                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows = 0, int mode = -1, bool bf16 = false);
 // tcgen05 version (head_dim 128); false when the shape / mode is not taken.  total_rows = rows of the q
 // buffer (bounds of its tensor map); mode -1 = env B200_PREFILL_ATTN (default tcgen05), 0 = mma.sync.
 bool launch_attn_prefill_tc(const AttnMaps& maps, void* out, const void* q, int q_stride, const uint32_t* cu_q,
                             const uint32_t* ctx_lens, const uint32_t* block_tables, int B, int H, int Hkv, int D,
                             int max_blocks, int max_seqlen_q, int total_rows, float scale, int mode,
-                            cudaStream_t st);
+                            cudaStream_t st, bool bf16 = false);
 // RoPE + KV write with explicit row strides (in halfs) so q|k|v can live in one fused
 // GEMM output row.
 void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,
                           int v_stride, const void* cos, const void* sin,
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
-                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8 = 0);
+                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8 = 0, bool bf16 = false);
 // FP8 cache pages of every sequence's context -> fp16 scratch blocks b * max_blocks + i (+ that identity
 // block table when scratch_bt != NULL): what the prefill attention kernels read in --fp8-kvcache mode.
 void launch_kv_fp8_gather(const void* k8, const void* v8, void* ks, void* vs, uint32_t* scratch_bt,

@@ -35,7 +35,7 @@ struct Smem {
 };
 }  // namespace pf
 
-template <int D>
+template <int D, bool BF>
 __global__ void __launch_bounds__(pf::kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                     const __half* __restrict__ q, __half* __restrict__ out,
@@ -156,8 +156,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
           const int tok = np * 16 + k_row;
           uint32_t r[4];
           ldsm_x4(r, kbase + hb * (kTok * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4));
-          mma_16816(sc[2 * np], qa[ks], r[0], r[1]);
-          mma_16816(sc[2 * np + 1], qa[ks], r[2], r[3]);
+          mma_16816_t<BF>(sc[2 * np], qa[ks], r[0], r[1]);
+          mma_16816_t<BF>(sc[2 * np + 1], qa[ks], r[2], r[3]);
         }
       }
       // ---- causal mask + online softmax (rows a: elements 0,1; rows b: elements 2,3)
@@ -211,10 +211,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t pa[4];
-        pa[0] = pack_half2(sc[2 * kk][0], sc[2 * kk][1]);
-        pa[1] = pack_half2(sc[2 * kk][2], sc[2 * kk][3]);
-        pa[2] = pack_half2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
-        pa[3] = pack_half2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+        pa[0] = pack16x2<BF>(sc[2 * kk][0], sc[2 * kk][1]);
+        pa[1] = pack16x2<BF>(sc[2 * kk][2], sc[2 * kk][3]);
+        pa[2] = pack16x2<BF>(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        pa[3] = pack16x2<BF>(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
         const int tb = page_base + kk * 16;
         const uint32_t vmask_lo = (tb + 2 * c < ctx ? 0x0000FFFFu : 0u) | (tb + 2 * c + 1 < ctx ? 0xFFFF0000u : 0u);
         const uint32_t vmask_hi = (tb + 8 + 2 * c < ctx ? 0x0000FFFFu : 0u) | (tb + 9 + 2 * c < ctx ? 0xFFFF0000u : 0u);
@@ -229,8 +229,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
             r[0] &= vmask_lo; r[2] &= vmask_lo;
             r[1] &= vmask_hi; r[3] &= vmask_hi;
           }
-          mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
-          mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
+          mma_16816_t<BF>(o_acc[2 * jj], pa, r[0], r[1]);
+          mma_16816_t<BF>(o_acc[2 * jj + 1], pa, r[2], r[3]);
         }
       }
     }
@@ -248,12 +248,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
   __half* ob = out + (static_cast<size_t>(row0 + tqb) * H + head) * D;
 #pragma unroll
   for (int j = 0; j < D / 8; ++j) {
-    if (va) *reinterpret_cast<uint32_t*>(oa + j * 8 + 2 * c) = pack_half2(o_acc[j][0] * inv_a, o_acc[j][1] * inv_a);
-    if (vb) *reinterpret_cast<uint32_t*>(ob + j * 8 + 2 * c) = pack_half2(o_acc[j][2] * inv_b, o_acc[j][3] * inv_b);
+    if (va) *reinterpret_cast<uint32_t*>(oa + j * 8 + 2 * c) = pack16x2<BF>(o_acc[j][0] * inv_a, o_acc[j][1] * inv_a);
+    if (vb) *reinterpret_cast<uint32_t*>(ob + j * 8 + 2 * c) = pack16x2<BF>(o_acc[j][2] * inv_b, o_acc[j][3] * inv_b);
   }
 }
 
-template <int D>
+template <int D, bool BF>
 static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stride,
                       const uint32_t* cu_q, const uint32_t* ctx_lens, const uint32_t* block_tables,
                       int B, int H, int Hkv, int max_blocks, int max_seqlen_q, float scale,
@@ -262,12 +262,12 @@ static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stri
   const int TQ = (pf::kWarps / G) * 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(attn_prefill_kernel<D, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          pf::Smem<D>::kAlloc);
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + TQ - 1) / TQ, Hkv, B);
-  launch_pdl(attn_prefill_kernel<D>, grid, dim3(pf::kThreads), pf::Smem<D>::kAlloc, st, maps.k, maps.v,
+  launch_pdl(attn_prefill_kernel<D, BF>, grid, dim3(pf::kThreads), pf::Smem<D>::kAlloc, st, maps.k, maps.v,
              reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out), cu_q, ctx_lens,
              block_tables, q_stride, H, Hkv, max_blocks, scale * 1.4426950408889634f);
   B200_CUDA_LAUNCH_CHECK();
@@ -276,29 +276,29 @@ static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stri
 void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_stride,
                          const uint32_t* cu_q, const uint32_t* ctx_lens,
                          const uint32_t* block_tables, int B, int H, int Hkv, int D, int max_blocks,
-                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows, int mode) {
+                         int max_seqlen_q, float scale, cudaStream_t st, int total_rows, int mode, bool bf16) {
   // total_rows > 0: the caller knows the extent of the q buffer, which the tcgen05 kernel's q tensor map needs
   if (total_rows > 0 && launch_attn_prefill_tc(maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, D,
-                                               max_blocks, max_seqlen_q, total_rows, scale, mode, st))
+                                               max_blocks, max_seqlen_q, total_rows, scale, mode, st, bf16))
     return;
-  if (D == 128)
-    launch_pf<128>(maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, max_blocks,
-                   max_seqlen_q, scale, st);
-  else
-    launch_pf<64>(maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, max_blocks,
-                  max_seqlen_q, scale, st);
+#define B200_PF_ARGS maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, max_blocks, max_seqlen_q, scale, st
+  if (D == 128 && bf16) launch_pf<128, true>(B200_PF_ARGS);
+  else if (D == 128) launch_pf<128, false>(B200_PF_ARGS);
+  else if (bf16) launch_pf<64, true>(B200_PF_ARGS);
+  else launch_pf<64, false>(B200_PF_ARGS);
+#undef B200_PF_ARGS
 }
 
 }  // namespace b200
 
-extern "C" void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k_cache,
-                                         const void* v_cache, const uint32_t* cu_seqlens_q,
-                                         const uint32_t* context_lens, const uint32_t* block_tables,
-                                         int32_t batch, int32_t num_heads, int32_t num_kv_heads,
-                                         int32_t head_dim, int32_t block_size,
-                                         int32_t max_blocks_per_seq, int32_t num_blocks,
-                                         int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
-                                         int64_t stream) {
+static void attn_prefill_ex_any(void* out, const void* q, const void* k_cache,
+                                const void* v_cache, const uint32_t* cu_seqlens_q,
+                                const uint32_t* context_lens, const uint32_t* block_tables,
+                                int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                                int32_t head_dim, int32_t block_size,
+                                int32_t max_blocks_per_seq, int32_t num_blocks,
+                                int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
+                                int64_t stream, bool bf16) {
   using namespace b200;
   B200_CHECK_ARG(block_size == 64, "attn_prefill: block_size must be 64");
   B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "attn_prefill: head_dim must be 64/128");
@@ -315,7 +315,33 @@ extern "C" void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k
   }
   launch_attn_prefill(maps, out, q, num_heads * head_dim, cu_seqlens_q, context_lens, block_tables,
                       batch, num_heads, num_kv_heads, head_dim, max_blocks_per_seq, max_seqlen_q,
-                      scale, reinterpret_cast<cudaStream_t>(stream), num_tokens, mode);
+                      scale, reinterpret_cast<cudaStream_t>(stream), num_tokens, mode, bf16);
+}
+
+extern "C" void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k_cache,
+                                         const void* v_cache, const uint32_t* cu_seqlens_q,
+                                         const uint32_t* context_lens, const uint32_t* block_tables,
+                                         int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                                         int32_t head_dim, int32_t block_size,
+                                         int32_t max_blocks_per_seq, int32_t num_blocks,
+                                         int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
+                                         int64_t stream) {
+  attn_prefill_ex_any(out, q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables, batch, num_heads,
+                      num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, max_seqlen_q, num_tokens,
+                      mode, scale, stream, false);
+}
+
+extern "C" void b200_attn_prefill_ex_bf16(void* out, const void* q, const void* k_cache,
+                                          const void* v_cache, const uint32_t* cu_seqlens_q,
+                                          const uint32_t* context_lens, const uint32_t* block_tables,
+                                          int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                                          int32_t head_dim, int32_t block_size,
+                                          int32_t max_blocks_per_seq, int32_t num_blocks,
+                                          int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
+                                          int64_t stream) {
+  attn_prefill_ex_any(out, q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables, batch, num_heads,
+                      num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, max_seqlen_q, num_tokens,
+                      mode, scale, stream, true);
 }
 
 extern "C" void b200_attn_prefill_f16(void* out, const void* q, const void* k_cache,

@@ -78,6 +78,7 @@ struct Args {
   int dbg;           // bit 0: swap LBO / SBO of the V descriptor (bring-up switch)
 };
 
+template <bool BF>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                        const __grid_constant__ CUtensorMap vmap, const Args a) {
@@ -165,8 +166,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(kRows, kTok);
-      const uint32_t idesc_o = make_idesc_f16(kRows, kD) | (1u << 16);       // B operand MN-major
+      constexpr uint32_t kFmt = BF ? ((1u << 7) | (1u << 10)) : 0u;          // a_format / b_format = BF16
+      const uint32_t idesc_s = make_idesc_f16(kRows, kTok) | kFmt;
+      const uint32_t idesc_o = make_idesc_f16(kRows, kD) | (1u << 16) | kFmt;   // B operand MN-major
       const uint32_t s_tmem = tmem_base + kSCol, p_tmem = tmem_base + kPCol, o_tmem = tmem_base + kOCol;
       const uint32_t q_addr = smem_u32(q_smem);
       auto issue_qk = [&](int j) {
@@ -256,7 +258,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
       for (int i = 0; i < 32; ++i) {
         const float p0 = exp2f(x[2 * i] - m_ref), p1 = exp2f(x[2 * i + 1] - m_ref);
         psum += p0 + p1;
-        pk[i] = pack_half2(p0, p1);
+        pk[i] = pack16x2<BF>(p0, p1);
       }
       l_run = l_run * corr + psum;
       // stale V rows past the context (uninitialised cache memory) must not meet the MMA: 0 * NaN
@@ -306,10 +308,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
-          w.x = pack_half2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          w.y = pack_half2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          w.z = pack_half2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          w.w = pack_half2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          w.x = pack16x2<BF>(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          w.y = pack16x2<BF>(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          w.z = pack16x2<BF>(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          w.w = pack16x2<BF>(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
           *reinterpret_cast<uint4*>(dst + c0 + i) = w;
         }
       }
@@ -340,7 +342,7 @@ static int prefill_attn_mode() {       // 0 = mma.sync kernel, 1 = tcgen05 kerne
 bool launch_attn_prefill_tc(const AttnMaps& maps, void* out, const void* q, int q_stride, const uint32_t* cu_q,
                             const uint32_t* ctx_lens, const uint32_t* block_tables, int B, int H, int Hkv, int D,
                             int max_blocks, int max_seqlen_q, int total_rows, float scale, int mode,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool bf16) {
   using namespace pft;
   if (mode < 0) mode = prefill_attn_mode();
   if (mode == 0 || D != kD) return false;
@@ -369,11 +371,13 @@ bool launch_attn_prefill_tc(const AttnMaps& maps, void* out, const void* q, int 
   a.dbg = mode == 2 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + TQ - 1) / TQ, Hkv, B);
-  launch_pdl(attn_prefill_tc_kernel, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
+  if (bf16) launch_pdl(attn_prefill_tc_kernel<true>, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
+  else launch_pdl(attn_prefill_tc_kernel<false>, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
 }

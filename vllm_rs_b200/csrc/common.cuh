@@ -4,6 +4,7 @@
 // and the legacy mma.sync used by the decode-attention kernel.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -322,6 +323,67 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------- 16-bit element flavours (BF: bf16, else fp16)
+// The bf16 entry points (the reference's default dtype, utils/mod.rs:1919-1925) are the fp16 kernels instantiated
+// with these: same loads / stores / schedule, only the conversions and the mma operand type differ.
+template <bool BF>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (BF) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  } else {
+    return pack_half2(lo, hi);
+  }
+}
+template <bool BF>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (BF) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  } else {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  }
+}
+template <bool BF>
+__device__ __forceinline__ uint16_t f32_to_bits16(float x) {
+  if constexpr (BF) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  } else {
+    return __half_as_ushort(__float2half_rn(x));
+  }
+}
+template <bool BF>
+__device__ __forceinline__ float bits16_to_f32(uint16_t b) {
+  if constexpr (BF) {
+    return __uint_as_float(static_cast<uint32_t>(b) << 16);
+  } else {
+    return __half2float(__ushort_as_half(b));
+  }
+}
+// a + b on two packed elements, in the element type (one rounding per lane)
+template <bool BF>
+__device__ __forceinline__ uint32_t add16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  if constexpr (BF) {
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  } else {
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  }
+  return r;
+}
+template <bool BF>
+__device__ __forceinline__ void mma_16816_t(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (BF) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    mma_16816(d, a, b0, b1);
+  }
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM

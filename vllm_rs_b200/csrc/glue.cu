@@ -35,13 +35,13 @@ __device__ __forceinline__ uint32_t half2x2_to_e4m3x4(uint32_t lo, uint32_t hi) 
 // ------------------------------------------------------------------ RoPE + KV write
 // grid = tokens; one thread per rotation pair / per 2 copied elements.
 // Cache layout [num_blocks, block_size, Hkv, D]: slot s -> row s of [.., Hkv, D].
-template <bool kCosSinF32>
-__global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict__ k,
-                                     const __half* __restrict__ v, const void* __restrict__ cosp,
+template <bool kCosSinF32, bool BF>
+__global__ void rope_kv_write_kernel(uint16_t* __restrict__ q, uint16_t* __restrict__ k,
+                                     const uint16_t* __restrict__ v, const void* __restrict__ cosp,
                                      const void* __restrict__ sinp,
                                      const int64_t* __restrict__ positions,
                                      const int64_t* __restrict__ slot_mapping,
-                                     __half* __restrict__ k_cache, __half* __restrict__ v_cache,
+                                     uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache,
                                      int q_stride, int k_stride, int v_stride, int H, int Hkv,
                                      int D, int rot_dim, int interleaved, int kv_fp8) {
   pdl_trigger();
@@ -50,11 +50,11 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
   const int64_t pos = positions ? positions[t] : 0;
   const int half_rot = rot_dim >> 1;
   const int64_t slot = (slot_mapping && k_cache) ? slot_mapping[t] : -1;
-  __half* qt = q + static_cast<size_t>(t) * q_stride;
-  __half* kt = k + static_cast<size_t>(t) * k_stride;
-  const __half* vt = v ? v + static_cast<size_t>(t) * v_stride : nullptr;
-  __half* kc = slot >= 0 ? k_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
-  __half* vc = (slot >= 0 && v_cache) ? v_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
+  uint16_t* qt = q + static_cast<size_t>(t) * q_stride;
+  uint16_t* kt = k + static_cast<size_t>(t) * k_stride;
+  const uint16_t* vt = v ? v + static_cast<size_t>(t) * v_stride : nullptr;
+  uint16_t* kc = slot >= 0 ? k_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
+  uint16_t* vc = (slot >= 0 && v_cache) ? v_cache + static_cast<size_t>(slot) * Hkv * D : nullptr;
   // FP8 cache: same [slot][Hkv][D] indexing over one-byte elements
   uint8_t* kc8 = slot >= 0 ? reinterpret_cast<uint8_t*>(k_cache) + static_cast<size_t>(slot) * Hkv * D : nullptr;
   uint8_t* vc8 = (slot >= 0 && v_cache) ? reinterpret_cast<uint8_t*>(v_cache) + static_cast<size_t>(slot) * Hkv * D
@@ -67,7 +67,7 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
     const int head = idx / pairs_per_head;
     const int p = idx - head * pairs_per_head;
     const bool is_q = head < H;
-    __half* base = is_q ? qt + head * D : kt + (head - H) * D;
+    uint16_t* base = is_q ? qt + head * D : kt + (head - H) * D;
     int i0, i1;
     bool rotate = p < half_rot;
     if (interleaved) {
@@ -81,25 +81,25 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
       i0 = rot_dim + 2 * (p - half_rot);
       i1 = i0 + 1;
     }
-    float x0 = __half2float(base[i0]), x1 = __half2float(base[i1]);
+    float x0 = bits16_to_f32<BF>(base[i0]), x1 = bits16_to_f32<BF>(base[i1]);
     if (rotate) {
       float cs, sn;
       if (kCosSinF32) {
         cs = reinterpret_cast<const float*>(cosp)[pos * half_rot + p];
         sn = reinterpret_cast<const float*>(sinp)[pos * half_rot + p];
       } else {
-        cs = __half2float(reinterpret_cast<const __half*>(cosp)[pos * half_rot + p]);
-        sn = __half2float(reinterpret_cast<const __half*>(sinp)[pos * half_rot + p]);
+        cs = bits16_to_f32<BF>(reinterpret_cast<const uint16_t*>(cosp)[pos * half_rot + p]);
+        sn = bits16_to_f32<BF>(reinterpret_cast<const uint16_t*>(sinp)[pos * half_rot + p]);
       }
       const float y0 = x0 * cs - x1 * sn;
       const float y1 = x1 * cs + x0 * sn;
-      const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+      const uint16_t h0 = f32_to_bits16<BF>(y0), h1 = f32_to_bits16<BF>(y1);
       base[i0] = h0;
       base[i1] = h1;
       if (!is_q && kc) {
         if (kv_fp8) {
-          kc8[(head - H) * D + i0] = half_to_e4m3(h0);
-          kc8[(head - H) * D + i1] = half_to_e4m3(h1);
+          kc8[(head - H) * D + i0] = half_to_e4m3(__ushort_as_half(h0));
+          kc8[(head - H) * D + i1] = half_to_e4m3(__ushort_as_half(h1));
         } else {
           kc[(head - H) * D + i0] = h0;
           kc[(head - H) * D + i1] = h1;
@@ -107,8 +107,8 @@ __global__ void rope_kv_write_kernel(__half* __restrict__ q, __half* __restrict_
       }
     } else if (!is_q && kc) {
       if (kv_fp8) {
-        kc8[(head - H) * D + i0] = half_to_e4m3(base[i0]);
-        kc8[(head - H) * D + i1] = half_to_e4m3(base[i1]);
+        kc8[(head - H) * D + i0] = half_to_e4m3(__ushort_as_half(base[i0]));
+        kc8[(head - H) * D + i1] = half_to_e4m3(__ushort_as_half(base[i1]));
       } else {
         kc[(head - H) * D + i0] = base[i0];
         kc[(head - H) * D + i1] = base[i1];
@@ -226,7 +226,7 @@ __global__ void kv_write_kernel(const __half* __restrict__ k, const __half* __re
 // ------------------------------------------------------------------ RMSNorm
 // One CTA per token.  kAdd: residual = fp16(residual + x) first (llama.rs:126-130
 // performs the add in model dtype), then out = fp16(residual * rsqrt(mean sq + eps) * w).
-template <bool kAdd>
+template <bool kAdd, bool BF>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
                const __half* __restrict__ x, const __half* __restrict__ w, int hidden,
@@ -246,17 +246,17 @@ rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
     uint4 a = xs[i];
     if (kAdd) {
       uint4 r = rs[i];
-      __half2* ah = reinterpret_cast<__half2*>(&a);
-      const __half2* rh = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ah[j] = __hadd2(ah[j], rh[j]);
+      a.x = add16x2<BF>(a.x, r.x);
+      a.y = add16x2<BF>(a.y, r.y);
+      a.z = add16x2<BF>(a.z, r.z);
+      a.w = add16x2<BF>(a.w, r.w);
       rs[i] = a;
     }
     row[i] = a;
-    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const uint32_t* ah = reinterpret_cast<const uint32_t*>(&a);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(ah[j]);
+      const float2 f = unpack16x2<BF>(ah[j]);
       ss += f.x * f.x + f.y * f.y;
     }
   }
@@ -270,13 +270,13 @@ rmsnorm_kernel(__half* __restrict__ out, __half* __restrict__ residual,
   for (int i = threadIdx.x; i < n8; i += blockDim.x) {
     uint4 a = row[i];
     const uint4 wv = ws[i];
-    __half2* ah = reinterpret_cast<__half2*>(&a);
-    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+    uint32_t* ah = reinterpret_cast<uint32_t*>(&a);
+    const uint32_t* wh = reinterpret_cast<const uint32_t*>(&wv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(ah[j]);
-      const float2 g = __half22float2(wh[j]);
-      ah[j] = __floats2half2_rn(f.x * inv * g.x, f.y * inv * g.y);
+      const float2 f = unpack16x2<BF>(ah[j]);
+      const float2 g = unpack16x2<BF>(wh[j]);
+      ah[j] = pack16x2<BF>(f.x * inv * g.x, f.y * inv * g.y);
     }
     os[i] = a;
   }
@@ -308,6 +308,7 @@ __global__ void rowscale_kernel(__half* __restrict__ out, const __half* __restri
 }
 
 // ------------------------------------------------------------------ SiLU(gate) * up
+template <bool BF>
 __global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restrict__ gate_up,
                                 int inter) {
   const int t = blockIdx.x;                              // tokens on grid.x: a prefill step may hold > 65535 of them
@@ -317,14 +318,14 @@ __global__ void silu_mul_kernel(__half* __restrict__ out, const __half* __restri
   const uint4 uv =
       reinterpret_cast<const uint4*>(gate_up + static_cast<size_t>(t) * 2 * inter + inter)[i];
   uint4 o;
-  const __half2* gh = reinterpret_cast<const __half2*>(&gv);
-  const __half2* uh = reinterpret_cast<const __half2*>(&uv);
-  __half2* oh = reinterpret_cast<__half2*>(&o);
+  const uint32_t* gh = reinterpret_cast<const uint32_t*>(&gv);
+  const uint32_t* uh = reinterpret_cast<const uint32_t*>(&uv);
+  uint32_t* oh = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 g = __half22float2(gh[j]);
-    const float2 u = __half22float2(uh[j]);
-    oh[j] = __floats2half2_rn(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
+    const float2 g = unpack16x2<BF>(gh[j]);
+    const float2 u = unpack16x2<BF>(uh[j]);
+    oh[j] = pack16x2<BF>(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
   }
   reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * inter)[i] = o;
 }
@@ -415,24 +416,63 @@ void launch_rowscale(void* out, const void* x, const float* ssq, int T, int hidd
   B200_CUDA_LAUNCH_CHECK();
 }
 
+template <bool F32, bool BF>
+static void launch_rope_kv_write_t(void* q, void* k, const void* v, int q_stride, int k_stride, int v_stride,
+                                   const void* cos, const void* sin, const int64_t* positions,
+                                   const int64_t* slot_mapping, void* k_cache, void* v_cache, int T, int H, int Hkv,
+                                   int D, int rot_dim, int interleaved, cudaStream_t st, int kv_fp8) {
+  const int pairs = (H + Hkv) * D / 2;
+  const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
+  launch_pdl(rope_kv_write_kernel<F32, BF>, dim3(T), dim3(threads), 0, st, (uint16_t*)q, (uint16_t*)k,
+             (const uint16_t*)v, cos, sin, positions, slot_mapping, (uint16_t*)k_cache, (uint16_t*)v_cache,
+             q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
 void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_stride,
                           int v_stride, const void* cos, const void* sin,
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
-                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8) {
-  const int pairs = (H + Hkv) * D / 2;
-  const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
-  if (cos_sin_f32)
-    launch_pdl(rope_kv_write_kernel<true>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
-               (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
-               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
-  else
-    launch_pdl(rope_kv_write_kernel<false>, dim3(T), dim3(threads), 0, st, (__half*)q, (__half*)k,
-               (const __half*)v, cos, sin, positions, slot_mapping, (__half*)k_cache,
-               (__half*)v_cache, q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
+                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8, bool bf16) {
+#define B200_ROPE_ARGS q, k, v, q_stride, k_stride, v_stride, cos, sin, positions, slot_mapping, k_cache, v_cache, T, \
+                       H, Hkv, D, rot_dim, interleaved, st, kv_fp8
+  if (bf16 && kv_fp8) {
+    set_error(1, "rope_kv_write: the e4m3 cache write is fp16 only");
+    return;
+  }
+  if (bf16) {
+    if (cos_sin_f32) launch_rope_kv_write_t<true, true>(B200_ROPE_ARGS);
+    else launch_rope_kv_write_t<false, true>(B200_ROPE_ARGS);
+  } else {
+    if (cos_sin_f32) launch_rope_kv_write_t<true, false>(B200_ROPE_ARGS);
+    else launch_rope_kv_write_t<false, false>(B200_ROPE_ARGS);
+  }
+#undef B200_ROPE_ARGS
+}
+
+template <bool kAdd, bool BF>
+static void rmsnorm_any(const char* what, void* out, void* residual, const void* x, const void* weight,
+                        int32_t num_tokens, int32_t hidden, float eps, int64_t stream) {
+  if (num_tokens <= 0) return;
+  if (hidden % 8 != 0 || hidden > 16384) {
+    set_error(1, what);
+    return;
+  }
+  launch_pdl(rmsnorm_kernel<kAdd, BF>, dim3(num_tokens), dim3(256), hidden * 2,
+             reinterpret_cast<cudaStream_t>(stream), (__half*)out, (__half*)residual, (const __half*)x,
+             (const __half*)weight, hidden, eps);
   B200_CUDA_LAUNCH_CHECK();
 }
 
+template <bool BF>
+static void silu_mul_any(void* out, const void* gate_up, int32_t num_tokens, int32_t inter, int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(inter % 8 == 0, "silu_mul: inter % 8 != 0");
+  dim3 grid(num_tokens, (inter / 8 + 255) / 256);
+  silu_mul_kernel<BF><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__half*)out, (const __half*)gate_up, inter);
+  B200_CUDA_LAUNCH_CHECK();
+}
 }  // namespace b200
 
 extern "C" {
@@ -453,6 +493,23 @@ void b200_rope_kv_write_f16(void* q, void* k, const void* v, const void* cos, co
                        num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
                        v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
                        interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream));
+}
+
+void b200_rope_kv_write_bf16(void* q, void* k, const void* v, const void* cos, const void* sin,
+                             const int64_t* positions, const int64_t* slot_mapping,
+                             void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                             int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                             int32_t block_size, int32_t interleaved, int32_t cos_sin_f32,
+                             int64_t stream) {
+  (void)block_size;
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(head_dim % 8 == 0 && rot_dim % 2 == 0 && rot_dim <= head_dim && rot_dim > 0,
+                 "rope_kv_write: bad head_dim / rot_dim");
+  B200_CHECK_ARG(q && k && cos && sin && positions, "rope_kv_write: NULL pointer");
+  launch_rope_kv_write(q, k, v, num_heads * head_dim, num_kv_heads * head_dim,
+                       num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
+                       v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
+                       interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream), 0, true);
 }
 
 void b200_rope_kv_write_fp8kv_f16(void* q, void* k, const void* v, const void* cos, const void* sin,
@@ -509,32 +566,33 @@ void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cach
 
 void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,
                       int32_t hidden, float eps, int64_t stream) {
-  if (num_tokens <= 0) return;
-  B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "rmsnorm: hidden % 8 != 0 or > 16384");
-  launch_pdl(rmsnorm_kernel<false>, dim3(num_tokens), dim3(256), hidden * 2,
-             reinterpret_cast<cudaStream_t>(stream), (__half*)out, (__half*)nullptr, (const __half*)x,
-             (const __half*)weight, hidden, eps);
-  B200_CUDA_LAUNCH_CHECK();
+  rmsnorm_any<false, false>("rmsnorm: hidden % 8 != 0 or > 16384", out, nullptr, x, weight, num_tokens, hidden, eps,
+                            stream);
+}
+void b200_rmsnorm_bf16(void* out, const void* x, const void* weight, int32_t num_tokens,
+                       int32_t hidden, float eps, int64_t stream) {
+  rmsnorm_any<false, true>("rmsnorm: hidden % 8 != 0 or > 16384", out, nullptr, x, weight, num_tokens, hidden, eps,
+                           stream);
 }
 
 void b200_add_rmsnorm_f16(void* out, void* residual, const void* x, const void* weight,
                           int32_t num_tokens, int32_t hidden, float eps, int64_t stream) {
-  if (num_tokens <= 0) return;
-  B200_CHECK_ARG(hidden % 8 == 0 && hidden <= 16384, "add_rmsnorm: hidden % 8 != 0 or > 16384");
-  launch_pdl(rmsnorm_kernel<true>, dim3(num_tokens), dim3(256), hidden * 2,
-             reinterpret_cast<cudaStream_t>(stream), (__half*)out, (__half*)residual, (const __half*)x,
-             (const __half*)weight, hidden, eps);
-  B200_CUDA_LAUNCH_CHECK();
+  rmsnorm_any<true, false>("add_rmsnorm: hidden % 8 != 0 or > 16384", out, residual, x, weight, num_tokens, hidden,
+                           eps, stream);
+}
+void b200_add_rmsnorm_bf16(void* out, void* residual, const void* x, const void* weight,
+                           int32_t num_tokens, int32_t hidden, float eps, int64_t stream) {
+  rmsnorm_any<true, true>("add_rmsnorm: hidden % 8 != 0 or > 16384", out, residual, x, weight, num_tokens, hidden,
+                          eps, stream);
 }
 
 void b200_silu_mul_f16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
                        int64_t stream) {
-  if (num_tokens <= 0) return;
-  B200_CHECK_ARG(inter % 8 == 0, "silu_mul: inter % 8 != 0");
-  dim3 grid(num_tokens, (inter / 8 + 255) / 256);
-  silu_mul_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (__half*)out, (const __half*)gate_up, inter);
-  B200_CUDA_LAUNCH_CHECK();
+  silu_mul_any<false>(out, gate_up, num_tokens, inter, stream);
+}
+void b200_silu_mul_bf16(void* out, const void* gate_up, int32_t num_tokens, int32_t inter,
+                        int64_t stream) {
+  silu_mul_any<true>(out, gate_up, num_tokens, inter, stream);
 }
 
 void b200_embedding_f16(void* out, const void* table, const uint32_t* ids, int32_t num_tokens,

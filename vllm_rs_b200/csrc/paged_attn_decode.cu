@@ -89,7 +89,7 @@ __device__ __forceinline__ int first_page_of(int ctx, int window) {
 
 // HI = false promises H / Hkv <= 8: rows 8..15 of every A fragment are the constant 0, which frees the 16
 // registers the fp8 instantiation needs to fit 3 CTAs per SM without spilling.
-template <int D, bool F8, bool HI, int NS>
+template <int D, bool F8, bool HI, int NS, bool BF>
 __device__ __forceinline__ void
 paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
                        const __half* __restrict__ q, __half* __restrict__ out,
@@ -102,6 +102,7 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
   using SM = AttnSmem<D, F8, NS>;
   constexpr int kNS = SM::kNumStages;
   static_assert(!F8 || D == 128, "fp8 tiles are one 128-byte row per token");
+  static_assert(!(F8 && BF), "the e4m3 cache is expanded to fp16 operands");
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   const int ctx = static_cast<int>(context_lens[b]);
   if (ctx <= 0) {
@@ -373,8 +374,8 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
           const int chunk = ((ks & 3) << 1) + k_chunk_sel;
           uint32_t r[4];
           ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
-          mma_16816(s0, qa[ks], r[0], r[1]);
-          mma_16816(s1, qa[ks], r[2], r[3]);
+          mma_16816_t<BF>(s0, qa[ks], r[0], r[1]);
+          mma_16816_t<BF>(s1, qa[ks], r[2], r[3]);
         }
         // ---- online softmax (rows g and, when G > 8, g + 8)
         uint32_t pa[4] = {0u, 0u, 0u, 0u};
@@ -411,8 +412,8 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
             o_acc[j][2 * rh] *= alpha;
             o_acc[j][2 * rh + 1] *= alpha;
           }
-          pa[rh] = pack_half2(p[0], p[1]);
-          pa[2 + rh] = pack_half2(p[2], p[3]);
+          pa[rh] = pack16x2<BF>(p[0], p[1]);
+          pa[2 + rh] = pack16x2<BF>(p[2], p[3]);
         }
         // ---- O += P V
         const bool partial = tok_base + 16 > ctx;
@@ -430,8 +431,8 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
             r[0] &= vmask_lo; r[2] &= vmask_lo;
             r[1] &= vmask_hi; r[3] &= vmask_hi;
           }
-          mma_16816(o_acc[2 * jj], pa, r[0], r[1]);
-          mma_16816(o_acc[2 * jj + 1], pa, r[2], r[3]);
+          mma_16816_t<BF>(o_acc[2 * jj], pa, r[0], r[1]);
+          mma_16816_t<BF>(o_acc[2 * jj + 1], pa, r[2], r[3]);
         }
       }
       __syncwarp();
@@ -493,7 +494,7 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
     }
     const int h = hkv * G + row;
     if (nsplits_seq == 1) {
-      out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(o / l_tot);
+      reinterpret_cast<uint16_t*>(out)[(static_cast<size_t>(b) * H + h) * D + d] = f32_to_bits16<BF>(o / l_tot);
     } else {
       const size_t pidx = (static_cast<size_t>(b) * H + h) * max_splits + split;
       part_o[pidx * D + d] = o;
@@ -516,14 +517,14 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
       pages_per_split, max_splits, scale_log2, softcap, window
 
 // 2 CTAs per SM (96 KB of stages each) for both cache formats
-template <int D, bool F8, bool HI>
+template <int D, bool F8, bool HI, bool BF>
 __global__ void __launch_bounds__(kThreads, 2) paged_attn_decode_kernel(B200_ATTN_DECODE_PARAMS) {
-  paged_attn_decode_body<D, F8, HI, F8 ? 6 : kStages>(B200_ATTN_DECODE_ARGS);
+  paged_attn_decode_body<D, F8, HI, F8 ? 6 : kStages, BF>(B200_ATTN_DECODE_ARGS);
 }
 // Split merge: one CTA per (head, sequence).  Launched with PDL right behind the main kernel, so
 // its launch latency hides under the main kernel's tail (a fused last-CTA merge was measured
 // slower: it serialises two L2 round trips behind the last wave).
-template <int D>
+template <int D, bool BF>
 __global__ void __launch_bounds__(D)
 paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ part_o,
                          const float* __restrict__ part_ml,
@@ -549,7 +550,7 @@ paged_attn_reduce_kernel(__half* __restrict__ out, const float* __restrict__ par
     l += part_ml[(base + s) * 2 + 1] * f;
     acc += part_o[(base + s) * D + d] * f;
   }
-  out[(static_cast<size_t>(b) * H + h) * D + d] = __float2half_rn(acc / l);
+  reinterpret_cast<uint16_t*>(out)[(static_cast<size_t>(b) * H + h) * D + d] = f32_to_bits16<BF>(acc / l);
 }
 
 struct SplitPlan {
@@ -611,14 +612,14 @@ bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int n
          make_cache_map(&m->v, v_cache, num_blocks, Hkv, D, fp8);
 }
 
-template <int D, bool F8 = false, bool HI = true>
+template <int D, bool F8 = false, bool HI = true, bool BF = false>
 static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                           const uint32_t* block_tables, const uint32_t* context_lens, int B,
                           int H, int Hkv, int max_blocks, float scale, float softcap, int window,
                           void* workspace, cudaStream_t st) {
   constexpr int NS = F8 ? 6 : kStages;
   using SM = AttnSmem<D, F8, NS>;
-  auto kern = paged_attn_decode_kernel<D, F8, HI>;
+  auto kern = paged_attn_decode_kernel<D, F8, HI, BF>;
   // resident CTAs per SM as the driver computes them (registers are allocated in per-warp units): the
   // wave model of the split planner must use the real number
   static int occ = 0;
@@ -641,7 +642,7 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
       sp.pages_per_split, sp.max_splits, scale * 1.4426950408889634f, softcap, window);
   B200_CUDA_LAUNCH_CHECK();
   if (sp.max_splits > 1) {      // one split per sequence: every CTA wrote its fp16 rows itself
-    launch_pdl(paged_attn_reduce_kernel<D>, dim3(H, B), dim3(D), 0, st, reinterpret_cast<__half*>(out),
+    launch_pdl(paged_attn_reduce_kernel<D, BF>, dim3(H, B), dim3(D), 0, st, reinterpret_cast<__half*>(out),
                static_cast<const float*>(part_o), static_cast<const float*>(part_ml), context_lens, H,
                sp.pages_per_split, sp.max_splits, window);
     B200_CUDA_LAUNCH_CHECK();
@@ -651,8 +652,14 @@ static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_
 void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
-                              int window, void* workspace, cudaStream_t st) {
-  if (maps.fp8 && H / Hkv <= 8)
+                              int window, void* workspace, cudaStream_t st, bool bf16) {
+  if (bf16 && !maps.fp8 && D == 128)
+    launch_decode<128, false, true, true>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv,
+                                          max_blocks, scale, softcap, window, workspace, st);
+  else if (bf16 && !maps.fp8)
+    launch_decode<64, false, true, true>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv,
+                                         max_blocks, scale, softcap, window, workspace, st);
+  else if (maps.fp8 && H / Hkv <= 8)
     launch_decode<128, true, false>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks,
                                     scale, softcap, window, workspace, st);
   else if (maps.fp8)
@@ -689,7 +696,7 @@ static void paged_attn_decode_any(void* out, const void* q, const void* k_cache,
                                 int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
                                 float softcap, int32_t window, void* workspace,
-                                int64_t stream, bool fp8) {
+                                int64_t stream, bool fp8, bool bf16 = false) {
   using namespace b200;
   B200_CHECK_ARG(!fp8 || head_dim == 128, "paged_attn_decode: the fp8 KV cache needs head_dim 128");
   B200_CHECK_ARG(block_size == kTok, "paged_attn_decode: block_size must be 64");
@@ -706,7 +713,7 @@ static void paged_attn_decode_any(void* out, const void* q, const void* k_cache,
   }
   launch_paged_attn_decode(maps, out, q, num_heads * head_dim, block_tables, context_lens, batch,
                            num_heads, num_kv_heads, head_dim, max_blocks_per_seq, scale, softcap,
-                           window, workspace, reinterpret_cast<cudaStream_t>(stream));
+                           window, workspace, reinterpret_cast<cudaStream_t>(stream), bf16);
 }
 
 void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
@@ -719,6 +726,18 @@ void b200_paged_attn_decode_f16(void* out, const void* q, const void* k_cache,
   paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
                         num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
                         window, workspace, stream, false);
+}
+
+void b200_paged_attn_decode_bf16(void* out, const void* q, const void* k_cache,
+                                 const void* v_cache, const uint32_t* block_tables,
+                                 const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                                 int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                                 float softcap, int32_t window, void* workspace,
+                                 int64_t stream) {
+  paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
+                        num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
+                        window, workspace, stream, false, true);
 }
 
 void b200_paged_attn_decode_fp8kv_f16(void* out, const void* q, const void* k_cache,

@@ -23,6 +23,16 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _sym(stem: str, t: torch.Tensor):
+    """The `_f16` or `_bf16` flavour of an entry point, by the dtype of the activations (bf16 is the reference's
+    default dtype, utils/mod.rs:1919-1925)."""
+    if t.dtype == torch.bfloat16:
+        return getattr(_lib.lib(), stem + "_bf16")
+    if t.dtype != torch.float16:
+        raise TypeError(f"{stem}: activations must be fp16 or bf16, got {t.dtype}")
+    return getattr(_lib.lib(), stem + "_f16")
+
+
 def _cuda(*ts):
     for t in ts:
         if t is not None and not (t.is_cuda and t.is_contiguous()):
@@ -105,7 +115,7 @@ def rope_kv_write(q, k, v, cos, sin, positions, slot_mapping=None, k_cache=None,
     Hkv = k.shape[1]
     bs = k_cache.shape[1] if k_cache is not None else 64
     fp8 = k_cache is not None and k_cache.dtype == torch.uint8        # --fp8-kvcache: e4m3 bytes
-    fn = _lib.lib().b200_rope_kv_write_fp8kv_f16 if fp8 else _lib.lib().b200_rope_kv_write_f16
+    fn = _lib.lib().b200_rope_kv_write_fp8kv_f16 if fp8 else _sym("b200_rope_kv_write", q)
     fn(
         _p(q), _p(k), _p(v), _p(cos), _p(sin), _p(positions), _p(slot_mapping), _p(k_cache),
         _p(v_cache), T, H, Hkv, D, rot_dim or D, bs, int(interleaved),
@@ -156,7 +166,7 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
     if out is None:
         out = torch.empty_like(q)
     fp8 = k_cache.dtype == torch.uint8                                # --fp8-kvcache: e4m3 bytes
-    fn = _lib.lib().b200_paged_attn_decode_fp8kv_f16 if fp8 else _lib.lib().b200_paged_attn_decode_f16
+    fn = _lib.lib().b200_paged_attn_decode_fp8kv_f16 if fp8 else _sym("b200_paged_attn_decode", q)
     fn(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(block_tables), _p(context_lens), B, H, Hkv, D, bs,
        mb, nb, float(scale), float(softcap), int(window), _p(workspace), _stream())
     _lib.check()
@@ -175,10 +185,10 @@ def attention_prefill(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tab
     B = cu_seqlens_q.shape[0] - 1
     if out is None:
         out = torch.empty_like(q)
-    _lib.lib().b200_attn_prefill_ex_f16(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q),
-                                        _p(context_lens), _p(block_tables), B, H, Hkv, D, bs,
-                                        block_tables.shape[1], nb, int(max_seqlen_q), T, mode, float(scale),
-                                        _stream())
+    _sym("b200_attn_prefill_ex", q)(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q),
+                                    _p(context_lens), _p(block_tables), B, H, Hkv, D, bs,
+                                    block_tables.shape[1], nb, int(max_seqlen_q), T, mode, float(scale),
+                                    _stream())
     _lib.check()
     return out
 
@@ -187,7 +197,7 @@ def attention_prefill(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tab
 def rmsnorm(x, w, eps, out=None):
     _cuda(x, w)
     out = torch.empty_like(x) if out is None else out
-    _lib.lib().b200_rmsnorm_f16(_p(out), _p(x), _p(w), x.shape[0], x.shape[1], eps, _stream())
+    _sym("b200_rmsnorm", x)(_p(out), _p(x), _p(w), x.shape[0], x.shape[1], eps, _stream())
     _lib.check()
     return out
 
@@ -196,8 +206,7 @@ def add_rmsnorm(residual, x, w, eps, out=None):
     """residual += x (in place); returns rmsnorm(residual) * w."""
     _cuda(residual, x, w)
     out = torch.empty_like(x) if out is None else out
-    _lib.lib().b200_add_rmsnorm_f16(_p(out), _p(residual), _p(x), _p(w), x.shape[0], x.shape[1],
-                                    eps, _stream())
+    _sym("b200_add_rmsnorm", x)(_p(out), _p(residual), _p(x), _p(w), x.shape[0], x.shape[1], eps, _stream())
     _lib.check()
     return out
 
@@ -206,7 +215,7 @@ def silu_mul(gate_up, out=None):
     _cuda(gate_up)
     T, n2 = gate_up.shape
     out = torch.empty(T, n2 // 2, dtype=gate_up.dtype, device=gate_up.device) if out is None else out
-    _lib.lib().b200_silu_mul_f16(_p(out), _p(gate_up), T, n2 // 2, _stream())
+    _sym("b200_silu_mul", gate_up)(_p(out), _p(gate_up), T, n2 // 2, _stream())
     _lib.check()
     return out
 
