@@ -249,6 +249,34 @@ void b200_wire_decode_metadata(int32_t n, const uint32_t* last_tokens, const uin
                                int32_t block_size, uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,
                                uint32_t* context_lens);
 
+/* ------------------------------------------------- the reference's default-build cache layout ("L1")
+ * kvcache_allocator.rs:150-173: without the flashattn / flashinfer features the caches are
+ *   K [num_blocks, Hkv, D/x, block_size, x] (x = 16 / element size = 8),   V [num_blocks, Hkv, D, block_size].
+ * These entry points read / write that layout directly (block_size 64, 16-bit elements; bf16 != 0 selects the bf16
+ * arithmetic): a (block, head) tile is 64*D*2 contiguous bytes, K feeds the MMAs as it lies (8 x 16-byte core
+ * matrices), V as a K-major operand.  Argument meaning as for the flash-layout functions of the same name.        */
+void b200_kv_write_l1(const void* k, const void* v, void* k_cache, void* v_cache,
+                      const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
+                      int32_t head_dim, int32_t block_size, int64_t stream);
+void b200_rope_kv_write_l1(void* q, void* k, const void* v, const void* cos, const void* sin,
+                           const int64_t* positions, const int64_t* slot_mapping,
+                           void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                           int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                           int32_t block_size, int32_t interleaved, int32_t cos_sin_f32, int32_t bf16,
+                           int64_t stream);
+void b200_paged_attn_decode_l1(void* out, const void* q, const void* k_cache,
+                               const void* v_cache, const uint32_t* block_tables,
+                               const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                               int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                               int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                               float softcap, int32_t window, void* workspace, int32_t bf16, int64_t stream);
+void b200_attn_prefill_l1(void* out, const void* q, const void* k_cache, const void* v_cache,
+                          const uint32_t* cu_seqlens_q, const uint32_t* context_lens,
+                          const uint32_t* block_tables, int32_t batch, int32_t num_heads,
+                          int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                          int32_t max_blocks_per_seq, int32_t num_blocks, int32_t max_seqlen_q,
+                          int32_t num_tokens, int32_t mode, float scale, int32_t bf16, int64_t stream);
+
 /* ------------------------------------------------- paged attention, decode
  * Replaces the decode branch of PagedAttention::forward (attention.rs:808-820).
  * out/q [B,H,D] fp16; block_tables u32 [B, max_blocks_per_seq] (zero padded);

@@ -190,6 +190,22 @@ def kv_write(k, v, k_cache, v_cache, slot_mapping):
             vc[slot] = to_e4m3(v[t]) if fp8 else v[t]
 
 
+def to_l1_layout(k_cache, v_cache):
+    """Flash layout [nb, bs, Hkv, D] -> the reference's default-build layout (kvcache_allocator.rs:150-173, no
+    flashattn / flashinfer feature): K [nb, Hkv, D/x, bs, x] with x = 16 / element size, V [nb, Hkv, D, bs]."""
+    nb, bs, Hkv, D = k_cache.shape
+    x = 16 // k_cache.element_size()
+    k1 = k_cache.view(nb, bs, Hkv, D // x, x).permute(0, 2, 3, 1, 4).contiguous()
+    v1 = v_cache.permute(0, 2, 3, 1).contiguous()
+    return k1, v1
+
+
+def from_l1_layout(k1, v1):
+    nb, Hkv, dx, bs, x = k1.shape
+    return (k1.permute(0, 3, 1, 2, 4).reshape(nb, bs, Hkv, dx * x).contiguous(),
+            v1.permute(0, 3, 1, 2).contiguous())
+
+
 def gather_kv(cache, block_table, ctx_len):
     bs = cache.shape[1]
     nblk = -(-ctx_len // bs)

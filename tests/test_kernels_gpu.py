@@ -622,3 +622,106 @@ def test_bf16_attention_prefill_paged(ops, H, Hkv, D, cases, mode):
                                 max(n for n, _ in cases), scale, mode=mode)
     assert out.dtype == BF16 and not torch.isnan(out).any()
     _close(out, ref, 1.6e-2, 1.6e-2)
+
+
+# ---------------------------------------------------------------- the reference's default-build cache layout (L1)
+# kvcache_allocator.rs:150-173: K [nb, Hkv, D/8, 64, 8], V [nb, Hkv, D, 64].  Same oracle, caches permuted.
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("H,Hkv,D", [(32, 8, 128), (32, 4, 64)])
+def test_l1_layout_cache_writes(ops, H, Hkv, D, dt):
+    cfg = om.ModelConfig(H * D, 1, H, Hkv, D, 64, 64, rope_theta=500000.0, max_pos=4096)
+    cos, sin = om.rope_tables(cfg, dtype=dt)
+    g = torch.Generator().manual_seed(5)
+    T, nb = 23, 6
+    q = torch.randn(T, H, D, generator=g).to(dt)
+    k = torch.randn(T, Hkv, D, generator=g).to(dt)
+    v = torch.randn(T, Hkv, D, generator=g).to(dt)
+    pos = torch.randint(0, 4096, (T,), generator=g)
+    slots = torch.randperm(nb * 64, generator=g)[:T]
+    slots[7] = -1
+    zeros = torch.zeros(nb, 64, Hkv, D, dtype=dt)
+    # reshape_and_cache only
+    kc1, vc1 = (t.cuda() for t in om.to_l1_layout(zeros, zeros))
+    ops.kv_write(k.cuda(), v.cuda(), kc1, vc1, slots.cuda())
+    exp_k, exp_v = zeros.clone(), zeros.clone()
+    om.kv_write(k, v, exp_k, exp_v, slots)
+    got_k, got_v = om.from_l1_layout(kc1.cpu(), vc1.cpu())
+    assert torch.equal(got_k, exp_k) and torch.equal(got_v, exp_v)
+    # RoPE + cache write in one launch: the same rotated values as the flash-layout call, at the L1 positions
+    qd, kd = q.cuda(), k.cuda()
+    kc1, vc1 = (t.cuda() for t in om.to_l1_layout(zeros, zeros))
+    ops.rope_kv_write(qd, kd, v.cuda(), cos.cuda(), sin.cuda(), pos.cuda(), slots.cuda(), kc1, vc1)
+    q2, k2 = q.cuda(), k.cuda()
+    kc2, vc2 = zeros.clone().cuda(), zeros.clone().cuda()
+    ops.rope_kv_write(q2, k2, v.cuda(), cos.cuda(), sin.cuda(), pos.cuda(), slots.cuda(), kc2, vc2)
+    assert torch.equal(qd, q2) and torch.equal(kd, k2)
+    got_k, got_v = om.from_l1_layout(kc1.cpu(), vc1.cpu())
+    assert torch.equal(got_k, kc2.cpu()) and torch.equal(got_v, vc2.cpu())
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("H,Hkv,D,ctxs", [
+    (32, 8, 128, [1, 63, 64, 65, 127, 129, 700, 4096]),
+    (32, 4, 64, [37, 1, 500, 0, 2048]),
+    (16, 1, 128, [130]),
+])
+def test_l1_layout_paged_attention_decode(ops, H, Hkv, D, ctxs, dt):
+    B = len(ctxs)
+    q, kc, vc, bt, cl = (t.to(dt) if t.dtype == F16 else t for t in _paged_case(B, H, Hkv, D, ctxs, seed=H + D + 1))
+    scale = 1.0 / math.sqrt(D)
+    with om.model_dtype(dt):
+        ref = om.paged_attention_decode(q, kc, vc, bt.tolist(), cl.tolist(), scale)
+    for b, c in enumerate(ctxs):                       # stale rows past the context must not leak
+        if c % 64:
+            kc[bt[b, (c - 1) // 64], c % 64:] = float("nan")
+            vc[bt[b, (c - 1) // 64], c % 64:] = float("nan")
+    k1, v1 = om.to_l1_layout(kc, vc)
+    out = ops.paged_attention_decode(q.cuda(), k1.cuda(), v1.cuda(), bt.cuda(), cl.cuda(), scale)
+    assert not torch.isnan(out).any()
+    tol = 2e-3 if dt == F16 else 1.6e-2
+    _close(out, ref, tol, tol)
+    # and it is the flash-layout kernel's answer to the last bit of the dtype: same MMAs on the same fragments
+    out2 = ops.paged_attention_decode(q.cuda(), kc.cuda(), vc.cuda(), bt.cuda(), cl.cuda(), scale)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("dt,mode", [(F16, -1), (BF16, -1), (F16, 0)])
+@pytest.mark.parametrize("H,Hkv,D,cases", [
+    (32, 8, 128, [(37, 0), (64, 0), (65, 0), (130, 64), (1, 0), (200, 128)]),
+    (32, 4, 64, [(300, 0), (5, 192)]),
+])
+def test_l1_layout_attention_prefill(ops, H, Hkv, D, cases, dt, mode):
+    g = torch.Generator().manual_seed(H * D + len(cases) + 1)
+    B = len(cases)
+    ctxs = [n + c for n, c in cases]
+    nblk = [-(-c // 64) for c in ctxs]
+    nb = sum(nblk) + 3
+    perm = torch.randperm(nb, generator=g).tolist()
+    kc = torch.randn(nb, 64, Hkv, D, generator=g).to(dt)
+    vc = torch.randn(nb, 64, Hkv, D, generator=g).to(dt)
+    bt = torch.zeros(B, max(nblk), dtype=torch.int32)
+    off = 0
+    for b, n in enumerate(nblk):
+        bt[b, :n] = torch.tensor(perm[off:off + n], dtype=torch.int32)
+        off += n
+    cu = [0]
+    for n, _ in cases:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    q = torch.randn(T, H, D, generator=g).to(dt)
+    scale = 1.0 / math.sqrt(D)
+    dummy = torch.zeros(T, Hkv, D, dtype=dt)
+    with om.model_dtype(dt):
+        ref = om.attention_prefill(q, dummy, dummy, cu, kc, vc, bt.tolist(), ctxs, scale)
+    for b, n in enumerate(nblk):
+        last = ctxs[b] % 64
+        if last:
+            kc[bt[b, n - 1], last:] = float("nan")
+            vc[bt[b, n - 1], last:] = float("nan")
+    k1, v1 = om.to_l1_layout(kc, vc)
+    out = ops.attention_prefill(q.cuda(), k1.cuda(), v1.cuda(), torch.tensor(cu, dtype=torch.int32).cuda(),
+                                torch.tensor(ctxs, dtype=torch.int32).cuda(), bt.cuda(),
+                                max(n for n, _ in cases), scale, mode=mode)
+    assert not torch.isnan(out).any()
+    tol = 2e-3 if dt == F16 else 1.6e-2
+    _close(out, ref, tol, tol)

@@ -105,6 +105,10 @@ _SIGS = {
     "b200_pd_import_blocks": (None, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_i64]),
     "b200_pd_copy_blocks_peer": (None, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_i64]),
     "b200_enable_peer_access": (c_i32, [c_i32, c_i32]),
+    "b200_kv_write_l1": (None, [c_vp] * 5 + [c_i32] * 4 + [c_i64]),
+    "b200_rope_kv_write_l1": (None, [c_vp] * 9 + [c_i32] * 9 + [c_i64]),
+    "b200_paged_attn_decode_l1": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i32, c_i64]),
+    "b200_attn_prefill_l1": (None, [c_vp] * 7 + [c_i32] * 10 + [c_f32, c_i32, c_i64]),
     "b200_wire_kind": (c_i32, [c_vp, c_i64]),
     "b200_wire_parse_run_decode": (c_i32, [c_vp, c_i64, c_i32, c_i32] + [c_vp] * 9),
     "b200_wire_frame_run_decode": (c_i64, [c_vp, c_i64, c_i32] + [c_vp] * 6 + [c_i32, c_vp, c_vp, c_i32]),

@@ -7,9 +7,10 @@ namespace b200 {
 struct AttnMaps {
   CUtensorMap k, v;
   bool fp8 = false;      // e4m3 cache (one byte per element, head_dim 128): decode kernel only
+  bool l1 = false;       // the reference's default-build layout: K [nb, Hkv, D/8, 64, 8], V [nb, Hkv, D, 64]
 };
 bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks,
-                    int Hkv, int D, bool fp8 = false);
+                    int Hkv, int D, bool fp8 = false, bool l1 = false);
 void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
@@ -30,7 +31,7 @@ void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_s
                           int v_stride, const void* cos, const void* sin,
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
-                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8 = 0, bool bf16 = false);
+                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8 = 0, bool bf16 = false, int l1 = 0);
 // FP8 cache pages of every sequence's context -> fp16 scratch blocks b * max_blocks + i (+ that identity
 // block table when scratch_bt != NULL): what the prefill attention kernels read in --fp8-kvcache mode.
 void launch_kv_fp8_gather(const void* k8, const void* v8, void* ks, void* vs, uint32_t* scratch_bt,

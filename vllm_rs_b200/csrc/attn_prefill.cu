@@ -35,7 +35,9 @@ struct Smem {
 };
 }  // namespace pf
 
-template <int D, bool BF>
+// L1: the reference's default-build cache layout, staged and read as in paged_attn_decode.cu (K tile as it lies,
+// V tile = D rows of 64 swizzled tokens through a non-transposed ldmatrix).
+template <int D, bool BF, bool L1>
 __global__ void __launch_bounds__(pf::kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                     const __half* __restrict__ q, __half* __restrict__ out,
@@ -94,10 +96,15 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
           mbar_arrive_expect_tx(&full_bar[s], SM::kStageBytes);
           uint8_t* kdst = smem + s * SM::kStageBytes;
           uint8_t* vdst = kdst + SM::kTileBytes;
+          if (L1) {
+            tma_load_4d(kdst, &kmap, &full_bar[s], 0, 0, hkv, blk);
+            tma_load_4d(vdst, &vmap, &full_bar[s], 0, 0, hkv, blk);
+          } else {
 #pragma unroll
-          for (int hb = 0; hb < D / 64; ++hb) {
-            tma_load_4d(kdst + hb * (kTok * 128), &kmap, &full_bar[s], hb * 64, hkv, 0, blk);
-            tma_load_4d(vdst + hb * (kTok * 128), &vmap, &full_bar[s], hb * 64, hkv, 0, blk);
+            for (int hb = 0; hb < D / 64; ++hb) {
+              tma_load_4d(kdst + hb * (kTok * 128), &kmap, &full_bar[s], hb * 64, hkv, 0, blk);
+              tma_load_4d(vdst + hb * (kTok * 128), &vmap, &full_bar[s], hb * 64, hkv, 0, blk);
+            }
           }
         }
       }
@@ -155,7 +162,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
         for (int np = 0; np < 4; ++np) {
           const int tok = np * 16 + k_row;
           uint32_t r[4];
-          ldsm_x4(r, kbase + hb * (kTok * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4));
+          if (L1) ldsm_x4(r, kbase + (2 * ks + k_chunk_sel) * (kTok * 16) + tok * 16);
+          else ldsm_x4(r, kbase + hb * (kTok * 128) + tok * 128 + ((chunk ^ (tok & 7)) << 4));
           mma_16816_t<BF>(sc[2 * np], qa[ks], r[0], r[1]);
           mma_16816_t<BF>(sc[2 * np + 1], qa[ks], r[2], r[3]);
         }
@@ -224,7 +232,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
           const int chunk = 2 * jj + v_chunk_sel;
           const int hb = chunk >> 3, c16 = chunk & 7;
           uint32_t r[4];
-          ldsm_x4_t(r, vbase + hb * (kTok * 128) + tok * 128 + ((c16 ^ (tok & 7)) << 4));
+          if (L1) {
+            const int dd = (2 * jj + (lane >> 4)) * 8 + (lane & 7);
+            const int tch = 2 * kk + ((lane >> 3) & 1);
+            ldsm_x4(r, vbase + dd * 128 + ((tch ^ (lane & 7)) << 4));
+          } else {
+            ldsm_x4_t(r, vbase + hb * (kTok * 128) + tok * 128 + ((c16 ^ (tok & 7)) << 4));
+          }
           if (partial) {
             r[0] &= vmask_lo; r[2] &= vmask_lo;
             r[1] &= vmask_hi; r[3] &= vmask_hi;
@@ -253,7 +267,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_const
   }
 }
 
-template <int D, bool BF>
+template <int D, bool BF, bool L1>
 static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stride,
                       const uint32_t* cu_q, const uint32_t* ctx_lens, const uint32_t* block_tables,
                       int B, int H, int Hkv, int max_blocks, int max_seqlen_q, float scale,
@@ -262,12 +276,12 @@ static void launch_pf(const AttnMaps& maps, void* out, const void* q, int q_stri
   const int TQ = (pf::kWarps / G) * 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_prefill_kernel<D, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(attn_prefill_kernel<D, BF, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          pf::Smem<D>::kAlloc);
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + TQ - 1) / TQ, Hkv, B);
-  launch_pdl(attn_prefill_kernel<D, BF>, grid, dim3(pf::kThreads), pf::Smem<D>::kAlloc, st, maps.k, maps.v,
+  launch_pdl(attn_prefill_kernel<D, BF, L1>, grid, dim3(pf::kThreads), pf::Smem<D>::kAlloc, st, maps.k, maps.v,
              reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out), cu_q, ctx_lens,
              block_tables, q_stride, H, Hkv, max_blocks, scale * 1.4426950408889634f);
   B200_CUDA_LAUNCH_CHECK();
@@ -282,10 +296,15 @@ void launch_attn_prefill(const AttnMaps& maps, void* out, const void* q, int q_s
                                                max_blocks, max_seqlen_q, total_rows, scale, mode, st, bf16))
     return;
 #define B200_PF_ARGS maps, out, q, q_stride, cu_q, ctx_lens, block_tables, B, H, Hkv, max_blocks, max_seqlen_q, scale, st
-  if (D == 128 && bf16) launch_pf<128, true>(B200_PF_ARGS);
-  else if (D == 128) launch_pf<128, false>(B200_PF_ARGS);
-  else if (bf16) launch_pf<64, true>(B200_PF_ARGS);
-  else launch_pf<64, false>(B200_PF_ARGS);
+  if (maps.l1) {
+    if (D == 128 && bf16) launch_pf<128, true, true>(B200_PF_ARGS);
+    else if (D == 128) launch_pf<128, false, true>(B200_PF_ARGS);
+    else if (bf16) launch_pf<64, true, true>(B200_PF_ARGS);
+    else launch_pf<64, false, true>(B200_PF_ARGS);
+  } else if (D == 128 && bf16) launch_pf<128, true, false>(B200_PF_ARGS);
+  else if (D == 128) launch_pf<128, false, false>(B200_PF_ARGS);
+  else if (bf16) launch_pf<64, true, false>(B200_PF_ARGS);
+  else launch_pf<64, false, false>(B200_PF_ARGS);
 #undef B200_PF_ARGS
 }
 
@@ -298,7 +317,7 @@ static void attn_prefill_ex_any(void* out, const void* q, const void* k_cache,
                                 int32_t head_dim, int32_t block_size,
                                 int32_t max_blocks_per_seq, int32_t num_blocks,
                                 int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
-                                int64_t stream, bool bf16) {
+                                int64_t stream, bool bf16, bool l1 = false) {
   using namespace b200;
   B200_CHECK_ARG(block_size == 64, "attn_prefill: block_size must be 64");
   B200_CHECK_ARG(head_dim == 64 || head_dim == 128, "attn_prefill: head_dim must be 64/128");
@@ -309,7 +328,7 @@ static void attn_prefill_ex_any(void* out, const void* q, const void* k_cache,
   B200_CHECK_ARG(batch > 0 && max_seqlen_q > 0 && num_tokens > 0 && block_tables && cu_seqlens_q,
                  "attn_prefill: bad sizes or NULL metadata");
   AttnMaps maps;
-  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim)) {
+  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim, false, l1)) {
     set_error(2, "attn_prefill: cuTensorMapEncodeTiled failed");
     return;
   }
@@ -329,6 +348,19 @@ extern "C" void b200_attn_prefill_ex_f16(void* out, const void* q, const void* k
   attn_prefill_ex_any(out, q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables, batch, num_heads,
                       num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, max_seqlen_q, num_tokens,
                       mode, scale, stream, false);
+}
+
+extern "C" void b200_attn_prefill_l1(void* out, const void* q, const void* k_cache,
+                                     const void* v_cache, const uint32_t* cu_seqlens_q,
+                                     const uint32_t* context_lens, const uint32_t* block_tables,
+                                     int32_t batch, int32_t num_heads, int32_t num_kv_heads,
+                                     int32_t head_dim, int32_t block_size,
+                                     int32_t max_blocks_per_seq, int32_t num_blocks,
+                                     int32_t max_seqlen_q, int32_t num_tokens, int32_t mode, float scale,
+                                     int32_t bf16, int64_t stream) {
+  attn_prefill_ex_any(out, q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables, batch, num_heads,
+                      num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, max_seqlen_q, num_tokens,
+                      mode, scale, stream, bf16 != 0, true);
 }
 
 extern "C" void b200_attn_prefill_ex_bf16(void* out, const void* q, const void* k_cache,

@@ -78,7 +78,22 @@ struct Args {
   int dbg;           // bit 0: swap LBO / SBO of the V descriptor (bring-up switch)
 };
 
-template <bool BF>
+// K-major operand without a swizzle ("interleave" layout, cute mma_traits_sm100: ((8,m),(T,2)):((1T,SBO),(1,LBO))):
+// a core matrix is 8 rows x 16 bytes stored as 128 contiguous bytes; LBO = distance between the two core matrices of
+// one k-step, SBO = distance between 8-row groups.  This is how a (block, head) K tile of the reference's
+// default-build cache lies in memory ([D/8][64 tokens][8]: LBO = 1024, SBO = 128), so the tile is consumed as copied.
+__device__ __forceinline__ uint64_t make_smem_desc_k_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  return d;
+}
+
+// L1 = the reference's default-build cache layout (K [nb, Hkv, D/8, 64, 8], V [nb, Hkv, D, 64]): K as above, V is a
+// K-major operand of the P V MMA (rows = d, 64 tokens = 128 swizzled bytes) instead of the flash layout's MN-major.
+template <bool BF, bool L1>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                        const __grid_constant__ CUtensorMap vmap, const Args a) {
@@ -156,10 +171,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
           mbar_arrive_expect_tx(&kv_full[s], kStageBytes);
           uint8_t* kdst = kv_smem + s * kStageBytes;
           uint8_t* vdst = kdst + kTileBytes;
-          tma_load_4d(kdst, &kmap, &kv_full[s], 0, hkv, 0, blk);
-          tma_load_4d(kdst + kTok * 128, &kmap, &kv_full[s], 64, hkv, 0, blk);
-          tma_load_4d(vdst, &vmap, &kv_full[s], 0, hkv, 0, blk);
-          tma_load_4d(vdst + kTok * 128, &vmap, &kv_full[s], 64, hkv, 0, blk);
+          if (L1) {
+            tma_load_4d(kdst, &kmap, &kv_full[s], 0, 0, hkv, blk);
+            tma_load_4d(vdst, &vmap, &kv_full[s], 0, 0, hkv, blk);
+          } else {
+            tma_load_4d(kdst, &kmap, &kv_full[s], 0, hkv, 0, blk);
+            tma_load_4d(kdst + kTok * 128, &kmap, &kv_full[s], 64, hkv, 0, blk);
+            tma_load_4d(vdst, &vmap, &kv_full[s], 0, hkv, 0, blk);
+            tma_load_4d(vdst + kTok * 128, &vmap, &kv_full[s], 64, hkv, 0, blk);
+          }
         }
       }
     }
@@ -168,7 +188,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
     if (lane == 0) {
       constexpr uint32_t kFmt = BF ? ((1u << 7) | (1u << 10)) : 0u;          // a_format / b_format = BF16
       const uint32_t idesc_s = make_idesc_f16(kRows, kTok) | kFmt;
-      const uint32_t idesc_o = make_idesc_f16(kRows, kD) | (1u << 16) | kFmt;   // B operand MN-major
+      const uint32_t idesc_o = make_idesc_f16(kRows, kD) | (L1 ? 0u : (1u << 16)) | kFmt;   // flash V: MN-major B
       const uint32_t s_tmem = tmem_base + kSCol, p_tmem = tmem_base + kPCol, o_tmem = tmem_base + kOCol;
       const uint32_t q_addr = smem_u32(q_smem);
       auto issue_qk = [&](int j) {
@@ -181,7 +201,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
         for (int ks = 0; ks < kD / 16; ++ks) {
           const uint32_t off = (ks >> 2) * 0 + (ks & 3) * 32;
           const uint64_t adesc = make_smem_desc_sw128(q_addr + (ks >> 2) * (kRows * 128) + off);
-          const uint64_t bdesc = make_smem_desc_sw128(k_addr + (ks >> 2) * (kTok * 128) + off);
+          const uint64_t bdesc = L1 ? ((a.dbg & 1) ? make_smem_desc_k_nosw(k_addr + ks * 2048, 128, 1024)
+                                                   : make_smem_desc_k_nosw(k_addr + ks * 2048, 1024, 128))
+                                    : make_smem_desc_sw128(k_addr + (ks >> 2) * (kTok * 128) + off);
           tc_mma_ss(s_tmem, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
         }
         tc_commit(s_full);
@@ -196,9 +218,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
         const uint32_t v_addr = smem_u32(kv_smem + s * kStageBytes + kTileBytes);
 #pragma unroll
         for (int ks = 0; ks < kTok / 16; ++ks) {
-          const uint64_t bdesc = (a.dbg & 1)
-                                     ? make_smem_desc_mn_sw128(v_addr + ks * 2048, 1024, kTok * 128)
-                                     : make_smem_desc_mn_sw128(v_addr + ks * 2048, kTok * 128, 1024);
+          const uint64_t bdesc = L1 ? make_smem_desc_sw128(v_addr + ks * 32)
+                                 : (a.dbg & 1) ? make_smem_desc_mn_sw128(v_addr + ks * 2048, 1024, kTok * 128)
+                                               : make_smem_desc_mn_sw128(v_addr + ks * 2048, kTok * 128, 1024);
           tc_mma_ts(o_tmem, p_tmem + ks * 8, bdesc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
         tc_commit(&kv_empty[s]);
@@ -266,6 +288,19 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
         mbar_wait_bounded(&kv_full[j & 1], (j >> 1) & 1);
         uint8_t* vt = kv_smem + (j & 1) * kStageBytes + kTileBytes;
         const int first_bad = ctx - page_base;             // rows [first_bad, 64) of both D halves
+        if (L1) {
+          // rows = d, tokens along the swizzled 128-byte row: 16-byte chunk c holds tokens 8c .. 8c+7
+          for (int idx = (warp - 2) * 32 + lane; idx < kD * 8; idx += 128) {
+            const int row = idx >> 3, c = idx & 7;
+            if (8 * c + 7 < first_bad) continue;
+            uint8_t* p = vt + row * 128 + ((c ^ (row & 7)) << 4);
+            if (8 * c >= first_bad) {
+              *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0);
+            } else {
+              for (int e = first_bad - 8 * c; e < 8; ++e) reinterpret_cast<uint16_t*>(p)[e] = 0;
+            }
+          }
+        } else
         for (int idx = (warp - 2) * 32 + lane; idx < (kTok - first_bad) * 16; idx += 128) {
           const int row = first_bad + (idx >> 4), c16 = idx & 15;
           *reinterpret_cast<uint4*>(vt + (c16 >> 3) * (kTok * 128) + row * 128 + (c16 & 7) * 16) =
@@ -371,13 +406,16 @@ bool launch_attn_prefill_tc(const AttnMaps& maps, void* out, const void* q, int 
   a.dbg = mode == 2 ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
-    cudaFuncSetAttribute(attn_prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
+    cudaFuncSetAttribute(attn_prefill_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc);
     attr_set = true;
   }
   dim3 grid((max_seqlen_q + TQ - 1) / TQ, Hkv, B);
-  if (bf16) launch_pdl(attn_prefill_tc_kernel<true>, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
-  else launch_pdl(attn_prefill_tc_kernel<false>, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
+  auto kern = maps.l1 ? (bf16 ? attn_prefill_tc_kernel<true, true> : attn_prefill_tc_kernel<false, true>)
+                      : (bf16 ? attn_prefill_tc_kernel<true, false> : attn_prefill_tc_kernel<false, false>);
+  launch_pdl(kern, grid, dim3(kThreads), kAlloc, st, qmap, maps.k, maps.v, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
 }

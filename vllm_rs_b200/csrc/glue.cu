@@ -32,6 +32,17 @@ __device__ __forceinline__ uint32_t half2x2_to_e4m3x4(uint32_t lo, uint32_t hi) 
          (static_cast<uint32_t>(__nv_cvt_halfraw2_to_fp8x2(b, __NV_SATFINITE, __NV_E4M3)) << 16);
 }
 
+// Element index in the reference's default-build cache layout (kvcache_allocator.rs:150-173): slot = block * 64 +
+// offset; K [num_blocks, Hkv, D/8, 64, 8], V [num_blocks, Hkv, D, 64].
+__device__ __forceinline__ size_t l1_k_index(int64_t slot, int h, int d, int Hkv, int D) {
+  const size_t blk = static_cast<size_t>(slot >> 6), off = static_cast<size_t>(slot & 63);
+  return (((blk * Hkv + h) * (D >> 3) + (d >> 3)) * 64 + off) * 8 + (d & 7);
+}
+__device__ __forceinline__ size_t l1_v_index(int64_t slot, int h, int d, int Hkv, int D) {
+  const size_t blk = static_cast<size_t>(slot >> 6), off = static_cast<size_t>(slot & 63);
+  return ((blk * Hkv + h) * D + d) * 64 + off;
+}
+
 // ------------------------------------------------------------------ RoPE + KV write
 // grid = tokens; one thread per rotation pair / per 2 copied elements.
 // Cache layout [num_blocks, block_size, Hkv, D]: slot s -> row s of [.., Hkv, D].
@@ -43,7 +54,7 @@ __global__ void rope_kv_write_kernel(uint16_t* __restrict__ q, uint16_t* __restr
                                      const int64_t* __restrict__ slot_mapping,
                                      uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache,
                                      int q_stride, int k_stride, int v_stride, int H, int Hkv,
-                                     int D, int rot_dim, int interleaved, int kv_fp8) {
+                                     int D, int rot_dim, int interleaved, int kv_fp8, int l1) {
   pdl_trigger();
   pdl_wait();
   const int t = blockIdx.x;
@@ -100,6 +111,9 @@ __global__ void rope_kv_write_kernel(uint16_t* __restrict__ q, uint16_t* __restr
         if (kv_fp8) {
           kc8[(head - H) * D + i0] = half_to_e4m3(__ushort_as_half(h0));
           kc8[(head - H) * D + i1] = half_to_e4m3(__ushort_as_half(h1));
+        } else if (l1) {
+          k_cache[l1_k_index(slot, head - H, i0, Hkv, D)] = h0;
+          k_cache[l1_k_index(slot, head - H, i1, Hkv, D)] = h1;
         } else {
           kc[(head - H) * D + i0] = h0;
           kc[(head - H) * D + i1] = h1;
@@ -109,11 +123,19 @@ __global__ void rope_kv_write_kernel(uint16_t* __restrict__ q, uint16_t* __restr
       if (kv_fp8) {
         kc8[(head - H) * D + i0] = half_to_e4m3(__ushort_as_half(base[i0]));
         kc8[(head - H) * D + i1] = half_to_e4m3(__ushort_as_half(base[i1]));
+      } else if (l1) {
+        k_cache[l1_k_index(slot, head - H, i0, Hkv, D)] = base[i0];
+        k_cache[l1_k_index(slot, head - H, i1, Hkv, D)] = base[i1];
       } else {
         kc[(head - H) * D + i0] = base[i0];
         kc[(head - H) * D + i1] = base[i1];
       }
     }
+  }
+  if (l1) {                                        // V [nb, Hkv, D, 64]: one element per (head, d) row of the block
+    if (vc && vt)
+      for (int i = threadIdx.x; i < Hkv * D; i += blockDim.x) v_cache[l1_v_index(slot, i / D, i % D, Hkv, D)] = vt[i];
+    return;
   }
   // V copy (8 halves per thread)
   if (vc && vt) {
@@ -208,10 +230,21 @@ void launch_kv_fp8_gather(const void* k8, const void* v8, void* ks, void* vs, ui
 
 __global__ void kv_write_kernel(const __half* __restrict__ k, const __half* __restrict__ v,
                                 __half* __restrict__ k_cache, __half* __restrict__ v_cache,
-                                const int64_t* __restrict__ slot_mapping, int row_halfs) {
+                                const int64_t* __restrict__ slot_mapping, int row_halfs, int Hkv, int D, int l1) {
   const int t = blockIdx.x;
   const int64_t slot = slot_mapping[t];
   if (slot < 0) return;
+  if (l1) {
+    // K: 16-byte chunks of 8 d-values keep together; V: one element per (head, d) row
+    const uint4* ks = reinterpret_cast<const uint4*>(k + static_cast<size_t>(t) * row_halfs);
+    for (int i = threadIdx.x; i < (row_halfs >> 3); i += blockDim.x) {
+      const int h = (i * 8) / D, d = (i * 8) % D;
+      *reinterpret_cast<uint4*>(k_cache + l1_k_index(slot, h, d, Hkv, D)) = ks[i];
+    }
+    const __half* vs = v + static_cast<size_t>(t) * row_halfs;
+    for (int i = threadIdx.x; i < row_halfs; i += blockDim.x) v_cache[l1_v_index(slot, i / D, i % D, Hkv, D)] = vs[i];
+    return;
+  }
   const int n16 = row_halfs >> 3;
   const uint4* ks = reinterpret_cast<const uint4*>(k + static_cast<size_t>(t) * row_halfs);
   const uint4* vs = reinterpret_cast<const uint4*>(v + static_cast<size_t>(t) * row_halfs);
@@ -420,12 +453,12 @@ template <bool F32, bool BF>
 static void launch_rope_kv_write_t(void* q, void* k, const void* v, int q_stride, int k_stride, int v_stride,
                                    const void* cos, const void* sin, const int64_t* positions,
                                    const int64_t* slot_mapping, void* k_cache, void* v_cache, int T, int H, int Hkv,
-                                   int D, int rot_dim, int interleaved, cudaStream_t st, int kv_fp8) {
+                                   int D, int rot_dim, int interleaved, cudaStream_t st, int kv_fp8, int l1) {
   const int pairs = (H + Hkv) * D / 2;
   const int threads = pairs >= 512 ? 512 : (pairs >= 256 ? 256 : 128);
   launch_pdl(rope_kv_write_kernel<F32, BF>, dim3(T), dim3(threads), 0, st, (uint16_t*)q, (uint16_t*)k,
              (const uint16_t*)v, cos, sin, positions, slot_mapping, (uint16_t*)k_cache, (uint16_t*)v_cache,
-             q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8);
+             q_stride, k_stride, v_stride, H, Hkv, D, rot_dim, interleaved, kv_fp8, l1);
   B200_CUDA_LAUNCH_CHECK();
 }
 
@@ -433,11 +466,11 @@ void launch_rope_kv_write(void* q, void* k, const void* v, int q_stride, int k_s
                           int v_stride, const void* cos, const void* sin,
                           const int64_t* positions, const int64_t* slot_mapping, void* k_cache,
                           void* v_cache, int T, int H, int Hkv, int D, int rot_dim,
-                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8, bool bf16) {
+                          int interleaved, int cos_sin_f32, cudaStream_t st, int kv_fp8, bool bf16, int l1) {
 #define B200_ROPE_ARGS q, k, v, q_stride, k_stride, v_stride, cos, sin, positions, slot_mapping, k_cache, v_cache, T, \
-                       H, Hkv, D, rot_dim, interleaved, st, kv_fp8
-  if (bf16 && kv_fp8) {
-    set_error(1, "rope_kv_write: the e4m3 cache write is fp16 only");
+                       H, Hkv, D, rot_dim, interleaved, st, kv_fp8, l1
+  if ((bf16 || l1) && kv_fp8) {
+    set_error(1, "rope_kv_write: the e4m3 cache write is fp16 / flash layout only");
     return;
   }
   if (bf16) {
@@ -560,8 +593,36 @@ void b200_kv_write_f16(const void* k, const void* v, void* k_cache, void* v_cach
   B200_CHECK_ARG((num_kv_heads * head_dim) % 8 == 0, "kv_write: row must be a multiple of 8");
   kv_write_kernel<<<num_tokens, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const __half*)k, (const __half*)v, (__half*)k_cache, (__half*)v_cache, slot_mapping,
-      num_kv_heads * head_dim);
+      num_kv_heads * head_dim, num_kv_heads, head_dim, 0);
   B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_kv_write_l1(const void* k, const void* v, void* k_cache, void* v_cache,
+                      const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
+                      int32_t head_dim, int32_t block_size, int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(block_size == 64 && head_dim % 8 == 0, "kv_write_l1: block_size must be 64, head_dim a multiple of 8");
+  kv_write_kernel<<<num_tokens, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __half*)k, (const __half*)v, (__half*)k_cache, (__half*)v_cache, slot_mapping,
+      num_kv_heads * head_dim, num_kv_heads, head_dim, 1);
+  B200_CUDA_LAUNCH_CHECK();
+}
+
+void b200_rope_kv_write_l1(void* q, void* k, const void* v, const void* cos, const void* sin,
+                           const int64_t* positions, const int64_t* slot_mapping,
+                           void* k_cache, void* v_cache, int32_t num_tokens, int32_t num_heads,
+                           int32_t num_kv_heads, int32_t head_dim, int32_t rot_dim,
+                           int32_t block_size, int32_t interleaved, int32_t cos_sin_f32, int32_t bf16,
+                           int64_t stream) {
+  if (num_tokens <= 0) return;
+  B200_CHECK_ARG(block_size == 64, "rope_kv_write_l1: block_size must be 64");
+  B200_CHECK_ARG(head_dim % 8 == 0 && rot_dim % 2 == 0 && rot_dim <= head_dim && rot_dim > 0,
+                 "rope_kv_write: bad head_dim / rot_dim");
+  B200_CHECK_ARG(q && k && cos && sin && positions, "rope_kv_write: NULL pointer");
+  launch_rope_kv_write(q, k, v, num_heads * head_dim, num_kv_heads * head_dim,
+                       num_kv_heads * head_dim, cos, sin, positions, slot_mapping, k_cache,
+                       v_cache, num_tokens, num_heads, num_kv_heads, head_dim, rot_dim,
+                       interleaved, cos_sin_f32, reinterpret_cast<cudaStream_t>(stream), 0, bf16 != 0, 1);
 }
 
 void b200_rmsnorm_f16(void* out, const void* x, const void* weight, int32_t num_tokens,

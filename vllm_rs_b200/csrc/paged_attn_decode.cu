@@ -89,7 +89,13 @@ __device__ __forceinline__ int first_page_of(int ctx, int window) {
 
 // HI = false promises H / Hkv <= 8: rows 8..15 of every A fragment are the constant 0, which frees the 16
 // registers the fp8 instantiation needs to fit 3 CTAs per SM without spilling.
-template <int D, bool F8, bool HI, int NS, bool BF>
+// L1 = the reference's default-build cache layout (kvcache_allocator.rs:150-173, no flashattn / flashinfer feature):
+// K [num_blocks, Hkv, D/8, 64, 8], V [num_blocks, Hkv, D, 64].  A (block, head) tile is 64*D*2 contiguous bytes in
+// both: K lands as it lies (16-byte chunks of 8 d-values, chunk-major, token-minor: eight consecutive token rows of
+// one chunk are 128 contiguous bytes, conflict-free for ldmatrix without a swizzle); V lands as D rows of 64 tokens
+// = 128 bytes under SWIZZLE_128B and feeds the P V MMA through a NON-transposed ldmatrix (rows = d, 16 bytes = 8
+// consecutive tokens, which is the B-fragment's k pairing).
+template <int D, bool F8, bool HI, int NS, bool BF, bool L1>
 __device__ __forceinline__ void
 paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
                        const __half* __restrict__ q, __half* __restrict__ out,
@@ -103,6 +109,7 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
   constexpr int kNS = SM::kNumStages;
   static_assert(!F8 || D == 128, "fp8 tiles are one 128-byte row per token");
   static_assert(!(F8 && BF), "the e4m3 cache is expanded to fp16 operands");
+  static_assert(!(F8 && L1), "the e4m3 cache is built for the flash layout only");
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   const int ctx = static_cast<int>(context_lens[b]);
   if (ctx <= 0) {
@@ -183,6 +190,9 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
         if (F8) {
           tma_load_4d(kdst, &kmap, &full_bar[s], 0, hkv, 0, blk);       // 64 rows x 128 e4m3 bytes
           tma_load_4d(vdst, &vmap, &full_bar[s], 0, hkv, 0, blk);
+        } else if (L1) {
+          tma_load_4d(kdst, &kmap, &full_bar[s], 0, 0, hkv, blk);       // the contiguous tile, as 512-byte rows
+          tma_load_4d(vdst, &vmap, &full_bar[s], 0, 0, hkv, blk);       // D rows x 64 tokens, swizzled
         } else {
 #pragma unroll
           for (int hb = 0; hb < D / 64; ++hb) {
@@ -373,7 +383,8 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
           const int hb = ks >> 2;
           const int chunk = ((ks & 3) << 1) + k_chunk_sel;
           uint32_t r[4];
-          ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
+          if (L1) ldsm_x4(r, kbase + (2 * ks + k_chunk_sel) * (kTok * 16) + k_tok * 16);
+          else ldsm_x4(r, kbase + hb * (kTok * 128) + k_tok * 128 + ((chunk ^ (k_tok & 7)) << 4));
           mma_16816_t<BF>(s0, qa[ks], r[0], r[1]);
           mma_16816_t<BF>(s1, qa[ks], r[2], r[3]);
         }
@@ -426,7 +437,14 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
           const int chunk = 2 * jj + v_chunk_sel;       // 16-byte chunk along d (0..D/8-1)
           const int hb = chunk >> 3, c16 = chunk & 7;
           uint32_t r[4];
-          ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
+          if (L1) {
+            // matrix m = lane / 8: d-tile 2 jj + (m >> 1), token chunk (t0 / 8) + (m & 1); row = d, 16 B = 8 tokens
+            const int dd = (2 * jj + (lane >> 4)) * 8 + (lane & 7);
+            const int tch = (t0 >> 3) + ((lane >> 3) & 1);
+            ldsm_x4(r, vbase + dd * 128 + ((tch ^ (lane & 7)) << 4));
+          } else {
+            ldsm_x4_t(r, vbase + hb * (kTok * 128) + v_tok * 128 + ((c16 ^ (v_tok & 7)) << 4));
+          }
           if (partial) {   // never let stale cache rows (possibly NaN) meet p == 0
             r[0] &= vmask_lo; r[2] &= vmask_lo;
             r[1] &= vmask_hi; r[3] &= vmask_hi;
@@ -517,9 +535,9 @@ paged_attn_decode_body(const CUtensorMap& kmap, const CUtensorMap& vmap,
       pages_per_split, max_splits, scale_log2, softcap, window
 
 // 2 CTAs per SM (96 KB of stages each) for both cache formats
-template <int D, bool F8, bool HI, bool BF>
+template <int D, bool F8, bool HI, bool BF, bool L1>
 __global__ void __launch_bounds__(kThreads, 2) paged_attn_decode_kernel(B200_ATTN_DECODE_PARAMS) {
-  paged_attn_decode_body<D, F8, HI, F8 ? 6 : kStages, BF>(B200_ATTN_DECODE_ARGS);
+  paged_attn_decode_body<D, F8, HI, F8 ? 6 : kStages, BF, L1>(B200_ATTN_DECODE_ARGS);
 }
 // Split merge: one CTA per (head, sequence).  Launched with PDL right behind the main kernel, so
 // its launch latency hides under the main kernel's tail (a fused last-CTA merge was measured
@@ -604,22 +622,46 @@ static bool make_cache_map(CUtensorMap* map, const void* cache, int num_blocks, 
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
 }
 
+// L1 layout (see paged_attn_decode_body): K tile = 64*D*2 contiguous bytes viewed as rows of 256 elements, no swizzle;
+// V tile = D rows of 64 tokens under the 128-byte swizzle.
+static bool make_cache_maps_l1(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks, int Hkv, int D) {
+  const uint64_t tile = static_cast<uint64_t>(kTok) * D * 2;
+  const uint32_t es[4] = {1, 1, 1, 1};
+  {
+    const uint64_t dims[4] = {256, static_cast<uint64_t>(D) / 4, static_cast<uint64_t>(Hkv),
+                              static_cast<uint64_t>(num_blocks)};
+    const uint64_t strides[3] = {512, tile, tile * Hkv};
+    const uint32_t box[4] = {256, static_cast<uint32_t>(D) / 4, 1, 1};
+    if (encode_tensor_map(&m->k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(k_cache), dims, strides, box,
+                          es, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS)
+      return false;
+  }
+  const uint64_t dims[4] = {kTok, static_cast<uint64_t>(D), static_cast<uint64_t>(Hkv),
+                            static_cast<uint64_t>(num_blocks)};
+  const uint64_t strides[3] = {kTok * 2, tile, tile * Hkv};
+  const uint32_t box[4] = {kTok, static_cast<uint32_t>(D), 1, 1};
+  return encode_tensor_map(&m->v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(v_cache), dims, strides, box,
+                           es, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) == CUDA_SUCCESS;
+}
+
 bool make_attn_maps(AttnMaps* m, const void* k_cache, const void* v_cache, int num_blocks,
-                    int Hkv, int D, bool fp8) {
+                    int Hkv, int D, bool fp8, bool l1) {
   m->fp8 = fp8;
-  if (fp8 && D != 128) return false;
+  m->l1 = l1;
+  if (fp8 && (D != 128 || l1)) return false;
+  if (l1) return make_cache_maps_l1(m, k_cache, v_cache, num_blocks, Hkv, D);
   return make_cache_map(&m->k, k_cache, num_blocks, Hkv, D, fp8) &&
          make_cache_map(&m->v, v_cache, num_blocks, Hkv, D, fp8);
 }
 
-template <int D, bool F8 = false, bool HI = true, bool BF = false>
+template <int D, bool F8 = false, bool HI = true, bool BF = false, bool L1 = false>
 static void launch_decode(const AttnMaps& maps, void* out, const void* q, int q_stride,
                           const uint32_t* block_tables, const uint32_t* context_lens, int B,
                           int H, int Hkv, int max_blocks, float scale, float softcap, int window,
                           void* workspace, cudaStream_t st) {
   constexpr int NS = F8 ? 6 : kStages;
   using SM = AttnSmem<D, F8, NS>;
-  auto kern = paged_attn_decode_kernel<D, F8, HI, BF>;
+  auto kern = paged_attn_decode_kernel<D, F8, HI, BF, L1>;
   // resident CTAs per SM as the driver computes them (registers are allocated in per-warp units): the
   // wave model of the split planner must use the real number
   static int occ = 0;
@@ -653,6 +695,16 @@ void launch_paged_attn_decode(const AttnMaps& maps, void* out, const void* q, in
                               const uint32_t* block_tables, const uint32_t* context_lens, int B,
                               int H, int Hkv, int D, int max_blocks, float scale, float softcap,
                               int window, void* workspace, cudaStream_t st, bool bf16) {
+#define B200_DEC_ARGS maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv, max_blocks, scale, softcap, window, \
+                      workspace, st
+  if (maps.l1) {
+    if (D == 128 && bf16) launch_decode<128, false, true, true, true>(B200_DEC_ARGS);
+    else if (D == 128) launch_decode<128, false, true, false, true>(B200_DEC_ARGS);
+    else if (bf16) launch_decode<64, false, true, true, true>(B200_DEC_ARGS);
+    else launch_decode<64, false, true, false, true>(B200_DEC_ARGS);
+    return;
+  }
+#undef B200_DEC_ARGS
   if (bf16 && !maps.fp8 && D == 128)
     launch_decode<128, false, true, true>(maps, out, q, q_stride, block_tables, context_lens, B, H, Hkv,
                                           max_blocks, scale, softcap, window, workspace, st);
@@ -696,7 +748,7 @@ static void paged_attn_decode_any(void* out, const void* q, const void* k_cache,
                                 int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
                                 int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
                                 float softcap, int32_t window, void* workspace,
-                                int64_t stream, bool fp8, bool bf16 = false) {
+                                int64_t stream, bool fp8, bool bf16 = false, bool l1 = false) {
   using namespace b200;
   B200_CHECK_ARG(!fp8 || head_dim == 128, "paged_attn_decode: the fp8 KV cache needs head_dim 128");
   B200_CHECK_ARG(block_size == kTok, "paged_attn_decode: block_size must be 64");
@@ -707,7 +759,7 @@ static void paged_attn_decode_any(void* out, const void* q, const void* k_cache,
   B200_CHECK_ARG(batch > 0 && max_blocks_per_seq > 0 && num_blocks > 0 && workspace != nullptr,
                  "paged_attn_decode: bad sizes or NULL workspace");
   AttnMaps maps;
-  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim, fp8)) {
+  if (!make_attn_maps(&maps, k_cache, v_cache, num_blocks, num_kv_heads, head_dim, fp8, l1)) {
     set_error(2, "paged_attn_decode: cuTensorMapEncodeTiled failed");
     return;
   }
@@ -738,6 +790,18 @@ void b200_paged_attn_decode_bf16(void* out, const void* q, const void* k_cache,
   paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
                         num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
                         window, workspace, stream, false, true);
+}
+
+void b200_paged_attn_decode_l1(void* out, const void* q, const void* k_cache,
+                               const void* v_cache, const uint32_t* block_tables,
+                               const uint32_t* context_lens, int32_t batch, int32_t num_heads,
+                               int32_t num_kv_heads, int32_t head_dim, int32_t block_size,
+                               int32_t max_blocks_per_seq, int32_t num_blocks, float scale,
+                               float softcap, int32_t window, void* workspace, int32_t bf16,
+                               int64_t stream) {
+  paged_attn_decode_any(out, q, k_cache, v_cache, block_tables, context_lens, batch, num_heads,
+                        num_kv_heads, head_dim, block_size, max_blocks_per_seq, num_blocks, scale, softcap,
+                        window, workspace, stream, false, bf16 != 0, true);
 }
 
 void b200_paged_attn_decode_fp8kv_f16(void* out, const void* q, const void* k_cache,

@@ -107,12 +107,24 @@ def wna16_dequant(w_packed, scales, qzeros, *, k: int, n: int, bits=4, group_siz
 
 
 # ------------------------------------------------------------------ attention side
+def _is_l1(k_cache, v_cache) -> bool:
+    """The reference's default-build layout (kvcache_allocator.rs:150-173): K [nb, Hkv, D/8, 64, 8] is 5-D."""
+    return k_cache is not None and k_cache.dim() == 5
+
+
 def rope_kv_write(q, k, v, cos, sin, positions, slot_mapping=None, k_cache=None, v_cache=None,
                   rot_dim=None, interleaved=False):
     """FusedRope::apply_inplace + cache write (rotary_emb.rs:88-104, attention.rs:808-820)."""
     _cuda(q, k, v, cos, sin, positions, slot_mapping, k_cache, v_cache)
     T, H, D = q.shape
     Hkv = k.shape[1]
+    if _is_l1(k_cache, v_cache):
+        _lib.lib().b200_rope_kv_write_l1(
+            _p(q), _p(k), _p(v), _p(cos), _p(sin), _p(positions), _p(slot_mapping), _p(k_cache), _p(v_cache), T, H,
+            Hkv, D, rot_dim or D, k_cache.shape[3], int(interleaved), int(cos.dtype == torch.float32),
+            int(q.dtype == torch.bfloat16), _stream())
+        _lib.check()
+        return
     bs = k_cache.shape[1] if k_cache is not None else 64
     fp8 = k_cache is not None and k_cache.dtype == torch.uint8        # --fp8-kvcache: e4m3 bytes
     fn = _lib.lib().b200_rope_kv_write_fp8kv_f16 if fp8 else _sym("b200_rope_kv_write", q)
@@ -126,6 +138,11 @@ def rope_kv_write(q, k, v, cos, sin, positions, slot_mapping=None, k_cache=None,
 def kv_write(k, v, k_cache, v_cache, slot_mapping):
     _cuda(k, v, k_cache, v_cache, slot_mapping)
     T, Hkv, D = k.shape
+    if _is_l1(k_cache, v_cache):
+        _lib.lib().b200_kv_write_l1(_p(k), _p(v), _p(k_cache), _p(v_cache), _p(slot_mapping), T, Hkv, D,
+                                    k_cache.shape[3], _stream())
+        _lib.check()
+        return
     _lib.lib().b200_kv_write_f16(_p(k), _p(v), _p(k_cache), _p(v_cache), _p(slot_mapping), T, Hkv,
                                  D, k_cache.shape[1], _stream())
     _lib.check()
@@ -159,12 +176,19 @@ def paged_attention_decode(q, k_cache, v_cache, block_tables, context_lens, scal
     block_tables u32/i32 [B, max_blocks]; context_lens u32/i32 [B]."""
     _cuda(q, k_cache, v_cache, block_tables, context_lens)
     B, H, D = q.shape
-    nb, bs, Hkv, _ = k_cache.shape
+    l1 = _is_l1(k_cache, v_cache)
+    nb, bs, Hkv = (k_cache.shape[0], k_cache.shape[3], k_cache.shape[1]) if l1 else k_cache.shape[:3]
     mb = block_tables.shape[1]
     if workspace is None:
         workspace = paged_attn_workspace(B, H, D, mb, q.device)
     if out is None:
         out = torch.empty_like(q)
+    if l1:
+        _lib.lib().b200_paged_attn_decode_l1(
+            _p(out), _p(q), _p(k_cache), _p(v_cache), _p(block_tables), _p(context_lens), B, H, Hkv, D, bs, mb, nb,
+            float(scale), float(softcap), int(window), _p(workspace), int(q.dtype == torch.bfloat16), _stream())
+        _lib.check()
+        return out
     fp8 = k_cache.dtype == torch.uint8                                # --fp8-kvcache: e4m3 bytes
     fn = _lib.lib().b200_paged_attn_decode_fp8kv_f16 if fp8 else _sym("b200_paged_attn_decode", q)
     fn(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(block_tables), _p(context_lens), B, H, Hkv, D, bs,
@@ -181,10 +205,18 @@ def attention_prefill(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tab
     """PagedAttention::forward, prefill branch over the paged cache (see b200_attn_prefill_ex_f16)."""
     _cuda(q, k_cache, v_cache, cu_seqlens_q, context_lens, block_tables)
     T, H, D = q.shape
-    nb, bs, Hkv, _ = k_cache.shape
+    l1 = _is_l1(k_cache, v_cache)
+    nb, bs, Hkv = (k_cache.shape[0], k_cache.shape[3], k_cache.shape[1]) if l1 else k_cache.shape[:3]
     B = cu_seqlens_q.shape[0] - 1
     if out is None:
         out = torch.empty_like(q)
+    if l1:
+        _lib.lib().b200_attn_prefill_l1(
+            _p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q), _p(context_lens), _p(block_tables), B, H,
+            Hkv, D, bs, block_tables.shape[1], nb, int(max_seqlen_q), T, mode, float(scale),
+            int(q.dtype == torch.bfloat16), _stream())
+        _lib.check()
+        return out
     _sym("b200_attn_prefill_ex", q)(_p(out), _p(q), _p(k_cache), _p(v_cache), _p(cu_seqlens_q),
                                     _p(context_lens), _p(block_tables), B, H, Hkv, D, bs,
                                     block_tables.shape[1], nb, int(max_seqlen_q), T, mode, float(scale),
