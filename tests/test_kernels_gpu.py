@@ -199,7 +199,7 @@ def _wna_case(K, N, M, fmt, bits, seed, group=128):
 
 
 # flat GEMV / round-1 tcgen05 decode kernel (M <= 64) / general tcgen05 / stream-K tcgen05 decode kernel (M <= 32)
-@pytest.mark.parametrize("variant", [1, 2, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6])
 @pytest.mark.parametrize("fmt,bits,K,N,M", [
     ("awq", 4, 4096, 1024, 1), ("awq", 4, 4096, 6144, 32), ("awq", 4, 14336, 4096, 5),
     ("gptq", 4, 2048, 256, 3), ("gptq_sym", 4, 1024, 512, 16), ("gptq", 8, 2048, 512, 7),
@@ -208,8 +208,10 @@ def _wna_case(K, N, M, fmt, bits, seed, group=128):
 def test_wna16_gemm(ops, fmt, bits, K, N, M, variant):
     if variant >= 2 and not _tc_available(ops):
         pytest.skip("tcgen05 variant not built yet")
-    if variant == 5 and M > 32:
+    if variant >= 5 and M > 32:
         pytest.skip("the stream-K decode kernel takes M <= 32")
+    if variant == 6 and bits != 4:
+        pytest.skip("the mma.sync stream-K flavour is 4-bit only")
     qw, qz, s, W, x = _wna_case(K, N, M, fmt, bits, seed=K + N + M)
     qwd = torch.from_numpy(qw).cuda()
     packed = ops.awq_prepack(qwd) if fmt == "awq" else ops.gptq_prepack(qwd, bits)
@@ -239,10 +241,13 @@ def test_wna16_gemm(ops, fmt, bits, K, N, M, variant):
     ("awq", 4, 256, 128, 1, 128, "none"),          # one tile, two units, one CTA
     ("awq", 4, 8192, 7168, 32, 128, "silu"),       # Llama-3-70B gate|up shard at TP = 8
 ])
-def test_wna16_streamk_decode(ops, fmt, bits, K, N, M, group, epi):
-    """wna16_sk.cu (variant 5): CTA ranges that cut tiles anywhere, per-CTA partial slots, every epilogue the
+@pytest.mark.parametrize("variant", [5, 6])
+def test_wna16_streamk_decode(ops, fmt, bits, K, N, M, group, epi, variant):
+    """wna16_sk.cu (variant 5 = tcgen05 flavour, 6 = mma.sync register flavour): CTA ranges that cut tiles anywhere, per-CTA partial slots, every epilogue the
     public entry exposes; and the post-MMA scale is at least as close to the fp32 truth as the fp16-rounded
     weights the reference multiplies with."""
+    if variant == 6 and bits != 4:
+        pytest.skip("the mma.sync stream-K flavour is 4-bit only")
     qw, qz, s, W, x = _wna_case(K, N, M, fmt, bits, seed=K + N + M + group, group=group)
     qwd = torch.from_numpy(qw).cuda()
     packed = ops.awq_prepack(qwd) if fmt == "awq" else ops.gptq_prepack(qwd, bits)
@@ -254,12 +259,12 @@ def test_wna16_streamk_decode(ops, fmt, bits, K, N, M, group, epi):
     kw = dict(k=K, n=N, bits=bits, group_size=group, qfmt=qf,
               epilogue=ops.EPI_SILU_MUL if epi == "silu" else ops.EPI_NONE,
               bias=None if bias is None else bias.cuda())
-    y = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=5, **kw)
+    y = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=variant, **kw)
     full = om.linear(x, W, bias)
     ref = om.silu_mul(full[:, :N // 2], full[:, N // 2:]) if epi == "silu" else full
     _close(y, ref, 2e-3, 4e-3 if epi == "silu" else 2e-3)
     assert int(ws[:16384].view(torch.int32).abs().sum()) == 0      # arrival counters back at rest
-    y2 = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=5, **kw)
+    y2 = ops.wna16_gemm(x.cuda(), packed, sd, zd, ws, variant=variant, **kw)
     assert torch.equal(y2, y)                                      # contributor-ordered sums: deterministic
     if epi == "none":
         # the exact product x @ ((q - z) * s), no fp16 rounding of the weights: the post-MMA scale must be at least

@@ -496,7 +496,7 @@ void launch_wna16_gemv(const WnaParams& p, cudaStream_t st);
 bool launch_wna16_tc(const WnaParams& p, cudaStream_t st);   // false: shape unsupported
 bool launch_wna16_tc_dec(const WnaParams& p, cudaStream_t st);   // decode shapes (M <= 64)
 // stream-K decode kernel (M <= 32); bf16: A, scales and C are bf16 (plain epilogue, 4-bit only)
-bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force = false, bool bf16 = false);
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force = false, bool bf16 = false, int flavour = -1);
 // Largest M the automatic dispatch still gives to the flat GEMV (env B200_GEMV_MAX_M, default 0: the tcgen05
 // decode kernel streams the weights faster than the GEMV even for one token, profiles/r1_v7_batch_sweep.txt;
 // the GEMV stays as `variant 1` and as the fallback for shapes the tensor-core kernels do not take).

@@ -297,8 +297,9 @@ void b200_wna16_gemm_ex(const void* a, const void* b_packed, const void* scales,
   const char* why = nullptr;
   if (!check_wna(p, &why)) { set_error(1, why); return; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (variant == 5) {
-    if (launch_wna16_sk(p, st, true)) return;
+  if (variant == 5 || variant == 6) {                  // stream-K decode kernel: 5 = tcgen05 flavour, 6 = mma.sync flavour
+    if (variant == 6 && bits != 4) { set_error(1, "wna16: the mma.sync stream-K flavour is 4-bit only"); return; }
+    if (launch_wna16_sk(p, st, true, false, variant == 6 ? 1 : 0)) return;
     set_error(1, "wna16: shape unsupported by the stream-K decode kernel");
     return;
   }

@@ -57,6 +57,7 @@ constexpr int kXProdWarp = kWProdWarp + 1;      // 15: activations, up to kDG * 
 constexpr int kIssWarp0 = kXProdWarp + 1;       // 16 .. 18 (one MMA issuer per dequant group)
 constexpr int kWarps = kIssWarp0 + kDG;
 constexpr int kThreads = kWarps * 32;           // 608: 19 warps leave 96 registers per thread
+constexpr int kThreadsMma = kIssWarp0 * 32;     // 512: the mma.sync flavour has no issuer warps (128 registers per thread)
 constexpr int kAS = 3;                          // A stages (one 64-K chunk = 32 TMEM columns) per dequant group
 constexpr int kDB = 2;                          // accumulators per dequant group (unit i + 1 runs while unit i is drained)
 constexpr int kMaxSeg = 8;                      // tile segments per CTA (one-shot barriers)
@@ -263,10 +264,19 @@ __device__ __forceinline__ void reduce_tile(const Args& a, const SplitOut& o, in
   }
 }
 
-template <int BITS, int NT, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+// MMA = true: the register flavour.  Same work list, rings, segment sums, meeting point and finalisers; but a
+// dequant warp keeps its weights: lane (g, c) of warp q4 dequantises words {2c, 2c+1} of channels 32 q4 + 8 t + g
+// (t = 0..3) of a 64-K chunk -- K values [16 c, 16 c + 16) -- straight into the B fragments of
+// mma.sync.m16n8k16 (tokens are the M rows, 8 channels the N columns), takes the matching activations from the
+// swizzled activation tile with two 16-byte loads per token row (the k-steps see K in the order 16 c + 4 s + {0..3},
+// the same permutation on both operands), and accumulates in registers.  No TMEM, no issuer warps, no
+// dequant -> store -> commit -> MMA hand-off chain per chunk: the only barriers left in the hot loop are the two
+// TMA rings.  4-bit, fp16.
+template <int BITS, int NT, int EPI, bool MMA>
+__global__ void __launch_bounds__(MMA ? kThreadsMma : kThreads, 1)
 wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   using C = Cfg<BITS, NT>;
+  static_assert(!MMA || (BITS == 4 && EPI != kEpiNoneBf16), "the mma.sync flavour is 4-bit fp16");
   constexpr bool kBf16 = EPI == kEpiNoneBf16;
   constexpr int EPX = kBf16 ? B200_EPI_NONE : EPI;     // the epilogue the finaliser templates see
   static_assert(!kBf16 || BITS == 4, "bf16 entry points are 4-bit only (gptq.rs:150-178)");
@@ -319,7 +329,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     }
     for (int i = 0; i < kDG * C::kSXS; ++i) {
       mbar_init(&xfull[i], 1);
-      mbar_init(&xempty[i], 1);
+      mbar_init(&xempty[i], MMA ? 4 : 1);                // the group's four warps / the issuer's commit
     }
     for (int i = 0; i < kDG * kAS; ++i) {
       mbar_init(&afree[i], 1);
@@ -335,7 +345,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     }
     fence_barrier_init();
   }
-  if (warp == kWProdWarp) {
+  if (!MMA && warp == kWProdWarp) {
     tmem_alloc(tmem_ptr, C::kTmemCols);
     tmem_relinquish();
   }
@@ -344,7 +354,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   __syncthreads();
   tc_fence_after();
   pdl_trigger();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = MMA ? 0u : *tmem_ptr;
 
   // ---- one tile segment's epilogue, run by `nw` cooperating warps (warp `wid`, thread `tid_c` of them, named barrier
   // `bar_id`): add the three groups' sums (fixed order), store the CTA's partial tile (or the output itself when
@@ -528,6 +538,164 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         if (seg_last) tc_commit(&dfull[grp * kDB + (k & 1)]);    // the group's sums of this tile are complete
         p = pn;
       }
+    }
+  } else if (MMA && warp < kDqWarps) {
+    // ------------------------------------------------------------ dequant + mma.sync groups (register flavour)
+    if constexpr (MMA) {
+    const int grp = warp >> 2, q4 = warp & 3;
+    const int g = lane >> 2, c = lane & 3;
+    constexpr int MT = NT / 16;                          // 16-token row tiles
+    const int ch = q4 * 32 + lane;                       // the channel whose zero point / scale this lane FETCHES
+    constexpr int ZWN = kTileN * 4 / 32;
+    const int zword = ch >> 3;
+    const int zshift = (a.qfmt == B200_QFMT_AWQ) ? 4 * awq_nibble_of(ch & 7) : 4 * (ch & 7);
+    const uint32_t zadd = (a.qfmt == B200_QFMT_AWQ) ? 0u : 1u;
+    const uint32_t zrow = static_cast<uint32_t>(N) * 4 / 32;
+    const bool has_z = a.qzeros != nullptr;
+    const unsigned short* scales_u16 = reinterpret_cast<const unsigned short*>(a.scales);
+    auto zload = [&](const Pos& q) -> uint32_t {
+      if (!has_z) return 0u;
+      return __ldg(a.qzeros + (static_cast<uint32_t>(q.pair >> a.gshift) * zrow + q.tile * ZWN + zword));
+    };
+    auto sload = [&](const Pos& q) -> uint32_t {
+      return __ldg(scales_u16 + (static_cast<uint32_t>(q.pair >> a.gshift) * N + q.tile * kTileN + ch));
+    };
+    // this lane's words of n-tile 0, chunk 0, stage 0: half (c >> 1) of the chunk, channel 32 q4 + g, words 2 (c & 1) ..
+    uint32_t s_w = s_base + C::kWOff + grp * C::kUnitW + (c >> 1) * (kTileN * 16) + (q4 * 32 + g) * 16 + (c & 1) * 8;
+    // activations: row r of a chunk is 128 swizzled bytes; rows g, g + 8, .. all have r & 7 == g
+    uint32_t s_x = s_base + C::kXOff + g * 128;
+    const uint32_t xo0 = static_cast<uint32_t>((2 * c) ^ g) << 4, xo1 = static_cast<uint32_t>((2 * c + 1) ^ g) << 4;
+    // segment sums: token row g (+ 8, + 16 ..), channels 32 q4 + 8 t + 2 c
+    uint32_t s_h = s_base + C::kHOff + grp * C::kHBytes + g * (kTileN * 4) + (q4 * 32 + 2 * c) * 4;
+    uint32_t lane0 = lane == 0 ? 1u : 0u;
+    asm volatile("" : "+r"(s_w), "+r"(s_x), "+r"(s_h), "+r"(lane0));
+    const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
+    float acc[MT][4][4];
+    auto zero_acc = [&]() {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][t][e] = 0.f;
+    };
+    zero_acc();
+    // a tile segment's sums of this group go to shared memory (zeros when the group had no unit in the segment)
+    auto flush = [&](int seg) {
+      if (seg >= 1) wait_bar(s_hfree + (seg - 1) * 8, 0);        // the previous segment's sums have been read
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t addr = s_h + mt * 16 * (kTileN * 4) + t * 32;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(acc[mt][t][0]), "f"(acc[mt][t][1]) : "memory");
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr + 8 * (kTileN * 4)), "f"(acc[mt][t][2]),
+                       "f"(acc[mt][t][3]) : "memory");
+        }
+      __syncwarp();
+      if (lane0) arrive_bar(s_segdone + seg * 8);
+      zero_acc();
+    };
+    int next_seg = 0;                                  // segments [0, next_seg) have been flushed by this warp
+    if (grp < n) {
+      Pos p = pos_of(u0 + grp, KP);
+      uint32_t zq[kPF], sq[kPF];                       // zero words / scale bits of this group's next kPF units
+      Pos pz = p;
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        zq[k] = 0;
+        sq[k] = 0;
+        if (grp + k * kDG < n) {
+          zq[k] = zload(pz);
+          sq[k] = sload(pz);
+          pos_advance(pz, kDG, KP);
+        }
+      }
+      int wslot = 0;
+      uint32_t wphase = 0;
+      int it = 0;
+      int cur_seg = p.tile - t_first;
+      while (next_seg < cur_seg) flush(next_seg++);    // segments before this group's first unit
+      for (int j = grp; j < n; j += kDG, ++it) {
+        const int seg = p.tile - t_first;
+        if (seg != cur_seg) {
+          flush(cur_seg);
+          next_seg = cur_seg + 1;
+          while (next_seg < seg) flush(next_seg++);
+          cur_seg = seg;
+        }
+        // zero point and scale of the lane's four channels: fetched by lane 8 t + g, handed over by shuffle
+        const uint32_t zmine = has_z ? ((zq[0] >> zshift) & 15u) + zadd : 8u;
+        DqConst dq[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t z = __shfl_sync(0xffffffffu, zmine, 8 * t + g);
+          const uint32_t sb = __shfl_sync(0xffffffffu, sq[0], 8 * t + g);
+          dq[t].s2 = u32_as_h2(sb * 0x00010001u);
+          dq[t].zlo = u32_as_h2((0x6400u | z) * 0x00010001u);
+          dq[t].zhi = u32_as_h2((0x5400u | (z << 4)) * 0x00010001u);
+        }
+#pragma unroll
+        for (int k = 0; k + 1 < kPF; ++k) {
+          zq[k] = zq[k + 1];
+          sq[k] = sq[k + 1];
+        }
+        if (j + kPF * kDG < n) {
+          zq[kPF - 1] = zload(pz);
+          sq[kPF - 1] = sload(pz);
+          pos_advance(pz, kDG, KP);
+        }
+        const int xs = (it % C::kSXS) * kDG + grp;               // unit j lives in ring slot j % (kDG * kSXS)
+        wait_bar(s_wfull + wslot * 8, wphase);
+        wait_bar(s_xfull + xs * 8, (it / C::kSXS) & 1);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          // activations of the chunk: rows g + 8 r, K [16 c, 16 c + 16) as two 16-byte pieces
+          uint32_t xa[2 * MT][2][4];
+          const uint32_t xb = s_x + xs * C::kXUnit + cc * C::kXBytes;
+#pragma unroll
+          for (int r = 0; r < 2 * MT; ++r) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(xa[r][0][0]), "=r"(xa[r][0][1]), "=r"(xa[r][0][2]), "=r"(xa[r][0][3])
+                         : "r"(xb + r * (8 * 128) + xo0));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(xa[r][1][0]), "=r"(xa[r][1][1]), "=r"(xa[r][1][2]), "=r"(xa[r][1][3])
+                         : "r"(xb + r * (8 * 128) + xo1));
+          }
+          const uint32_t wb = s_w + wslot * C::kWStage + cc * C::kWBytes;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(wb + t * (8 * 16)));
+            uint32_t o[2][4];
+            dequant4_word(w0, dq[t], o[0]);
+            dequant4_word(w1, dq[t], o[1]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t af[4] = {xa[2 * mt][i][2 * hh], xa[2 * mt + 1][i][2 * hh], xa[2 * mt][i][2 * hh + 1],
+                                          xa[2 * mt + 1][i][2 * hh + 1]};
+                  mma_16816(acc[mt][t], af, o[i][2 * hh], o[i][2 * hh + 1]);
+                }
+          }
+        }
+        __syncwarp();
+        if (lane0) {
+          arrive_bar(s_wempty + wslot * 8);              // this warp's part of the stage has been consumed
+          arrive_bar(s_xempty + xs * 8);
+        }
+        if (++wslot == C::kSWS) { wslot = 0; wphase ^= 1; }
+        pos_advance(p, kDG, KP);
+      }
+      flush(cur_seg);
+      next_seg = cur_seg + 1;
+    }
+    while (next_seg <= t_last - t_first) flush(next_seg++);
+    pdl_wait();                                          // first global writes of this role
+    segment_epilogue(t_last, t_last - t_first, warp, kAllEpiWarps, warp * 32 + lane, 3, false);
     }
   } else if (warp < kDqWarps) {
     // ------------------------------------------------------------ dequant groups
@@ -732,7 +900,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     segment_epilogue(t_last, t_last - t_first, kDqWarps + ewarp, kAllEpiWarps, kDqWarps * 32 + tid, 3, false);
   }
   __syncthreads();
-  if (warp == kWProdWarp) {
+  if (!MMA && warp == kWProdWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -754,7 +922,7 @@ static int sk_mode() {
   return v;
 }
 
-template <int BITS, int NT, int EPI>
+template <int BITS, int NT, int EPI, bool MMA = false>
 static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   using C = Cfg<BITS, NT>;
   const int KC = p.K / kChunkK, KP = p.K / kUnitK;
@@ -805,30 +973,42 @@ static bool launch_epi(const WnaParams& p, cudaStream_t st) {
   if (EPI == kEpiNoneBf16) a.fe.out_bf16 = 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(wna16_sk_kernel<BITS, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kAlloc);
+    cudaFuncSetAttribute(wna16_sk_kernel<BITS, NT, EPI, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kAlloc);
     attr_set = true;
   }
-  launch_pdl(wna16_sk_kernel<BITS, NT, EPI>, dim3(static_cast<unsigned>(G)), dim3(kThreads), C::kAlloc, st, xmap, a);
+  launch_pdl(wna16_sk_kernel<BITS, NT, EPI, MMA>, dim3(static_cast<unsigned>(G)), dim3(MMA ? kThreadsMma : kThreads),
+             C::kAlloc, st, xmap, a);
   B200_CUDA_LAUNCH_CHECK();
   return true;
 }
 
-template <int BITS, int NT>
+template <int BITS, int NT, bool MMA = false>
 static bool launch_nt(const WnaParams& p, cudaStream_t st) {
   switch (p.epilogue) {
-    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL>(p, st);
-    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm>(p, st);
-    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv>(p, st);
-    case kEpiPushPeers: return launch_epi<BITS, NT, kEpiPushPeers>(p, st);
-    default: return launch_epi<BITS, NT, B200_EPI_NONE>(p, st);
+    case B200_EPI_SILU_MUL: return launch_epi<BITS, NT, B200_EPI_SILU_MUL, MMA>(p, st);
+    case kEpiResidNorm: return launch_epi<BITS, NT, kEpiResidNorm, MMA>(p, st);
+    case kEpiRopeKv: return launch_epi<BITS, NT, kEpiRopeKv, MMA>(p, st);
+    case kEpiPushPeers: return launch_epi<BITS, NT, kEpiPushPeers, MMA>(p, st);
+    default: return launch_epi<BITS, NT, B200_EPI_NONE, MMA>(p, st);
   }
+}
+
+// B200_DEC_SKM: which of the two flavours runs where the stream-K kernel is taken: 0 = tcgen05 (TMEM) flavour,
+// 1 = mma.sync register flavour (4-bit fp16 only).
+static int skm_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_DEC_SKM");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 }  // namespace sk
 
 // Decode-shape entry (M <= 32): false when the shape needs another kernel.  `force` skips the B200_DEC_SK switch
 // (b200_wna16_gemm_ex variant 5, the bf16 entry points).
-bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16) {
+bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16, int flavour) {
   if (!force && sk::sk_mode() == 0) return false;
   if (p.M > 32) return false;
   if (!force && sk::sk_mode() == 2) {
@@ -848,6 +1028,8 @@ bool launch_wna16_sk(const WnaParams& p, cudaStream_t st, bool force, bool bf16)
     return p.M <= 16 ? sk::launch_epi<4, 16, sk::kEpiNoneBf16>(p, st) : sk::launch_epi<4, 32, sk::kEpiNoneBf16>(p, st);
   }
   static const bool force_nt32 = getenv("B200_SK_FORCE_NT32") != nullptr;      // experiment: 32-column tiles for any M
+  const bool mma = flavour < 0 ? sk::skm_mode() == 1 : flavour == 1;
+  if (p.bits == 4 && mma) return p.M <= 16 ? sk::launch_nt<4, 16, true>(p, st) : sk::launch_nt<4, 32, true>(p, st);
   if (p.bits == 4) return (p.M <= 16 && !force_nt32) ? sk::launch_nt<4, 16>(p, st) : sk::launch_nt<4, 32>(p, st);
   return p.M <= 16 ? sk::launch_nt<8, 16>(p, st) : sk::launch_nt<8, 32>(p, st);
 }
