@@ -266,10 +266,11 @@ __device__ __forceinline__ void reduce_tile(const Args& a, const SplitOut& o, in
 
 // MMA = true: the register flavour.  Same work list, rings, segment sums, meeting point and finalisers; but a
 // dequant warp keeps its weights: lane (g, c) of warp q4 dequantises words {2c, 2c+1} of channels 32 q4 + 8 t + g
-// (t = 0..3) of a 64-K chunk -- K values [16 c, 16 c + 16) -- straight into the B fragments of
-// mma.sync.m16n8k16 (tokens are the M rows, 8 channels the N columns), takes the matching activations from the
-// swizzled activation tile with two 16-byte loads per token row (the k-steps see K in the order 16 c + 4 s + {0..3},
-// the same permutation on both operands), and accumulates in registers.  No TMEM, no issuer warps, no
+// (t = 0..3) of a 64-K chunk -- K values [16 c, 16 c + 16) -- straight into the A fragments of
+// mma.sync.m16n8k16 (16 channels are the M rows, 8 tokens the N columns: the dequantised pairs of channels g and
+// g + 8 ARE the register quad, no moves; token tiles beyond the batch are skipped), takes the matching activations
+// from the swizzled activation tile with two 16-byte loads per token row (the k-steps see K in the order
+// 16 c + 4 s + {0..3}, the same permutation on both operands), and accumulates in registers.  No TMEM, no issuer warps, no
 // dequant -> store -> commit -> MMA hand-off chain per chunk: the only barriers left in the hot loop are the two
 // TMA rings.  4-bit, fp16.
 template <int BITS, int NT, int EPI, bool MMA>
@@ -544,7 +545,7 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     if constexpr (MMA) {
     const int grp = warp >> 2, q4 = warp & 3;
     const int g = lane >> 2, c = lane & 3;
-    constexpr int MT = NT / 16;                          // 16-token row tiles
+    constexpr int NT8 = NT / 8;                          // 8-token column tiles
     const int ch = q4 * 32 + lane;                       // the channel whose zero point / scale this lane FETCHES
     constexpr int ZWN = kTileN * 4 / 32;
     const int zword = ch >> 3;
@@ -560,38 +561,38 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     auto sload = [&](const Pos& q) -> uint32_t {
       return __ldg(scales_u16 + (static_cast<uint32_t>(q.pair >> a.gshift) * N + q.tile * kTileN + ch));
     };
-    // this lane's words of n-tile 0, chunk 0, stage 0: half (c >> 1) of the chunk, channel 32 q4 + g, words 2 (c & 1) ..
+    // this lane's words of channel 32 q4 + g (+ 8 t), chunk 0, stage 0: half (c >> 1) of the chunk, words 2 (c & 1) ..
     uint32_t s_w = s_base + C::kWOff + grp * C::kUnitW + (c >> 1) * (kTileN * 16) + (q4 * 32 + g) * 16 + (c & 1) * 8;
-    // activations: row r of a chunk is 128 swizzled bytes; rows g, g + 8, .. all have r & 7 == g
+    // activations: token row r of a chunk is 128 swizzled bytes; rows g, g + 8, .. all have r & 7 == g
     uint32_t s_x = s_base + C::kXOff + g * 128;
     const uint32_t xo0 = static_cast<uint32_t>((2 * c) ^ g) << 4, xo1 = static_cast<uint32_t>((2 * c + 1) ^ g) << 4;
-    // segment sums: token row g (+ 8, + 16 ..), channels 32 q4 + 8 t + 2 c
-    uint32_t s_h = s_base + C::kHOff + grp * C::kHBytes + g * (kTileN * 4) + (q4 * 32 + 2 * c) * 4;
+    // segment sums [token][channel]: tokens 2 c (+ 1, + 8 nt), channels 32 q4 + g (+ 8, + 16 mt)
+    uint32_t s_h = s_base + C::kHOff + grp * C::kHBytes + (2 * c) * (kTileN * 4) + (q4 * 32 + g) * 4;
     uint32_t lane0 = lane == 0 ? 1u : 0u;
     asm volatile("" : "+r"(s_w), "+r"(s_x), "+r"(s_h), "+r"(lane0));
     const int t_first = pos_of(u0, KP).tile, t_last = pos_of(u0 + n - 1, KP).tile;
-    float acc[MT][4][4];
+    const int ntiles = (M + 7) >> 3;                     // token tiles that hold a row (the others stay zero)
+    float acc[2][NT8][4];                                // [16-channel tile][8-token tile]
     auto zero_acc = [&]() {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+        for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[mt][t][e] = 0.f;
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
     };
     zero_acc();
     // a tile segment's sums of this group go to shared memory (zeros when the group had no unit in the segment)
     auto flush = [&](int seg) {
       if (seg >= 1) wait_bar(s_hfree + (seg - 1) * 8, 0);        // the previous segment's sums have been read
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t addr = s_h + mt * 16 * (kTileN * 4) + t * 32;
-          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(acc[mt][t][0]), "f"(acc[mt][t][1]) : "memory");
-          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr + 8 * (kTileN * 4)), "f"(acc[mt][t][2]),
-                       "f"(acc[mt][t][3]) : "memory");
-        }
+        for (int nt = 0; nt < NT8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_h + (8 * nt + (e & 1)) * (kTileN * 4) +
+                                                         (16 * mt + 8 * (e >> 1)) * 4), "f"(acc[mt][nt][e]) : "memory");
       __syncwarp();
       if (lane0) arrive_bar(s_segdone + seg * 8);
       zero_acc();
@@ -650,36 +651,42 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
         wait_bar(s_xfull + xs * 8, (it / C::kSXS) & 1);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          // activations of the chunk: rows g + 8 r, K [16 c, 16 c + 16) as two 16-byte pieces
-          uint32_t xa[2 * MT][2][4];
-          const uint32_t xb = s_x + xs * C::kXUnit + cc * C::kXBytes;
+          // activations of the chunk (the B fragments): token rows g + 8 nt, K [16 c, 16 c + 16) as two 16-byte
+          // pieces = the (b0, b1) pairs of four k-steps
+          uint32_t xb[NT8][2][4];
+          const uint32_t xa = s_x + xs * C::kXUnit + cc * C::kXBytes;
 #pragma unroll
-          for (int r = 0; r < 2 * MT; ++r) {
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(xa[r][0][0]), "=r"(xa[r][0][1]), "=r"(xa[r][0][2]), "=r"(xa[r][0][3])
-                         : "r"(xb + r * (8 * 128) + xo0));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(xa[r][1][0]), "=r"(xa[r][1][1]), "=r"(xa[r][1][2]), "=r"(xa[r][1][3])
-                         : "r"(xb + r * (8 * 128) + xo1));
+          for (int nt = 0; nt < NT8; ++nt) {
+            if (nt < ntiles) {
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(xb[nt][0][0]), "=r"(xb[nt][0][1]), "=r"(xb[nt][0][2]), "=r"(xb[nt][0][3])
+                           : "r"(xa + nt * (8 * 128) + xo0));
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(xb[nt][1][0]), "=r"(xb[nt][1][1]), "=r"(xb[nt][1][2]), "=r"(xb[nt][1][3])
+                           : "r"(xa + nt * (8 * 128) + xo1));
+            }
           }
           const uint32_t wb = s_w + wslot * C::kWStage + cc * C::kWBytes;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t w0, w1;
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(wb + t * (8 * 16)));
-            uint32_t o[2][4];
-            dequant4_word(w0, dq[t], o[0]);
-            dequant4_word(w1, dq[t], o[1]);
+          for (int mt = 0; mt < 2; ++mt) {
+            // the A fragments: channels g and g + 8 of the 16-channel tile, dequantised into place
+            uint32_t wlo[2], whi[2];
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wlo[0]), "=r"(wlo[1]) : "r"(wb + (2 * mt) * (8 * 16)));
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(whi[0]), "=r"(whi[1]) : "r"(wb + (2 * mt + 1) * (8 * 16)));
+            uint32_t olo[2][4], ohi[2][4];
+            dequant4_word(wlo[0], dq[2 * mt], olo[0]);
+            dequant4_word(wlo[1], dq[2 * mt], olo[1]);
+            dequant4_word(whi[0], dq[2 * mt + 1], ohi[0]);
+            dequant4_word(whi[1], dq[2 * mt + 1], ohi[1]);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh)
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t af[4] = {olo[i][2 * hh], ohi[i][2 * hh], olo[i][2 * hh + 1], ohi[i][2 * hh + 1]};
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint32_t af[4] = {xa[2 * mt][i][2 * hh], xa[2 * mt + 1][i][2 * hh], xa[2 * mt][i][2 * hh + 1],
-                                          xa[2 * mt + 1][i][2 * hh + 1]};
-                  mma_16816(acc[mt][t], af, o[i][2 * hh], o[i][2 * hh + 1]);
-                }
+                for (int nt = 0; nt < NT8; ++nt)
+                  if (nt < ntiles) mma_16816(acc[mt][nt], af, xb[nt][i][2 * hh], xb[nt][i][2 * hh + 1]);
+              }
           }
         }
         __syncwarp();
