@@ -162,3 +162,47 @@ def test_decode_metadata_from_the_wire_equals_prepare_decode(lib):
                                   ii.ctypes.data, pos.ctypes.data, slot.ctypes.data, cl.ctypes.data)
     assert (ii.tolist(), pos.tolist(), slot.tolist(), cl.tolist()) == (meta["input_ids"], meta["positions"],
                                                                        meta["slot_mapping"], meta["context_lens"])
+
+
+def test_run_decode_frames_property(lib):
+    """Random batches: the oracle's bincode bytes parse back to the same fields, and the native writer reproduces the
+    oracle's bytes (string-valued sampling fields None, as the engine sends them for plain requests)."""
+    from hypothesis import given, settings, strategies as st
+    from vllm_rs_b200 import _lib
+
+    seq = st.tuples(st.integers(0, (1 << 63) - 1), st.integers(0, (1 << 32) - 1), st.integers(1, 1 << 20),
+                    st.lists(st.integers(0, (1 << 32) - 1), min_size=1, max_size=24),
+                    st.one_of(st.none(), st.floats(0, 2, width=32)), st.one_of(st.none(), st.integers(-1, 1 << 20)),
+                    st.one_of(st.none(), st.floats(0, 1, width=32)), st.one_of(st.none(), st.integers(0, 1 << 40)),
+                    st.booleans())
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(seq, min_size=0, max_size=12), st.booleans())
+    def check(batch, is_prefill):
+        seqs = [dict(id=i, last_token=tok, len=ln, last_block_tokens=(ln - 1) % 64 + 1, block_table_last=bt[-1],
+                     block_tables=bt, sampling=ot.sampling_params(temperature=t, top_k=k, top_p=p, max_tokens=mt,
+                                                                  ignore_eos=ie))
+                for i, tok, ln, bt, t, k, p, mt, ie in batch]
+        want = ot.run_decode_frame(seqs, is_prefill)
+        fr = np.frombuffer(want, np.uint8).copy()
+        MS, MB = 12, 24
+        ids, lt, ln_, lbt = np.zeros(MS, np.uint64), np.zeros(MS, np.uint32), np.zeros(MS, np.uint64), np.zeros(MS, np.uint64)
+        btl, bt_, nblk = np.zeros(MS, np.uint32), np.zeros((MS, MB), np.uint32), np.zeros(MS, np.int32)
+        samp = (_lib.WireSampling * MS)()
+        pf = C.c_int32(-1)
+        n = lib.b200_wire_parse_run_decode(fr.ctypes.data, len(fr), MS, MB, ids.ctypes.data, lt.ctypes.data,
+                                           ln_.ctypes.data, lbt.ctypes.data, btl.ctypes.data, bt_.ctypes.data,
+                                           nblk.ctypes.data, samp, C.byref(pf))
+        assert n == len(seqs) and pf.value == int(is_prefill)
+        for i, q in enumerate(seqs):
+            assert (int(ids[i]), int(lt[i]), int(ln_[i]), int(btl[i])) == (q["id"], q["last_token"], q["len"],
+                                                                          q["block_table_last"])
+            assert bt_[i, :nblk[i]].tolist() == q["block_tables"]
+        out = np.zeros(len(want) + 16, np.uint8)
+        got = lib.b200_wire_frame_run_decode(out.ctypes.data, len(out), n, ids.ctypes.data, lt.ctypes.data,
+                                             ln_.ctypes.data, lbt.ctypes.data, btl.ctypes.data, bt_.ctypes.data, MB,
+                                             nblk.ctypes.data, samp, int(is_prefill))
+        assert got == len(want) and out[:got].tobytes() == want       # parse -> frame is the identity on these frames
+
+    check()
+    lib.b200_clear_error()
