@@ -244,6 +244,19 @@ int32_t b200_wire_parse_run_response(const uint8_t* frame, int64_t len, uint32_t
 int32_t b200_wire_parse_kv_swap(const uint8_t* frame, int64_t len, int64_t* pairs, int32_t cap, int32_t* swap_in);
 int64_t b200_wire_frame_kv_swap(uint8_t* out, int64_t cap, const int64_t* pairs, int32_t n, int32_t swap_in);
 int64_t b200_wire_frame_simple(uint8_t* out, int64_t cap, int32_t kind, int32_t payload_bytes, uint64_t value);
+/* RunPrefill((Vec<Sequence>, bool)) (variant 3; Sequence as core/sequence.rs:32-50).  The engine side frames the
+ * sequences `indices` of its scheduler; the runner side loads such a frame into a scheduler object used as a plain
+ * sequence container (its running list is REPLACED; indices[0..n) = 0..n-1) and calls b200_prepare_prefill on it.
+ * Fields the mirror does not keep travel as the reference's defaults (created_time 0, the Option fields None) and are
+ * skipped on read; first_sampling (may be NULL) receives the SamplingParams of the first sequence, which pick the
+ * step's strategy (core/runner.rs:1390-1570).  load returns n, or -1 malformed, -2 more than cap sequences, -3 a
+ * sequence prepare_prefill cannot walk (other block size, short block table), -4 a sequence with images.           */
+struct b200_scheduler;
+int64_t b200_scheduler_frame_run_prefill(const struct b200_scheduler* s, const int32_t* indices, int32_t n,
+                                         uint8_t* out, int64_t cap, int32_t is_prefill);
+int32_t b200_scheduler_load_run_prefill(struct b200_scheduler* s, const uint8_t* frame, int64_t len,
+                                        int32_t* indices, int32_t cap, int32_t* is_prefill,
+                                        b200_wire_sampling* first_sampling);
 void b200_wire_decode_metadata(int32_t n, const uint32_t* last_tokens, const uint64_t* lens,
                                const uint64_t* last_block_tokens, const uint32_t* block_table_last,
                                int32_t block_size, uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,

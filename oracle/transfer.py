@@ -130,3 +130,29 @@ def decode_metadata(seqs, block_size=64):
     return dict(input_ids=[q["last_token"] for q in seqs], positions=[q["len"] - 1 for q in seqs],
                 context_lens=[q["len"] for q in seqs],
                 slot_mapping=[(q["block_table_last"] * block_size + q["last_block_tokens"] - 1) & 0xFFFFFFFF for q in seqs])
+
+
+MT_RUN_PREFILL = 3
+
+
+def sequence_bytes(q) -> bytes:
+    """core/sequence.rs:32-50, field by field.  q: dict with id, status (0 Waiting .. 5 FinishSwapped), token_ids,
+    output_ids, block_table, num_cached_tokens, last_token, block_size and optionally created_time, swapped_time,
+    mamba_prefix_hash, sampling (bytes), pd_first_token, stop_sequence (bytes); images is None (multimodal data is
+    out of scope)."""
+    def vec(v):
+        return struct.pack("<Q", len(v)) + struct.pack(f"<{len(v)}I", *v)
+    b = struct.pack("<QQ", q["id"], q.get("created_time", 0)) + _opt("<Q", q.get("swapped_time"))
+    b += struct.pack("<I", q["status"]) + vec(q["token_ids"]) + vec(q["output_ids"]) + vec(q["block_table"])
+    b += struct.pack("<Q", q["num_cached_tokens"]) + _opt("<Q", q.get("mamba_prefix_hash"))
+    b += struct.pack("<IQ", q["last_token"], q["block_size"]) + q.get("sampling", sampling_params())
+    b += _opt("<I", q.get("pd_first_token")) + b"\x00"               # images: None
+    b += struct.pack("<BB", int(q.get("is_tool_call_end", False)), int(q.get("hit_stop_sequence", False)))
+    b += _opt_str(q.get("stop_sequence"))
+    return b
+
+
+def run_prefill_frame(seqs, is_prefill=True) -> bytes:
+    """MessageType::RunPrefill((Vec<Sequence>, bool)) (runner/mod.rs:178)."""
+    b = struct.pack("<IQ", MT_RUN_PREFILL, len(seqs)) + b"".join(sequence_bytes(q) for q in seqs)
+    return frame(b + struct.pack("<B", 1 if is_prefill else 0))

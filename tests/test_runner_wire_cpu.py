@@ -206,3 +206,87 @@ def test_run_decode_frames_property(lib):
 
     check()
     lib.b200_clear_error()
+
+
+# ---------------------------------------------------------------- RunPrefill((Vec<Sequence>, bool))
+def _hand_run_prefill():
+    """RunPrefill(([Sequence{id 7, created_time 0, swapped_time None, status Running, token_ids [11, 12, 13],
+    output_ids [], block_table [5], num_cached_tokens 0, mamba_prefix_hash None, last_token 13, block_size 64,
+    SamplingParams{max_tokens Some(9), rest None / false}, pd_first_token None, images None, false, false, None}],
+    true)) byte by byte."""
+    b = bytes([3, 0, 0, 0]) + bytes([1, 0, 0, 0, 0, 0, 0, 0])        # variant 3, one sequence
+    b += bytes([7, 0, 0, 0, 0, 0, 0, 0]) + bytes(8) + bytes([0])     # id, created_time, swapped_time None
+    b += bytes([1, 0, 0, 0])                                         # status: Running
+    b += bytes([3, 0, 0, 0, 0, 0, 0, 0]) + bytes([11, 0, 0, 0, 12, 0, 0, 0, 13, 0, 0, 0])   # token_ids
+    b += bytes(8)                                                    # output_ids: empty
+    b += bytes([1, 0, 0, 0, 0, 0, 0, 0]) + bytes([5, 0, 0, 0])       # block_table
+    b += bytes(8) + bytes([0])                                       # num_cached_tokens, mamba_prefix_hash None
+    b += bytes([13, 0, 0, 0]) + bytes([64, 0, 0, 0, 0, 0, 0, 0])     # last_token, block_size
+    b += bytes([0]) + bytes([1, 9, 0, 0, 0, 0, 0, 0, 0]) + bytes([0])   # temperature None, max_tokens Some(9), ignore_eos
+    b += bytes(11)                                                   # top_k .. reasoning_effort: eleven None tags
+    b += bytes([0, 0, 0, 0, 0])                                      # pd_first_token, images, two flags, stop_sequence
+    b += bytes([1])                                                  # is_prefill
+    return struct.pack("<I", len(b)) + b
+
+
+def test_run_prefill_frame_golden_and_round_trip(lib):
+    from vllm_rs_b200.engine import Scheduler
+    q = dict(id=7, status=1, token_ids=[11, 12, 13], output_ids=[], block_table=[5], num_cached_tokens=0,
+             last_token=13, block_size=64, sampling=ot.sampling_params(max_tokens=9))
+    assert ot.run_prefill_frame([q], True) == _hand_run_prefill()
+    # engine side: three prompts scheduled for prefill, framed by the native scheduler == the oracle's bytes
+    rng = np.random.default_rng(3)
+    eng = Scheduler(64, 64, 8)
+    prompts = [rng.integers(0, 1000, size=L).tolist() for L in (37, 64, 130)]
+    for t in prompts:
+        eng.add(t, max_tokens=12)
+    ids, pf = eng.schedule()
+    assert pf and len(ids) == 3
+    fr = eng.frame_run_prefill(ids, True)
+    want = ot.run_prefill_frame(
+        [dict(id=eng.seq_info(i)["id"], status=1, token_ids=eng.tokens(i), output_ids=[], block_table=eng.block_table(i),
+              num_cached_tokens=0, last_token=eng.tokens(i)[-1], block_size=64,
+              sampling=ot.sampling_params(max_tokens=12)) for i in ids], True)
+    assert fr == want
+    assert lib.b200_wire_kind(np.frombuffer(fr, np.uint8).ctypes.data, len(fr)) == ot.MT_RUN_PREFILL
+    # runner side: a fresh container loads the frame and derives the SAME step metadata
+    run = Scheduler(64, 64, 8)
+    rids, rpf, sp = run.load_run_prefill(fr)
+    assert rpf and rids == [0, 1, 2] and (sp.has_max_tokens, sp.max_tokens, sp.has_temperature) == (1, 12, 0)
+    a, b = eng.prepare_prefill(ids), run.prepare_prefill(rids)
+    for k in a:
+        if a[k] is None:
+            assert b[k] is None
+        else:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    # the oracle's frame of a sequence with fields the mirror ignores (session id, stop sequences, swapped_time, a
+    # second chunk with cached tokens) still loads, and the metadata is the oracle's prepare_prefill
+    sch = osched.Scheduler(64, 64, 8)
+    sch.add(osched.Sequence(rng.integers(0, 1000, size=200).tolist(), 64, max_tokens=4))
+    oids, _ = sch.schedule()
+    s0 = sch.running[oids[0]]
+    s0.num_cached_tokens = 128                                       # as after a 128-token chunk / prefix hit
+    ofr = ot.run_prefill_frame([dict(
+        id=s0.id, created_time=1700000000, swapped_time=55, status=1, token_ids=list(s0.token_ids), output_ids=[],
+        block_table=list(s0.block_table), num_cached_tokens=128, mamba_prefix_hash=99, last_token=s0.last_token,
+        block_size=64, pd_first_token=4, stop_sequence=b"END", hit_stop_sequence=True,
+        sampling=ot.sampling_params(temperature=0.5, session_id=b"s", stop_sequences=[b"a", b"bc"], top_k=5))], True)
+    rids, _, sp = run.load_run_prefill(ofr)
+    meta = run.prepare_prefill(rids)
+    want_meta = osched.prepare_prefill([s0], 64)
+    for k in ("input_ids", "positions", "slot_mapping", "cu_seqlens_q", "cu_seqlens_k", "context_lens"):
+        assert np.asarray(meta[k]).tolist() == list(want_meta[k]), k
+    assert np.asarray(meta["block_tables"]).tolist() == [list(r) for r in want_meta["block_tables"]]
+    assert (sp.has_temperature, sp.temperature, sp.top_k) == (1, 0.5, 5)
+    # refused: truncated frame, a foreign block size, a block table too short for the tokens
+    import pytest
+    from vllm_rs_b200 import _lib
+    with pytest.raises(_lib.B200Error, match="-1"):
+        run.load_run_prefill(fr[:-3])
+    bad = dict(q, block_size=16)
+    with pytest.raises(_lib.B200Error, match="-3"):
+        run.load_run_prefill(ot.run_prefill_frame([bad], True))
+    bad = dict(q, token_ids=list(range(70)))
+    with pytest.raises(_lib.B200Error, match="-3"):
+        run.load_run_prefill(ot.run_prefill_frame([bad], True))
+    lib.b200_clear_error()

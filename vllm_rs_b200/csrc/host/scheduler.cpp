@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../../include/b200_vllm.h"
+#include "bincode.hpp"
 
 namespace b200 {
 void set_error(int code, const char* msg);
@@ -964,6 +965,109 @@ int32_t b200_prepare_prefill(const b200_scheduler* s, const int32_t* indices, in
   if (max_seqlen_k) *max_seqlen_k = mk;
   if (max_context_len) *max_context_len = mctx;
   return static_cast<int32_t>(T);
+}
+
+// ---------------------------------------------------------------- RunPrefill frames (runner/mod.rs:178, 248-295)
+// MessageType::RunPrefill((Vec<Sequence>, bool)): what the engine sends a runner process for a prefill step
+// (`send_local`, u32 length + bincode 1.3.1), with `Sequence` as core/sequence.rs:32-50 declares it.  The engine side
+// frames the scheduled sequences; the runner side loads a frame into a scheduler object it uses as a plain sequence
+// container and runs b200_prepare_prefill on it -- the same metadata the engine's own prepare_prefill would give.
+// Fields the mirror does not keep are written as the reference's defaults (created_time 0 -- the engine's wall
+// clock --, mamba_prefix_hash / pd_first_token / images / stop_sequence None, the two flags false) and skipped on
+// read; a sequence that carries images is refused (multimodal is out of scope).
+int64_t b200_scheduler_frame_run_prefill(const b200_scheduler* s, const int32_t* indices, int32_t n, uint8_t* out,
+                                         int64_t cap, int32_t is_prefill) {
+  using namespace b200::wire;
+  Wr w{out, cap};
+  w.u32(0);                                            // frame length, patched below
+  w.u32(kRunPrefill);
+  w.u64(static_cast<uint64_t>(n));
+  for (int32_t i = 0; i < n; ++i) {
+    if (indices[i] < 0 || static_cast<size_t>(indices[i]) >= s->running.size()) {
+      b200::set_error(1, "scheduler_frame_run_prefill: index out of range");
+      return -1;
+    }
+    const Sequence& q = s->running[indices[i]];
+    w.u64(static_cast<uint64_t>(q.id));
+    w.u64(0);                                          // created_time
+    w.u8(q.has_swapped_time ? 1 : 0);
+    if (q.has_swapped_time) w.u64(static_cast<uint64_t>(q.swapped_time));
+    w.u32(static_cast<uint32_t>(q.status));
+    for (const std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
+      w.u64(v->size());
+      w.raw(v->data(), static_cast<int64_t>(v->size() * 4));
+    }
+    w.u64(q.num_cached_tokens);
+    w.u8(0);                                           // mamba_prefix_hash
+    w.u32(q.last_token);
+    w.u64(q.block_size);
+    b200_wire_sampling sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.has_max_tokens = 1;
+    sp.max_tokens = static_cast<int64_t>(q.max_tokens);
+    write_sampling(w, &sp);
+    w.u8(0);                                           // pd_first_token
+    w.u8(0);                                           // images
+    w.u8(0); w.u8(0);                                  // is_tool_call_end, hit_stop_sequence
+    w.u8(0);                                           // stop_sequence
+  }
+  w.u8(is_prefill ? 1 : 0);
+  if (!w.ok) {
+    b200::set_error(1, "scheduler_frame_run_prefill: buffer too small");
+    return -1;
+  }
+  const uint32_t body = static_cast<uint32_t>(w.off - 4);
+  std::memcpy(out, &body, 4);
+  return w.off;
+}
+
+int32_t b200_scheduler_load_run_prefill(b200_scheduler* s, const uint8_t* frame, int64_t len, int32_t* indices,
+                                        int32_t cap, int32_t* is_prefill, b200_wire_sampling* first_sampling) {
+  using namespace b200::wire;
+  Rd r{frame, len};
+  const uint32_t body = r.u32();
+  if (!r.ok || static_cast<int64_t>(body) + 4 != len || r.u32() != kRunPrefill) return -1;
+  const uint64_t n = r.u64();
+  if (!r.ok || n > static_cast<uint64_t>(cap)) return -2;
+  std::vector<Sequence> seqs(n);
+  for (uint64_t i = 0; i < n && r.ok; ++i) {
+    Sequence& q = seqs[i];
+    q.id = static_cast<int64_t>(r.u64());
+    r.u64();                                           // created_time
+    q.has_swapped_time = r.opt();
+    if (q.has_swapped_time) q.swapped_time = static_cast<int64_t>(r.u64());
+    const uint32_t st = r.u32();
+    if (st > 5) return -1;
+    q.status = static_cast<Status>(st);
+    for (std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
+      const uint64_t m = r.u64();
+      if (!r.ok || !r.need(static_cast<int64_t>(m) * 4)) return -1;
+      v->resize(m);
+      std::memcpy(v->data(), r.p + r.off, m * 4);
+      r.off += static_cast<int64_t>(m) * 4;
+    }
+    q.num_cached_tokens = r.u64();
+    if (r.opt()) r.u64();                              // mamba_prefix_hash
+    q.last_token = r.u32();
+    q.block_size = r.u64();
+    b200_wire_sampling sp;
+    read_sampling(r, &sp);
+    q.max_tokens = sp.has_max_tokens ? static_cast<size_t>(sp.max_tokens) : 16384;
+    if (i == 0 && first_sampling) *first_sampling = sp;   // the strategy of a step comes from its first sequence
+    if (r.opt()) r.u32();                              // pd_first_token
+    if (r.opt()) return -4;                            // images: multimodal sequences are not taken
+    r.u8(); r.u8();                                    // is_tool_call_end, hit_stop_sequence
+    if (r.opt()) r.skip_string();                      // stop_sequence
+    if (r.ok && (q.block_size != s->block_size || q.num_cached_tokens > q.token_ids.size() ||
+                 q.block_table.size() < q.num_blocks()))
+      return -3;                                       // not a sequence prepare_prefill can walk
+  }
+  const uint8_t pf = r.u8();
+  if (!r.ok || r.off != len) return -1;
+  s->running = std::move(seqs);
+  for (uint64_t i = 0; i < n; ++i) indices[i] = static_cast<int32_t>(i);
+  if (is_prefill) *is_prefill = pf;
+  return static_cast<int32_t>(n);
 }
 
 // KVCacheAllocator::plan_allocation for dense models

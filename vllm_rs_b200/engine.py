@@ -211,6 +211,30 @@ class Scheduler:
         return out
 
 
+    # ---- RunPrefill frames (runner/mod.rs:178): the engine side frames its scheduled sequences, a runner side loads them
+    def frame_run_prefill(self, ids, is_prefill=True) -> bytes:
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        cap = 64 + sum(256 + 4 * (2 * len(self.tokens(i)) + len(self.block_table(i))) for i in ids)
+        out = np.zeros(cap, np.uint8)
+        n = self._l.b200_scheduler_frame_run_prefill(self._h, a.ctypes.data, len(a), out.ctypes.data, cap,
+                                                     int(is_prefill))
+        _lib.check()
+        return out[:n].tobytes()
+
+    def load_run_prefill(self, frame: bytes, cap=1024):
+        """Replace this scheduler's running list with the sequences of a RunPrefill frame; returns (ids, is_prefill,
+        sampling of the first sequence)."""
+        buf = np.frombuffer(frame, np.uint8)
+        idx = np.zeros(cap, np.int32)
+        pf = C.c_int32()
+        sp = _lib.WireSampling()
+        n = self._l.b200_scheduler_load_run_prefill(self._h, buf.ctypes.data, len(buf), idx.ctypes.data, cap,
+                                                    C.byref(pf), C.byref(sp))
+        if n < 0:
+            raise _lib.B200Error(f"load_run_prefill: {n}")
+        return idx[:n].tolist(), bool(pf.value), sp
+
+
 def plan_kvcache(available_bytes, *, num_layers, num_kv_heads, head_dim, num_shards=1, block_size=64,
                  dtype_size=2, config_model_len=8192, max_num_seqs=None, max_model_len=None,
                  cpu_mem_fold=0.5) -> dict:
