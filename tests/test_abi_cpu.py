@@ -78,3 +78,17 @@ def test_bindings_match_the_header_prototypes(lib):
         want = "void" if res is None else klass_c(res)
         got = "void" if ret == "void" else klass_h(ret + " x") if "*" not in ret else "ptr"
         assert want == got, f"{name}: return bound {res} vs header '{ret}'"
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under vllm_rs_b200/ may import, load or execute it, and the library
+    front door must fail loudly (never fall back) when the CUDA library is missing."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.]_build|oracle[/.]_ref|libdecode_ref", re.M)
+    for p in sorted((root / "vllm_rs_b200").rglob("*")):
+        if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".hpp", ".h"):
+            assert not pat.search(p.read_text()), p
+    src = (root / "vllm_rs_b200" / "_lib.py").read_text()
+    assert "B200Error" in src and "libb200_vllm.so" in src
