@@ -48,7 +48,6 @@ namespace sk {
 constexpr int kDG = 3;                          // dequant groups (4 warps = 128 channels each)
 constexpr int kDqWarps = 4 * kDG;               // warps 0 .. 11 (warp % 4 == TMEM lane quarter)
 constexpr int kEpiWarps = 2;                    // (four would push the CTA past 20 warps = below 96 registers per thread)
-constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEpiWarp0 = kDqWarps;             // 12 .. 13
 constexpr int kWProdWarp = kEpiWarp0 + kEpiWarps;   // 14
 constexpr int kXProdWarp = kWProdWarp + 1;      // 15: activations, up to kDG * kSXS units ahead of the MMAs (fetching
@@ -279,7 +278,6 @@ wna16_sk_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
   using C = Cfg<BITS, NT>;
   static_assert(!MMA || (BITS == 4 && EPI != kEpiNoneBf16), "the mma.sync flavour is 4-bit fp16");
   constexpr bool kBf16 = EPI == kEpiNoneBf16;
-  constexpr int EPX = kBf16 ? B200_EPI_NONE : EPI;     // the epilogue the finaliser templates see
   static_assert(!kBf16 || BITS == 4, "bf16 entry points are 4-bit only (gptq.rs:150-178)");
   const int b = blockIdx.x;
   const int KP = a.KP, N = a.N, M = a.M;
