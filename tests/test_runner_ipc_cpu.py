@@ -125,3 +125,118 @@ def test_handshake_rejects_a_wrong_acknowledgment():
     finally:
         a.close()
         b.close()
+
+
+# ---------------------------------------------------------------- with a paged "KV cache" on the runner side
+class PagedTokenStore:
+    """Stand-in for the KV cache of a runner process: every step writes its input ids at the step's slots; a
+    sequence's next token is a hash of what its block table READS BACK for the whole context.  KVCacheSwap frames
+    move blocks between the GPU array and the CPU swap array exactly as swap_kvcache does (dst[d] = src[s])."""
+
+    def __init__(self, num_blocks, num_cpu_blocks):
+        self.gpu = np.full((num_blocks, 64), -1, np.int64)
+        self.cpu = np.full((max(num_cpu_blocks, 1), 64), -1, np.int64)
+        self.swaps = 0
+
+    def swap(self, pairs, swap_in):
+        self.swaps += 1
+        for s, d in pairs:
+            if swap_in:
+                self.gpu[d] = self.cpu[s]
+            else:
+                self.cpu[d] = self.gpu[s]
+
+    def read(self, table, ctx):
+        return self.gpu[np.asarray(table[:-(-ctx // 64)], np.int64)].reshape(-1)[:ctx]
+
+    def step(self, kind, meta):
+        flat = self.gpu.reshape(-1)
+        out = []
+        if kind == "prefill":
+            cu = np.asarray(meta["cu_seqlens_q"]).tolist()
+            flat[np.asarray(meta["slot_mapping"], np.int64)] = np.asarray(meta["input_ids"], np.int64)
+            for b in range(len(cu) - 1):
+                ctx = meta["num_cached_tokens"][b] + cu[b + 1] - cu[b]
+                out.append(_mix(*self.read(meta["seq_block_tables"][b], ctx).tolist()))
+        else:
+            flat[np.asarray(meta["slot_mapping"], np.int64)] = np.asarray(meta["input_ids"], np.int64)
+            for b in range(len(meta["input_ids"])):
+                out.append(_mix(*self.read(meta["block_tables"][b], int(meta["context_lens"][b])).tolist()))
+        return out
+
+
+def test_whole_run_with_cpu_swap_over_the_wire_reads_back_every_history(lib):
+    """Few GPU blocks, CPU swap on: sequences are swapped out and back while others reuse their blocks.  The runner's
+    paged store only ever sees frames (RunPrefill, RunDecode, KVCacheSwap); the direct run hashes each sequence's true
+    token history.  Equal tokens <=> every slot, block table and swap copy list that crossed the wire was right."""
+    from vllm_rs_b200.engine import Scheduler
+    from vllm_rs_b200 import runner_ipc as ipc
+    rng = np.random.default_rng(5)
+    reqs = [(rng.integers(0, VOCAB, size=int(L)).tolist(), int(mt))
+            for L, mt in zip(rng.integers(150, 300, size=10), rng.integers(150, 260, size=10))]
+    # a swap-in wants 1000 tokens of head-room beyond the sequence (scheduler.rs:50): 30 blocks give that to a lone
+    # sequence, while six running ones of up to 9 blocks each do not fit
+    NB, NCPU = 30, 48
+
+    def fresh():
+        s = Scheduler(NB, 64, 6)
+        s.enable_cpu_swap(NCPU)
+        for toks, mt in reqs:
+            s.add(toks, max_tokens=mt)
+        return s
+
+    def run(sched, run_prefill, run_decode, on_swap, on_finished):
+        gen, now, steps = {}, 0, 0
+        for steps in range(4000):
+            now += (100, 700, 2600)[steps % 3]
+            sched.set_time_ms(now)
+            ids, pf = sched.schedule()
+            for swap_in, pairs in sched.pop_swap_ops():              # the host runs these before the forward
+                on_swap(pairs, swap_in)
+            if not ids:
+                if sched.num_swapped == 0 and sched.num_waiting == 0:
+                    break
+                continue
+            infos = {i: sched.seq_info(i) for i in ids}
+            assert all(v["status"] != 2 for v in infos.values())     # sizes chosen so no sequence is stranded
+            if pf:
+                toks = run_prefill(ids)
+                pos, fin = sched.filter_prefill_finished(ids)
+                sched.postprocess(fin, [toks[p] for p in pos])
+                rows = list(zip(fin, [toks[p] for p in pos]))
+            else:
+                toks = run_decode(ids)
+                sched.postprocess(ids, toks)
+                rows = list(zip(ids, toks))
+            for i, t in rows:
+                gen.setdefault(infos[i]["id"], []).append(t)
+                if sched.seq_info(i)["status"] == 2:
+                    on_finished(infos[i]["id"])
+            sched.clear_finished()
+        assert sched.num_running == 0 and sched.num_waiting == 0 and sched.num_swapped == 0
+        return gen
+
+    # direct run: the token after a step is the hash of the sequence's true history up to and including the step's input
+    d = fresh()
+    swaps = []
+    want = run(d, lambda ids: [_mix(*d.tokens(i)[:d.seq_info(i)["num_cached_tokens"] + min(8192, d.seq_info(i)["len"] - d.seq_info(i)["num_cached_tokens"])]) for i in ids],
+               lambda ids: [_mix(*d.tokens(i)) for i in ids], lambda p, f: swaps.append(f), lambda sid: None)
+    assert len(want) == len(reqs) and True in swaps and False in swaps      # swapped out AND back in
+
+    store = PagedTokenStore(NB, NCPU)
+    a, b = socket.socketpair()
+    th = threading.Thread(target=lambda: ipc.serve(b, store.step, on_swap=store.swap))
+    th.start()
+    try:
+        es = fresh()
+        eng = ipc.WireEngine(es, a)
+        got = run(es, eng.run_prefill, eng.run_decode, lambda p, f: eng.kv_swap(p, f), eng.finish)
+        eng.shutdown()
+    finally:
+        th.join(timeout=60)
+        a.close()
+        b.close()
+    assert not th.is_alive()
+    assert got == want
+    assert store.swaps == len(swaps)
+    lib.b200_clear_error()

@@ -18,6 +18,7 @@ from . import _lib
 from .engine import Scheduler
 
 MT_RUN_PREFILL, MT_RUN_DECODE, MT_RUN_RESPONSE, MT_FINISH_DECODE, MT_HEARTBEAT, MT_SHUTDOWN = 3, 4, 5, 8, 14, 34
+MT_KV_SWAP, MT_KV_SWAP_RESPONSE = 21, 22
 
 
 def _recv_exact(sock, n: int) -> bytes:
@@ -101,6 +102,17 @@ class WireEngine:
         send_local(self.sock, out[:m].tobytes())
         return self._recv_ids(n)
 
+    def kv_swap(self, pairs, swap_in: bool) -> bool:
+        """KVCacheSwap((HashMap<usize, usize>, bool)) -> KVCacheSwapResponse(bool) (runner.rs:1626-1645 runs it)."""
+        a = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        out = np.zeros(32 + 16 * len(a), np.uint8)
+        n = self._l.b200_wire_frame_kv_swap(out.ctypes.data, len(out), a.ctypes.data, len(a), int(swap_in))
+        send_local(self.sock, out[:n].tobytes())
+        fr = receive_local(self.sock)
+        if _kind(fr) != MT_KV_SWAP_RESPONSE:
+            raise _lib.B200Error("expected KVCacheSwapResponse")
+        return fr[8] == 1
+
     def finish(self, seq_id: int) -> None:
         send_local(self.sock, _simple(MT_FINISH_DECODE, 8, seq_id))
 
@@ -108,7 +120,8 @@ class WireEngine:
         send_local(self.sock, _simple(MT_SHUTDOWN))
 
 
-def serve(sock, step_fn, *, num_blocks=1 << 16, block_size=64, max_seqs=256, max_blocks=1024, on_finish=None) -> int:
+def serve(sock, step_fn, *, num_blocks=1 << 16, block_size=64, max_seqs=256, max_blocks=1024, on_finish=None,
+          on_swap=None) -> int:
     """The runner side: answer RunPrefill / RunDecode with RunResponse(step_fn(kind, metadata)) until Shutdown; returns
     the number of steps served.  metadata is what prepare_prefill / prepare_decode give for the frame's sequences."""
     l = _lib.lib()
@@ -123,6 +136,9 @@ def serve(sock, step_fn, *, num_blocks=1 << 16, block_size=64, max_seqs=256, max
         if kind == MT_RUN_PREFILL:
             ids, _, _ = box.load_run_prefill(fr, cap=max_seqs)
             meta = box.prepare_prefill(ids, max_blocks_cap=max_blocks)
+            meta["seq_ids"] = [box.seq_info(i)["id"] for i in ids]
+            meta["num_cached_tokens"] = [box.seq_info(i)["num_cached_tokens"] for i in ids]
+            meta["seq_block_tables"] = [box.block_table(i) for i in ids]
             send_local(sock, _response(step_fn("prefill", meta)))
             steps += 1
         elif kind == MT_RUN_DECODE:
@@ -143,6 +159,13 @@ def serve(sock, step_fn, *, num_blocks=1 << 16, block_size=64, max_seqs=256, max
                         block_tables=bt[:n, :mb].copy(), max_blocks=mb, seq_ids=sid[:n].copy())
             send_local(sock, _response(step_fn("decode", meta)))
             steps += 1
+        elif kind == MT_KV_SWAP:
+            pairs, flag = np.zeros((4096, 2), np.int64), C.c_int32()
+            n = l.b200_wire_parse_kv_swap(buf.ctypes.data, len(buf), pairs.ctypes.data, 4096, C.byref(flag))
+            ok = n >= 0 and on_swap is not None
+            if ok:
+                on_swap(pairs[:n].tolist(), bool(flag.value))
+            send_local(sock, _simple(MT_KV_SWAP_RESPONSE, 1, 1 if ok else 0))
         elif kind == MT_FINISH_DECODE:
             if on_finish:
                 on_finish(int.from_bytes(fr[8:16], "little"))
