@@ -257,6 +257,21 @@ int64_t b200_scheduler_frame_run_prefill(const struct b200_scheduler* s, const i
 int32_t b200_scheduler_load_run_prefill(struct b200_scheduler* s, const uint8_t* frame, int64_t len,
                                         int32_t* indices, int32_t cap, int32_t* is_prefill,
                                         b200_wire_sampling* first_sampling);
+/* Single-Sequence messages of the PD hand-off.  family 0 = runner IPC MessageType (runner/mod.rs:168-249): kind 15
+ * TransferPrefill(Sequence), 18 ReceivePrefillResponse((bool, Option<Sequence>)), 23 KvCacheSend((Sequence, u32)),
+ * 25 KvCacheReceive(Sequence); family 1 = client <-> PD server TransferMessage (transfer/mod.rs:113-122): kind 0
+ * TransferPrefill(Sequence).  `extra` = the bool of kind 18 / the first token of kind 23; index < 0 with kind 18 frames
+ * (extra, None).  load puts the sequence into the container as running[0]; returns 1, 0 (kind 18 with None), -1, -4.  */
+int64_t b200_scheduler_frame_sequence(const struct b200_scheduler* s, int32_t index, int32_t family, int32_t kind,
+                                      uint32_t extra, uint8_t* out, int64_t cap);
+int32_t b200_scheduler_load_sequence(struct b200_scheduler* s, const uint8_t* frame, int64_t len, int32_t family,
+                                     int32_t* kind, uint32_t* extra);
+/* KvCacheReceiveResponse((bool, u32, usize, usize)) (variant 26): success, first token, the server's sending time
+ * and the prefix-cache hit length recorded there (transfer/mod.rs:319).  parse returns 0, -1 malformed.            */
+int64_t b200_wire_frame_kv_receive_response(uint8_t* out, int64_t cap, int32_t ok, uint32_t first_token, uint64_t sending_time,
+                                            uint64_t num_cached_tokens);
+int32_t b200_wire_parse_kv_receive_response(const uint8_t* frame, int64_t len, int32_t* ok, uint32_t* first_token,
+                                            uint64_t* sending_time, uint64_t* num_cached_tokens);
 void b200_wire_decode_metadata(int32_t n, const uint32_t* last_tokens, const uint64_t* lens,
                                const uint64_t* last_block_tokens, const uint32_t* block_table_last,
                                int32_t block_size, uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,

@@ -156,3 +156,28 @@ def run_prefill_frame(seqs, is_prefill=True) -> bytes:
     """MessageType::RunPrefill((Vec<Sequence>, bool)) (runner/mod.rs:178)."""
     b = struct.pack("<IQ", MT_RUN_PREFILL, len(seqs)) + b"".join(sequence_bytes(q) for q in seqs)
     return frame(b + struct.pack("<B", 1 if is_prefill else 0))
+
+
+# single-Sequence messages of the PD hand-off (runner/mod.rs:205-231, transfer/mod.rs:113-122)
+MT_TRANSFER_PREFILL, MT_RECEIVE_PREFILL_RESPONSE, MT_KV_SEND, MT_KV_RECEIVE, MT_KV_RECEIVE_RESPONSE = 15, 18, 23, 25, 26
+
+
+def transfer_prefill_frame(q, tcp=False) -> bytes:
+    """MessageType::TransferPrefill(Sequence) (variant 15) or, tcp=True, TransferMessage::TransferPrefill (variant 0)."""
+    return frame(struct.pack("<I", 0 if tcp else MT_TRANSFER_PREFILL) + sequence_bytes(q))
+
+
+def receive_prefill_response_frame(ok, q=None) -> bytes:
+    return frame(struct.pack("<IB", MT_RECEIVE_PREFILL_RESPONSE, int(ok)) + (b"\x00" if q is None else b"\x01" + sequence_bytes(q)))
+
+
+def kv_send_frame(q, first_token) -> bytes:
+    return frame(struct.pack("<I", MT_KV_SEND) + sequence_bytes(q) + struct.pack("<I", first_token))
+
+
+def kv_receive_frame(q) -> bytes:
+    return frame(struct.pack("<I", MT_KV_RECEIVE) + sequence_bytes(q))
+
+
+def kv_receive_response_frame(ok, first_token, sending_time, num_cached_tokens) -> bytes:
+    return frame(struct.pack("<IBIQQ", MT_KV_RECEIVE_RESPONSE, int(ok), first_token, sending_time, num_cached_tokens))

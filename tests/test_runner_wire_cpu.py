@@ -290,3 +290,43 @@ def test_run_prefill_frame_golden_and_round_trip(lib):
     with pytest.raises(_lib.B200Error, match="-3"):
         run.load_run_prefill(ot.run_prefill_frame([bad], True))
     lib.b200_clear_error()
+
+
+def test_pd_sequence_messages(lib):
+    """TransferPrefill (runner IPC and client -> PD server TCP), ReceivePrefillResponse, KvCacheSend, KvCacheReceive:
+    one Sequence each (pinned by the hand-written RunPrefill frame above), plus KvCacheReceiveResponse."""
+    import pytest
+    from vllm_rs_b200 import _lib
+    from vllm_rs_b200.engine import Scheduler
+    rng = np.random.default_rng(9)
+    eng = Scheduler(64, 64, 8)
+    eng.add(rng.integers(0, 1000, size=150).tolist(), max_tokens=21)
+    ids, pf = eng.schedule()
+    i = ids[0]
+    q = dict(id=eng.seq_info(i)["id"], status=1, token_ids=eng.tokens(i), output_ids=[], block_table=eng.block_table(i),
+             num_cached_tokens=0, last_token=eng.tokens(i)[-1], block_size=64, sampling=ot.sampling_params(max_tokens=21))
+    cases = [((15, 0, 0), ot.transfer_prefill_frame(q)), ((0, 1, 0), ot.transfer_prefill_frame(q, tcp=True)),
+             ((18, 0, 1), ot.receive_prefill_response_frame(True, q)), ((23, 0, 777), ot.kv_send_frame(q, 777)),
+             ((25, 0, 0), ot.kv_receive_frame(q))]
+    box = Scheduler(64, 64, 8)
+    for (kind, family, extra), want in cases:
+        assert eng.frame_sequence(i, kind, family, extra) == want, kind
+        assert box.load_sequence(want, family) == (True, kind, extra)
+        assert (box.seq_info(0)["id"], box.tokens(0), box.block_table(0)) == (q["id"], q["token_ids"], q["block_table"])
+        assert box.frame_sequence(0, kind, family, extra) == want          # load -> frame is the identity
+    none = ot.receive_prefill_response_frame(True, None)
+    assert eng.frame_sequence(-1, 18, 0, 1) == none and box.load_sequence(none) == (False, 18, 1)
+    assert box.num_running == 0
+    with pytest.raises(_lib.B200Error):
+        box.load_sequence(ot.kv_send_frame(q, 5), family=1)                 # not a TransferMessage
+    with pytest.raises(_lib.B200Error):
+        box.load_sequence(cases[0][1][:-1])
+    want = ot.kv_receive_response_frame(True, 4242, 1760000000123, 128)
+    out = np.zeros(64, np.uint8)
+    assert lib.b200_wire_frame_kv_receive_response(out.ctypes.data, 64, 1, 4242, 1760000000123, 128) == len(want)
+    assert out[:len(want)].tobytes() == want
+    ok, tok, t, c = C.c_int32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+    assert lib.b200_wire_parse_kv_receive_response(out.ctypes.data, len(want), C.byref(ok), C.byref(tok), C.byref(t),
+                                                   C.byref(c)) == 0
+    assert (ok.value, tok.value, t.value, c.value) == (1, 4242, 1760000000123, 128)
+    lib.b200_clear_error()

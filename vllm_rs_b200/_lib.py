@@ -119,6 +119,10 @@ _SIGS = {
     "b200_wire_frame_simple": (c_i64, [c_vp, c_i64, c_i32, c_i32, C.c_uint64]),
     "b200_scheduler_frame_run_prefill": (c_i64, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32]),
     "b200_scheduler_load_run_prefill": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),
+    "b200_scheduler_frame_sequence": (c_i64, [c_vp, c_i32, c_i32, c_i32, C.c_uint32, c_vp, c_i64]),
+    "b200_scheduler_load_sequence": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "b200_wire_frame_kv_receive_response": (c_i64, [c_vp, c_i64, c_i32, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "b200_wire_parse_kv_receive_response": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "b200_wire_decode_metadata": (None, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b200_paged_attn_decode_f16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),
     "b200_paged_attn_decode_bf16": (None, [c_vp] * 6 + [c_i32] * 7 + [c_f32, c_f32, c_i32, c_vp, c_i64]),

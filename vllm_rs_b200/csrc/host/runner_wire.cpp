@@ -166,6 +166,35 @@ int64_t b200_wire_frame_simple(uint8_t* out, int64_t cap, int32_t kind, int32_t 
 
 // The decode metadata a runner derives from a RunDecode message (runner.rs:1248-1264): input id = last token,
 // position = len - 1, context length = len, slot = last block * block_size + tokens in the last block - 1.
+int64_t b200_wire_frame_kv_receive_response(uint8_t* out, int64_t cap, int32_t ok, uint32_t first_token, uint64_t sending_time,
+                                            uint64_t num_cached_tokens) {
+  Wr w{out, cap};
+  w.u32(4 + 1 + 4 + 8 + 8);
+  w.u32(26);
+  w.u8(ok ? 1 : 0);
+  w.u32(first_token);
+  w.u64(sending_time);
+  w.u64(num_cached_tokens);
+  if (!out || !w.ok) { b200::set_error(1, "wire_frame_kv_receive_response: buffer too small"); return -1; }
+  return w.off;
+}
+
+int32_t b200_wire_parse_kv_receive_response(const uint8_t* frame, int64_t len, int32_t* ok, uint32_t* first_token,
+                                            uint64_t* sending_time, uint64_t* num_cached_tokens) {
+  Rd r{frame, len};
+  const uint32_t body = r.u32();
+  if (!r.ok || static_cast<int64_t>(body) + 4 != len || r.u32() != 26) return -1;
+  const uint8_t f = r.u8();
+  const uint32_t t = r.u32();
+  const uint64_t x = r.u64(), y = r.u64();
+  if (!r.ok || r.off != len || f > 1) return -1;
+  if (ok) *ok = f;
+  if (first_token) *first_token = t;
+  if (sending_time) *sending_time = x;
+  if (num_cached_tokens) *num_cached_tokens = y;
+  return 0;
+}
+
 void b200_wire_decode_metadata(int32_t n, const uint32_t* last_tokens, const uint64_t* lens,
                                const uint64_t* last_block_tokens, const uint32_t* block_table_last, int32_t block_size,
                                uint32_t* input_ids, int64_t* positions, int64_t* slot_mapping,

@@ -975,6 +975,64 @@ int32_t b200_prepare_prefill(const b200_scheduler* s, const int32_t* indices, in
 // Fields the mirror does not keep are written as the reference's defaults (created_time 0 -- the engine's wall
 // clock --, mamba_prefix_hash / pd_first_token / images / stop_sequence None, the two flags false) and skipped on
 // read; a sequence that carries images is refused (multimodal is out of scope).
+static void write_sequence(b200::wire::Wr& w, const Sequence& q) {               // core/sequence.rs:32-50, in order
+  using namespace b200::wire;
+  w.u64(static_cast<uint64_t>(q.id));
+  w.u64(0);                                            // created_time
+  w.u8(q.has_swapped_time ? 1 : 0);
+  if (q.has_swapped_time) w.u64(static_cast<uint64_t>(q.swapped_time));
+  w.u32(static_cast<uint32_t>(q.status));
+  for (const std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
+    w.u64(v->size());
+    w.raw(v->data(), static_cast<int64_t>(v->size() * 4));
+  }
+  w.u64(q.num_cached_tokens);
+  w.u8(0);                                             // mamba_prefix_hash
+  w.u32(q.last_token);
+  w.u64(q.block_size);
+  b200_wire_sampling sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.has_max_tokens = 1;
+  sp.max_tokens = static_cast<int64_t>(q.max_tokens);
+  write_sampling(w, &sp);
+  w.u8(0);                                             // pd_first_token
+  w.u8(0);                                             // images
+  w.u8(0); w.u8(0);                                    // is_tool_call_end, hit_stop_sequence
+  w.u8(0);                                             // stop_sequence
+}
+
+// 0 ok, -1 malformed, -4 carries images
+static int read_sequence(b200::wire::Rd& r, Sequence& q, b200_wire_sampling* sampling) {
+  using namespace b200::wire;
+  q.id = static_cast<int64_t>(r.u64());
+  r.u64();                                             // created_time
+  q.has_swapped_time = r.opt();
+  if (q.has_swapped_time) q.swapped_time = static_cast<int64_t>(r.u64());
+  const uint32_t st = r.u32();
+  if (!r.ok || st > 5) return -1;
+  q.status = static_cast<Status>(st);
+  for (std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
+    const uint64_t m = r.u64();
+    if (!r.ok || m > (1ull << 32) || !r.need(static_cast<int64_t>(m) * 4)) return -1;
+    v->resize(m);
+    std::memcpy(v->data(), r.p + r.off, m * 4);
+    r.off += static_cast<int64_t>(m) * 4;
+  }
+  q.num_cached_tokens = r.u64();
+  if (r.opt()) r.u64();                                // mamba_prefix_hash
+  q.last_token = r.u32();
+  q.block_size = r.u64();
+  b200_wire_sampling sp;
+  read_sampling(r, &sp);
+  q.max_tokens = sp.has_max_tokens ? static_cast<size_t>(sp.max_tokens) : 16384;
+  if (sampling) *sampling = sp;
+  if (r.opt()) r.u32();                                // pd_first_token
+  if (r.opt()) return -4;                              // images: multimodal sequences are not taken
+  r.u8(); r.u8();                                      // is_tool_call_end, hit_stop_sequence
+  if (r.opt()) r.skip_string();                        // stop_sequence
+  return r.ok ? 0 : -1;
+}
+
 int64_t b200_scheduler_frame_run_prefill(const b200_scheduler* s, const int32_t* indices, int32_t n, uint8_t* out,
                                          int64_t cap, int32_t is_prefill) {
   using namespace b200::wire;
@@ -987,29 +1045,7 @@ int64_t b200_scheduler_frame_run_prefill(const b200_scheduler* s, const int32_t*
       b200::set_error(1, "scheduler_frame_run_prefill: index out of range");
       return -1;
     }
-    const Sequence& q = s->running[indices[i]];
-    w.u64(static_cast<uint64_t>(q.id));
-    w.u64(0);                                          // created_time
-    w.u8(q.has_swapped_time ? 1 : 0);
-    if (q.has_swapped_time) w.u64(static_cast<uint64_t>(q.swapped_time));
-    w.u32(static_cast<uint32_t>(q.status));
-    for (const std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
-      w.u64(v->size());
-      w.raw(v->data(), static_cast<int64_t>(v->size() * 4));
-    }
-    w.u64(q.num_cached_tokens);
-    w.u8(0);                                           // mamba_prefix_hash
-    w.u32(q.last_token);
-    w.u64(q.block_size);
-    b200_wire_sampling sp;
-    std::memset(&sp, 0, sizeof(sp));
-    sp.has_max_tokens = 1;
-    sp.max_tokens = static_cast<int64_t>(q.max_tokens);
-    write_sampling(w, &sp);
-    w.u8(0);                                           // pd_first_token
-    w.u8(0);                                           // images
-    w.u8(0); w.u8(0);                                  // is_tool_call_end, hit_stop_sequence
-    w.u8(0);                                           // stop_sequence
+    write_sequence(w, s->running[indices[i]]);
   }
   w.u8(is_prefill ? 1 : 0);
   if (!w.ok) {
@@ -1030,36 +1066,12 @@ int32_t b200_scheduler_load_run_prefill(b200_scheduler* s, const uint8_t* frame,
   const uint64_t n = r.u64();
   if (!r.ok || n > static_cast<uint64_t>(cap)) return -2;
   std::vector<Sequence> seqs(n);
-  for (uint64_t i = 0; i < n && r.ok; ++i) {
+  for (uint64_t i = 0; i < n; ++i) {
     Sequence& q = seqs[i];
-    q.id = static_cast<int64_t>(r.u64());
-    r.u64();                                           // created_time
-    q.has_swapped_time = r.opt();
-    if (q.has_swapped_time) q.swapped_time = static_cast<int64_t>(r.u64());
-    const uint32_t st = r.u32();
-    if (st > 5) return -1;
-    q.status = static_cast<Status>(st);
-    for (std::vector<uint32_t>* v : {&q.token_ids, &q.output_ids, &q.block_table}) {
-      const uint64_t m = r.u64();
-      if (!r.ok || !r.need(static_cast<int64_t>(m) * 4)) return -1;
-      v->resize(m);
-      std::memcpy(v->data(), r.p + r.off, m * 4);
-      r.off += static_cast<int64_t>(m) * 4;
-    }
-    q.num_cached_tokens = r.u64();
-    if (r.opt()) r.u64();                              // mamba_prefix_hash
-    q.last_token = r.u32();
-    q.block_size = r.u64();
-    b200_wire_sampling sp;
-    read_sampling(r, &sp);
-    q.max_tokens = sp.has_max_tokens ? static_cast<size_t>(sp.max_tokens) : 16384;
-    if (i == 0 && first_sampling) *first_sampling = sp;   // the strategy of a step comes from its first sequence
-    if (r.opt()) r.u32();                              // pd_first_token
-    if (r.opt()) return -4;                            // images: multimodal sequences are not taken
-    r.u8(); r.u8();                                    // is_tool_call_end, hit_stop_sequence
-    if (r.opt()) r.skip_string();                      // stop_sequence
-    if (r.ok && (q.block_size != s->block_size || q.num_cached_tokens > q.token_ids.size() ||
-                 q.block_table.size() < q.num_blocks()))
+    const int rc = read_sequence(r, q, i == 0 ? first_sampling : nullptr);   // the step's strategy: its first sequence
+    if (rc != 0) return rc;
+    if (q.block_size != s->block_size || q.num_cached_tokens > q.token_ids.size() ||
+        q.block_table.size() < q.num_blocks())
       return -3;                                       // not a sequence prepare_prefill can walk
   }
   const uint8_t pf = r.u8();
@@ -1068,6 +1080,68 @@ int32_t b200_scheduler_load_run_prefill(b200_scheduler* s, const uint8_t* frame,
   for (uint64_t i = 0; i < n; ++i) indices[i] = static_cast<int32_t>(i);
   if (is_prefill) *is_prefill = pf;
   return static_cast<int32_t>(n);
+}
+
+// ---------------------------------------------------------------- single-Sequence messages of the PD hand-off
+// family 0 = runner IPC `MessageType` (runner/mod.rs:168-249): 15 TransferPrefill(Sequence),
+//   18 ReceivePrefillResponse((bool, Option<Sequence>)), 23 KvCacheSend((Sequence, u32)), 25 KvCacheReceive(Sequence);
+// family 1 = client <-> PD server `TransferMessage` (transfer/mod.rs:113-122): 0 TransferPrefill(Sequence).
+// `extra`: the bool of kind 18, the first token of kind 23.  index < 0 with kind 18 frames `(extra, None)`.
+int64_t b200_scheduler_frame_sequence(const b200_scheduler* s, int32_t index, int32_t family, int32_t kind,
+                                      uint32_t extra, uint8_t* out, int64_t cap) {
+  using namespace b200::wire;
+  const bool ok_kind = family == 1 ? kind == 0 : (kind == 15 || kind == 18 || kind == 23 || kind == 25);
+  const bool none = family == 0 && kind == 18 && index < 0;
+  if (!ok_kind || (!none && (index < 0 || static_cast<size_t>(index) >= s->running.size()))) {
+    b200::set_error(1, "scheduler_frame_sequence: bad message kind or index");
+    return -1;
+  }
+  Wr w{out, cap};
+  w.u32(0);
+  w.u32(static_cast<uint32_t>(kind));
+  if (family == 0 && kind == 18) {
+    w.u8(extra ? 1 : 0);
+    w.u8(none ? 0 : 1);
+  }
+  if (!none) write_sequence(w, s->running[index]);
+  if (family == 0 && kind == 23) w.u32(extra);
+  if (!w.ok) {
+    b200::set_error(1, "scheduler_frame_sequence: buffer too small");
+    return -1;
+  }
+  const uint32_t body = static_cast<uint32_t>(w.off - 4);
+  std::memcpy(out, &body, 4);
+  return w.off;
+}
+
+// Loads the message's sequence as the container's only running sequence (index 0).  Returns 1, 0 for
+// ReceivePrefillResponse((_, None)), or -1 malformed / not one of the kinds above, -4 a sequence with images.
+int32_t b200_scheduler_load_sequence(b200_scheduler* s, const uint8_t* frame, int64_t len, int32_t family,
+                                     int32_t* kind, uint32_t* extra) {
+  using namespace b200::wire;
+  Rd r{frame, len};
+  const uint32_t body = r.u32();
+  const uint32_t k = r.u32();
+  if (!r.ok || static_cast<int64_t>(body) + 4 != len) return -1;
+  if (family == 1 ? k != 0 : (k != 15 && k != 18 && k != 23 && k != 25)) return -1;
+  uint32_t ex = 0;
+  bool some = true;
+  if (family == 0 && k == 18) {
+    ex = r.u8();
+    some = r.opt();
+  }
+  std::vector<Sequence> seqs;
+  if (some) {
+    seqs.resize(1);
+    const int rc = read_sequence(r, seqs[0], nullptr);
+    if (rc != 0) return rc;
+  }
+  if (family == 0 && k == 23) ex = r.u32();
+  if (!r.ok || r.off != len) return -1;
+  s->running = std::move(seqs);
+  if (kind) *kind = static_cast<int32_t>(k);
+  if (extra) *extra = ex;
+  return some ? 1 : 0;
 }
 
 // KVCacheAllocator::plan_allocation for dense models

@@ -235,6 +235,25 @@ class Scheduler:
         return idx[:n].tolist(), bool(pf.value), sp
 
 
+    # ---- single-Sequence messages of the PD hand-off (family 0: runner IPC, 1: client <-> PD server TCP)
+    def frame_sequence(self, i, kind, family=0, extra=0) -> bytes:
+        n_tok = 0 if i < 0 else 2 * len(self.tokens(i)) + len(self.block_table(i))
+        out = np.zeros(512 + 4 * n_tok, np.uint8)
+        n = self._l.b200_scheduler_frame_sequence(self._h, int(i), family, kind, int(extra), out.ctypes.data, len(out))
+        _lib.check()
+        return out[:n].tobytes()
+
+    def load_sequence(self, frame: bytes, family=0):
+        """Returns (has_sequence, kind, extra); the sequence becomes running[0] of this container."""
+        buf = np.frombuffer(frame, np.uint8)
+        kind, extra = C.c_int32(), C.c_uint32()
+        n = self._l.b200_scheduler_load_sequence(self._h, buf.ctypes.data, len(buf), family, C.byref(kind),
+                                                 C.byref(extra))
+        if n < 0:
+            raise _lib.B200Error(f"load_sequence: {n}")
+        return bool(n), kind.value, extra.value
+
+
 def plan_kvcache(available_bytes, *, num_layers, num_kv_heads, head_dim, num_shards=1, block_size=64,
                  dtype_size=2, config_model_len=8192, max_num_seqs=None, max_model_len=None,
                  cpu_mem_fold=0.5) -> dict:
