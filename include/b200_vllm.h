@@ -200,6 +200,16 @@ int64_t b200_pd_kv_frame_begin(uint8_t* frame, int64_t cap, const b200_pd_kv_hea
                                int64_t* v_off);
 int32_t b200_pd_kv_frame_parse(const uint8_t* frame, int64_t len, b200_pd_kv_header* h, int64_t* k_off,
                                int64_t* v_off, int32_t max_layers);
+/* The LocalIpc flavour of the same message (transfer/mod.rs:77,84-90): per layer a (K, V) pair of
+ * CudaIpcMemHandle(64 handle bytes, tensor shape, SerializableDType: U8 0, U32 1, I64 2, BF16 3, F16 4, F32 5, F64 6)
+ * and the server's block ids of the sequence (h->num_blocks of them; h->layer_bytes is unused).  k_handles / v_handles
+ * are [num_layers][64] bytes as cudaIpcGetMemHandle returned them; every layer shares one shape and dtype.           */
+int64_t b200_pd_ipc_frame(uint8_t* out, int64_t cap, const b200_pd_kv_header* h, const uint8_t* k_handles,
+                          const uint8_t* v_handles, const uint64_t* shape, int32_t ndim, int32_t dtype,
+                          const uint32_t* server_block_ids);
+int32_t b200_pd_ipc_frame_parse(const uint8_t* frame, int64_t len, b200_pd_kv_header* h, uint8_t* k_handles,
+                                uint8_t* v_handles, int32_t max_layers, uint64_t* shape, int32_t* ndim,
+                                int32_t* dtype, uint32_t* server_block_ids, int32_t max_blocks);
 /* kind 1 = AvailableTokenResponse(value), 3 = ReleaseKvCache(value); returns the frame length (16) */
 int64_t b200_pd_frame_small(uint8_t* out, int64_t cap, int32_t kind, uint64_t value);
 /* TransferMessage variant of a frame (0..3), -1 if malformed; *value for kinds 1 and 3 */

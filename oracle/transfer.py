@@ -181,3 +181,22 @@ def kv_receive_frame(q) -> bytes:
 
 def kv_receive_response_frame(ok, first_token, sending_time, num_cached_tokens) -> bytes:
     return frame(struct.pack("<IBIQQ", MT_KV_RECEIVE_RESPONSE, int(ok), first_token, sending_time, num_cached_tokens))
+
+
+DTYPE_U8, DTYPE_U32, DTYPE_I64, DTYPE_BF16, DTYPE_F16, DTYPE_F32, DTYPE_F64 = range(7)   # runner/mod.rs:123-133
+
+
+def kv_ipc_frame(seq_id, first_token, layer_handles, shape, dtype, server_block_ids, sending_time,
+                 num_cached_tokens) -> bytes:
+    """TransferKvCache(FinishedPrefillData { LocalIpc }) (transfer/mod.rs:77,84-90): layer_handles =
+    [(k_handle_64_bytes, v_handle_64_bytes), ...]; CudaIpcMemHandle(Vec<i8>, Vec<usize>, SerializableDType)."""
+    def handle(hb):
+        assert len(hb) == 64
+        return (struct.pack("<Q", 64) + bytes(hb) + struct.pack("<Q", len(shape)) +
+                struct.pack(f"<{len(shape)}Q", *shape) + struct.pack("<I", dtype))
+    b = struct.pack("<IQII", MSG_KV, seq_id, first_token, 0) + struct.pack("<Q", len(layer_handles))
+    for k, v in layer_handles:
+        b += handle(k) + handle(v)
+    b += struct.pack("<Q", len(server_block_ids)) + struct.pack(f"<{len(server_block_ids)}I", *server_block_ids)
+    b += struct.pack("<QQ", sending_time, num_cached_tokens)
+    return frame(b)

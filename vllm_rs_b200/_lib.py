@@ -99,6 +99,8 @@ _SIGS = {
     "b200_pd_kv_frame_bytes": (c_i64, [c_i32, c_i64]),
     "b200_pd_kv_frame_begin": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "b200_pd_kv_frame_parse": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32]),
+    "b200_pd_ipc_frame": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "b200_pd_ipc_frame_parse": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32]),
     "b200_pd_frame_small": (c_i64, [c_vp, c_i64, c_i32, C.c_uint64]),
     "b200_pd_frame_kind": (c_i32, [c_vp, c_i64, c_vp]),
     "b200_pd_export_blocks": (None, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_i64]),

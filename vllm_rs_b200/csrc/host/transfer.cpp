@@ -132,6 +132,95 @@ int32_t b200_pd_kv_frame_parse(const uint8_t* frame, int64_t len, b200_pd_kv_hea
   return 0;
 }
 
+// TransferKvCache(FinishedPrefillData { transfer_handle: LocalIpc { layer_handles, server_block_ids }, .. })
+// (transfer/mod.rs:77,82-101,430-470): per layer a (K, V) pair of CudaIpcMemHandle(Vec<i8> = the 64 handle bytes,
+// Vec<usize> = the tensor's shape, SerializableDType = runner/mod.rs:123-133: U8 0, U32 1, I64 2, BF16 3, F16 4,
+// F32 5, F64 6), then the server's block ids of the sequence.  The handle bytes are cudaIpcGetMemHandle's, taken by
+// the host; opened on the client they are the `remote_k` / `remote_v` of b200_pd_copy_blocks_peer.
+int64_t b200_pd_ipc_frame(uint8_t* out, int64_t cap, const b200_pd_kv_header* h, const uint8_t* k_handles,
+                          const uint8_t* v_handles, const uint64_t* shape, int32_t ndim, int32_t dtype,
+                          const uint32_t* server_block_ids) {
+  if (!out || !h || !k_handles || !v_handles || !shape || h->num_layers <= 0 || ndim <= 0 || ndim > 8 || dtype < 0 ||
+      dtype > 6 || (h->num_blocks > 0 && !server_block_ids)) {
+    b200::set_error(1, "pd_ipc_frame: bad arguments");
+    return -1;
+  }
+  Writer w{out, cap};
+  w.u32(0);
+  w.u32(kMsgTransferKvCache);
+  w.u64(h->seq_id);
+  w.u32(h->first_token);
+  w.u32(kHandleLocalIpc);
+  w.u64(static_cast<uint64_t>(h->num_layers));
+  for (int32_t l = 0; l < h->num_layers; ++l)
+    for (int kv = 0; kv < 2; ++kv) {
+      w.u64(64);
+      w.raw((kv == 0 ? k_handles : v_handles) + static_cast<size_t>(l) * 64, 64);
+      w.u64(static_cast<uint64_t>(ndim));
+      for (int32_t d = 0; d < ndim; ++d) w.u64(shape[d]);
+      w.u32(static_cast<uint32_t>(dtype));
+    }
+  w.u64(h->num_blocks);
+  w.raw(server_block_ids, static_cast<int64_t>(h->num_blocks) * 4);
+  w.u64(h->sending_time);
+  w.u64(h->num_cached_tokens);
+  if (!w.ok) {
+    b200::set_error(1, "pd_ipc_frame: buffer too small");
+    return -1;
+  }
+  const uint32_t body = static_cast<uint32_t>(w.off - 4);
+  std::memcpy(out, &body, 4);
+  return w.off;
+}
+
+// Returns 0, or < 0: malformed (-2 length, -3 not TransferKvCache, -4 not LocalIpc, -5 layer count, -6 handle / shape
+// fields, -7 layers that differ in shape or dtype, -8 block list / tail).  k_handles / v_handles: [max_layers][64].
+int32_t b200_pd_ipc_frame_parse(const uint8_t* frame, int64_t len, b200_pd_kv_header* h, uint8_t* k_handles,
+                                uint8_t* v_handles, int32_t max_layers, uint64_t* shape, int32_t* ndim, int32_t* dtype,
+                                uint32_t* server_block_ids, int32_t max_blocks) {
+  if (!frame || !h || !k_handles || !v_handles || !shape || !ndim || !dtype) return -1;
+  Reader r{frame, len};
+  const uint32_t body = r.u32();
+  if (!r.ok || static_cast<int64_t>(body) + 4 != len) return -2;
+  if (r.u32() != kMsgTransferKvCache) return -3;
+  h->seq_id = r.u64();
+  h->first_token = r.u32();
+  if (r.u32() != kHandleLocalIpc) return -4;
+  const uint64_t nl = r.u64();
+  if (!r.ok || nl == 0 || nl > static_cast<uint64_t>(max_layers)) return -5;
+  h->num_layers = static_cast<int32_t>(nl);
+  h->layer_bytes = 0;
+  for (uint64_t l = 0; l < nl; ++l)
+    for (int kv = 0; kv < 2; ++kv) {
+      if (r.u64() != 64 || !r.ok || r.off + 64 > len) return -6;
+      std::memcpy((kv == 0 ? k_handles : v_handles) + l * 64, frame + r.off, 64);
+      r.off += 64;
+      const uint64_t nd = r.u64();
+      if (!r.ok || nd == 0 || nd > 8) return -6;
+      uint64_t dims[8];
+      for (uint64_t d = 0; d < nd; ++d) dims[d] = r.u64();
+      const uint32_t dt = r.u32();
+      if (!r.ok || dt > 6) return -6;
+      if (l == 0 && kv == 0) {
+        *ndim = static_cast<int32_t>(nd);
+        *dtype = static_cast<int32_t>(dt);
+        std::memcpy(shape, dims, nd * 8);
+      } else if (static_cast<int32_t>(nd) != *ndim || static_cast<int32_t>(dt) != *dtype ||
+                 std::memcmp(shape, dims, nd * 8) != 0) {
+        return -7;                                         // one cache geometry for the whole model
+      }
+    }
+  const uint64_t nb = r.u64();
+  if (!r.ok || nb > static_cast<uint64_t>(max_blocks) || r.off + static_cast<int64_t>(nb) * 4 > len) return -8;
+  if (nb) std::memcpy(server_block_ids, frame + r.off, nb * 4);
+  r.off += static_cast<int64_t>(nb) * 4;
+  h->num_blocks = nb;
+  h->sending_time = r.u64();
+  h->num_cached_tokens = r.u64();
+  if (!r.ok || r.off != len) return -8;
+  return 0;
+}
+
 int64_t b200_pd_frame_small(uint8_t* out, int64_t cap, int32_t kind, uint64_t value) {
   // AvailableTokenResponse(usize) / ReleaseKvCache(usize): len | variant | u64
   if (!out || cap < 16 || (kind != static_cast<int32_t>(kMsgAvailableTokens) && kind != static_cast<int32_t>(kMsgReleaseKvCache))) {
@@ -155,7 +244,6 @@ int32_t b200_pd_frame_kind(const uint8_t* frame, int64_t len, uint64_t* value) {
     if (!r.ok) return -1;
   }
   (void)kMsgTransferPrefill;
-  (void)kHandleLocalIpc;
   return static_cast<int32_t>(kind);
 }
 
